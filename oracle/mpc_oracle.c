@@ -665,7 +665,7 @@ int oracle_mpc_solve(const oracle_params* p, const double* state6, const double*
   int N = p->N, n = s->q.n, m = s->q.m, nb = s->q.nb;
   s->n = n; s->m = m; s->nb = nb; s->b0 = s->q.ds;
   int d = n + m;
-  size_t nd = (size_t)(8 * n + 6 * m + 10 * nb + 2 * d) + (size_t)m * n + (size_t)n * n + (size_t)d * d + 16;
+  size_t nd = (size_t)(8 * n + 8 * m + 12 * nb + 2 * d) + (size_t)m * n + (size_t)n * n + (size_t)d * d + 16;
   double* mem = (double*)calloc(nd, sizeof(double));
   double* q = mem;
 #define TAKE(k) (q += (k), q - (k))
