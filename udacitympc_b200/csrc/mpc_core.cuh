@@ -1,0 +1,934 @@
+// b200mpc solver core: one nonlinear-MPC problem per thread, primal-dual interior point with a
+// structure-exploiting Riccati (block-tridiagonal Schur-complement) KKT solve.
+//
+// What this replaces in the reference (/root/reference):
+//   mpc_to_line/solution/MPC.cpp:45-140   FG_eval cost + constraints (here: closed-form residuals, Jacobian
+//                                         blocks A_t,B_t and Lagrangian-Hessian blocks, no tape)
+//   mpc_to_line/solution/MPC.cpp:149-257  MPC::Solve (start point, bounds, solve, returned 8-vector)
+//   Ipopt-3.12.7/Ipopt/src/Algorithm/     the interior-point algorithm with the default options MPC.cpp leaves
+//                                         untouched: IpDefaultIterateInitializer.cpp:175-344, IpLeastSquareMults.cpp:40-94,
+//                                         IpMonotoneMuUpdate.cpp:132-232, IpPDSearchDirCalc.cpp:60-139,
+//                                         IpPDPerturbationHandler.cpp:148-420, IpBacktrackingLineSearch.cpp:261-797,852-941,
+//                                         IpFilterLSAcceptor.cpp:227-587,800-813, IpIpoptAlg.cpp:559-727,880-951,
+//                                         IpOptErrorConvCheck.cpp:204-329, IpGradientScaling.cpp:69-119,
+//                                         IpOrigIpoptNLP.cpp:361-372,466-482,875-883
+//   Ipopt .../LinearSolvers + MUMPS       generic sparse LDL^T of the 348x348 augmented system -> the stage-wise
+//                                         Riccati recursion below (inertia test = all 2x2 control blocks positive definite)
+//
+// The same source is compiled by nvcc for the device and, for the CPU-side algorithm tests only
+// (tests/hostsim), by g++.  The product (libb200mpc.so) has no CPU solve path.
+//
+// Stage structure.  Variables s_t=(x,y,psi,v,cte,epsi), t=0..N-1, u_t=(delta,a), t=0..N-2.  Constraint rows
+// at time t+1:  c_{t+1} = s_{t+1} - F(s_t,u_t).  Newton step of the barrier problem (Ipopt's augmented system
+// [[W+Sigma+dw I, J^T],[J, 0]] (dx,dlam) = -(grad_x L_mu, c)) is the LQ problem
+//     min 1/2 dx^T H dx + r^T dx   s.t.  ds_{t+1} = A_t ds_t + B_t du_t - c_{t+1},  ds_0 = 0
+// whose multipliers are dlam.  cte_{t+1} does not influence any later row (column cte of A is zero) so it is
+// folded into stage t as a quadratic on a linear output; the (u_{t+1},u_t) smoothness coupling is carried by
+// augmenting the recursion state with the previous control: xi_t = (x,y,psi,v,epsi | delta_{t-1},a_{t-1}) in R^7.
+#pragma once
+#include <float.h>
+#include <math.h>
+
+#ifdef __CUDACC__
+#define MPC_HD __host__ __device__ __forceinline__
+#else
+#define MPC_HD inline
+#endif
+
+namespace b200mpc {
+
+// Mirrors b200mpc_params (include/b200mpc.h).  Defaults = the reference's hard-coded values.
+struct Params {
+  int N;
+  double dt, Lf, ref_v;
+  double w_cte, w_epsi, w_v, w_delta, w_a, w_ddelta, w_da;
+  double delta_max, a_max;
+  double tol;
+  int max_iter;
+};
+
+// Ipopt return codes used (Ipopt/src/Interfaces/IpReturnCodes_inc.h:16-39)
+enum Status {
+  kSolveSucceeded = 0,
+  kSolvedToAcceptableLevel = 1,
+  kSearchDirectionTooSmall = 3,
+  kDivergingIterates = 4,
+  kMaxIterExceeded = -1,
+  kRestorationFailed = -2,      // line search failed; the restoration phase is not implemented
+  kErrorInStepComputation = -3  // inertia correction exhausted
+};
+
+constexpr int kMaxCoef = 4;   // reference polynomial degree <= 3
+constexpr int kMaxFilter = 12;
+constexpr int kKF = 13;       // Riccati factors stored per stage: K (2x4), Lambda^-1 (3), k (2)
+
+// Workspace of one problem, in doubles.  Element i of the problem owned by lane l of a 32-problem group lives
+// at group_base[i*LANES + l]  (LANES = 32 on the device: every access of a warp is one 256-byte row).
+struct Layout {
+  int S, U, LAM, ZL, ZU, DS, DU, TR, C, CSOC, KF, total;
+  MPC_HD explicit Layout(int N) {
+    const int M = N - 1;
+    int o = 0;
+    S = o; o += 6 * N;
+    U = o; o += 2 * M;
+    LAM = o; o += 6 * N;
+    ZL = o; o += 2 * M;
+    ZU = o; o += 2 * M;
+    DS = o; o += 6 * N;
+    DU = o; o += 2 * M;
+    TR = o; o += 2 * 4 * M;   // two buffers (current / trial)
+    C = o; o += 2 * 6 * N;    // two buffers (current / trial)
+    CSOC = o; o += 6 * N;
+    KF = o; o += kKF * M;
+    total = o;
+  }
+};
+
+template <int LANES>
+struct Ws {
+  double* b;
+  MPC_HD double& operator()(int i) const { return b[(size_t)i * LANES]; }
+};
+
+MPC_HD double dmax(double a, double b) { return a > b ? a : b; }
+MPC_HD double dmin(double a, double b) { return a < b ? a : b; }
+MPC_HD double dclamp(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// value and first three derivatives of the reference polynomial (MPC.cpp:117-118 generalised; identical
+// arithmetic to the degree-1 shipped form when c2=c3=0).
+MPC_HD void poly_eval(const double* c, double x, double& p0, double& p1, double& p2, double& p3) {
+  double a = 0.0, b = 0.0, d = 0.0, e = 0.0;
+#pragma unroll
+  for (int i = kMaxCoef - 1; i >= 0; --i) {
+    e = e * x + 3.0 * d;
+    d = d * x + 2.0 * b;
+    b = b * x + a;
+    a = a * x + c[i];
+  }
+  p0 = a; p1 = b; p2 = d; p3 = e;
+}
+
+// IpIpoptCalculatedQuantities.cpp:444-507 (slack safeguard; practically never active)
+MPC_HD double safe_slack(double v, double mu, double z, double bnd) {
+  const double smin = DBL_EPSILON * dmin(mu, 1.0);
+  if (v < smin) {
+    double t = dmax(mu / z, smin);
+    double cap = dmax(fabs(bnd), 1.0) * 1.8189894035458565e-12 /* eps^0.75 */ + dmax(v, 0.0);
+    v = dmin(t, cap);
+  }
+  return v;
+}
+
+// Linearised dynamics of one stage: non-trivial entries of A_t (6x6) and B_t (6x2), MPC.cpp:130-137.
+struct Lin {
+  double a1, a2, a3, a4, a5, beta, pp, kap, sed, vce;
+};
+MPC_HD Lin make_lin(const Params& P, double v, double delta, double sp, double cp, double se, double ce, double p1,
+                    double p2) {
+  Lin L;
+  L.a1 = -v * sp * P.dt;      // d x1 / d psi0
+  L.a2 = v * cp * P.dt;       // d y1 / d psi0
+  L.a3 = cp * P.dt;           // d x1 / d v0
+  L.a4 = sp * P.dt;           // d y1 / d v0
+  L.a5 = delta / P.Lf * P.dt; // d psi1 / d v0 = d epsi1 / d v0
+  L.beta = v / P.Lf * P.dt;   // d psi1 / d delta0 = d epsi1 / d delta0
+  L.pp = p1;                  // d cte1 / d x0
+  L.kap = p2 / (1.0 + p1 * p1);  // -d epsi1 / d x0
+  L.sed = se * P.dt;          // d cte1 / d v0
+  L.vce = v * ce * P.dt;      // d cte1 / d epsi0
+  return L;
+}
+// out = r * Abar over the reduced state (x,y,psi,v,epsi); column epsi of Abar is zero, so 4 outputs.
+MPC_HD void applyA(const Lin& L, double rx, double ry, double rp, double rv, double re, double& ox, double& oy,
+                   double& op, double& ov) {
+  const double rpe = rp + re;
+  ox = rx - L.kap * re;
+  oy = ry;
+  op = L.a1 * rx + L.a2 * ry + rpe;
+  ov = L.a3 * rx + L.a4 * ry + L.a5 * rpe + rv;
+}
+// A_t^T m for the full 6-vector m=(x,y,psi,v,cte,epsi); component cte of the result is 0.
+MPC_HD void applyAT6(const Lin& L, const double* m, double* o) {
+  o[0] = m[0] + L.pp * m[4] - L.kap * m[5];
+  o[1] = m[1] - m[4];
+  o[2] = L.a1 * m[0] + L.a2 * m[1] + m[2] + m[5];
+  o[3] = L.a3 * m[0] + L.a4 * m[1] + L.a5 * (m[2] + m[5]) + m[3] + L.sed * m[4];
+  o[4] = 0.0;
+  o[5] = L.vce * m[4];
+}
+
+// Lagrangian-Hessian entries contributed by the constraint rows of time t+1 to the variables of time t
+// (SURVEY Appendix A), multipliers lam = lambda_{t+1}.
+struct Hes {
+  double xx, pp, vp, ee, ev, m;
+};
+MPC_HD Hes make_hes(const Params& P, const double* lam, double v, double sp, double cp, double se, double ce, double p1,
+                    double p2, double p3) {
+  Hes H;
+  const double q = 1.0 + p1 * p1;
+  H.xx = -lam[4] * p2 + lam[5] * (p3 * q - 2.0 * p1 * p2 * p2) / (q * q);
+  H.pp = lam[0] * v * cp * P.dt + lam[1] * v * sp * P.dt;
+  H.vp = lam[0] * sp * P.dt - lam[1] * cp * P.dt;
+  H.ee = lam[4] * v * se * P.dt;
+  H.ev = -lam[4] * ce * P.dt;
+  H.m = -(lam[2] + lam[5]) * P.dt / P.Lf;
+  return H;
+}
+
+#define PS(i, j) pss[((i) >= (j)) ? ((i) * ((i) + 1) / 2 + (j)) : ((j) * ((j) + 1) / 2 + (i))]
+
+// Result of one MPC::Solve.
+struct Result {
+  int status, iters;
+  double obj;
+  double out8[8];
+};
+
+enum Phase { PH_FACTOR = 0, PH_FORWARD = 1, PH_TRIAL = 2, PH_ACCEPT = 3, PH_DONE = 4 };
+
+// The per-problem solver.  All "passes" are loops over the horizon that touch the workspace once per stage.
+template <int LANES>
+struct Solver {
+  const Params& P;
+  Ws<LANES> w;
+  const Layout L;
+  const int N, M;
+  double cf[kMaxCoef];
+  double psides_c;   // unused for degree>1
+  // ---- algorithm state
+  double df, mu, tau, mu_min;
+  double dw_curr, dw_last;          // PDPerturbationHandler delta_x
+  double fphi[kMaxFilter], fth[kMaxFilter];
+  int nf;
+  double theta_max, theta_min;
+  int cur;                          // which TR/C buffer holds the current iterate
+  int iter;
+  int status;
+  // quantities at the current iterate
+  double f_cur, theta_cur, priminf, dualinf, lam1, z1, sz_max, sz_min, sumlog, xmaxabs, dlam_max;
+  // line-search state
+  double ref_theta, ref_barr, ref_gbd, alpha, alpha_max, alpha_min, alpha_du, alpha_test;
+  double tr_f, tr_theta, tr_priminf, tr_sumlog;   // at the last evaluated trial point
+  int n_steps, soc_count, tiny_now;
+  double theta_soc_old, alpha_soc;
+  bool in_soc, soc_done, ls_mode, lam_zero, tiny_last, tiny_flag;
+  int acceptable_counter;
+  double curr_obj, last_obj;
+  int phase;
+
+  MPC_HD Solver(const Params& p, double* base) : P(p), w{base}, L(p.N), N(p.N), M(p.N - 1) {}
+
+  MPC_HD double bnd(int j) const { return j == 0 ? P.delta_max : P.a_max; }
+  MPC_HD double relax(int j) const { return 1e-8 * dmax(1.0, fabs(bnd(j))); }  // IpOrigIpoptNLP.cpp:369-372
+  MPC_HD double xU(int j) const { return bnd(j) + relax(j); }
+  MPC_HD double xL(int j) const { return -bnd(j) - relax(j); }
+  MPC_HD int TRo(int buf, int t) const { return L.TR + (buf * M + t) * 4; }
+  MPC_HD int Co(int buf, int t) const { return L.C + (buf * N + t) * 6; }
+
+  // objective gradient w.r.t. u_t (scaled by df); um/up = u_{t-1}/u_{t+1}
+  MPC_HD double grad_u(int j, int t, double u, double um, double up) const {
+    const double wq = j == 0 ? P.w_delta : P.w_a, wd = j == 0 ? P.w_ddelta : P.w_da;
+    double g = 2.0 * wq * u;
+    if (t > 0) g += 2.0 * wd * (u - um);
+    if (t < M - 1) g -= 2.0 * wd * (up - u);
+    return df * g;
+  }
+  MPC_HD double hess_u(int j, int t) const {
+    const double wq = j == 0 ? P.w_delta : P.w_a, wd = j == 0 ? P.w_ddelta : P.w_da;
+    const double nd = (t > 0 ? 1.0 : 0.0) + (t < M - 1 ? 1.0 : 0.0);
+    return 2.0 * df * (wq + nd * wd);
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // start point, bounds, scaling, z, mu  (MPC.cpp:167-203; IpGradientScaling.cpp:99-116;
+  // IpDefaultIterateInitializer.cpp:230-266, 469-649)
+  MPC_HD void init(const double* s0, const double* coef, int ncoef) {
+#pragma unroll
+    for (int i = 0; i < kMaxCoef; ++i) cf[i] = i < ncoef ? coef[i] : 0.0;
+    for (int t = 0; t < N; ++t)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) w(L.S + 6 * t + k) = t == 0 ? s0[k] : 0.0;
+    // gradient of f at the user's start point: states zero except t=0, controls zero
+    double gmax = dmax(fabs(2.0 * P.w_cte * s0[4]), fabs(2.0 * P.w_epsi * s0[5]));
+    gmax = dmax(gmax, fabs(2.0 * P.w_v * (s0[3] - P.ref_v)));
+    if (N > 1) gmax = dmax(gmax, fabs(2.0 * P.w_v * (0.0 - P.ref_v)));
+    df = 1.0;
+    if (gmax > 100.0) df = 100.0 / gmax;
+    if (df < 1e-8) df = 1e-8;
+    for (int t = 0; t < M; ++t)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const double l = xL(j), u = xU(j);
+        double v = dclamp(0.0, l, u);
+        const double ql = 0.01 * (u - l);
+        const double pl = dmin(0.01 * dmax(fabs(l), 1.0), ql), pu = dmin(0.01 * dmax(fabs(u), 1.0), ql);
+        v = dclamp(v, l + pl, u - pu);
+        w(L.U + 2 * t + j) = v;
+        w(L.ZL + 2 * t + j) = 1.0;
+        w(L.ZU + 2 * t + j) = 1.0;
+      }
+    for (int i = 0; i < 6 * N; ++i) w(L.LAM + i) = 0.0;
+    mu = 0.1;
+    tau = dmax(0.99, 1.0 - mu);
+    mu_min = dmin(P.tol, 1e-4 * df) / (10.0 + 1.0);
+    theta_max = theta_min = -1.0;
+    nf = 0;
+    dw_curr = dw_last = 0.0;
+    cur = 0;
+    iter = 0;
+    status = -100;
+    acceptable_counter = 0;
+    curr_obj = last_obj = -1e50;
+    tiny_last = tiny_flag = false;
+    in_soc = soc_done = false;
+    lam_zero = false;
+    dlam_max = 0.0;
+    ls_mode = true;
+    alpha = 0.0; alpha_du = 0.0;
+    // residuals / trig at the start point, then least-square multipliers through the same passes
+    eval_point(0.0, cur);
+    f_cur = tr_f; theta_cur = tr_theta; priminf = tr_priminf; sumlog = tr_sumlog;
+    phase = PH_FACTOR;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // f, c, trig at x + a*dx  -> TR[buf], C[buf]; scalars tr_*  (MPC.cpp:57-138)
+  MPC_HD void eval_point(double a, int buf) {
+    double s[6], sn[6], u[2], un[2];
+    const bool step = a != 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s[k] = w(L.S + k);   // ds_0 = 0
+    double f = 0.0, th = 0.0, cm = 0.0, sl = 0.0;
+    u[0] = u[1] = 0.0;
+    for (int t = 0; t < M; ++t) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        un[j] = w(L.U + 2 * t + j);
+        if (step) un[j] += a * w(L.DU + 2 * t + j);
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        sn[k] = w(L.S + 6 * (t + 1) + k);
+        if (step) sn[k] += a * w(L.DS + 6 * (t + 1) + k);
+      }
+      double sp, cp, se, ce, p0, p1, p2, p3;
+      sincos(s[2], &sp, &cp);
+      sincos(s[5], &se, &ce);
+      poly_eval(cf, s[0], p0, p1, p2, p3);
+      const double psides = atan(p1);
+      double c[6];
+      c[0] = sn[0] - (s[0] + s[3] * cp * P.dt);
+      c[1] = sn[1] - (s[1] + s[3] * sp * P.dt);
+      c[2] = sn[2] - (s[2] + s[3] * un[0] / P.Lf * P.dt);
+      c[3] = sn[3] - (s[3] + un[1] * P.dt);
+      c[4] = sn[4] - ((p0 - s[1]) + (s[3] * se * P.dt));
+      c[5] = sn[5] - ((s[2] - psides) + s[3] * un[0] / P.Lf * P.dt);
+      const int to = TRo(buf, t), co = Co(buf, t + 1);
+      w(to + 0) = sp; w(to + 1) = cp; w(to + 2) = se; w(to + 3) = ce;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { w(co + k) = c[k]; th += fabs(c[k]); cm = dmax(cm, fabs(c[k])); }
+      // cost of time t
+      f += P.w_cte * (s[4] * s[4]) + P.w_epsi * (s[5] * s[5]) + P.w_v * ((s[3] - P.ref_v) * (s[3] - P.ref_v));
+      f += P.w_delta * (un[0] * un[0]) + P.w_a * (un[1] * un[1]);
+      if (t > 0) f += P.w_ddelta * ((un[0] - u[0]) * (un[0] - u[0])) + P.w_da * ((un[1] - u[1]) * (un[1] - u[1]));
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const double zl = w(L.ZL + 2 * t + j), zu = w(L.ZU + 2 * t + j);
+        sl += log(safe_slack(un[j] - xL(j), mu, zl, xL(j))) + log(safe_slack(xU(j) - un[j], mu, zu, xU(j)));
+        u[j] = un[j];
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s[k] = sn[k];
+    }
+    f += P.w_cte * (s[4] * s[4]) + P.w_epsi * (s[5] * s[5]) + P.w_v * ((s[3] - P.ref_v) * (s[3] - P.ref_v));
+    tr_f = df * f; tr_theta = th; tr_priminf = cm; tr_sumlog = sl;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // Backward Riccati sweep: factor + feed-forward for the right-hand side (grad L_mu, c).  csoc selects the
+  // constraint right-hand side (second-order correction).  Returns false on wrong inertia.
+  MPC_HD bool factor(double dw, bool use_csoc) {
+    const bool ls = ls_mode;
+    const double qv = ls ? 1.0 : 2.0 * P.w_v * df + dw, qe = ls ? 1.0 : 2.0 * P.w_epsi * df + dw,
+                 qc = ls ? 1.0 : 2.0 * P.w_cte * df + dw, q0 = ls ? 1.0 : dw;
+    double pss[15], psu[4][2], puu00 = 0.0, puu10 = 0.0, puu11 = 0.0, pv[5], pu0 = 0.0, pu1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 15; ++i) pss[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) psu[i][0] = psu[i][1] = 0.0;
+    double lamn[6];   // lambda_{t+1}
+    double sT[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { lamn[k] = ls ? 0.0 : w(L.LAM + 6 * M + k); sT[k] = w(L.S + 6 * M + k); }
+    PS(0, 0) = q0; PS(1, 1) = q0; PS(2, 2) = q0; PS(3, 3) = qv; PS(4, 4) = qe;
+    // r_s at the terminal time: grad f + lambda
+    pv[0] = lamn[0]; pv[1] = lamn[1]; pv[2] = lamn[2];
+    pv[3] = 2.0 * P.w_v * df * (sT[3] - P.ref_v) + lamn[3];
+    pv[4] = 2.0 * P.w_epsi * df * sT[5] + lamn[5];
+    double rc_next = 2.0 * P.w_cte * df * sT[4] + lamn[4];   // grad L wrt cte_{t+1}
+    double un0 = 0.0, un1 = 0.0;                            // u_{t+1}
+    bool ok = true;
+    for (int t = M - 1; t >= 0; --t) {
+      double s[6], lam[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { s[k] = w(L.S + 6 * t + k); lam[k] = ls ? 0.0 : w(L.LAM + 6 * t + k); }
+      const double u0 = w(L.U + 2 * t), u1 = w(L.U + 2 * t + 1);
+      double um0 = 0.0, um1 = 0.0;
+      if (t > 0) { um0 = w(L.U + 2 * t - 2); um1 = w(L.U + 2 * t - 1); }
+      const int to = TRo(cur, t);
+      const double sp = w(to), cp = w(to + 1), se = w(to + 2), ce = w(to + 3);
+      double p0, p1, p2, p3;
+      poly_eval(cf, s[0], p0, p1, p2, p3);
+      const Lin A = make_lin(P, s[3], u0, sp, cp, se, ce, p1, p2);
+      Hes H;
+      if (ls) { H.xx = H.pp = H.vp = H.ee = H.ev = H.m = 0.0; }
+      else H = make_hes(P, lamn, s[3], sp, cp, se, ce, p1, p2, p3);
+      // constraint right-hand side of rows t+1
+      double rb[5], cc;
+      if (ls) { rb[0] = rb[1] = rb[2] = rb[3] = rb[4] = 0.0; cc = 0.0; }
+      else {
+        const int co = use_csoc ? L.CSOC + 6 * (t + 1) : Co(cur, t + 1);
+        rb[0] = -w(co); rb[1] = -w(co + 1); rb[2] = -w(co + 2); rb[3] = -w(co + 3); cc = w(co + 4); rb[4] = -w(co + 5);
+      }
+      // bound terms of u_t
+      const double zl0 = w(L.ZL + 2 * t), zl1 = w(L.ZL + 2 * t + 1), zu0 = w(L.ZU + 2 * t), zu1 = w(L.ZU + 2 * t + 1);
+      double r0, r1, ru0, ru1;
+      {
+        double ATl[6];
+        applyAT6(A, lamn, ATl);   // A_t^T lambda_{t+1}
+        const double gu0 = grad_u(0, t, u0, um0, un0), gu1 = grad_u(1, t, u1, um1, un1);
+        const double bl0 = A.beta * (lamn[2] + lamn[5]), bl1 = P.dt * lamn[3];   // B_t^T lambda_{t+1}
+        if (ls) {
+          r0 = 1.0; r1 = 1.0;
+          ru0 = gu0 - zl0 + zu0; ru1 = gu1 - zl1 + zu1;
+        } else {
+          const double sl0 = safe_slack(u0 - xL(0), mu, zl0, xL(0)), su0 = safe_slack(xU(0) - u0, mu, zu0, xU(0));
+          const double sl1 = safe_slack(u1 - xL(1), mu, zl1, xL(1)), su1 = safe_slack(xU(1) - u1, mu, zu1, xU(1));
+          r0 = hess_u(0, t) + dw + zl0 / sl0 + zu0 / su0;
+          r1 = hess_u(1, t) + dw + zl1 / sl1 + zu1 / su1;
+          ru0 = gu0 - bl0 - mu / sl0 + mu / su0;
+          ru1 = gu1 - bl1 - mu / sl1 + mu / su1;
+        }
+        // r_s at time t (reduced: x,y,psi,v,epsi) and the cte fold
+        const double gc = rc_next - qc * cc;   // linear coefficient on a_c^T dsigma
+        // ---- recursion
+        double wv[5], wu0 = pu0, wu1 = pu1;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          double a = pv[i];
+#pragma unroll
+          for (int j = 0; j < 5; ++j) a += PS(i, j) * rb[j];
+          wv[i] = a;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { wu0 += psu[i][0] * rb[i]; wu1 += psu[i][1] * rb[i]; }
+        double T0[5], T1[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          T0[j] = A.beta * (PS(2, j) + PS(4, j)) + (j < 4 ? psu[j < 4 ? j : 0][0] : 0.0);
+          T1[j] = P.dt * PS(3, j) + (j < 4 ? psu[j < 4 ? j : 0][1] : 0.0);
+        }
+        const double Tu00 = A.beta * psu[2][0] + puu00, Tu10 = P.dt * psu[3][0] + puu10, Tu11 = P.dt * psu[3][1] + puu11;
+        const double L00 = r0 + A.beta * (T0[2] + T0[4]) + Tu00;
+        const double L10 = A.beta * (T1[2] + T1[4]) + Tu10;
+        const double L11 = r1 + P.dt * T1[3] + Tu11;
+        const double det = L00 * L11 - L10 * L10;
+        if (!(L00 > 0.0) || !(det > 0.0)) ok = false;
+        const double idet = 1.0 / det;
+        const double i00 = L11 * idet, i10 = -L10 * idet, i11 = L00 * idet;
+        double G0[4], G1[4];
+        applyA(A, T0[0], T0[1], T0[2], T0[3], T0[4], G0[0], G0[1], G0[2], G0[3]);
+        applyA(A, T1[0], T1[1], T1[2], T1[3], T1[4], G1[0], G1[1], G1[2], G1[3]);
+        G0[3] += H.m;
+        const double h0 = ru0 + A.beta * (wv[2] + wv[4]) + wu0, h1 = ru1 + P.dt * wv[3] + wu1;
+        double K0[4], K1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { K0[j] = i00 * G0[j] + i10 * G1[j]; K1[j] = i10 * G0[j] + i11 * G1[j]; }
+        const double k0 = i00 * h0 + i10 * h1, k1 = i10 * h0 + i11 * h1;
+        const int ko = L.KF + kKF * t;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { w(ko + j) = K0[j]; w(ko + 4 + j) = K1[j]; }
+        w(ko + 8) = i00; w(ko + 9) = i10; w(ko + 10) = i11; w(ko + 11) = k0; w(ko + 12) = k1;
+        // Y = Pss * Abar (5x4), S = Abar^T Y (4x4, lower)
+        double Y[5][4];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) applyA(A, PS(i, 0), PS(i, 1), PS(i, 2), PS(i, 3), PS(i, 4), Y[i][0], Y[i][1], Y[i][2], Y[i][3]);
+        double Sm[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) applyA(A, Y[0][j], Y[1][j], Y[2][j], Y[3][j], Y[4][j], Sm[0][j], Sm[1][j], Sm[2][j], Sm[3][j]);
+        double aw[4];
+        applyA(A, wv[0], wv[1], wv[2], wv[3], wv[4], aw[0], aw[1], aw[2], aw[3]);
+        const double ac[4] = {A.pp, -1.0, 0.0, A.sed};
+        // r_s,t = grad f_s + lambda_t - A^T lambda_{t+1}
+        double rs[5];
+        rs[0] = lam[0] - ATl[0];
+        rs[1] = lam[1] - ATl[1];
+        rs[2] = lam[2] - ATl[2];
+        rs[3] = 2.0 * P.w_v * df * (s[3] - P.ref_v) + lam[3] - ATl[3];
+        rs[4] = 2.0 * P.w_epsi * df * s[5] + lam[5] - ATl[5];
+        // new P, p
+        double nss[15];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j <= i; ++j)
+            nss[i * (i + 1) / 2 + j] = Sm[i][j] + qc * ac[i] * ac[j] - (G0[i] * K0[j] + G1[i] * K1[j]);
+        nss[0] += q0 + H.xx;
+        nss[2] += q0;
+        nss[5] += q0 + H.pp;
+        nss[8] += H.vp;          // (v,psi)
+        nss[9] += qv;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nss[10 + j] = qc * A.vce * ac[j];
+        nss[13] += H.ev;         // (epsi,v)
+        nss[14] = qe + H.ee + qc * A.vce * A.vce;
+        double d0 = 0.0, d1 = 0.0;   // coupling with u_{t-1}
+        if (t > 0 && !ls) { d0 = 2.0 * df * P.w_ddelta; d1 = 2.0 * df * P.w_da; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { psu[i][0] = K0[i] * d0; psu[i][1] = K1[i] * d1; }
+        puu00 = -d0 * d0 * i00; puu10 = -d0 * d1 * i10; puu11 = -d1 * d1 * i11;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pv[i] = rs[i] + aw[i] + gc * ac[i] - (G0[i] * k0 + G1[i] * k1);
+        pv[4] = rs[4] + gc * A.vce;
+        pu0 = d0 * k0; pu1 = d1 * k1;
+#pragma unroll
+        for (int i = 0; i < 15; ++i) pss[i] = nss[i];
+      }
+      rc_next = 2.0 * P.w_cte * df * s[4] + lam[4];
+      un0 = u0; un1 = u1;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) lamn[k] = lam[k];
+    }
+    return ok;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // Forward sweep: dx (-> DS, DU), fraction-to-the-boundary steps, directional derivative of the barrier.
+  MPC_HD void forward(bool use_csoc, double dw) {
+    const bool ls = ls_mode;
+    double ds[6] = {0, 0, 0, 0, 0, 0}, dup0 = 0.0, dup1 = 0.0;
+    double a_pr = 1.0, a_du = 1.0, gbd = 0.0, tiny = 0.0;
+    double um0 = 0.0, um1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) w(L.DS + k) = 0.0;
+    (void)dw;
+    for (int t = 0; t < M; ++t) {
+      const int ko = L.KF + kKF * t;
+      double K0[4], K1[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { K0[j] = w(ko + j); K1[j] = w(ko + 4 + j); }
+      const double i00 = w(ko + 8), i10 = w(ko + 9), i11 = w(ko + 10), k0 = w(ko + 11), k1 = w(ko + 12);
+      double d0 = 0.0, d1 = 0.0;
+      if (t > 0 && !ls) { d0 = 2.0 * df * P.w_ddelta; d1 = 2.0 * df * P.w_da; }
+      const double e0 = d0 * dup0, e1 = d1 * dup1;
+      const double du0 = -(K0[0] * ds[0] + K0[1] * ds[1] + K0[2] * ds[2] + K0[3] * ds[3] + k0) + (i00 * e0 + i10 * e1);
+      const double du1 = -(K1[0] * ds[0] + K1[1] * ds[1] + K1[2] * ds[2] + K1[3] * ds[3] + k1) + (i10 * e0 + i11 * e1);
+      w(L.DU + 2 * t) = du0; w(L.DU + 2 * t + 1) = du1;
+      double s[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s[k] = w(L.S + 6 * t + k);
+      const double u0 = w(L.U + 2 * t), u1 = w(L.U + 2 * t + 1);
+      const int to = TRo(cur, t);
+      const double sp = w(to), cp = w(to + 1), se = w(to + 2), ce = w(to + 3);
+      double p0, p1, p2, p3;
+      poly_eval(cf, s[0], p0, p1, p2, p3);
+      const Lin A = make_lin(P, s[3], u0, sp, cp, se, ce, p1, p2);
+      double c[6];
+      if (ls) { c[0] = c[1] = c[2] = c[3] = c[4] = c[5] = 0.0; }
+      else {
+        const int co = use_csoc ? L.CSOC + 6 * (t + 1) : Co(cur, t + 1);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) c[k] = w(co + k);
+      }
+      if (!ls) {
+        // objective / barrier directional derivative and step bounds for u_t
+        double un0 = 0.0, un1 = 0.0;
+        if (t < M - 1) { un0 = w(L.U + 2 * t + 2); un1 = w(L.U + 2 * t + 3); }
+        const double zl0 = w(L.ZL + 2 * t), zl1 = w(L.ZL + 2 * t + 1), zu0 = w(L.ZU + 2 * t), zu1 = w(L.ZU + 2 * t + 1);
+        const double sl0 = safe_slack(u0 - xL(0), mu, zl0, xL(0)), su0 = safe_slack(xU(0) - u0, mu, zu0, xU(0));
+        const double sl1 = safe_slack(u1 - xL(1), mu, zl1, xL(1)), su1 = safe_slack(xU(1) - u1, mu, zu1, xU(1));
+        gbd += (grad_u(0, t, u0, um0, un0) - mu / sl0 + mu / su0) * du0 + (grad_u(1, t, u1, um1, un1) - mu / sl1 + mu / su1) * du1;
+        gbd += 2.0 * df * (P.w_v * (s[3] - P.ref_v) * ds[3] + P.w_cte * s[4] * ds[4] + P.w_epsi * s[5] * ds[5]);
+        if (du0 < 0.0) a_pr = dmin(a_pr, -tau / du0 * sl0);
+        if (du0 > 0.0) a_pr = dmin(a_pr, tau / du0 * su0);
+        if (du1 < 0.0) a_pr = dmin(a_pr, -tau / du1 * sl1);
+        if (du1 > 0.0) a_pr = dmin(a_pr, tau / du1 * su1);
+        const double dzl0 = (mu - sl0 * zl0 - zl0 * du0) / sl0, dzu0 = (mu - su0 * zu0 + zu0 * du0) / su0;
+        const double dzl1 = (mu - sl1 * zl1 - zl1 * du1) / sl1, dzu1 = (mu - su1 * zu1 + zu1 * du1) / su1;
+        if (dzl0 < 0.0) a_du = dmin(a_du, -tau / dzl0 * zl0);
+        if (dzu0 < 0.0) a_du = dmin(a_du, -tau / dzu0 * zu0);
+        if (dzl1 < 0.0) a_du = dmin(a_du, -tau / dzl1 * zl1);
+        if (dzu1 < 0.0) a_du = dmin(a_du, -tau / dzu1 * zu1);
+        tiny = dmax(tiny, dmax(fabs(du0) / (fabs(u0) + 1.0), fabs(du1) / (fabs(u1) + 1.0)));
+#pragma unroll
+        for (int k = 0; k < 6; ++k) tiny = dmax(tiny, fabs(ds[k]) / (fabs(s[k]) + 1.0));
+      }
+      double dn[6];
+      dn[0] = ds[0] + A.a1 * ds[2] + A.a3 * ds[3] - c[0];
+      dn[1] = ds[1] + A.a2 * ds[2] + A.a4 * ds[3] - c[1];
+      dn[2] = ds[2] + A.a5 * ds[3] + A.beta * du0 - c[2];
+      dn[3] = ds[3] + P.dt * du1 - c[3];
+      dn[4] = A.pp * ds[0] - ds[1] + A.sed * ds[3] + A.vce * ds[5] - c[4];
+      dn[5] = -A.kap * ds[0] + ds[2] + A.a5 * ds[3] + A.beta * du0 - c[5];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { ds[k] = dn[k]; w(L.DS + 6 * (t + 1) + k) = dn[k]; }
+      dup0 = du0; dup1 = du1; um0 = u0; um1 = u1;
+    }
+    if (!ls) {
+      double s[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { s[k] = w(L.S + 6 * M + k); tiny = dmax(tiny, fabs(ds[k]) / (fabs(s[k]) + 1.0)); }
+      gbd += 2.0 * df * (P.w_v * (s[3] - P.ref_v) * ds[3] + P.w_cte * s[4] * ds[4] + P.w_epsi * s[5] * ds[5]);
+    }
+    fw_alpha_pr = a_pr; fw_alpha_du = a_du; fw_gbd = gbd; fw_tiny = tiny;
+  }
+  double fw_alpha_pr, fw_alpha_du, fw_gbd, fw_tiny;
+
+  // ------------------------------------------------------------------------------------------
+  // Backward sweep after the line search: dlam from the stationarity rows, then the new iterate
+  // (x += a dx, lam += a dlam, z += a_du dz with the kappa_sigma safeguard, IpIpoptAlg.cpp:880-951) and
+  // every norm the convergence test / mu update need at it (IpIpoptCalculatedQuantities.cpp:2672-2832,3279-3306).
+  // nbuf = TR/C buffer that holds the accepted trial point.
+  MPC_HD void accept(double a, double a_du, double dw, int nbuf) {
+    const bool ls = ls_mode;
+    const double qv = ls ? 1.0 : 2.0 * P.w_v * df + dw, qe = ls ? 1.0 : 2.0 * P.w_epsi * df + dw,
+                 qc = ls ? 1.0 : 2.0 * P.w_cte * df + dw, q0 = ls ? 1.0 : dw;
+    double lp[6], ln[6], lo[6];   // lambda^+_{t+1}, lambda_new_{t+1}, lambda_old_{t+1}
+    double dinf = 0.0, l1 = 0.0, zz1 = 0.0, szmx = 0.0, szmn = 1e300, slog = 0.0, xm = 0.0, dlm = 0.0;
+    {
+      double s[6], ds[6], lam[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { s[k] = w(L.S + 6 * M + k); ds[k] = w(L.DS + 6 * M + k); lam[k] = (ls) ? 0.0 : w(L.LAM + 6 * M + k); }
+      lp[0] = -q0 * ds[0]; lp[1] = -q0 * ds[1]; lp[2] = -q0 * ds[2];
+      lp[3] = -qv * ds[3] - 2.0 * P.w_v * df * (s[3] - P.ref_v);
+      lp[4] = -qc * ds[4] - 2.0 * P.w_cte * df * s[4];
+      lp[5] = -qe * ds[5] - 2.0 * P.w_epsi * df * s[5];
+      double sn[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        lo[k] = lam[k];
+        dlm = dmax(dlm, fabs(lp[k] - lam[k]));
+        ln[k] = lam_zero ? 0.0 : (ls ? lp[k] : lam[k] + a * (lp[k] - lam[k]));
+        sn[k] = ls ? s[k] : s[k] + a * ds[k];
+        w(L.LAM + 6 * M + k) = ln[k];
+        if (!ls) w(L.S + 6 * M + k) = sn[k];
+        l1 += fabs(ln[k]);
+        xm = dmax(xm, fabs(sn[k]));
+      }
+      dinf = dmax(dinf, dmax(fabs(ln[0]), dmax(fabs(ln[1]), fabs(ln[2]))));
+      dinf = dmax(dinf, fabs(2.0 * P.w_v * df * (sn[3] - P.ref_v) + ln[3]));
+      dinf = dmax(dinf, fabs(2.0 * P.w_cte * df * sn[4] + ln[4]));
+      dinf = dmax(dinf, fabs(2.0 * P.w_epsi * df * sn[5] + ln[5]));
+    }
+    double unn0 = 0.0, unn1 = 0.0;   // u_new at t+1
+    // u_new at t (needed one stage ahead for grad_u): prefetch
+    double uc0 = 0.0, uc1 = 0.0, duc0 = 0.0, duc1 = 0.0;
+    if (M > 0) { uc0 = w(L.U + 2 * (M - 1)); uc1 = w(L.U + 2 * (M - 1) + 1); duc0 = w(L.DU + 2 * (M - 1)); duc1 = w(L.DU + 2 * (M - 1) + 1); }
+    for (int t = M - 1; t >= 0; --t) {
+      double s[6], ds[6], lam[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { s[k] = w(L.S + 6 * t + k); ds[k] = w(L.DS + 6 * t + k); lam[k] = ls ? 0.0 : w(L.LAM + 6 * t + k); }
+      const double u0 = uc0, u1 = uc1, du0 = duc0, du1 = duc1;
+      double um0 = 0.0, um1 = 0.0, dum0 = 0.0, dum1 = 0.0;
+      if (t > 0) { um0 = w(L.U + 2 * t - 2); um1 = w(L.U + 2 * t - 1); dum0 = w(L.DU + 2 * t - 2); dum1 = w(L.DU + 2 * t - 1); }
+      // ---- old point: lambda^+_t
+      {
+        const int to = TRo(cur, t);
+        const double sp = w(to), cp = w(to + 1), se = w(to + 2), ce = w(to + 3);
+        double p0, p1, p2, p3;
+        poly_eval(cf, s[0], p0, p1, p2, p3);
+        const Lin A = make_lin(P, s[3], u0, sp, cp, se, ce, p1, p2);
+        Hes H;
+        if (ls) { H.xx = H.pp = H.vp = H.ee = H.ev = H.m = 0.0; }
+        else H = make_hes(P, lo, s[3], sp, cp, se, ce, p1, p2, p3);
+        double at[6];
+        applyAT6(A, lp, at);
+        double nl[6];
+        nl[0] = at[0] - (q0 + H.xx) * ds[0];
+        nl[1] = at[1] - q0 * ds[1];
+        nl[2] = at[2] - ((q0 + H.pp) * ds[2] + H.vp * ds[3]);
+        nl[3] = at[3] - (H.vp * ds[2] + qv * ds[3] + H.ev * ds[5] + H.m * du0) - 2.0 * P.w_v * df * (s[3] - P.ref_v);
+        nl[4] = -qc * ds[4] - 2.0 * P.w_cte * df * s[4];
+        nl[5] = at[5] - ((qe + H.ee) * ds[5] + H.ev * ds[3]) - 2.0 * P.w_epsi * df * s[5];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { lp[k] = nl[k]; lo[k] = lam[k]; dlm = dmax(dlm, fabs(nl[k] - lam[k])); }
+      }
+      // ---- new point
+      double sn[6], lnew[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        sn[k] = ls ? s[k] : s[k] + a * ds[k];
+        lnew[k] = lam_zero ? 0.0 : (ls ? lp[k] : lam[k] + a * (lp[k] - lam[k]));
+        w(L.LAM + 6 * t + k) = lnew[k];
+        if (!ls && t > 0) w(L.S + 6 * t + k) = sn[k];
+        l1 += fabs(lnew[k]);
+        xm = dmax(xm, fabs(sn[k]));
+      }
+      const double un0 = ls ? u0 : u0 + a * du0, un1 = ls ? u1 : u1 + a * du1;
+      const double umn0 = ls ? um0 : um0 + a * dum0, umn1 = ls ? um1 : um1 + a * dum1;
+      xm = dmax(xm, dmax(fabs(un0), fabs(un1)));
+      double zl0 = w(L.ZL + 2 * t), zl1 = w(L.ZL + 2 * t + 1), zu0 = w(L.ZU + 2 * t), zu1 = w(L.ZU + 2 * t + 1);
+      if (!ls) {
+        const double sl0 = safe_slack(u0 - xL(0), mu, zl0, xL(0)), su0 = safe_slack(xU(0) - u0, mu, zu0, xU(0));
+        const double sl1 = safe_slack(u1 - xL(1), mu, zl1, xL(1)), su1 = safe_slack(xU(1) - u1, mu, zu1, xU(1));
+        zl0 += a_du * ((mu - sl0 * zl0 - zl0 * du0) / sl0);
+        zu0 += a_du * ((mu - su0 * zu0 + zu0 * du0) / su0);
+        zl1 += a_du * ((mu - sl1 * zl1 - zl1 * du1) / sl1);
+        zu1 += a_du * ((mu - su1 * zu1 + zu1 * du1) / su1);
+      }
+      double nsl0 = safe_slack(un0 - xL(0), mu, zl0, xL(0)), nsu0 = safe_slack(xU(0) - un0, mu, zu0, xU(0));
+      double nsl1 = safe_slack(un1 - xL(1), mu, zl1, xL(1)), nsu1 = safe_slack(xU(1) - un1, mu, zu1, xU(1));
+      if (!ls) {   // kappa_sigma = 1e10
+        zl0 = dclamp(zl0, mu / (1e10 * nsl0), 1e10 * mu / nsl0);
+        zu0 = dclamp(zu0, mu / (1e10 * nsu0), 1e10 * mu / nsu0);
+        zl1 = dclamp(zl1, mu / (1e10 * nsl1), 1e10 * mu / nsl1);
+        zu1 = dclamp(zu1, mu / (1e10 * nsu1), 1e10 * mu / nsu1);
+        w(L.ZL + 2 * t) = zl0; w(L.ZL + 2 * t + 1) = zl1; w(L.ZU + 2 * t) = zu0; w(L.ZU + 2 * t + 1) = zu1;
+        w(L.U + 2 * t) = un0; w(L.U + 2 * t + 1) = un1;
+      }
+      zz1 += zl0 + zl1 + zu0 + zu1;
+      {
+        const double c0 = nsl0 * zl0, c1 = nsl1 * zl1, c2 = nsu0 * zu0, c3 = nsu1 * zu1;
+        szmx = dmax(szmx, dmax(dmax(c0, c1), dmax(c2, c3)));
+        szmn = dmin(szmn, dmin(dmin(c0, c1), dmin(c2, c3)));
+        slog += log(nsl0) + log(nsl1) + log(nsu0) + log(nsu1);
+      }
+      // grad_x L at the new point
+      {
+        const int to = TRo(nbuf, t);
+        const double sp = w(to), cp = w(to + 1), se = w(to + 2), ce = w(to + 3);
+        double p0, p1, p2, p3;
+        poly_eval(cf, sn[0], p0, p1, p2, p3);
+        const Lin A = make_lin(P, sn[3], un0, sp, cp, se, ce, p1, p2);
+        double at[6];
+        applyAT6(A, ln, at);
+        dinf = dmax(dinf, dmax(fabs(lnew[0] - at[0]), dmax(fabs(lnew[1] - at[1]), fabs(lnew[2] - at[2]))));
+        dinf = dmax(dinf, fabs(2.0 * P.w_v * df * (sn[3] - P.ref_v) + lnew[3] - at[3]));
+        dinf = dmax(dinf, fabs(2.0 * P.w_cte * df * sn[4] + lnew[4]));
+        dinf = dmax(dinf, fabs(2.0 * P.w_epsi * df * sn[5] + lnew[5] - at[5]));
+        const double g0 = grad_u(0, t, un0, umn0, unn0) - A.beta * (ln[2] + ln[5]) - zl0 + zu0;
+        const double g1 = grad_u(1, t, un1, umn1, unn1) - P.dt * ln[3] - zl1 + zu1;
+        dinf = dmax(dinf, dmax(fabs(g0), fabs(g1)));
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) ln[k] = lnew[k];
+      unn0 = un0; unn1 = un1;
+      uc0 = um0; uc1 = um1; duc0 = dum0; duc1 = dum1;
+    }
+    dualinf = dinf; lam1 = l1; z1 = zz1; sz_max = szmx; sz_min = szmn; sumlog = slog; xmaxabs = xm; dlam_max = dlm;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // filter (IpFilter.cpp:41-77) and acceptance tests (IpFilterLSAcceptor.cpp:246-382)
+  MPC_HD static bool cmp_le(double lhs, double rhs, double bas) { return lhs - rhs <= 10.0 * DBL_EPSILON * fabs(bas); }
+  MPC_HD bool filter_ok(double phi, double th) const {
+    bool ok = true;
+    for (int i = 0; i < kMaxFilter; ++i)
+      if (i < nf && !(phi <= fphi[i] || th <= fth[i])) ok = false;
+    return ok;
+  }
+  MPC_HD void filter_add(double phi, double th) {
+    int wr = 0;
+    for (int i = 0; i < kMaxFilter; ++i)
+      if (i < nf && !(fphi[i] >= phi && fth[i] >= th)) { fphi[wr] = fphi[i]; fth[wr] = fth[i]; ++wr; }
+    nf = wr;
+    if (nf < kMaxFilter) { fphi[nf] = phi; fth[nf] = th; ++nf; }
+  }
+  MPC_HD bool is_ftype(double at) const { return ref_gbd < 0.0 && at * pow(-ref_gbd, 2.3) > 1.0 * pow(ref_theta, 1.1); }
+  MPC_HD bool armijo(double at, double trial_barr) const { return cmp_le(trial_barr - ref_barr, 1e-8 * at * ref_gbd, ref_barr); }
+  MPC_HD bool check_accept(double at, double trial_theta, double trial_barr) {
+    if (theta_max < 0.0) theta_max = 1e4 * dmax(1.0, ref_theta);
+    if (theta_min < 0.0) theta_min = 1e-4 * dmax(1.0, ref_theta);
+    if (theta_max > 0.0 && trial_theta > theta_max) return false;
+    bool acc;
+    if (at > 0.0 && is_ftype(at) && ref_theta <= theta_min) acc = armijo(at, trial_barr);
+    else {
+      acc = true;
+      if (trial_barr > ref_barr) {
+        double bas = 1.0;
+        if (fabs(ref_barr) > 10.0) bas = log10(fabs(ref_barr));
+        if (log10(trial_barr - ref_barr) > 5.0 + bas) acc = false;
+      }
+      if (acc)
+        acc = cmp_le(trial_theta, (1.0 - 1e-5) * ref_theta, ref_theta) || cmp_le(trial_barr - ref_barr, -1e-8 * ref_theta, ref_barr);
+    }
+    if (!acc) return false;
+    return filter_ok(trial_barr, trial_theta);
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // Top of Ipopt's main loop at the current iterate: convergence tests and the monotone barrier update.
+  // Returns false when the solve is finished (status set).
+  MPC_HD bool top_of_loop() {
+    const int nb = 2 * M, m = 6 * N;
+    const double sc = dmax(100.0, z1 / (2.0 * nb)) / 100.0;
+    const double sd = dmax(100.0, (lam1 + z1) / (m + 2.0 * nb)) / 100.0;
+    const double compl0 = sz_max;
+    const double E0 = dmax(dualinf / sd, dmax(priminf, compl0 / sc));
+    const double u_dual = dualinf / df, u_compl = compl0 / df;
+    if (E0 <= P.tol && u_dual <= 1.0 && priminf <= 1e-4 && u_compl <= 1e-4) { status = kSolveSucceeded; return false; }
+    last_obj = curr_obj; curr_obj = f_cur;
+    const bool acc = E0 <= 1e-6 && u_dual <= 1e10 && priminf <= 1e-2 && u_compl <= 1e-2;
+    if (acc) { if (++acceptable_counter >= 15) { status = kSolvedToAcceptableLevel; return false; } }
+    else acceptable_counter = 0;
+    if (xmaxabs > 1e20) { status = kDivergingIterates; return false; }
+    if (iter >= P.max_iter) { status = kMaxIterExceeded; return false; }
+    // IpMonotoneMuUpdate.cpp:132-232
+    double Emu = dmax(dualinf / sd, dmax(priminf, dmax(sz_max - mu, mu - sz_min) / sc));
+    bool done = false, tiny = tiny_flag;
+    tiny_flag = false;
+    while ((Emu <= 10.0 * mu || tiny) && !done) {
+      const double nm = dmax(dmin(0.2 * mu, pow(mu, 1.5)), mu_min);
+      const double nt = dmax(0.99, 1.0 - nm);
+      const bool changed = nm != mu;
+      if (!changed && tiny) { status = kSearchDirectionTooSmall; return false; }
+      mu = nm; tau = nt;
+      if (!changed) done = true;
+      else {
+        Emu = dmax(dualinf / sd, dmax(priminf, dmax(sz_max - mu, mu - sz_min) / sc));
+        done = Emu > 10.0 * mu;
+      }
+      if (done && changed) nf = 0;
+      tiny = false;
+    }
+    return true;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // One trip through the phase machine.  In the common case a problem runs FACTOR -> FORWARD -> TRIAL ->
+  // ACCEPT (one interior-point iteration) per trip; rare events (inertia correction, backtracking, second
+  // order correction) take extra trips without stalling the other problems of the warp.
+  MPC_HD void trip() {
+    if (phase == PH_FACTOR) {
+      bool ok = factor(dw_curr, in_soc);
+      if (ok) phase = PH_FORWARD;
+      else {   // IpPDPerturbationHandler.cpp:347-391
+        if (dw_curr == 0.0) dw_curr = dw_last == 0.0 ? 1e-4 : dmax(1e-20, dw_last / 3.0);
+        else dw_curr *= (dw_last == 0.0 || 1e5 * dw_last < dw_curr) ? 100.0 : 8.0;
+        if (dw_curr > 1e20) { status = kErrorInStepComputation; phase = PH_DONE; }
+      }
+    }
+    if (phase == PH_FORWARD) {
+      forward(in_soc, dw_curr);
+      if (ls_mode) { phase = PH_ACCEPT; }
+      else if (in_soc) {
+        alpha = fw_alpha_pr;   // alpha_primal_soc
+        phase = PH_TRIAL;
+      } else if (soc_done) {   // direction restored after a failed SOC: resume backtracking
+        phase = PH_TRIAL;
+      } else {
+        alpha_du = fw_alpha_du;
+        ref_theta = theta_cur;
+        ref_barr = f_cur - mu * sumlog;
+        ref_gbd = fw_gbd;
+        tiny_now = fw_tiny <= 10.0 * DBL_EPSILON;
+        alpha_max = fw_alpha_pr;
+        alpha = alpha_max;
+        n_steps = 0;
+        if (tiny_now) {
+          if (tiny_last) tiny_flag = true;
+        } else {
+          double am = 1e-5;   // CalculateAlphaMin IpFilterLSAcceptor.cpp:393-410
+          if (ref_gbd < 0.0) {
+            am = dmin(am, 1e-8 * ref_theta / (-ref_gbd));
+            if (ref_theta <= theta_min) am = dmin(am, 1.0 * pow(ref_theta, 1.1) / pow(-ref_gbd, 2.3));
+          }
+          alpha_min = 0.05 * am;
+        }
+        phase = PH_TRIAL;
+      }
+    }
+    if (phase == PH_TRIAL) {
+      eval_point(alpha, cur ^ 1);
+      const double tbarr = tr_f - mu * tr_sumlog;
+      bool acc;
+      if (tiny_now) acc = true;
+      else {
+        if (!in_soc) alpha_test = alpha;
+        acc = check_accept(alpha_test, tr_theta, tbarr);
+      }
+      if (acc) {
+        if (!tiny_now && (!is_ftype(alpha_test) || !armijo(alpha_test, tbarr)))
+          filter_add(ref_barr - 1e-8 * ref_theta, (1.0 - 1e-5) * ref_theta);
+        phase = PH_ACCEPT;
+      } else if (in_soc) {
+        ++soc_count;
+        if (soc_count < 4 && tr_theta <= 0.99 * theta_soc_old) {   // another correction
+          theta_soc_old = tr_theta;
+          alpha_soc = alpha;
+          build_csoc(alpha_soc);
+          phase = PH_FACTOR;
+        } else {   // give up: restore the Newton direction, continue backtracking
+          in_soc = false; soc_done = true;
+          alpha = 0.5 * alpha_max; n_steps = 1;
+          phase = alpha > alpha_min ? PH_FACTOR : PH_DONE;
+          if (phase == PH_DONE) status = kRestorationFailed;
+        }
+      } else if (!soc_done && alpha == alpha_max && ref_theta <= tr_theta) {   // start SOC (IpFilterLSAcceptor.cpp:473-587)
+        in_soc = true; soc_count = 0;
+        theta_soc_old = tr_theta;
+        alpha_soc = alpha;
+        init_csoc();
+        build_csoc(alpha_soc);
+        phase = PH_FACTOR;
+      } else {
+        alpha *= 0.5; ++n_steps;
+        if (!(alpha > alpha_min)) { status = kRestorationFailed; phase = PH_DONE; }
+      }
+    }
+    if (phase == PH_ACCEPT) {
+      if (ls_mode) {
+        accept(0.0, 0.0, 0.0, cur);
+        if (!lam_zero && dlam_max > 1000.0) { lam_zero = true; }   // constr_mult_init_max: redo with lambda = 0
+        else {
+          ls_mode = false; lam_zero = false;
+          phase = top_of_loop() ? PH_FACTOR : PH_DONE;
+          if (phase == PH_FACTOR) begin_iteration();
+        }
+      } else {
+        accept(alpha, alpha_du, dw_curr, cur ^ 1);
+        cur ^= 1;
+        f_cur = tr_f; theta_cur = tr_theta; priminf = tr_priminf;
+        tiny_last = tiny_now ? dlam_max < 1e-2 : false;
+        in_soc = false; soc_done = false;
+        ++iter;
+        phase = top_of_loop() ? PH_FACTOR : PH_DONE;
+        if (phase == PH_FACTOR) begin_iteration();
+      }
+    }
+  }
+  MPC_HD void begin_iteration() {   // PDPerturbationHandler::ConsiderNewSystem
+    if (dw_curr > 0.0) dw_last = dw_curr;
+    dw_curr = 0.0;
+  }
+  MPC_HD void init_csoc() {
+    for (int i = 6; i < 6 * N; ++i) w(L.CSOC + i) = w(L.C + cur * 6 * N + i);
+  }
+  MPC_HD void build_csoc(double a) {   // c_soc = c(trial) + alpha_soc * c_soc
+    for (int i = 6; i < 6 * N; ++i) w(L.CSOC + i) = w(L.C + (cur ^ 1) * 6 * N + i) + a * w(L.CSOC + i);
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // finalize: honor_original_bounds (IpOrigIpoptNLP.cpp:875-883), unscaled objective, MPC.cpp:253-256.
+  // traj (optional): full variable vector in the reference layout (MPC.cpp:36-43), element i at traj[i*tstride].
+  MPC_HD void finish(Result& R, double* traj, size_t tstride) {
+    R.status = status; R.iters = iter; R.obj = f_cur / df;
+    R.out8[0] = w(L.S + 6 + 0); R.out8[1] = w(L.S + 6 + 1); R.out8[2] = w(L.S + 6 + 2); R.out8[3] = w(L.S + 6 + 3);
+    R.out8[4] = w(L.S + 6 + 4); R.out8[5] = w(L.S + 6 + 5);
+    R.out8[6] = dclamp(w(L.U + 0), -bnd(0), bnd(0));
+    R.out8[7] = dclamp(w(L.U + 1), -bnd(1), bnd(1));
+    if (traj) {
+      for (int t = 0; t < N; ++t)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) traj[(size_t)(k * N + t) * tstride] = w(L.S + 6 * t + k);
+      for (int t = 0; t < M; ++t) {
+        traj[(size_t)(6 * N + t) * tstride] = dclamp(w(L.U + 2 * t), -bnd(0), bnd(0));
+        traj[(size_t)(6 * N + M + t) * tstride] = dclamp(w(L.U + 2 * t + 1), -bnd(1), bnd(1));
+      }
+    }
+  }
+};
+
+#undef PS
+
+}  // namespace b200mpc
