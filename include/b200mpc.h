@@ -1,0 +1,139 @@
+/* b200mpc -- C ABI of the B200-native batched nonlinear-MPC solver (libb200mpc.so).
+ *
+ * This is the drop-in boundary for the reference's mpc_to_line hot path.  Every entry point cites the
+ * reference interface it replaces (paths relative to the reference checkout, cyscgzx33/UdacityMPC):
+ *
+ *   b200mpc_solve_batch        class MPC { std::vector<double> Solve(const VectorXd& x0, const VectorXd& coeffs); }
+ *                              mpc_to_line/src/MPC.h:7-17, implementation mpc_to_line/solution/MPC.cpp:149-257
+ *                              (FG_eval :45-140; CppAD::ipopt::solve :241-243)
+ *   b200mpc_polyfit_batch      VectorXd polyfit(const VectorXd& xvals, const VectorXd& yvals, int order)
+ *                              mpc_to_line/src/helpers.h:24-44
+ *   b200mpc_polyeval_batch     double polyeval(const VectorXd& coeffs, double x)     mpc_to_line/src/helpers.h:13-19
+ *   b200mpc_rollout_batch      VectorXd globalKinematic(const VectorXd& state, const VectorXd& actuators, double dt)
+ *                              global_kinematic_model/solution/main.cpp:18-19, 36-62
+ *   b200mpc_closed_loop_batch  the feed-forward loop of mpc_to_line/solution/main.cpp:51-76
+ *   b200mpc_params             the file-scope globals of MPC.cpp:14-31 (N, dt, Lf, ref_v), the unit cost weights of
+ *                              :57-76, the actuator bounds of :194-203, and the Ipopt options tol / max_iter that
+ *                              the option string at :232-235 leaves at their defaults
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no exceptions cross this boundary; every function returns 0 on success or a
+ *     negative b200mpc_error, and b200mpc_last_error() describes the most recent failure of the calling thread.
+ *   - *_batch functions take HOST buffers in the reference's per-problem ("array of structures") order and do the
+ *     host<->device copies themselves; *_batch_device functions take DEVICE buffers in the structure-of-arrays
+ *     layout the kernels consume (field-major: element k of problem b at ptr[k*B + b]) and are asynchronous on
+ *     the given cudaStream_t (passed as void*; NULL = the handle's own stream).
+ *   - a handle is bound to one CUDA device and is the unit of thread safety (one handle per host thread).
+ *   - there is no CPU fallback: without a CUDA device b200mpc_create fails with B200MPC_ERR_CUDA.
+ *   - per-problem status values are Ipopt's ApplicationReturnStatus numbers
+ *     (Ipopt-3.12.7/Ipopt/src/Interfaces/IpReturnCodes_inc.h:16-39): 0 Solve_Succeeded, 1 Solved_To_Acceptable_Level,
+ *     3 Search_Direction_Becomes_Too_Small, 4 Diverging_Iterates, -1 Maximum_Iterations_Exceeded,
+ *     -2 Restoration_Failed (the line search failed; the restoration phase is not implemented),
+ *     -3 Error_In_Step_Computation.  Like MPC::Solve (MPC.cpp:248-249) the solution is returned regardless.
+ */
+#ifndef B200MPC_H
+#define B200MPC_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200mpc_params {
+  int N;            /* horizon length, MPC.cpp:14 (25) */
+  double dt;        /* MPC.cpp:15 (0.05) */
+  double Lf;        /* MPC.cpp:27 (2.67) */
+  double ref_v;     /* MPC.cpp:31 (40) */
+  double w_cte, w_epsi, w_v;     /* MPC.cpp:60-64 (1,1,1) */
+  double w_delta, w_a;           /* MPC.cpp:67-70 (1,1) */
+  double w_ddelta, w_da;         /* MPC.cpp:73-76 (1,1) */
+  double delta_max; /* MPC.cpp:194-195 (0.436332, the literal) */
+  double a_max;     /* MPC.cpp:200-201 (1.0) */
+  double tol;       /* Ipopt "tol" default 1e-8 */
+  int max_iter;     /* Ipopt "max_iter" default 3000 */
+} b200mpc_params;
+
+typedef struct b200mpc_handle b200mpc_handle;
+
+enum b200mpc_error {
+  B200MPC_OK = 0,
+  B200MPC_ERR_ARG = -1,     /* bad argument (null pointer, size out of range, unsupported degree) */
+  B200MPC_ERR_CUDA = -2,    /* CUDA runtime error, or no CUDA device */
+  B200MPC_ERR_NOMEM = -3    /* device or host allocation failed */
+};
+
+#define B200MPC_MAX_COEFFS 4      /* reference polynomial degree <= 3 in the solver */
+#define B200MPC_MAX_FIT_POINTS 16 /* polyfit: m <= 16, 1 <= order <= min(m-1, 7) */
+#define B200MPC_MAX_FIT_ORDER 7
+
+/* Fills *p with the values the reference hard-codes (see b200mpc_params). */
+void b200mpc_default_params(b200mpc_params* p);
+
+/* Creates a solver bound to CUDA device `device`.  Work buffers grow on demand. */
+int b200mpc_create(const b200mpc_params* p, int device, b200mpc_handle** out);
+void b200mpc_destroy(b200mpc_handle* h);
+const char* b200mpc_last_error(void);
+/* 8N-2: length of the full variable vector [x|y|psi|v|cte|epsi|delta|a] (MPC.cpp:36-43, 161). */
+int b200mpc_num_vars(const b200mpc_handle* h);
+
+/* B independent MPC::Solve calls.
+ *   state6  B x 6   (x, y, psi, v, cte, epsi) per problem                 MPC.cpp:152-157
+ *   coeffs  B x ncoef, ascending powers, 2 <= ncoef <= 4                  MPC.cpp:117-118 (degree 1 as shipped)
+ *   out8    B x 8   (x1, y1, psi1, v1, cte1, epsi1, delta0, a0)           MPC.cpp:253-256
+ *   traj    B x (8N-2) full solution in the reference's variable order, or NULL
+ *   obj     B       objective value (the "Cost" line, MPC.cpp:251-252), or NULL
+ *   status  B       see above, or NULL;   iters  B  interior-point iterations, or NULL */
+int b200mpc_solve_batch(b200mpc_handle* h, int B, const double* state6, const double* coeffs, int ncoef, double* out8,
+                        double* traj, double* obj, int* status, int* iters);
+
+/* Same on device buffers, field-major: d_state6[k*B+b], d_coeffs[i*B+b], d_out8[k*B+b], d_traj[i*B+b]. */
+int b200mpc_solve_batch_device(b200mpc_handle* h, int B, const double* d_state6, const double* d_coeffs, int ncoef,
+                               double* d_out8, double* d_traj, double* d_obj, int* d_status, int* d_iters,
+                               void* stream);
+
+/* The same batch sharded by contiguous index ranges over several handles (one per device), one host thread per
+ * device, no inter-device communication.  Host buffers as b200mpc_solve_batch. */
+int b200mpc_solve_batch_multi(b200mpc_handle* const* hs, int n_handles, int B, const double* state6,
+                              const double* coeffs, int ncoef, double* out8, double* traj, double* obj, int* status,
+                              int* iters);
+
+/* Closed loop of solution/main.cpp:51-76 for B vehicles: `steps` consecutive solves, each fed the previous solve's
+ * predicted state out8[0..5]; the state never leaves the device between steps.
+ *   state6  B x 6 initial states, coeffs B x ncoef (constant over the loop)
+ *   hist8   steps x B x 8 the returned vector of every step;  cost  steps x B (or NULL);  iters steps x B (or NULL) */
+int b200mpc_closed_loop_batch(b200mpc_handle* h, int B, int steps, const double* state6, const double* coeffs,
+                              int ncoef, double* hist8, double* cost, int* iters);
+
+/* B least-squares polynomial fits (unpivoted Householder QR of the Vandermonde matrix, as Eigen 3.3.3 does for
+ * helpers.h:24-44).  xs, ys: B x m;  coeffs_out: B x (order+1).  Requires 1 <= order <= m-1 (helpers.h:26 assert). */
+int b200mpc_polyfit_batch(b200mpc_handle* h, int B, const double* xs, const double* ys, int m, int order,
+                          double* coeffs_out);
+/* Device buffers, field-major: d_xs[j*B+b], d_ys[j*B+b], d_coeffs_out[i*B+b]. */
+int b200mpc_polyfit_batch_device(b200mpc_handle* h, int B, const double* d_xs, const double* d_ys, int m, int order,
+                                 double* d_coeffs_out, void* stream);
+
+/* y[b] = sum_i coeffs[b][i] * x[b]^i  (helpers.h:13-19).  coeffs: B x ncoef. */
+int b200mpc_polyeval_batch(b200mpc_handle* h, int B, const double* coeffs, int ncoef, const double* x, double* y);
+int b200mpc_polyeval_batch_device(b200mpc_handle* h, int B, const double* d_coeffs, int ncoef, const double* d_x,
+                                  double* d_y, void* stream);
+
+/* B bicycle-model rollouts of H Euler steps (global_kinematic_model/solution/main.cpp:36-62; H=1 is globalKinematic).
+ *   state4 B x 4 (x,y,psi,v);  act B x H x 2 (delta,a);  out B x H x 4 (the state after each step). */
+int b200mpc_rollout_batch(b200mpc_handle* h, int B, int H, const double* state4, const double* act, double dt,
+                          double Lf, double* out);
+/* Device buffers, field-major: d_state4[k*B+b], d_act[(s*2+j)*B+b], d_out[(s*4+k)*B+b]. */
+int b200mpc_rollout_batch_device(b200mpc_handle* h, int B, int H, const double* d_state4, const double* d_act,
+                                 double dt, double Lf, double* d_out, void* stream);
+
+/* Measurement helpers (used by bench.py; not part of the reference interface). */
+/* Average device time in ms of the solver kernel over all its launches since the last reset (CUDA events on the
+ * launching stream), and the number of launches. */
+int b200mpc_kernel_time_ms(b200mpc_handle* h, double* total_ms, int* launches, int reset);
+/* Sustained FP64 FMA throughput of the device in TFLOP/s (dependent-chain DFMA microbenchmark, 2 FLOP per FMA). */
+int b200mpc_measure_fp64_peak(b200mpc_handle* h, double* tflops);
+/* Number of kernels this handle has launched since creation. */
+long long b200mpc_launch_count(const b200mpc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MPC_H */

@@ -1,0 +1,64 @@
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _build_everything():
+    """Builds the test-only oracle (+ oracle/_ref when /root/reference is present), the host build of the solver
+    core used by the CPU algorithm tests, and the product library."""
+    import __graft_entry__ as ge
+    ge.build()
+    yield
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+# ---- host build of the solver core (tests/hostsim): algorithm tests without a GPU
+class _HostSim:
+    def __init__(self):
+        import oracle_bindings as ob
+        self.ob = ob
+        self.lib = ctypes.CDLL(os.path.join(ROOT, "tests", "hostsim", "libhostsim.so"))
+        self.dp = ctypes.POINTER(ctypes.c_double)
+
+    def solve(self, state6, coeffs, **params):
+        ob, dp = self.ob, self.dp
+        p = ob.default_params(**params)
+        N = p.N
+        st = np.ascontiguousarray(state6, dtype=np.float64)
+        c = np.ascontiguousarray(coeffs, dtype=np.float64)
+        x = np.zeros(8 * N - 2); o8 = np.zeros(8); obj = ctypes.c_double(); it = ctypes.c_int()
+        lam = np.zeros(6 * N); tr = np.zeros((400, 8)); nr = ctypes.c_int()
+        rc = self.lib.hostsim_solve(ctypes.byref(p), st.ctypes.data_as(dp), c.ctypes.data_as(dp), len(c),
+                                    x.ctypes.data_as(dp), o8.ctypes.data_as(dp), ctypes.byref(obj), ctypes.byref(it),
+                                    lam.ctypes.data_as(dp), tr.ctypes.data_as(dp), 400, ctypes.byref(nr))
+        return dict(status=rc, x=x, out8=o8, obj=obj.value, iters=it.value, lam=lam, trace=tr[:nr.value])
+
+
+@pytest.fixture(scope="session")
+def hostsim(_build_everything):
+    return _HostSim()

@@ -1,0 +1,118 @@
+"""Generates the golden fixtures in this directory by running THE REFERENCE ITSELF in the build container:
+  * oracle/_ref/libmpc_ref.so      the reference's prebuilt Ipopt 3.12.7 + MUMPS 4.10.0 binaries driven on the NLP of
+                                   mpc_to_line/solution/MPC.cpp (default options + print_level 0)
+  * oracle/_ref/libhelpers_ref.so  the reference's polyfit / polyeval / globalKinematic compiled from where they lie
+and extracts the roadmap centre line (mpc_to_line/roadmap.csv columns 4,5) as an input data fixture.
+
+    python tests/golden/make_golden.py        (needs /root/reference; `make -C oracle` first)
+
+The fixtures are small .npz files; tests never read /root/reference.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
+
+import oracle_bindings as ob  # noqa: E402
+
+REF = os.environ.get("REFERENCE_ROOT", "/root/reference")
+
+
+def write_centerline():
+    rm = np.loadtxt(os.path.join(REF, "mpc_to_line", "roadmap.csv"), delimiter=",")
+    out = os.path.join(ROOT, "udacitympc_b200", "data")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "roadmap_centerline.csv"), "w") as f:
+        for x, y in rm[:, 4:6]:
+            f.write(f"{float(x)!r},{float(y)!r}\n")
+
+
+def solve_set(states, coeffs, **kw):
+    B = len(states)
+    N = kw.get("N", 25)
+    out8 = np.zeros((B, 8)); x = np.zeros((B, 8 * N - 2)); obj = np.zeros(B)
+    st = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32); resto = np.zeros(B, dtype=np.int32)
+    regu = np.zeros(B); lsmax = np.zeros(B, dtype=np.int32)
+    for b in range(B):
+        r = ob.ref_solve(states[b], coeffs[b], trace=True, **kw)
+        out8[b] = r["out8"]; x[b] = r["x"]; obj[b] = r["obj"]; st[b] = r["status"]; it[b] = r["iters"]
+        tr = r["trace"]
+        resto[b] = int((tr[:, 9] >= 100).any())
+        regu[b] = tr[:, 6].max()
+        lsmax[b] = int((tr[:, 9] % 100).max())
+    return dict(out8=out8, x=x, obj=obj, status=st, iters=it, used_restoration=resto, max_regu=regu, max_ls_trials=lsmax)
+
+
+def main():
+    from udacitympc_b200 import synth
+    write_centerline()
+
+    # ---- config 1: solution/main.cpp closed loop, 50 steps
+    coeffs = ob.ref_polyfit([-100.0, 100.0], [-1.0, -1.0], 1)
+    x, y, psi, v = -1.0, 10.0, 0.0, 10.0
+    cte = ob.ref_polyeval(coeffs, x) - y
+    epsi = psi - np.arctan(coeffs[1])
+    state = np.array([x, y, psi, v, cte, epsi])
+    rows8, rowsx, cost, iters, states = [], [], [], [], []
+    for _ in range(50):
+        states.append(state.copy())
+        r = ob.ref_solve(state, coeffs)
+        assert r["status"] == 0
+        rows8.append(r["out8"].copy()); rowsx.append(r["x"].copy()); cost.append(r["obj"]); iters.append(r["iters"])
+        state = r["out8"][:6].copy()
+    np.savez_compressed(os.path.join(HERE, "config1_closed_loop.npz"), coeffs=coeffs, states=np.array(states),
+                        out8=np.array(rows8), x=np.array(rowsx), cost=np.array(cost), iters=np.array(iters, dtype=np.int32))
+
+    # ---- config 3 slice: 256 randomized degree-1 problems
+    st, cf = synth.line_problems(256)
+    np.savez_compressed(os.path.join(HERE, "line_256.npz"), states=st, coeffs=cf, **solve_set(st, cf))
+
+    # ---- config 2(ii) + 4 slice: 256 roadmap windows, reference polyfit (degree 3), then degree-3 MPC
+    xs, ys = synth.roadmap_windows(256)
+    fit = np.array([ob.ref_polyfit(xs[b], ys[b], 3) for b in range(256)])
+    st3 = synth.roadmap_problems(256, fit)
+    np.savez_compressed(os.path.join(HERE, "roadmap_256.npz"), xs=xs, ys=ys, fit=fit, states=st3, **solve_set(st3, fit))
+
+    # ---- other horizons (degree 3): N=10 and N=50, 64 problems each
+    for N in (10, 50):
+        np.savez_compressed(os.path.join(HERE, f"roadmap_N{N}_64.npz"), states=st3[:64], coeffs=fit[:64],
+                            **solve_set(st3[:64], fit[:64], N=N))
+
+    # ---- non-default parameters (weights, bounds, Lf, dt, ref_v) through the same reference binaries is not
+    # possible: the TNLP restates MPC.cpp with unit weights.  Lf/dt/ref_v/bounds ARE parameters of it:
+    kw = dict(N=20, dt=0.08, Lf=2.0, ref_v=25.0, delta_max=0.3, a_max=0.7)
+    np.savez_compressed(os.path.join(HERE, "line_params_64.npz"), states=st[:64], coeffs=cf[:64],
+                        params=np.array([kw["N"], kw["dt"], kw["Lf"], kw["ref_v"], kw["delta_max"], kw["a_max"]]),
+                        **solve_set(st[:64], cf[:64], **kw))
+
+    # ---- config 2(i): bicycle steps with the reference's globalKinematic (dt=0.3, Lf=2) and 25-step rollouts
+    ks, ka = synth.kinematic_inputs(256, H=25)
+    one = np.array([ob.ref_kinematic(ks[b], ka[b, 0], 0.3) for b in range(256)])
+    roll = np.zeros((256, 25, 4))
+    for b in range(256):
+        s = ks[b].copy()
+        for h in range(25):
+            s = ob.ref_kinematic(s, ka[b, h], 0.3)
+            roll[b, h] = s
+    np.savez_compressed(os.path.join(HERE, "kinematic_256.npz"), states=ks, act=ka, one_step=one, rollout=roll)
+
+    # ---- polyfit on other shapes with the reference's helpers.h
+    rng = np.random.default_rng(7)
+    shapes = {}
+    for (m, order) in [(2, 1), (3, 2), (4, 3), (6, 1), (6, 2), (6, 3), (8, 3), (7, 4), (12, 5)]:
+        px = np.sort(rng.uniform(-3, 3, size=(32, m)), axis=1)
+        py = rng.uniform(-2, 2, size=(32, m))
+        shapes[f"xs_{m}_{order}"] = px
+        shapes[f"ys_{m}_{order}"] = py
+        shapes[f"fit_{m}_{order}"] = np.array([ob.ref_polyfit(px[b], py[b], order) for b in range(32)])
+    np.savez_compressed(os.path.join(HERE, "polyfit_shapes.npz"), **shapes)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,429 @@
+// C ABI of libb200mpc.so (include/b200mpc.h): handles, device buffers, host<->device staging, multi-device
+// sharding.  No CPU compute path exists here: every entry point launches the sm_100a kernels or fails.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/b200mpc.h"
+#include "kernels.h"
+
+using namespace b200mpc;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(B200MPC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return cuda_fail(e_, #x); } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+}  // namespace
+
+struct b200mpc_handle {
+  Params P;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf ws, in_aos, st_soa, cf_soa, out_soa, out_aos, traj_soa, traj_aos, obj, status, iters, misc0, misc1, misc2, misc3;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;   // around every solver-kernel launch
+  long long launches = 0;
+};
+
+namespace {
+
+Params to_core(const b200mpc_params& p) {
+  Params P;
+  P.N = p.N; P.dt = p.dt; P.Lf = p.Lf; P.ref_v = p.ref_v;
+  P.w_cte = p.w_cte; P.w_epsi = p.w_epsi; P.w_v = p.w_v; P.w_delta = p.w_delta; P.w_a = p.w_a;
+  P.w_ddelta = p.w_ddelta; P.w_da = p.w_da; P.delta_max = p.delta_max; P.a_max = p.a_max;
+  P.tol = p.tol; P.max_iter = p.max_iter;
+  return P;
+}
+
+int check_solve_args(const b200mpc_handle* h, int B, const void* st, const void* cf, int ncoef, const void* out8) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  if (B < 0) return fail(B200MPC_ERR_ARG, "negative batch size");
+  if (ncoef < 2 || ncoef > B200MPC_MAX_COEFFS) return fail(B200MPC_ERR_ARG, "ncoef must be in [2, 4] (polynomial degree 1..3)");
+  if (B > 0 && (!st || !cf || !out8)) return fail(B200MPC_ERR_ARG, "null state6 / coeffs / out8");
+  return 0;
+}
+
+// records a pair of events around the solver kernel so bench.py can read the kernel's own device time
+int timed_solve(b200mpc_handle* h, int B, int steps, const double* st, const double* cf, int ncoef, double* out8,
+                double* traj, double* obj, int* status, int* iters, cudaStream_t s) {
+  CU(h->ws.ensure(solve_workspace_doubles(h->P.N, B) * sizeof(double)));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const bool rec = h->timing.size() < 8192;
+  if (rec) {
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, s));
+  }
+  CU(launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, s));
+  h->launches += 1;
+  if (rec) {
+    CU(cudaEventRecord(e1, s));
+    h->timing.emplace_back(e0, e1);
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void b200mpc_default_params(b200mpc_params* p) {
+  if (!p) return;
+  p->N = 25; p->dt = 0.05; p->Lf = 2.67; p->ref_v = 40.0;
+  p->w_cte = p->w_epsi = p->w_v = p->w_delta = p->w_a = p->w_ddelta = p->w_da = 1.0;
+  p->delta_max = 0.436332; p->a_max = 1.0;
+  p->tol = 1e-8; p->max_iter = 3000;
+}
+
+const char* b200mpc_last_error(void) { return g_err.c_str(); }
+
+int b200mpc_create(const b200mpc_params* p, int device, b200mpc_handle** out) {
+  if (!p || !out) return fail(B200MPC_ERR_ARG, "null params / out");
+  if (p->N < 2 || p->N > 1024) return fail(B200MPC_ERR_ARG, "N must be in [2, 1024]");
+  if (!(p->dt > 0) || !(p->Lf > 0) || !(p->delta_max > 0) || !(p->a_max > 0) || !(p->tol > 0) || p->max_iter < 0)
+    return fail(B200MPC_ERR_ARG, "dt, Lf, delta_max, a_max, tol must be positive");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(B200MPC_ERR_CUDA, std::string("no CUDA device available (b200mpc has no CPU path): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(B200MPC_ERR_ARG, "device index out of range");
+  CU(cudaSetDevice(device));
+  b200mpc_handle* h = new (std::nothrow) b200mpc_handle();
+  if (!h) return fail(B200MPC_ERR_NOMEM, "out of host memory");
+  h->P = to_core(*p);
+  h->device = device;
+  e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
+  *out = h;
+  return 0;
+}
+
+void b200mpc_destroy(b200mpc_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& ev : h->timing) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  DevBuf* bufs[] = {&h->ws, &h->in_aos, &h->st_soa, &h->cf_soa, &h->out_soa, &h->out_aos, &h->traj_soa, &h->traj_aos,
+                    &h->obj, &h->status, &h->iters, &h->misc0, &h->misc1, &h->misc2, &h->misc3};
+  for (DevBuf* b : bufs) b->release();
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int b200mpc_num_vars(const b200mpc_handle* h) { return h ? 8 * h->P.N - 2 : 0; }
+long long b200mpc_launch_count(const b200mpc_handle* h) { return h ? h->launches : 0; }
+
+int b200mpc_solve_batch_device(b200mpc_handle* h, int B, const double* d_state6, const double* d_coeffs, int ncoef,
+                               double* d_out8, double* d_traj, double* d_obj, int* d_status, int* d_iters,
+                               void* stream) {
+  if (int rc = check_solve_args(h, B, d_state6, d_coeffs, ncoef, d_out8)) return rc;
+  if (B == 0) return 0;
+  CU(cudaSetDevice(h->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  return timed_solve(h, B, 1, d_state6, d_coeffs, ncoef, d_out8, d_traj, d_obj, d_status, d_iters, s);
+}
+
+int b200mpc_solve_batch(b200mpc_handle* h, int B, const double* state6, const double* coeffs, int ncoef, double* out8,
+                        double* traj, double* obj, int* status, int* iters) {
+  if (int rc = check_solve_args(h, B, state6, coeffs, ncoef, out8)) return rc;
+  if (B == 0) return 0;
+  CU(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int nv = 8 * h->P.N - 2;
+  const size_t nb = (size_t)B;
+  // stage: H2D (reference order) -> K6 transpose -> solve -> K6 transpose -> D2H
+  CU(h->in_aos.ensure(nb * (6 + ncoef) * sizeof(double)));
+  CU(h->st_soa.ensure(nb * 6 * sizeof(double)));
+  CU(h->cf_soa.ensure(nb * ncoef * sizeof(double)));
+  CU(h->out_soa.ensure(nb * 8 * sizeof(double)));
+  CU(h->out_aos.ensure(nb * 8 * sizeof(double)));
+  CU(h->obj.ensure(nb * sizeof(double)));
+  CU(h->status.ensure(nb * sizeof(int)));
+  CU(h->iters.ensure(nb * sizeof(int)));
+  if (traj) { CU(h->traj_soa.ensure(nb * nv * sizeof(double))); CU(h->traj_aos.ensure(nb * nv * sizeof(double))); }
+  double* d_st = h->in_aos.as<double>();
+  double* d_cf = d_st + nb * 6;
+  CU(cudaMemcpyAsync(d_st, state6, nb * 6 * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d_cf, coeffs, nb * ncoef * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(launch_aos_to_soa(d_st, h->st_soa.as<double>(), B, 6, s));
+  CU(launch_aos_to_soa(d_cf, h->cf_soa.as<double>(), B, ncoef, s));
+  h->launches += 2;
+  if (int rc = timed_solve(h, B, 1, h->st_soa.as<double>(), h->cf_soa.as<double>(), ncoef, h->out_soa.as<double>(),
+                           traj ? h->traj_soa.as<double>() : nullptr, h->obj.as<double>(), h->status.as<int>(),
+                           h->iters.as<int>(), s))
+    return rc;
+  CU(launch_soa_to_aos(h->out_soa.as<double>(), h->out_aos.as<double>(), B, 8, s));
+  h->launches += 1;
+  CU(cudaMemcpyAsync(out8, h->out_aos.p, nb * 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (traj) {
+    CU(launch_soa_to_aos(h->traj_soa.as<double>(), h->traj_aos.as<double>(), B, nv, s));
+    h->launches += 1;
+    CU(cudaMemcpyAsync(traj, h->traj_aos.p, nb * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
+  if (obj) CU(cudaMemcpyAsync(obj, h->obj.p, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (status) CU(cudaMemcpyAsync(status, h->status.p, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (iters) CU(cudaMemcpyAsync(iters, h->iters.p, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int b200mpc_solve_batch_multi(b200mpc_handle* const* hs, int n_handles, int B, const double* state6,
+                              const double* coeffs, int ncoef, double* out8, double* traj, double* obj, int* status,
+                              int* iters) {
+  if (!hs || n_handles <= 0) return fail(B200MPC_ERR_ARG, "no handles");
+  for (int g = 0; g < n_handles; ++g)
+    if (!hs[g]) return fail(B200MPC_ERR_ARG, "null handle in list");
+  if (B < 0) return fail(B200MPC_ERR_ARG, "negative batch size");
+  std::vector<int> rc(n_handles, 0);
+  std::vector<std::string> msg(n_handles);
+  std::vector<std::thread> th;
+  const int nv = 8 * hs[0]->P.N - 2;
+  for (int g = 0; g < n_handles; ++g) {
+    // contiguous index ranges, remainder to the last device
+    const long long lo = (long long)B / n_handles * g;
+    const long long hi = g == n_handles - 1 ? B : (long long)B / n_handles * (g + 1);
+    th.emplace_back([=, &rc, &msg]() {
+      const int n = (int)(hi - lo);
+      rc[g] = b200mpc_solve_batch(hs[g], n, state6 + lo * 6, coeffs + lo * ncoef, ncoef, out8 + lo * 8,
+                                  traj ? traj + lo * nv : nullptr, obj ? obj + lo : nullptr,
+                                  status ? status + lo : nullptr, iters ? iters + lo : nullptr);
+      if (rc[g]) msg[g] = b200mpc_last_error();
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int g = 0; g < n_handles; ++g)
+    if (rc[g]) return fail(rc[g], "device shard " + std::to_string(g) + ": " + msg[g]);
+  return 0;
+}
+
+int b200mpc_closed_loop_batch(b200mpc_handle* h, int B, int steps, const double* state6, const double* coeffs,
+                              int ncoef, double* hist8, double* cost, int* iters) {
+  if (int rc = check_solve_args(h, B, state6, coeffs, ncoef, hist8)) return rc;
+  if (steps < 1) return fail(B200MPC_ERR_ARG, "steps must be >= 1");
+  if (B == 0) return 0;
+  CU(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const size_t nb = (size_t)B, ns = (size_t)steps;
+  CU(h->in_aos.ensure(nb * (6 + ncoef) * sizeof(double)));
+  CU(h->st_soa.ensure(nb * 6 * sizeof(double)));
+  CU(h->cf_soa.ensure(nb * ncoef * sizeof(double)));
+  CU(h->out_soa.ensure(ns * nb * 8 * sizeof(double)));
+  CU(h->out_aos.ensure(ns * nb * 8 * sizeof(double)));
+  CU(h->obj.ensure(ns * nb * sizeof(double)));
+  CU(h->iters.ensure(ns * nb * sizeof(int)));
+  double* d_st = h->in_aos.as<double>();
+  double* d_cf = d_st + nb * 6;
+  CU(cudaMemcpyAsync(d_st, state6, nb * 6 * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d_cf, coeffs, nb * ncoef * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(launch_aos_to_soa(d_st, h->st_soa.as<double>(), B, 6, s));
+  CU(launch_aos_to_soa(d_cf, h->cf_soa.as<double>(), B, ncoef, s));
+  h->launches += 2;
+  if (int rc = timed_solve(h, B, steps, h->st_soa.as<double>(), h->cf_soa.as<double>(), ncoef, h->out_soa.as<double>(),
+                           nullptr, h->obj.as<double>(), nullptr, h->iters.as<int>(), s))
+    return rc;
+  for (int k = 0; k < steps; ++k) {   // [8][B] -> [B][8] per step
+    CU(launch_soa_to_aos(h->out_soa.as<double>() + (size_t)k * 8 * nb, h->out_aos.as<double>() + (size_t)k * 8 * nb, B, 8, s));
+    h->launches += 1;
+  }
+  CU(cudaMemcpyAsync(hist8, h->out_aos.p, ns * nb * 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (cost) CU(cudaMemcpyAsync(cost, h->obj.p, ns * nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (iters) CU(cudaMemcpyAsync(iters, h->iters.p, ns * nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int check_fit_args(const b200mpc_handle* h, int B, const void* xs, const void* ys, int m, int order, const void* out) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  if (B < 0) return fail(B200MPC_ERR_ARG, "negative batch size");
+  if (m < 2 || m > B200MPC_MAX_FIT_POINTS) return fail(B200MPC_ERR_ARG, "polyfit: m must be in [2, 16]");
+  if (!(order >= 1 && order <= m - 1)) return fail(B200MPC_ERR_ARG, "polyfit: requires 1 <= order <= m-1 (helpers.h:26)");
+  if (order > B200MPC_MAX_FIT_ORDER) return fail(B200MPC_ERR_ARG, "polyfit: order must be <= 7");
+  if (B > 0 && (!xs || !ys || !out)) return fail(B200MPC_ERR_ARG, "null xs / ys / coeffs_out");
+  return 0;
+}
+
+int b200mpc_polyfit_batch_device(b200mpc_handle* h, int B, const double* d_xs, const double* d_ys, int m, int order,
+                                 double* d_coeffs_out, void* stream) {
+  if (int rc = check_fit_args(h, B, d_xs, d_ys, m, order, d_coeffs_out)) return rc;
+  if (B == 0) return 0;
+  CU(cudaSetDevice(h->device));
+  CU(launch_polyfit(d_xs, d_ys, B, m, order, d_coeffs_out, stream ? (cudaStream_t)stream : h->stream));
+  h->launches += 1;
+  return 0;
+}
+
+int b200mpc_polyfit_batch(b200mpc_handle* h, int B, const double* xs, const double* ys, int m, int order,
+                          double* coeffs_out) {
+  if (int rc = check_fit_args(h, B, xs, ys, m, order, coeffs_out)) return rc;
+  if (B == 0) return 0;
+  CU(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const size_t nb = (size_t)B;
+  const int n = order + 1;
+  CU(h->misc0.ensure(nb * 2 * m * sizeof(double)));   // AoS xs | ys
+  CU(h->misc1.ensure(nb * 2 * m * sizeof(double)));   // SoA xs | ys
+  CU(h->misc2.ensure(nb * n * sizeof(double)));       // SoA coeffs
+  CU(h->misc3.ensure(nb * n * sizeof(double)));       // AoS coeffs
+  double* a = h->misc0.as<double>();
+  double* so = h->misc1.as<double>();
+  CU(cudaMemcpyAsync(a, xs, nb * m * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(a + nb * m, ys, nb * m * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(launch_aos_to_soa(a, so, B, m, s));
+  CU(launch_aos_to_soa(a + nb * m, so + nb * m, B, m, s));
+  CU(launch_polyfit(so, so + nb * m, B, m, order, h->misc2.as<double>(), s));
+  CU(launch_soa_to_aos(h->misc2.as<double>(), h->misc3.as<double>(), B, n, s));
+  h->launches += 4;
+  CU(cudaMemcpyAsync(coeffs_out, h->misc3.p, nb * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int b200mpc_polyeval_batch_device(b200mpc_handle* h, int B, const double* d_coeffs, int ncoef, const double* d_x,
+                                  double* d_y, void* stream) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  if (B < 0 || ncoef < 1 || ncoef > 64) return fail(B200MPC_ERR_ARG, "polyeval: bad B / ncoef");
+  if (B == 0) return 0;
+  if (!d_coeffs || !d_x || !d_y) return fail(B200MPC_ERR_ARG, "null pointer");
+  CU(cudaSetDevice(h->device));
+  CU(launch_polyeval(d_coeffs, ncoef, d_x, d_y, B, stream ? (cudaStream_t)stream : h->stream));
+  h->launches += 1;
+  return 0;
+}
+
+int b200mpc_polyeval_batch(b200mpc_handle* h, int B, const double* coeffs, int ncoef, const double* x, double* y) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  if (B < 0 || ncoef < 1 || ncoef > 64) return fail(B200MPC_ERR_ARG, "polyeval: bad B / ncoef");
+  if (B == 0) return 0;
+  if (!coeffs || !x || !y) return fail(B200MPC_ERR_ARG, "null pointer");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const size_t nb = (size_t)B;
+  CU(h->misc0.ensure(nb * (ncoef + 1) * sizeof(double)));
+  CU(h->misc1.ensure(nb * (ncoef + 1) * sizeof(double)));
+  double* a = h->misc0.as<double>();
+  double* so = h->misc1.as<double>();
+  CU(cudaMemcpyAsync(a, coeffs, nb * ncoef * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(a + nb * ncoef, x, nb * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(launch_aos_to_soa(a, so, B, ncoef, s));
+  CU(launch_polyeval(so, ncoef, a + nb * ncoef, so + nb * ncoef, B, s));
+  h->launches += 2;
+  CU(cudaMemcpyAsync(y, so + nb * ncoef, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int b200mpc_rollout_batch_device(b200mpc_handle* h, int B, int H, const double* d_state4, const double* d_act,
+                                 double dt, double Lf, double* d_out, void* stream) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  if (B < 0 || H < 1 || H > 4096) return fail(B200MPC_ERR_ARG, "rollout: bad B / H");
+  if (!(Lf > 0)) return fail(B200MPC_ERR_ARG, "rollout: Lf must be positive");
+  if (B == 0) return 0;
+  if (!d_state4 || !d_act || !d_out) return fail(B200MPC_ERR_ARG, "null pointer");
+  CU(cudaSetDevice(h->device));
+  CU(launch_rollout(d_state4, d_act, B, H, dt, Lf, d_out, stream ? (cudaStream_t)stream : h->stream));
+  h->launches += 1;
+  return 0;
+}
+
+int b200mpc_rollout_batch(b200mpc_handle* h, int B, int H, const double* state4, const double* act, double dt,
+                          double Lf, double* out) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  if (B < 0 || H < 1 || H > 1024) return fail(B200MPC_ERR_ARG, "rollout: bad B / H (host entry: H <= 1024)");
+  if (!(Lf > 0)) return fail(B200MPC_ERR_ARG, "rollout: Lf must be positive");
+  if (B == 0) return 0;
+  if (!state4 || !act || !out) return fail(B200MPC_ERR_ARG, "null pointer");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const size_t nb = (size_t)B, hh = (size_t)H;
+  CU(h->misc0.ensure(nb * (4 + 2 * hh) * sizeof(double)));   // AoS state | act
+  CU(h->misc1.ensure(nb * (4 + 2 * hh) * sizeof(double)));   // SoA state | act
+  CU(h->misc2.ensure(nb * 4 * hh * sizeof(double)));         // SoA out
+  CU(h->misc3.ensure(nb * 4 * hh * sizeof(double)));         // AoS out
+  double* a = h->misc0.as<double>();
+  double* so = h->misc1.as<double>();
+  CU(cudaMemcpyAsync(a, state4, nb * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(a + nb * 4, act, nb * 2 * hh * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(launch_aos_to_soa(a, so, B, 4, s));
+  CU(launch_aos_to_soa(a + nb * 4, so + nb * 4, B, 2 * H, s));
+  CU(launch_rollout(so, so + nb * 4, B, H, dt, Lf, h->misc2.as<double>(), s));
+  CU(launch_soa_to_aos(h->misc2.as<double>(), h->misc3.as<double>(), B, 4 * H, s));
+  h->launches += 4;
+  CU(cudaMemcpyAsync(out, h->misc3.p, nb * 4 * hh * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+int b200mpc_kernel_time_ms(b200mpc_handle* h, double* total_ms, int* launches, int reset) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  double tot = 0.0;
+  for (auto& ev : h->timing) {
+    CU(cudaEventSynchronize(ev.second));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (int)h->timing.size();
+  if (reset) {
+    for (auto& ev : h->timing) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    h->timing.clear();
+  }
+  return 0;
+}
+
+int b200mpc_measure_fp64_peak(b200mpc_handle* h, double* tflops) {
+  if (!h || !tflops) return fail(B200MPC_ERR_ARG, "null handle / output");
+  CU(cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, h->device));
+  CU(h->misc0.ensure(1024));
+  cudaStream_t s = h->stream;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  double flop = 0.0, best = 0.0;
+  CU(launch_fp64_peak(h->misc0.as<double>(), blocks, threads, 64, s, &flop));   // warm-up
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(e0, s));
+    CU(launch_fp64_peak(h->misc0.as<double>(), blocks, threads, iters, s, &flop));
+    CU(cudaEventRecord(e1, s));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = flop / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  h->launches += 6;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *tflops = best;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,270 @@
+// HBM-bound batch kernels for sm_100a (compiled with -fmad=false so the arithmetic is the x86-64 reference's
+// operation-for-operation; these kernels are bandwidth bound, so the un-fused multiplies are free):
+//   K4 polyfit    /root/reference/mpc_to_line/src/helpers.h:24-44 (+ Eigen 3.3.3 HouseholderQR.h:256-287,350-369,
+//                 Householder.h:64-131), polyeval helpers.h:13-19
+//   K5 rollout    /root/reference/global_kinematic_model/solution/main.cpp:36-62
+//   K6 batch I/O  the per-call unpack / pack of MPC.cpp:152-177 and :253-256, batched: [B][K] <-> [K][B]
+// Compute kernels read and write field-major (SoA) arrays: consecutive threads touch consecutive doubles.
+#include <float.h>
+
+#include "kernels.h"
+
+namespace b200mpc {
+
+// ---------------------------------------------------------------------------------------------
+// K6: tiled transpose through shared memory; both the global read and the global write are coalesced.
+constexpr int kTile = 128;   // problems per block
+
+__global__ void __launch_bounds__(kTile) aos_to_soa_kernel(const double* __restrict__ in, double* __restrict__ out, int B, int K) {
+  extern __shared__ double tile[];   // kTile x K, row pitch K+1 when K is even (bank conflicts)
+  const int pitch = K | 1;
+  const size_t b0 = (size_t)blockIdx.x * kTile;
+  const int nb = (int)(B - b0 < (size_t)kTile ? B - b0 : (size_t)kTile);
+  for (int i = threadIdx.x; i < nb * K; i += kTile) tile[(i / K) * pitch + (i % K)] = in[b0 * K + i];
+  __syncthreads();
+  if ((int)threadIdx.x < nb)
+    for (int k = 0; k < K; ++k) out[(size_t)k * B + b0 + threadIdx.x] = tile[threadIdx.x * pitch + k];
+}
+
+__global__ void __launch_bounds__(kTile) soa_to_aos_kernel(const double* __restrict__ in, double* __restrict__ out, int B, int K) {
+  extern __shared__ double tile[];
+  const int pitch = K | 1;
+  const size_t b0 = (size_t)blockIdx.x * kTile;
+  const int nb = (int)(B - b0 < (size_t)kTile ? B - b0 : (size_t)kTile);
+  if ((int)threadIdx.x < nb)
+    for (int k = 0; k < K; ++k) tile[threadIdx.x * pitch + k] = in[(size_t)k * B + b0 + threadIdx.x];
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb * K; i += kTile) out[b0 * K + i] = tile[(i / K) * pitch + (i % K)];
+}
+
+cudaError_t launch_aos_to_soa(const double* in, double* out, int B, int K, cudaStream_t stream) {
+  if (B <= 0 || K <= 0) return cudaSuccess;
+  const size_t smem = (size_t)kTile * (K | 1) * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(aos_to_soa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  aos_to_soa_kernel<<<(B + kTile - 1) / kTile, kTile, smem, stream>>>(in, out, B, K);
+  return cudaGetLastError();
+}
+cudaError_t launch_soa_to_aos(const double* in, double* out, int B, int K, cudaStream_t stream) {
+  if (B <= 0 || K <= 0) return cudaSuccess;
+  const size_t smem = (size_t)kTile * (K | 1) * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(soa_to_aos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  soa_to_aos_kernel<<<(B + kTile - 1) / kTile, kTile, smem, stream>>>(in, out, B, K);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: one fit per thread; the m x n Vandermonde matrix lives in registers (MM, NN compile-time).
+template <int MM, int NN>
+__device__ __forceinline__ void polyfit_regs(const double* xs, const double* ys, double* out) {
+  double A[NN][MM];   // column major like Eigen
+#pragma unroll
+  for (int j = 0; j < MM; ++j) A[0][j] = 1.0;
+#pragma unroll
+  for (int i = 0; i < NN - 1; ++i)
+#pragma unroll
+    for (int j = 0; j < MM; ++j) A[i + 1][j] = A[i][j] * xs[j];   // helpers.h:34-38
+  double c[MM], h[NN];
+#pragma unroll
+  for (int j = 0; j < MM; ++j) c[j] = ys[j];
+  constexpr int size = MM < NN ? MM : NN;
+#pragma unroll
+  for (int k = 0; k < size; ++k) {   // HouseholderQR.h:274-286
+    const int rr = MM - k;
+    double tail = 0.0;
+#pragma unroll
+    for (int i = 1; i < rr; ++i) tail += A[k][k + i] * A[k][k + i];
+    const double c0 = A[k][k];
+    double beta, tau;
+    if (tail <= DBL_MIN) {   // Householder.h:79-84
+      tau = 0.0; beta = c0;
+#pragma unroll
+      for (int i = 1; i < rr; ++i) A[k][k + i] = 0.0;
+    } else {
+      beta = sqrt(c0 * c0 + tail);
+      if (c0 >= 0.0) beta = -beta;
+#pragma unroll
+      for (int i = 1; i < rr; ++i) A[k][k + i] = A[k][k + i] / (c0 - beta);
+      tau = (beta - c0) / beta;
+    }
+    h[k] = tau; A[k][k] = beta;
+#pragma unroll
+    for (int j = k + 1; j < NN; ++j) {   // applyHouseholderOnTheLeft, Householder.h:113-131
+      if (rr == 1) { A[j][k] *= 1.0 - tau; continue; }
+      if (tau == 0.0) continue;
+      double t = 0.0;
+#pragma unroll
+      for (int i = 1; i < rr; ++i) t += A[k][k + i] * A[j][k + i];
+      t += A[j][k];
+      A[j][k] -= tau * t;
+#pragma unroll
+      for (int i = 1; i < rr; ++i) A[j][k + i] -= tau * A[k][k + i] * t;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < size; ++k) {   // Q^T y, HouseholderQR.h:358-362
+    const int rr = MM - k;
+    const double tau = h[k];
+    if (rr == 1) { c[k] *= 1.0 - tau; continue; }
+    if (tau == 0.0) continue;
+    double t = 0.0;
+#pragma unroll
+    for (int i = 1; i < rr; ++i) t += A[k][k + i] * c[k + i];
+    t += c[k];
+    c[k] -= tau * t;
+#pragma unroll
+    for (int i = 1; i < rr; ++i) c[k + i] -= tau * A[k][k + i] * t;
+  }
+#pragma unroll
+  for (int i = size - 1; i >= 0; --i) {   // back substitution on the top triangle
+    double s = c[i];
+#pragma unroll
+    for (int j = i + 1; j < size; ++j) s -= A[j][i] * out[j];
+    out[i] = s / A[i][i];
+  }
+}
+
+template <int MM, int NN>
+__global__ void __launch_bounds__(128) polyfit_kernel(const double* __restrict__ xs, const double* __restrict__ ys, int B,
+                                                      double* __restrict__ coeffs) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x[MM], y[MM], o[NN];
+#pragma unroll
+  for (int j = 0; j < MM; ++j) { x[j] = xs[(size_t)j * B + b]; y[j] = ys[(size_t)j * B + b]; }
+  polyfit_regs<MM, NN>(x, y, o);
+#pragma unroll
+  for (int i = 0; i < NN; ++i) coeffs[(size_t)i * B + b] = o[i];
+}
+
+// generic shapes (m <= 16, order <= 7): same algorithm on thread-local arrays with run-time sizes
+__global__ void __launch_bounds__(128) polyfit_generic_kernel(const double* __restrict__ xs, const double* __restrict__ ys, int B,
+                                                              int m, int n, double* __restrict__ coeffs) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double A[8 * 16], c[16], h[8], out[8];
+  for (int j = 0; j < m; ++j) { A[j] = 1.0; c[j] = ys[(size_t)j * B + b]; }
+  for (int i = 0; i < n - 1; ++i)
+    for (int j = 0; j < m; ++j) A[(i + 1) * m + j] = A[i * m + j] * xs[(size_t)j * B + b];
+  const int size = m < n ? m : n;
+  for (int k = 0; k < size; ++k) {
+    const int rr = m - k;
+    double* col = A + k + k * m;
+    double tail = 0.0;
+    for (int i = 1; i < rr; ++i) tail += col[i] * col[i];
+    const double c0 = col[0];
+    double beta, tau;
+    if (tail <= DBL_MIN) {
+      tau = 0.0; beta = c0;
+      for (int i = 1; i < rr; ++i) col[i] = 0.0;
+    } else {
+      beta = sqrt(c0 * c0 + tail);
+      if (c0 >= 0.0) beta = -beta;
+      for (int i = 1; i < rr; ++i) col[i] = col[i] / (c0 - beta);
+      tau = (beta - c0) / beta;
+    }
+    h[k] = tau; col[0] = beta;
+    for (int j = k + 1; j < n; ++j) {
+      double* cj = A + k + j * m;
+      if (rr == 1) { cj[0] *= 1.0 - tau; continue; }
+      if (tau == 0.0) continue;
+      double t = 0.0;
+      for (int i = 1; i < rr; ++i) t += col[i] * cj[i];
+      t += cj[0];
+      cj[0] -= tau * t;
+      for (int i = 1; i < rr; ++i) cj[i] -= tau * col[i] * t;
+    }
+  }
+  for (int k = 0; k < size; ++k) {
+    const int rr = m - k;
+    const double* col = A + k + k * m;
+    const double tau = h[k];
+    if (rr == 1) { c[k] *= 1.0 - tau; continue; }
+    if (tau == 0.0) continue;
+    double t = 0.0;
+    for (int i = 1; i < rr; ++i) t += col[i] * c[k + i];
+    t += c[k];
+    c[k] -= tau * t;
+    for (int i = 1; i < rr; ++i) c[k + i] -= tau * col[i] * t;
+  }
+  for (int i = size - 1; i >= 0; --i) {
+    double s = c[i];
+    for (int j = i + 1; j < size; ++j) s -= A[i + j * m] * out[j];
+    out[i] = s / A[i + i * m];
+  }
+  for (int i = 0; i < n; ++i) coeffs[(size_t)i * B + b] = out[i];
+}
+
+template <int MM, int NN>
+static cudaError_t polyfit_launch_t(const double* xs, const double* ys, int B, double* coeffs, cudaStream_t stream) {
+  polyfit_kernel<MM, NN><<<(B + 127) / 128, 128, 0, stream>>>(xs, ys, B, coeffs);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_polyfit(const double* xs, const double* ys, int B, int m, int order, double* coeffs,
+                           cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  const int n = order + 1;
+#define PF_CASE(MM, NN) if (m == MM && n == NN) return polyfit_launch_t<MM, NN>(xs, ys, B, coeffs, stream);
+  PF_CASE(2, 2) PF_CASE(3, 2) PF_CASE(3, 3) PF_CASE(4, 2) PF_CASE(4, 3) PF_CASE(4, 4) PF_CASE(5, 3) PF_CASE(5, 4)
+  PF_CASE(6, 2) PF_CASE(6, 3) PF_CASE(6, 4) PF_CASE(8, 4)
+#undef PF_CASE
+  polyfit_generic_kernel<<<(B + 127) / 128, 128, 0, stream>>>(xs, ys, B, m, n, coeffs);
+  return cudaGetLastError();
+}
+
+// helpers.h:13-19: result += coeffs[i] * pow(x, i), i ascending
+__global__ void __launch_bounds__(256) polyeval_kernel(const double* __restrict__ coeffs, int ncoef, const double* __restrict__ x,
+                                                       double* __restrict__ y, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double xv = x[b];
+  double r = 0.0, xp = 1.0;
+  for (int i = 0; i < ncoef; ++i) {
+    r += coeffs[(size_t)i * B + b] * xp;
+    xp *= xv;
+  }
+  y[b] = r;
+}
+cudaError_t launch_polyeval(const double* coeffs, int ncoef, const double* x, double* y, int B, cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  polyeval_kernel<<<(B + 255) / 256, 256, 0, stream>>>(coeffs, ncoef, x, y, B);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: H Euler steps of the bicycle model per vehicle, global_kinematic_model/solution/main.cpp:56-59
+// (note the evaluation order v / Lf * delta * dt there).
+__global__ void __launch_bounds__(256) rollout_kernel(const double* __restrict__ state4, const double* __restrict__ act, int B, int H,
+                                                      double dt, double Lf, double* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x = state4[b], y = state4[(size_t)B + b], psi = state4[(size_t)2 * B + b], v = state4[(size_t)3 * B + b];
+  for (int s = 0; s < H; ++s) {
+    const double delta = act[(size_t)(2 * s) * B + b], a = act[(size_t)(2 * s + 1) * B + b];
+    double sp, cp;
+    sincos(psi, &sp, &cp);
+    const double nx = x + v * cp * dt;
+    const double ny = y + v * sp * dt;
+    const double np = psi + v / Lf * delta * dt;
+    const double nv = v + a * dt;
+    x = nx; y = ny; psi = np; v = nv;
+    out[(size_t)(4 * s + 0) * B + b] = x;
+    out[(size_t)(4 * s + 1) * B + b] = y;
+    out[(size_t)(4 * s + 2) * B + b] = psi;
+    out[(size_t)(4 * s + 3) * B + b] = v;
+  }
+}
+cudaError_t launch_rollout(const double* state4, const double* act, int B, int H, double dt, double Lf, double* out,
+                           cudaStream_t stream) {
+  if (B <= 0 || H <= 0) return cudaSuccess;
+  rollout_kernel<<<(B + 255) / 256, 256, 0, stream>>>(state4, act, B, H, dt, Lf, out);
+  return cudaGetLastError();
+}
+
+}  // namespace b200mpc

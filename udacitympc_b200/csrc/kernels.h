@@ -1,0 +1,34 @@
+// Launchers of the sm_100a kernels behind the C ABI (include/b200mpc.h).  Device pointers only.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "mpc_core.cuh"
+
+namespace b200mpc {
+
+// doubles of workspace needed to solve B problems at horizon N
+size_t solve_workspace_doubles(int N, int B);
+
+// K1+K2+K3 fused: `steps` consecutive interior-point solves per problem (steps > 1 = closed loop, each solve
+// starting from the previous solve's predicted state).  All arrays field-major (SoA) over the batch.
+//   state6 [6][B], coeffs [ncoef][B], out8 [steps][8][B], traj [8N-2][B] (last step, optional),
+//   obj [steps][B] (optional), status [B] (last step, optional), iters [steps][B] (optional)
+cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6, const double* coeffs, int ncoef,
+                         double* ws, double* out8, double* traj, double* obj, int* status, int* iters,
+                         cudaStream_t stream);
+
+// K6 batch I/O: [B][K] <-> [K][B]
+cudaError_t launch_aos_to_soa(const double* in, double* out, int B, int K, cudaStream_t stream);
+cudaError_t launch_soa_to_aos(const double* in, double* out, int B, int K, cudaStream_t stream);
+
+// K4 polyfit / polyeval, K5 rollout (SoA)
+cudaError_t launch_polyfit(const double* xs, const double* ys, int B, int m, int order, double* coeffs,
+                           cudaStream_t stream);
+cudaError_t launch_polyeval(const double* coeffs, int ncoef, const double* x, double* y, int B, cudaStream_t stream);
+cudaError_t launch_rollout(const double* state4, const double* act, int B, int H, double dt, double Lf, double* out,
+                           cudaStream_t stream);
+
+// DFMA throughput microbenchmark: returns FLOP executed per launch; time it outside.
+cudaError_t launch_fp64_peak(double* sink, int blocks, int threads, int iters, cudaStream_t stream, double* flop);
+
+}  // namespace b200mpc
