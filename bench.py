@@ -200,7 +200,8 @@ def run_ours(args):
     d_obj = torch.empty(B, dtype=torch.float64, device=dev)
     d_status = torch.empty(B, dtype=torch.int32, device=dev)
     d_iters = torch.empty(B, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)   # a real (non-default) stream: kernels and timing events share it
+    torch.cuda.synchronize()
 
     def dev_step(i):
         st, cf = d_in[i % nsets]

@@ -13,49 +13,68 @@ namespace b200mpc {
 
 // ---------------------------------------------------------------------------------------------
 // K6: tiled transpose through shared memory; both the global read and the global write are coalesced.
-constexpr int kTile = 128;   // problems per block
+// Tile = TB problems x K fields, stored field-major in shared memory with pitch TB+1.
+constexpr int kIoThreads = 128;
 
-__global__ void __launch_bounds__(kTile) aos_to_soa_kernel(const double* __restrict__ in, double* __restrict__ out, int B, int K) {
-  extern __shared__ double tile[];   // kTile x K, row pitch K+1 when K is even (bank conflicts)
-  const int pitch = K | 1;
-  const size_t b0 = (size_t)blockIdx.x * kTile;
-  const int nb = (int)(B - b0 < (size_t)kTile ? B - b0 : (size_t)kTile);
-  for (int i = threadIdx.x; i < nb * K; i += kTile) tile[(i / K) * pitch + (i % K)] = in[b0 * K + i];
+__global__ void __launch_bounds__(kIoThreads) aos_to_soa_kernel(const double* __restrict__ in, double* __restrict__ out, int B, int K, int TB) {
+  extern __shared__ double tile[];
+  const int pitch = TB + 1;
+  const size_t b0 = (size_t)blockIdx.x * TB;
+  const int nb = (int)(B - b0 < (size_t)TB ? B - b0 : (size_t)TB);
+  for (int i = threadIdx.x; i < nb * K; i += kIoThreads) tile[(i % K) * pitch + (i / K)] = in[b0 * K + i];
   __syncthreads();
-  if ((int)threadIdx.x < nb)
-    for (int k = 0; k < K; ++k) out[(size_t)k * B + b0 + threadIdx.x] = tile[threadIdx.x * pitch + k];
+  for (int j = threadIdx.x; j < nb * K; j += kIoThreads) {
+    const int k = j / nb, b = j % nb;
+    out[(size_t)k * B + b0 + b] = tile[k * pitch + b];
+  }
 }
 
-__global__ void __launch_bounds__(kTile) soa_to_aos_kernel(const double* __restrict__ in, double* __restrict__ out, int B, int K) {
+__global__ void __launch_bounds__(kIoThreads) soa_to_aos_kernel(const double* __restrict__ in, double* __restrict__ out, int B, int K, int TB) {
   extern __shared__ double tile[];
-  const int pitch = K | 1;
-  const size_t b0 = (size_t)blockIdx.x * kTile;
-  const int nb = (int)(B - b0 < (size_t)kTile ? B - b0 : (size_t)kTile);
-  if ((int)threadIdx.x < nb)
-    for (int k = 0; k < K; ++k) tile[threadIdx.x * pitch + k] = in[(size_t)k * B + b0 + threadIdx.x];
+  const int pitch = TB + 1;
+  const size_t b0 = (size_t)blockIdx.x * TB;
+  const int nb = (int)(B - b0 < (size_t)TB ? B - b0 : (size_t)TB);
+  for (int j = threadIdx.x; j < nb * K; j += kIoThreads) {
+    const int k = j / nb, b = j % nb;
+    tile[k * pitch + b] = in[(size_t)k * B + b0 + b];
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < nb * K; i += kTile) out[b0 * K + i] = tile[(i / K) * pitch + (i % K)];
+  for (int i = threadIdx.x; i < nb * K; i += kIoThreads) out[b0 * K + i] = tile[(i % K) * pitch + (i / K)];
+}
+
+// very wide records (K > 2048): plain element-wise transpose, coalesced on the field-major side only
+__global__ void __launch_bounds__(256) transpose_wide_kernel(const double* __restrict__ in, double* __restrict__ out, int B, int K, int to_soa) {
+  const size_t n = (size_t)B * K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t k = i / B, b = i % B;   // i indexes the field-major array
+    if (to_soa) out[i] = in[b * K + k]; else out[b * K + k] = in[i];
+  }
+}
+
+static int tile_problems(int K) { return K <= 48 ? 128 : (K <= 400 ? 32 : 8); }
+
+template <class Kern>
+static cudaError_t launch_transpose(Kern kern, const double* in, double* out, int B, int K, int to_soa, cudaStream_t stream) {
+  if (B <= 0 || K <= 0) return cudaSuccess;
+  if (K > 2048) {
+    transpose_wide_kernel<<<1184, 256, 0, stream>>>(in, out, B, K, to_soa);
+    return cudaGetLastError();
+  }
+  const int TB = tile_problems(K);
+  const size_t smem = (size_t)K * (TB + 1) * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<(B + TB - 1) / TB, kIoThreads, smem, stream>>>(in, out, B, K, TB);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_aos_to_soa(const double* in, double* out, int B, int K, cudaStream_t stream) {
-  if (B <= 0 || K <= 0) return cudaSuccess;
-  const size_t smem = (size_t)kTile * (K | 1) * sizeof(double);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(aos_to_soa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  aos_to_soa_kernel<<<(B + kTile - 1) / kTile, kTile, smem, stream>>>(in, out, B, K);
-  return cudaGetLastError();
+  return launch_transpose(aos_to_soa_kernel, in, out, B, K, 1, stream);
 }
 cudaError_t launch_soa_to_aos(const double* in, double* out, int B, int K, cudaStream_t stream) {
-  if (B <= 0 || K <= 0) return cudaSuccess;
-  const size_t smem = (size_t)kTile * (K | 1) * sizeof(double);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(soa_to_aos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  soa_to_aos_kernel<<<(B + kTile - 1) / kTile, kTile, smem, stream>>>(in, out, B, K);
-  return cudaGetLastError();
+  return launch_transpose(soa_to_aos_kernel, in, out, B, K, 0, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
