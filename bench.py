@@ -190,6 +190,7 @@ def run_ours(args):
     B, K, W = args.batch, args.steps, args.warmup
 
     mpc = mpcmod.MPC(device=local)
+    mpc.set_solver_mode({"perpass": 0, "fused": 1}[args.mode], args.rounds, -1)
     nsets = 2
     sets = [make_workload(args.workload, B, seed_shift=rank * nsets + s, mpc=mpc) for s in range(nsets)]
     ncoef = sets[0][1].shape[1]
@@ -307,7 +308,10 @@ def run_ours(args):
             gpu_launches=int(launches),
             clocks=clocks,
             roofline=dict(bound="fp64", achieved=achieved, peak=fp64_peak, unit="TFLOP/s", frac=achieved / fp64_peak if fp64_peak else None,
-                          traffic=None, kernel="mpc_solve_kernel", avg_kernel_ms=avg_kernel_ms, launches_timed=kern_n,
+                          traffic=None,
+                          kernel=("mpc_{init,factor,forward,trial,accept,fused}_kernel: all solver kernels of one step, first to last"
+                                  if args.mode == "perpass" else "mpc_fused_kernel"),
+                          avg_kernel_ms=avg_kernel_ms, launches_timed=kern_n, solver_mode=args.mode,
                           flop_per_launch=flop_per_launch, mean_ip_iters=mean_it,
                           peak_source="DFMA microbenchmark in this run (b200mpc_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                           hbm_peak_gbs=peaks.get("hbm_gbs"), algorithmic_io_bytes_per_solve=(6 + ncoef + 8 + 2) * 8,
@@ -334,6 +338,8 @@ def main():
     ap.add_argument("--latency-reps", type=int, default=100)
     ap.add_argument("--cpu-per-core", type=int, default=150, help="cpu_baseline: solves per host core in the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="perpass", choices=["perpass", "fused"], help="solver execution mode (include/b200mpc.h)")
+    ap.add_argument("--rounds", type=int, default=0, help="per-pass mode: rounds before the fused finisher (0 = library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

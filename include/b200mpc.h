@@ -124,9 +124,16 @@ int b200mpc_rollout_batch(b200mpc_handle* h, int B, int H, const double* state4,
 int b200mpc_rollout_batch_device(b200mpc_handle* h, int B, int H, const double* d_state4, const double* d_act,
                                  double dt, double Lf, double* d_out, void* stream);
 
+/* Execution mode of the solver (tuning; results do not depend on it).
+ *   mode 0 (default)  per-pass kernels: init, then `rounds` rounds of (factor, forward, trial, accept) launched back to
+ *                     back on the stream, then one fused launch that finishes any problem still iterating
+ *   mode 1            the fused kernel alone (one launch per solve; lowest latency for small batches)
+ * rounds <= 0 / fused_below < 0 keep the current value.  Batches smaller than fused_below always use mode 1. */
+int b200mpc_set_solver_mode(b200mpc_handle* h, int mode, int rounds, int fused_below);
+
 /* Measurement helpers (used by bench.py; not part of the reference interface). */
-/* Average device time in ms of the solver kernel over all its launches since the last reset (CUDA events on the
- * launching stream), and the number of launches. */
+/* Total device time in ms of the solver's kernels (one interval per batch: first to last kernel of a solve) since the
+ * last reset, measured with CUDA events on the launching stream, and the number of intervals. */
 int b200mpc_kernel_time_ms(b200mpc_handle* h, double* total_ms, int* launches, int reset);
 /* Sustained FP64 FMA throughput of the device in TFLOP/s (dependent-chain DFMA microbenchmark, 2 FLOP per FMA). */
 int b200mpc_measure_fp64_peak(b200mpc_handle* h, double* tflops);

@@ -45,7 +45,7 @@ class _HostSim:
         self.lib = ctypes.CDLL(os.path.join(ROOT, "tests", "hostsim", "libhostsim.so"))
         self.dp = ctypes.POINTER(ctypes.c_double)
 
-    def solve(self, state6, coeffs, **params):
+    def solve(self, state6, coeffs, mode=0, **params):
         ob, dp = self.ob, self.dp
         p = ob.default_params(**params)
         N = p.N
@@ -53,9 +53,9 @@ class _HostSim:
         c = np.ascontiguousarray(coeffs, dtype=np.float64)
         x = np.zeros(8 * N - 2); o8 = np.zeros(8); obj = ctypes.c_double(); it = ctypes.c_int()
         lam = np.zeros(6 * N); tr = np.zeros((400, 8)); nr = ctypes.c_int()
-        rc = self.lib.hostsim_solve(ctypes.byref(p), st.ctypes.data_as(dp), c.ctypes.data_as(dp), len(c),
-                                    x.ctypes.data_as(dp), o8.ctypes.data_as(dp), ctypes.byref(obj), ctypes.byref(it),
-                                    lam.ctypes.data_as(dp), tr.ctypes.data_as(dp), 400, ctypes.byref(nr))
+        rc = self.lib.hostsim_solve_mode(ctypes.byref(p), st.ctypes.data_as(dp), c.ctypes.data_as(dp), len(c),
+                                         x.ctypes.data_as(dp), o8.ctypes.data_as(dp), ctypes.byref(obj), ctypes.byref(it),
+                                         lam.ctypes.data_as(dp), tr.ctypes.data_as(dp), 400, ctypes.byref(nr), mode)
         return dict(status=rc, x=x, out8=o8, obj=obj.value, iters=it.value, lam=lam, trace=tr[:nr.value])
 
 

@@ -18,34 +18,69 @@ struct hostsim_params {
 };
 
 // trace rows of 8: iter, mu, alpha_pr, alpha_du, dw, f, theta, phase-trips
-int hostsim_solve(const hostsim_params* hp, const double* state6, const double* coeffs, int ncoef, double* x_out,
-                  double* out8, double* obj, int* iters, double* lam_out, double* trace, int trace_cap, int* trace_rows) {
+// mode 0: one Solver object loops trip() (what the single fused kernel does)
+// mode 1: every pass runs on a FRESH Solver object whose scalar state is loaded from / stored to the workspace
+//         (what the per-pass kernels do) -- catches any state that is not persisted.
+int hostsim_solve_mode(const hostsim_params* hp, const double* state6, const double* coeffs, int ncoef, double* x_out,
+                       double* out8, double* obj, int* iters, double* lam_out, double* trace, int trace_cap,
+                       int* trace_rows, int mode) {
   Params P;
   P.N = hp->N; P.dt = hp->dt; P.Lf = hp->Lf; P.ref_v = hp->ref_v;
   P.w_cte = hp->w_cte; P.w_epsi = hp->w_epsi; P.w_v = hp->w_v; P.w_delta = hp->w_delta; P.w_a = hp->w_a;
   P.w_ddelta = hp->w_ddelta; P.w_da = hp->w_da; P.delta_max = hp->delta_max; P.a_max = hp->a_max; P.tol = hp->tol;
   P.max_iter = hp->max_iter;
-  Layout L(P.N);
-  std::vector<double> ws((size_t)L.total, 0.0);
-  Solver<1> S(P, ws.data());
-  S.init(state6, coeffs, ncoef);
+  P.finalize();
+  std::vector<double> ws((size_t)workspace_doubles_per_problem(P.N), 0.0);
   int rows = 0, trips = 0, last_iter = -1;
-  while (S.phase != PH_DONE && trips < 100000) {
-    S.trip();
-    ++trips;
+  Result R;
+  double df = 1.0;
+  auto log_row = [&](Solver<1>& S) {
     if (trace && S.iter != last_iter && rows < trace_cap) {
       double* r = trace + 8 * rows++;
       r[0] = S.iter; r[1] = S.mu; r[2] = S.alpha; r[3] = S.alpha_du; r[4] = S.dw_curr; r[5] = S.f_cur / S.df;
       r[6] = S.theta_cur; r[7] = trips;
       last_iter = S.iter;
     }
+  };
+  if (mode == 0) {
+    Solver<1> S(P, ws.data());
+    S.init(state6, coeffs, ncoef);
+    while (S.phase != PH_DONE && trips < 100000) { S.trip(); ++trips; log_row(S); }
+    S.finish(R, x_out, 1);
+    df = S.df;
+  } else {
+    { Solver<1> S(P, ws.data()); S.init(state6, coeffs, ncoef); S.store_state(); }
+    int phase = PH_FACTOR;
+    while (phase != PH_DONE && trips < 400000) {
+      for (int k = 0; k < 4; ++k) {   // the four kernels of one round
+        Solver<1> S(P, ws.data());
+        if (S.load_phase() != k) continue;
+        S.set_coeffs(coeffs, ncoef);
+        if (k == PH_FACTOR) S.kernel_factor();
+        else if (k == PH_FORWARD) S.kernel_forward();
+        else if (k == PH_TRIAL) S.kernel_trial();
+        else S.kernel_accept();
+        phase = S.load_phase();
+        if (k == PH_ACCEPT) S.load_state();
+        if (k == PH_ACCEPT) log_row(S);
+      }
+      ++trips;
+    }
+    Solver<1> S(P, ws.data());
+    S.set_coeffs(coeffs, ncoef);
+    S.load_state();
+    S.finish(R, x_out, 1);
+    df = S.df;
   }
-  Result R;
-  S.finish(R, x_out, 1);
   for (int i = 0; i < 8; ++i) out8[i] = R.out8[i];
   *obj = R.obj; *iters = R.iters;
-  if (lam_out) for (int t = 0; t < P.N; ++t) for (int k = 0; k < 6; ++k) lam_out[k * P.N + t] = ws[L.LAM + 6 * t + k] / S.df;
+  if (lam_out) for (int t = 0; t < P.N; ++t) for (int k = 0; k < 6; ++k) lam_out[k * P.N + t] = ws[(size_t)(t + 1) * kRec + oLAM + k] / df;
   if (trace_rows) *trace_rows = rows;
   return R.status;
+}
+
+int hostsim_solve(const hostsim_params* hp, const double* state6, const double* coeffs, int ncoef, double* x_out,
+                  double* out8, double* obj, int* iters, double* lam_out, double* trace, int trace_cap, int* trace_rows) {
+  return hostsim_solve_mode(hp, state6, coeffs, ncoef, x_out, out8, obj, iters, lam_out, trace, trace_cap, trace_rows, 0);
 }
 }

@@ -102,3 +102,22 @@ def test_weights_against_port(hostsim):
         o = ob.port_solve(g["states"][b], g["coeffs"][b], params=ob.default_params(**kw))
         assert r["status"] == o["status"] and r["iters"] == o["iters"]
         np.testing.assert_allclose(r["x"], o["x"], rtol=0, atol=1e-8)
+
+
+def test_per_pass_state_persistence(hostsim):
+    """mode 1 = every pass on a fresh Solver whose scalars come from the workspace record (what the per-pass CUDA
+    kernels do): must give bit-identical results to the single-object loop (mode 0), including on problems that
+    take the rare paths (regularisation, backtracking, second-order correction)."""
+    sets = [("line_256.npz", {}, range(0, 256, 4)), ("roadmap_N50_64.npz", dict(N=50), range(64))]
+    g = golden("line_params_64.npz")
+    N, dt, Lf, ref_v, dmax, amax = g["params"]
+    sets.append(("line_params_64.npz", dict(N=int(N), dt=dt, Lf=Lf, ref_v=ref_v, delta_max=dmax, a_max=amax), range(64)))
+    for name, kw, idx in sets:
+        g = golden(name)
+        cf = g["coeffs"] if "coeffs" in g.files else g["fit"]
+        for b in idx:
+            a = hostsim.solve(g["states"][b], cf[b], mode=0, **kw)
+            c = hostsim.solve(g["states"][b], cf[b], mode=1, **kw)
+            assert a["status"] == c["status"] and a["iters"] == c["iters"]
+            np.testing.assert_array_equal(a["x"], c["x"])
+            assert a["obj"] == c["obj"]

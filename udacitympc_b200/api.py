@@ -43,6 +43,7 @@ SYMBOLS = {
     "b200mpc_rollout_batch": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _dp, _dp, ctypes.c_double, ctypes.c_double, _dp]),
     "b200mpc_rollout_batch_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_double,
                                                     ctypes.c_double, _vp, _vp]),
+    "b200mpc_set_solver_mode": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "b200mpc_kernel_time_ms": (ctypes.c_int, [_vp, _dp, _ip, ctypes.c_int]),
     "b200mpc_measure_fp64_peak": (ctypes.c_int, [_vp, _dp]),
     "b200mpc_launch_count": (ctypes.c_longlong, [_vp]),
@@ -209,6 +210,10 @@ class MPC:
         _check(self._lib.b200mpc_closed_loop_batch(self._h, B, steps, _ptr(states), _ptr(coeffs), coeffs.shape[1],
                                                    _ptr(hist), _ptr(cost), iters.ctypes.data_as(_ip)))
         return dict(hist8=hist, cost=cost, iters=iters)
+
+    def set_solver_mode(self, mode=0, rounds=0, fused_below=-1):
+        """mode 0 = per-pass kernels (default), 1 = fused kernel; see include/b200mpc.h."""
+        _check(self._lib.b200mpc_set_solver_mode(self._h, mode, rounds, fused_below))
 
     # -- measurement helpers
     def kernel_time_ms(self, reset=True):

@@ -42,6 +42,7 @@ struct DevBuf {
 
 struct b200mpc_handle {
   Params P;
+  SolveConfig cfg;
   int device = 0;
   cudaStream_t stream = nullptr;
   DevBuf ws, in_aos, st_soa, cf_soa, out_soa, out_aos, traj_soa, traj_aos, obj, status, iters, misc0, misc1, misc2, misc3;
@@ -57,6 +58,7 @@ Params to_core(const b200mpc_params& p) {
   P.w_cte = p.w_cte; P.w_epsi = p.w_epsi; P.w_v = p.w_v; P.w_delta = p.w_delta; P.w_a = p.w_a;
   P.w_ddelta = p.w_ddelta; P.w_da = p.w_da; P.delta_max = p.delta_max; P.a_max = p.a_max;
   P.tol = p.tol; P.max_iter = p.max_iter;
+  P.finalize();
   return P;
 }
 
@@ -78,8 +80,7 @@ int timed_solve(b200mpc_handle* h, int B, int steps, const double* st, const dou
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, s));
   }
-  CU(launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, s));
-  h->launches += 1;
+  CU(launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, &h->launches));
   if (rec) {
     CU(cudaEventRecord(e1, s));
     h->timing.emplace_back(e0, e1);
@@ -132,6 +133,16 @@ void b200mpc_destroy(b200mpc_handle* h) {
   for (DevBuf* b : bufs) b->release();
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+}
+
+int b200mpc_set_solver_mode(b200mpc_handle* h, int mode, int rounds, int fused_below) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  if (mode != kModePerPass && mode != kModeFused) return fail(B200MPC_ERR_ARG, "mode must be 0 (per-pass kernels) or 1 (fused kernel)");
+  if (rounds < 0 || rounds > 100000) return fail(B200MPC_ERR_ARG, "rounds out of range");
+  h->cfg.mode = mode;
+  if (rounds > 0) h->cfg.rounds = rounds;
+  if (fused_below >= 0) h->cfg.fused_below = fused_below;
+  return 0;
 }
 
 int b200mpc_num_vars(const b200mpc_handle* h) { return h ? 8 * h->P.N - 2 : 0; }

@@ -13,9 +13,15 @@ size_t solve_workspace_doubles(int N, int B);
 // starting from the previous solve's predicted state).  All arrays field-major (SoA) over the batch.
 //   state6 [6][B], coeffs [ncoef][B], out8 [steps][8][B], traj [8N-2][B] (last step, optional),
 //   obj [steps][B] (optional), status [B] (last step, optional), iters [steps][B] (optional)
+enum SolveMode { kModePerPass = 0, kModeFused = 1 };
+struct SolveConfig {
+  int mode = kModePerPass;
+  int rounds = 24;        // per-pass mode: rounds of (factor, forward, trial, accept) before the fused finisher
+  int fused_below = 2048; // batches smaller than this use the fused kernel alone (launch latency dominates)
+};
 cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6, const double* coeffs, int ncoef,
                          double* ws, double* out8, double* traj, double* obj, int* status, int* iters,
-                         cudaStream_t stream);
+                         const SolveConfig& cfg, cudaStream_t stream, long long* n_launches);
 
 // K6 batch I/O: [B][K] <-> [K][B]
 cudaError_t launch_aos_to_soa(const double* in, double* out, int B, int K, cudaStream_t stream);

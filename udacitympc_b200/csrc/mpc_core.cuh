@@ -25,6 +25,15 @@
 // whose multipliers are dlam.  cte_{t+1} does not influence any later row (column cte of A is zero) so it is
 // folded into stage t as a quadratic on a linear output; the (u_{t+1},u_t) smoothness coupling is carried by
 // augmenting the recursion state with the previous control: xi_t = (x,y,psi,v,epsi | delta_{t-1},a_{t-1}) in R^7.
+//
+// Execution structure.  One interior-point iteration = four sweeps over the horizon ("passes"):
+//   FACTOR  (backward)  K1 derivative blocks + K2 Riccati factorisation and feed-forward
+//   FORWARD (forward)   K2 back-substitution: dx, fraction-to-the-boundary step sizes, barrier slope
+//   TRIAL   (forward)   K1 residuals/objective at the trial point + K3 filter / Armijo acceptance
+//   ACCEPT  (backward)  K2 multiplier recovery + K3 step, kappa_sigma reset, error norms, mu update, convergence
+// Every pass touches the per-problem workspace once per stage.  A problem's scalar algorithm state lives in the
+// same workspace (record -1), so each pass can run as its own kernel (high occupancy for the light passes) or all
+// four can be looped inside one kernel.
 #pragma once
 #include <float.h>
 #include <math.h>
@@ -37,7 +46,7 @@
 
 namespace b200mpc {
 
-// Mirrors b200mpc_params (include/b200mpc.h).  Defaults = the reference's hard-coded values.
+// Mirrors b200mpc_params (include/b200mpc.h) + constants derived from it once on the host (finalize()).
 struct Params {
   int N;
   double dt, Lf, ref_v;
@@ -45,6 +54,27 @@ struct Params {
   double delta_max, a_max;
   double tol;
   int max_iter;
+  // derived
+  double dtLf;          // dt / Lf
+  double xl[2], xu[2];  // relaxed bounds of (delta, a): +-(b + 1e-8 max(1,|b|)), IpOrigIpoptNLP.cpp:369-372
+  double ob[2];         // original bounds
+  double u_init[2];     // start value of the controls after the bound push (IpDefaultIterateInitializer.cpp:469-649)
+  MPC_HD void finalize() {
+    dtLf = dt / Lf;
+    ob[0] = delta_max; ob[1] = a_max;
+    for (int j = 0; j < 2; ++j) {
+      const double b = ob[j], rel = 1e-8 * (fabs(b) > 1.0 ? fabs(b) : 1.0);
+      xl[j] = -b - rel; xu[j] = b + rel;
+      const double l = xl[j], u = xu[j];
+      double v = 0.0 < l ? l : (0.0 > u ? u : 0.0);
+      const double ql = 0.01 * (u - l);
+      double pl = 0.01 * (fabs(l) > 1.0 ? fabs(l) : 1.0), pu = 0.01 * (fabs(u) > 1.0 ? fabs(u) : 1.0);
+      if (ql < pl) pl = ql;
+      if (ql < pu) pu = ql;
+      v = v < l + pl ? l + pl : (v > u - pu ? u - pu : v);
+      u_init[j] = v;
+    }
+  }
 };
 
 // Ipopt return codes used (Ipopt/src/Interfaces/IpReturnCodes_inc.h:16-39)
@@ -59,30 +89,33 @@ enum Status {
 };
 
 constexpr int kMaxCoef = 4;   // reference polynomial degree <= 3
-constexpr int kMaxFilter = 12;
-constexpr int kKF = 13;       // Riccati factors stored per stage: K (2x4), Lambda^-1 (3), k (2)
+constexpr int kMaxFilter = 8;
 
-// Workspace of one problem, in doubles.  Element i of the problem owned by lane l of a 32-problem group lives
-// at group_base[i*LANES + l]  (LANES = 32 on the device: every access of a warp is one 256-byte row).
-struct Layout {
-  int S, U, LAM, ZL, ZU, DS, DU, TR, C, CSOC, KF, total;
-  MPC_HD explicit Layout(int N) {
-    const int M = N - 1;
-    int o = 0;
-    S = o; o += 6 * N;
-    U = o; o += 2 * M;
-    LAM = o; o += 6 * N;
-    ZL = o; o += 2 * M;
-    ZU = o; o += 2 * M;
-    DS = o; o += 6 * N;
-    DU = o; o += 2 * M;
-    TR = o; o += 2 * 4 * M;   // two buffers (current / trial)
-    C = o; o += 2 * 6 * N;    // two buffers (current / trial)
-    CSOC = o; o += 6 * N;
-    KF = o; o += kKF * M;
-    total = o;
-  }
+// ---- workspace of one problem, in doubles -----------------------------------------------------------------
+// Element i of the problem owned by lane l of a 32-problem group lives at group_base[i*LANES + l] (LANES = 32 on
+// the device: every access of a warp is one coalesced 256-byte row).  Record 0 holds the scalar state, records
+// 1..N the per-stage data of time t = 0..N-1 at fixed offsets.
+enum StageOff {
+  oS = 0,      // state s_t (6)
+  oU = 6,      // control u_t (2)
+  oLAM = 8,    // multipliers of the rows of time t (6)
+  oZL = 14, oZU = 16,   // bound multipliers of u_t (2+2)
+  oDS = 18, oDU = 24,   // search direction (6+2)
+  oTR = 26,    // sin/cos(psi_t), sin/cos(epsi_t): two buffers of 4 (current / trial)
+  oC = 34,     // constraint residual of the rows of time t: two buffers of 6
+  oCSOC = 46,  // second-order-correction right-hand side (6)
+  oKF = 52,    // Riccati factors of stage t: K (2x4), Lambda^-1 (3), k (2)
+  kRec = 65
 };
+enum ScalarD {
+  dDF, dMU, dTAU, dMUMIN, dDWC, dDWL, dTHMAX, dTHMIN, dF, dTH, dPINF, dDINF, dLAM1, dZ1, dSZMAX, dSZMIN, dSLOG, dXMAX,
+  dDLMAX, dRTH, dRBARR, dRGBD, dALPHA, dAMAX, dAMIN, dADU, dATEST, dTRF, dTRTH, dTRPINF, dTRSLOG, dTHSOC, dASOC, dCOBJ,
+  dLOBJ, dFILT /* 2*kMaxFilter */, kNumD = dFILT + 2 * kMaxFilter
+};
+enum ScalarI { iPHASE = kNumD, iFLAGS, iCUR, iITER, iSTATUS, iNSTEPS, iSOCCNT, iACCCNT, iNF, kNumScal };
+static_assert(kNumScal <= kRec, "scalar record must fit one stage record");
+
+MPC_HD int workspace_doubles_per_problem(int N) { return kRec * (N + 1); }
 
 template <int LANES>
 struct Ws {
@@ -110,8 +143,8 @@ MPC_HD void poly_eval(const double* c, double x, double& p0, double& p1, double&
 
 // IpIpoptCalculatedQuantities.cpp:444-507 (slack safeguard; practically never active)
 MPC_HD double safe_slack(double v, double mu, double z, double bnd) {
-  const double smin = DBL_EPSILON * dmin(mu, 1.0);
-  if (v < smin) {
+  if (v < DBL_EPSILON * dmin(mu, 1.0)) {
+    const double smin = DBL_EPSILON * dmin(mu, 1.0);
     double t = dmax(mu / z, smin);
     double cap = dmax(fabs(bnd), 1.0) * 1.8189894035458565e-12 /* eps^0.75 */ + dmax(v, 0.0);
     v = dmin(t, cap);
@@ -126,16 +159,17 @@ struct Lin {
 MPC_HD Lin make_lin(const Params& P, double v, double delta, double sp, double cp, double se, double ce, double p1,
                     double p2) {
   Lin L;
-  L.a1 = -v * sp * P.dt;      // d x1 / d psi0
-  L.a2 = v * cp * P.dt;       // d y1 / d psi0
+  const double vdt = v * P.dt;
+  L.a1 = -vdt * sp;           // d x1 / d psi0
+  L.a2 = vdt * cp;            // d y1 / d psi0
   L.a3 = cp * P.dt;           // d x1 / d v0
   L.a4 = sp * P.dt;           // d y1 / d v0
-  L.a5 = delta / P.Lf * P.dt; // d psi1 / d v0 = d epsi1 / d v0
-  L.beta = v / P.Lf * P.dt;   // d psi1 / d delta0 = d epsi1 / d delta0
+  L.a5 = delta * P.dtLf;      // d psi1 / d v0 = d epsi1 / d v0
+  L.beta = v * P.dtLf;        // d psi1 / d delta0 = d epsi1 / d delta0
   L.pp = p1;                  // d cte1 / d x0
-  L.kap = p2 / (1.0 + p1 * p1);  // -d epsi1 / d x0
+  L.kap = p2 == 0.0 ? 0.0 : p2 / (1.0 + p1 * p1);  // -d epsi1 / d x0
   L.sed = se * P.dt;          // d cte1 / d v0
-  L.vce = v * ce * P.dt;      // d cte1 / d epsi0
+  L.vce = vdt * ce;           // d cte1 / d epsi0
   return L;
 }
 // out = r * Abar over the reduced state (x,y,psi,v,epsi); column epsi of Abar is zero, so 4 outputs.
@@ -165,13 +199,17 @@ struct Hes {
 MPC_HD Hes make_hes(const Params& P, const double* lam, double v, double sp, double cp, double se, double ce, double p1,
                     double p2, double p3) {
   Hes H;
-  const double q = 1.0 + p1 * p1;
-  H.xx = -lam[4] * p2 + lam[5] * (p3 * q - 2.0 * p1 * p2 * p2) / (q * q);
-  H.pp = lam[0] * v * cp * P.dt + lam[1] * v * sp * P.dt;
-  H.vp = lam[0] * sp * P.dt - lam[1] * cp * P.dt;
-  H.ee = lam[4] * v * se * P.dt;
+  H.xx = 0.0;
+  if (p2 != 0.0 || p3 != 0.0) {
+    const double q = 1.0 + p1 * p1;
+    H.xx = -lam[4] * p2 + lam[5] * (p3 * q - 2.0 * p1 * p2 * p2) / (q * q);
+  }
+  const double vdt = v * P.dt;
+  H.pp = (lam[0] * cp + lam[1] * sp) * vdt;
+  H.vp = (lam[0] * sp - lam[1] * cp) * P.dt;
+  H.ee = lam[4] * vdt * se;
   H.ev = -lam[4] * ce * P.dt;
-  H.m = -(lam[2] + lam[5]) * P.dt / P.Lf;
+  H.m = -(lam[2] + lam[5]) * P.dtLf;
   return H;
 }
 
@@ -185,53 +223,78 @@ struct Result {
 };
 
 enum Phase { PH_FACTOR = 0, PH_FORWARD = 1, PH_TRIAL = 2, PH_ACCEPT = 3, PH_DONE = 4 };
+enum Flags { F_INSOC = 1, F_SOCDONE = 2, F_LS = 4, F_LAMZERO = 8, F_TINYLAST = 16, F_TINYFLAG = 32, F_TINYNOW = 64 };
 
 // The per-problem solver.  All "passes" are loops over the horizon that touch the workspace once per stage.
 template <int LANES>
 struct Solver {
   const Params& P;
   Ws<LANES> w;
-  const Layout L;
   const int N, M;
   double cf[kMaxCoef];
-  double psides_c;   // unused for degree>1
-  // ---- algorithm state
+  // ---- scalar algorithm state (persisted in record 0 of the workspace between passes)
   double df, mu, tau, mu_min;
   double dw_curr, dw_last;          // PDPerturbationHandler delta_x
-  double fphi[kMaxFilter], fth[kMaxFilter];
-  int nf;
   double theta_max, theta_min;
-  int cur;                          // which TR/C buffer holds the current iterate
-  int iter;
-  int status;
-  // quantities at the current iterate
   double f_cur, theta_cur, priminf, dualinf, lam1, z1, sz_max, sz_min, sumlog, xmaxabs, dlam_max;
-  // line-search state
   double ref_theta, ref_barr, ref_gbd, alpha, alpha_max, alpha_min, alpha_du, alpha_test;
   double tr_f, tr_theta, tr_priminf, tr_sumlog;   // at the last evaluated trial point
-  int n_steps, soc_count, tiny_now;
   double theta_soc_old, alpha_soc;
-  bool in_soc, soc_done, ls_mode, lam_zero, tiny_last, tiny_flag;
-  int acceptable_counter;
   double curr_obj, last_obj;
-  int phase;
+  int phase, flags, cur, iter, status, n_steps, soc_count, acceptable_counter, nf;
+  // transient (within a pass)
+  double fw_alpha_pr, fw_alpha_du, fw_gbd;
+  bool fw_tiny;
 
-  MPC_HD Solver(const Params& p, double* base) : P(p), w{base}, L(p.N), N(p.N), M(p.N - 1) {}
+  MPC_HD Solver(const Params& p, double* base) : P(p), w{base}, N(p.N), M(p.N - 1) {}
 
-  MPC_HD double bnd(int j) const { return j == 0 ? P.delta_max : P.a_max; }
-  MPC_HD double relax(int j) const { return 1e-8 * dmax(1.0, fabs(bnd(j))); }  // IpOrigIpoptNLP.cpp:369-372
-  MPC_HD double xU(int j) const { return bnd(j) + relax(j); }
-  MPC_HD double xL(int j) const { return -bnd(j) - relax(j); }
-  MPC_HD int TRo(int buf, int t) const { return L.TR + (buf * M + t) * 4; }
-  MPC_HD int Co(int buf, int t) const { return L.C + (buf * N + t) * 6; }
+  MPC_HD bool fl(int f) const { return (flags & f) != 0; }
+  MPC_HD void setfl(int f, bool v) { flags = v ? (flags | f) : (flags & ~f); }
+  // record of time t starts at (t+1)*kRec
+  MPC_HD int rec(int t) const { return (t + 1) * kRec; }
+  MPC_HD double& filt(int i) const { return w(dFILT + i); }
+
+  MPC_HD void set_coeffs(const double* coef, int ncoef) {
+#pragma unroll
+    for (int i = 0; i < kMaxCoef; ++i) cf[i] = i < ncoef ? coef[i] : 0.0;
+  }
+
+  // ---- scalar state <-> workspace record 0
+#define MPC_SCALARS(X)                                                                                                  \
+  X(dDF, df) X(dMU, mu) X(dTAU, tau) X(dMUMIN, mu_min) X(dDWC, dw_curr) X(dDWL, dw_last) X(dTHMAX, theta_max)            \
+  X(dTHMIN, theta_min) X(dF, f_cur) X(dTH, theta_cur) X(dPINF, priminf) X(dDINF, dualinf) X(dLAM1, lam1) X(dZ1, z1)      \
+  X(dSZMAX, sz_max) X(dSZMIN, sz_min) X(dSLOG, sumlog) X(dXMAX, xmaxabs) X(dDLMAX, dlam_max) X(dRTH, ref_theta)          \
+  X(dRBARR, ref_barr) X(dRGBD, ref_gbd) X(dALPHA, alpha) X(dAMAX, alpha_max) X(dAMIN, alpha_min) X(dADU, alpha_du)       \
+  X(dATEST, alpha_test) X(dTRF, tr_f) X(dTRTH, tr_theta) X(dTRPINF, tr_priminf) X(dTRSLOG, tr_sumlog)                   \
+  X(dTHSOC, theta_soc_old) X(dASOC, alpha_soc) X(dCOBJ, curr_obj) X(dLOBJ, last_obj)
+#define MPC_SCALARS_I(X)                                                                                                \
+  X(iPHASE, phase) X(iFLAGS, flags) X(iCUR, cur) X(iITER, iter) X(iSTATUS, status) X(iNSTEPS, n_steps)                   \
+  X(iSOCCNT, soc_count) X(iACCCNT, acceptable_counter) X(iNF, nf)
+  MPC_HD void load_state() {
+#define X(idx, name) name = w(idx);
+    MPC_SCALARS(X)
+#undef X
+#define X(idx, name) name = (int)w(idx);
+    MPC_SCALARS_I(X)
+#undef X
+  }
+  MPC_HD void store_state() {
+#define X(idx, name) w(idx) = name;
+    MPC_SCALARS(X)
+#undef X
+#define X(idx, name) w(idx) = (double)name;
+    MPC_SCALARS_I(X)
+#undef X
+  }
+  MPC_HD int load_phase() const { return (int)w(iPHASE); }
 
   // objective gradient w.r.t. u_t (scaled by df); um/up = u_{t-1}/u_{t+1}
   MPC_HD double grad_u(int j, int t, double u, double um, double up) const {
     const double wq = j == 0 ? P.w_delta : P.w_a, wd = j == 0 ? P.w_ddelta : P.w_da;
-    double g = 2.0 * wq * u;
-    if (t > 0) g += 2.0 * wd * (u - um);
-    if (t < M - 1) g -= 2.0 * wd * (up - u);
-    return df * g;
+    double g = wq * u;
+    if (t > 0) g += wd * (u - um);
+    if (t < M - 1) g -= wd * (up - u);
+    return (2.0 * df) * g;
   }
   MPC_HD double hess_u(int j, int t) const {
     const double wq = j == 0 ? P.w_delta : P.w_a, wd = j == 0 ? P.w_ddelta : P.w_da;
@@ -243,11 +306,16 @@ struct Solver {
   // start point, bounds, scaling, z, mu  (MPC.cpp:167-203; IpGradientScaling.cpp:99-116;
   // IpDefaultIterateInitializer.cpp:230-266, 469-649)
   MPC_HD void init(const double* s0, const double* coef, int ncoef) {
+    set_coeffs(coef, ncoef);
+    for (int t = 0; t < N; ++t) {
+      const int r = rec(t);
 #pragma unroll
-    for (int i = 0; i < kMaxCoef; ++i) cf[i] = i < ncoef ? coef[i] : 0.0;
-    for (int t = 0; t < N; ++t)
+      for (int k = 0; k < 6; ++k) { w(r + oS + k) = t == 0 ? s0[k] : 0.0; w(r + oLAM + k) = 0.0; }
+      if (t < M) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) w(L.S + 6 * t + k) = t == 0 ? s0[k] : 0.0;
+        for (int j = 0; j < 2; ++j) { w(r + oU + j) = P.u_init[j]; w(r + oZL + j) = 1.0; w(r + oZU + j) = 1.0; }
+      }
+    }
     // gradient of f at the user's start point: states zero except t=0, controls zero
     double gmax = dmax(fabs(2.0 * P.w_cte * s0[4]), fabs(2.0 * P.w_epsi * s0[5]));
     gmax = dmax(gmax, fabs(2.0 * P.w_v * (s0[3] - P.ref_v)));
@@ -255,36 +323,22 @@ struct Solver {
     df = 1.0;
     if (gmax > 100.0) df = 100.0 / gmax;
     if (df < 1e-8) df = 1e-8;
-    for (int t = 0; t < M; ++t)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const double l = xL(j), u = xU(j);
-        double v = dclamp(0.0, l, u);
-        const double ql = 0.01 * (u - l);
-        const double pl = dmin(0.01 * dmax(fabs(l), 1.0), ql), pu = dmin(0.01 * dmax(fabs(u), 1.0), ql);
-        v = dclamp(v, l + pl, u - pu);
-        w(L.U + 2 * t + j) = v;
-        w(L.ZL + 2 * t + j) = 1.0;
-        w(L.ZU + 2 * t + j) = 1.0;
-      }
-    for (int i = 0; i < 6 * N; ++i) w(L.LAM + i) = 0.0;
     mu = 0.1;
     tau = dmax(0.99, 1.0 - mu);
     mu_min = dmin(P.tol, 1e-4 * df) / (10.0 + 1.0);
     theta_max = theta_min = -1.0;
     nf = 0;
     dw_curr = dw_last = 0.0;
-    cur = 0;
-    iter = 0;
-    status = -100;
+    cur = 0; iter = 0; status = -100;
     acceptable_counter = 0;
     curr_obj = last_obj = -1e50;
-    tiny_last = tiny_flag = false;
-    in_soc = soc_done = false;
-    lam_zero = false;
+    flags = F_LS;
     dlam_max = 0.0;
-    ls_mode = true;
-    alpha = 0.0; alpha_du = 0.0;
+    alpha = alpha_du = alpha_max = alpha_min = alpha_test = 0.0;
+    ref_theta = ref_barr = ref_gbd = 0.0;
+    theta_soc_old = alpha_soc = 0.0;
+    n_steps = soc_count = 0;
+    dualinf = lam1 = z1 = sz_max = sz_min = xmaxabs = 0.0;
     // residuals / trig at the start point, then least-square multipliers through the same passes
     eval_point(0.0, cur);
     f_cur = tr_f; theta_cur = tr_theta; priminf = tr_priminf; sumlog = tr_sumlog;
@@ -297,46 +351,48 @@ struct Solver {
     double s[6], sn[6], u[2], un[2];
     const bool step = a != 0.0;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) s[k] = w(L.S + k);   // ds_0 = 0
+    for (int k = 0; k < 6; ++k) s[k] = w(rec(0) + oS + k);   // ds_0 = 0
     double f = 0.0, th = 0.0, cm = 0.0, sl = 0.0;
     u[0] = u[1] = 0.0;
+    const int bT = oTR + 4 * buf, bC = oC + 6 * buf;
     for (int t = 0; t < M; ++t) {
+      const int r = rec(t), rn = rec(t + 1);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        un[j] = w(L.U + 2 * t + j);
-        if (step) un[j] += a * w(L.DU + 2 * t + j);
+        un[j] = w(r + oU + j);
+        if (step) un[j] += a * w(r + oDU + j);
       }
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
-        sn[k] = w(L.S + 6 * (t + 1) + k);
-        if (step) sn[k] += a * w(L.DS + 6 * (t + 1) + k);
+        sn[k] = w(rn + oS + k);
+        if (step) sn[k] += a * w(rn + oDS + k);
       }
+      const double zl0 = w(r + oZL), zl1 = w(r + oZL + 1), zu0 = w(r + oZU), zu1 = w(r + oZU + 1);
       double sp, cp, se, ce, p0, p1, p2, p3;
       sincos(s[2], &sp, &cp);
       sincos(s[5], &se, &ce);
       poly_eval(cf, s[0], p0, p1, p2, p3);
       const double psides = atan(p1);
+      const double vd = s[3] * un[0] * P.dtLf;
       double c[6];
       c[0] = sn[0] - (s[0] + s[3] * cp * P.dt);
       c[1] = sn[1] - (s[1] + s[3] * sp * P.dt);
-      c[2] = sn[2] - (s[2] + s[3] * un[0] / P.Lf * P.dt);
+      c[2] = sn[2] - (s[2] + vd);
       c[3] = sn[3] - (s[3] + un[1] * P.dt);
       c[4] = sn[4] - ((p0 - s[1]) + (s[3] * se * P.dt));
-      c[5] = sn[5] - ((s[2] - psides) + s[3] * un[0] / P.Lf * P.dt);
-      const int to = TRo(buf, t), co = Co(buf, t + 1);
-      w(to + 0) = sp; w(to + 1) = cp; w(to + 2) = se; w(to + 3) = ce;
+      c[5] = sn[5] - ((s[2] - psides) + vd);
+      w(r + bT + 0) = sp; w(r + bT + 1) = cp; w(r + bT + 2) = se; w(r + bT + 3) = ce;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { w(co + k) = c[k]; th += fabs(c[k]); cm = dmax(cm, fabs(c[k])); }
+      for (int k = 0; k < 6; ++k) { w(rn + bC + k) = c[k]; th += fabs(c[k]); cm = dmax(cm, fabs(c[k])); }
       // cost of time t
       f += P.w_cte * (s[4] * s[4]) + P.w_epsi * (s[5] * s[5]) + P.w_v * ((s[3] - P.ref_v) * (s[3] - P.ref_v));
       f += P.w_delta * (un[0] * un[0]) + P.w_a * (un[1] * un[1]);
       if (t > 0) f += P.w_ddelta * ((un[0] - u[0]) * (un[0] - u[0])) + P.w_da * ((un[1] - u[1]) * (un[1] - u[1]));
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const double zl = w(L.ZL + 2 * t + j), zu = w(L.ZU + 2 * t + j);
-        sl += log(safe_slack(un[j] - xL(j), mu, zl, xL(j))) + log(safe_slack(xU(j) - un[j], mu, zu, xU(j)));
-        u[j] = un[j];
-      }
+      // log-barrier of the four slacks of u_t: one log of their product
+      const double q0 = safe_slack(un[0] - P.xl[0], mu, zl0, P.xl[0]) * safe_slack(P.xu[0] - un[0], mu, zu0, P.xu[0]);
+      const double q1 = safe_slack(un[1] - P.xl[1], mu, zl1, P.xl[1]) * safe_slack(P.xu[1] - un[1], mu, zu1, P.xu[1]);
+      sl += log(q0 * q1);
+      u[0] = un[0]; u[1] = un[1];
 #pragma unroll
       for (int k = 0; k < 6; ++k) s[k] = sn[k];
     }
@@ -345,156 +401,160 @@ struct Solver {
   }
 
   // ------------------------------------------------------------------------------------------
-  // Backward Riccati sweep: factor + feed-forward for the right-hand side (grad L_mu, c).  csoc selects the
+  // Backward Riccati sweep: factor + feed-forward for the right-hand side (grad L_mu, c).  use_csoc selects the
   // constraint right-hand side (second-order correction).  Returns false on wrong inertia.
   MPC_HD bool factor(double dw, bool use_csoc) {
-    const bool ls = ls_mode;
+    const bool ls = fl(F_LS);
     const double qv = ls ? 1.0 : 2.0 * P.w_v * df + dw, qe = ls ? 1.0 : 2.0 * P.w_epsi * df + dw,
                  qc = ls ? 1.0 : 2.0 * P.w_cte * df + dw, q0 = ls ? 1.0 : dw;
+    const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df, gc2 = 2.0 * P.w_cte * df;
+    const int bT = oTR + 4 * cur, bC = use_csoc ? (int)oCSOC : oC + 6 * cur;
     double pss[15], psu[4][2], puu00 = 0.0, puu10 = 0.0, puu11 = 0.0, pv[5], pu0 = 0.0, pu1 = 0.0;
 #pragma unroll
     for (int i = 0; i < 15; ++i) pss[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) psu[i][0] = psu[i][1] = 0.0;
     double lamn[6];   // lambda_{t+1}
-    double sT[6];
+    double rc_next;
+    {
+      const int r = rec(M);
+      double sT[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { lamn[k] = ls ? 0.0 : w(L.LAM + 6 * M + k); sT[k] = w(L.S + 6 * M + k); }
-    PS(0, 0) = q0; PS(1, 1) = q0; PS(2, 2) = q0; PS(3, 3) = qv; PS(4, 4) = qe;
-    // r_s at the terminal time: grad f + lambda
-    pv[0] = lamn[0]; pv[1] = lamn[1]; pv[2] = lamn[2];
-    pv[3] = 2.0 * P.w_v * df * (sT[3] - P.ref_v) + lamn[3];
-    pv[4] = 2.0 * P.w_epsi * df * sT[5] + lamn[5];
-    double rc_next = 2.0 * P.w_cte * df * sT[4] + lamn[4];   // grad L wrt cte_{t+1}
-    double un0 = 0.0, un1 = 0.0;                            // u_{t+1}
+      for (int k = 0; k < 6; ++k) { lamn[k] = ls ? 0.0 : w(r + oLAM + k); sT[k] = w(r + oS + k); }
+      PS(0, 0) = q0; PS(1, 1) = q0; PS(2, 2) = q0; PS(3, 3) = qv; PS(4, 4) = qe;
+      // r_s at the terminal time: grad f + lambda
+      pv[0] = lamn[0]; pv[1] = lamn[1]; pv[2] = lamn[2];
+      pv[3] = gv2 * (sT[3] - P.ref_v) + lamn[3];
+      pv[4] = ge2 * sT[5] + lamn[5];
+      rc_next = gc2 * sT[4] + lamn[4];   // grad L wrt cte_{t+1}
+    }
+    double un0 = 0.0, un1 = 0.0;         // u_{t+1}
+    double d0n = 0.0, d1n = 0.0;         // unused at the last stage
+    (void)d0n; (void)d1n;
     bool ok = true;
     for (int t = M - 1; t >= 0; --t) {
+      const int r = rec(t), rn = rec(t + 1);
       double s[6], lam[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { s[k] = w(L.S + 6 * t + k); lam[k] = ls ? 0.0 : w(L.LAM + 6 * t + k); }
-      const double u0 = w(L.U + 2 * t), u1 = w(L.U + 2 * t + 1);
+      for (int k = 0; k < 6; ++k) { s[k] = w(r + oS + k); lam[k] = ls ? 0.0 : w(r + oLAM + k); }
+      const double u0 = w(r + oU), u1 = w(r + oU + 1);
       double um0 = 0.0, um1 = 0.0;
-      if (t > 0) { um0 = w(L.U + 2 * t - 2); um1 = w(L.U + 2 * t - 1); }
-      const int to = TRo(cur, t);
-      const double sp = w(to), cp = w(to + 1), se = w(to + 2), ce = w(to + 3);
+      if (t > 0) { um0 = w(r - kRec + oU); um1 = w(r - kRec + oU + 1); }
+      const double sp = w(r + bT), cp = w(r + bT + 1), se = w(r + bT + 2), ce = w(r + bT + 3);
+      const double zl0 = w(r + oZL), zl1 = w(r + oZL + 1), zu0 = w(r + oZU), zu1 = w(r + oZU + 1);
+      // constraint right-hand side of rows t+1
+      double rb[5], cc;
+      if (ls) { rb[0] = rb[1] = rb[2] = rb[3] = rb[4] = 0.0; cc = 0.0; }
+      else {
+        rb[0] = -w(rn + bC); rb[1] = -w(rn + bC + 1); rb[2] = -w(rn + bC + 2); rb[3] = -w(rn + bC + 3);
+        cc = w(rn + bC + 4); rb[4] = -w(rn + bC + 5);
+      }
       double p0, p1, p2, p3;
       poly_eval(cf, s[0], p0, p1, p2, p3);
       const Lin A = make_lin(P, s[3], u0, sp, cp, se, ce, p1, p2);
       Hes H;
       if (ls) { H.xx = H.pp = H.vp = H.ee = H.ev = H.m = 0.0; }
       else H = make_hes(P, lamn, s[3], sp, cp, se, ce, p1, p2, p3);
-      // constraint right-hand side of rows t+1
-      double rb[5], cc;
-      if (ls) { rb[0] = rb[1] = rb[2] = rb[3] = rb[4] = 0.0; cc = 0.0; }
-      else {
-        const int co = use_csoc ? L.CSOC + 6 * (t + 1) : Co(cur, t + 1);
-        rb[0] = -w(co); rb[1] = -w(co + 1); rb[2] = -w(co + 2); rb[3] = -w(co + 3); cc = w(co + 4); rb[4] = -w(co + 5);
-      }
-      // bound terms of u_t
-      const double zl0 = w(L.ZL + 2 * t), zl1 = w(L.ZL + 2 * t + 1), zu0 = w(L.ZU + 2 * t), zu1 = w(L.ZU + 2 * t + 1);
       double r0, r1, ru0, ru1;
-      {
-        double ATl[6];
-        applyAT6(A, lamn, ATl);   // A_t^T lambda_{t+1}
-        const double gu0 = grad_u(0, t, u0, um0, un0), gu1 = grad_u(1, t, u1, um1, un1);
+      double ATl[6];
+      applyAT6(A, lamn, ATl);   // A_t^T lambda_{t+1}
+      const double gu0 = grad_u(0, t, u0, um0, un0), gu1 = grad_u(1, t, u1, um1, un1);
+      if (ls) {
+        r0 = 1.0; r1 = 1.0;
+        ru0 = gu0 - zl0 + zu0; ru1 = gu1 - zl1 + zu1;
+      } else {
         const double bl0 = A.beta * (lamn[2] + lamn[5]), bl1 = P.dt * lamn[3];   // B_t^T lambda_{t+1}
-        if (ls) {
-          r0 = 1.0; r1 = 1.0;
-          ru0 = gu0 - zl0 + zu0; ru1 = gu1 - zl1 + zu1;
-        } else {
-          const double sl0 = safe_slack(u0 - xL(0), mu, zl0, xL(0)), su0 = safe_slack(xU(0) - u0, mu, zu0, xU(0));
-          const double sl1 = safe_slack(u1 - xL(1), mu, zl1, xL(1)), su1 = safe_slack(xU(1) - u1, mu, zu1, xU(1));
-          r0 = hess_u(0, t) + dw + zl0 / sl0 + zu0 / su0;
-          r1 = hess_u(1, t) + dw + zl1 / sl1 + zu1 / su1;
-          ru0 = gu0 - bl0 - mu / sl0 + mu / su0;
-          ru1 = gu1 - bl1 - mu / sl1 + mu / su1;
-        }
-        // r_s at time t (reduced: x,y,psi,v,epsi) and the cte fold
-        const double gc = rc_next - qc * cc;   // linear coefficient on a_c^T dsigma
-        // ---- recursion
-        double wv[5], wu0 = pu0, wu1 = pu1;
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          double a = pv[i];
-#pragma unroll
-          for (int j = 0; j < 5; ++j) a += PS(i, j) * rb[j];
-          wv[i] = a;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { wu0 += psu[i][0] * rb[i]; wu1 += psu[i][1] * rb[i]; }
-        double T0[5], T1[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          T0[j] = A.beta * (PS(2, j) + PS(4, j)) + (j < 4 ? psu[j < 4 ? j : 0][0] : 0.0);
-          T1[j] = P.dt * PS(3, j) + (j < 4 ? psu[j < 4 ? j : 0][1] : 0.0);
-        }
-        const double Tu00 = A.beta * psu[2][0] + puu00, Tu10 = P.dt * psu[3][0] + puu10, Tu11 = P.dt * psu[3][1] + puu11;
-        const double L00 = r0 + A.beta * (T0[2] + T0[4]) + Tu00;
-        const double L10 = A.beta * (T1[2] + T1[4]) + Tu10;
-        const double L11 = r1 + P.dt * T1[3] + Tu11;
-        const double det = L00 * L11 - L10 * L10;
-        if (!(L00 > 0.0) || !(det > 0.0)) ok = false;
-        const double idet = 1.0 / det;
-        const double i00 = L11 * idet, i10 = -L10 * idet, i11 = L00 * idet;
-        double G0[4], G1[4];
-        applyA(A, T0[0], T0[1], T0[2], T0[3], T0[4], G0[0], G0[1], G0[2], G0[3]);
-        applyA(A, T1[0], T1[1], T1[2], T1[3], T1[4], G1[0], G1[1], G1[2], G1[3]);
-        G0[3] += H.m;
-        const double h0 = ru0 + A.beta * (wv[2] + wv[4]) + wu0, h1 = ru1 + P.dt * wv[3] + wu1;
-        double K0[4], K1[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { K0[j] = i00 * G0[j] + i10 * G1[j]; K1[j] = i10 * G0[j] + i11 * G1[j]; }
-        const double k0 = i00 * h0 + i10 * h1, k1 = i10 * h0 + i11 * h1;
-        const int ko = L.KF + kKF * t;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { w(ko + j) = K0[j]; w(ko + 4 + j) = K1[j]; }
-        w(ko + 8) = i00; w(ko + 9) = i10; w(ko + 10) = i11; w(ko + 11) = k0; w(ko + 12) = k1;
-        // Y = Pss * Abar (5x4), S = Abar^T Y (4x4, lower)
-        double Y[5][4];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) applyA(A, PS(i, 0), PS(i, 1), PS(i, 2), PS(i, 3), PS(i, 4), Y[i][0], Y[i][1], Y[i][2], Y[i][3]);
-        double Sm[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) applyA(A, Y[0][j], Y[1][j], Y[2][j], Y[3][j], Y[4][j], Sm[0][j], Sm[1][j], Sm[2][j], Sm[3][j]);
-        double aw[4];
-        applyA(A, wv[0], wv[1], wv[2], wv[3], wv[4], aw[0], aw[1], aw[2], aw[3]);
-        const double ac[4] = {A.pp, -1.0, 0.0, A.sed};
-        // r_s,t = grad f_s + lambda_t - A^T lambda_{t+1}
-        double rs[5];
-        rs[0] = lam[0] - ATl[0];
-        rs[1] = lam[1] - ATl[1];
-        rs[2] = lam[2] - ATl[2];
-        rs[3] = 2.0 * P.w_v * df * (s[3] - P.ref_v) + lam[3] - ATl[3];
-        rs[4] = 2.0 * P.w_epsi * df * s[5] + lam[5] - ATl[5];
-        // new P, p
-        double nss[15];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j <= i; ++j)
-            nss[i * (i + 1) / 2 + j] = Sm[i][j] + qc * ac[i] * ac[j] - (G0[i] * K0[j] + G1[i] * K1[j]);
-        nss[0] += q0 + H.xx;
-        nss[2] += q0;
-        nss[5] += q0 + H.pp;
-        nss[8] += H.vp;          // (v,psi)
-        nss[9] += qv;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) nss[10 + j] = qc * A.vce * ac[j];
-        nss[13] += H.ev;         // (epsi,v)
-        nss[14] = qe + H.ee + qc * A.vce * A.vce;
-        double d0 = 0.0, d1 = 0.0;   // coupling with u_{t-1}
-        if (t > 0 && !ls) { d0 = 2.0 * df * P.w_ddelta; d1 = 2.0 * df * P.w_da; }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { psu[i][0] = K0[i] * d0; psu[i][1] = K1[i] * d1; }
-        puu00 = -d0 * d0 * i00; puu10 = -d0 * d1 * i10; puu11 = -d1 * d1 * i11;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) pv[i] = rs[i] + aw[i] + gc * ac[i] - (G0[i] * k0 + G1[i] * k1);
-        pv[4] = rs[4] + gc * A.vce;
-        pu0 = d0 * k0; pu1 = d1 * k1;
-#pragma unroll
-        for (int i = 0; i < 15; ++i) pss[i] = nss[i];
+        const double isl0 = 1.0 / safe_slack(u0 - P.xl[0], mu, zl0, P.xl[0]), isu0 = 1.0 / safe_slack(P.xu[0] - u0, mu, zu0, P.xu[0]);
+        const double isl1 = 1.0 / safe_slack(u1 - P.xl[1], mu, zl1, P.xl[1]), isu1 = 1.0 / safe_slack(P.xu[1] - u1, mu, zu1, P.xu[1]);
+        r0 = hess_u(0, t) + dw + zl0 * isl0 + zu0 * isu0;
+        r1 = hess_u(1, t) + dw + zl1 * isl1 + zu1 * isu1;
+        ru0 = gu0 - bl0 - mu * isl0 + mu * isu0;
+        ru1 = gu1 - bl1 - mu * isl1 + mu * isu1;
       }
-      rc_next = 2.0 * P.w_cte * df * s[4] + lam[4];
+      const double gc = rc_next - qc * cc;   // linear coefficient on a_c^T dsigma (cte fold)
+      // ---- recursion
+      double wv[5], wu0 = pu0, wu1 = pu1;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        double a = pv[i];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) a += PS(i, j) * rb[j];
+        wv[i] = a;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { wu0 += psu[i][0] * rb[i]; wu1 += psu[i][1] * rb[i]; }
+      double T0[5], T1[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        T0[j] = A.beta * (PS(2, j) + PS(4, j)) + (j < 4 ? psu[j < 4 ? j : 0][0] : 0.0);
+        T1[j] = P.dt * PS(3, j) + (j < 4 ? psu[j < 4 ? j : 0][1] : 0.0);
+      }
+      const double Tu00 = A.beta * psu[2][0] + puu00, Tu10 = P.dt * psu[3][0] + puu10, Tu11 = P.dt * psu[3][1] + puu11;
+      const double L00 = r0 + A.beta * (T0[2] + T0[4]) + Tu00;
+      const double L10 = A.beta * (T1[2] + T1[4]) + Tu10;
+      const double L11 = r1 + P.dt * T1[3] + Tu11;
+      const double det = L00 * L11 - L10 * L10;
+      if (!(L00 > 0.0) || !(det > 0.0)) ok = false;
+      const double idet = 1.0 / det;
+      const double i00 = L11 * idet, i10 = -L10 * idet, i11 = L00 * idet;
+      double G0[4], G1[4];
+      applyA(A, T0[0], T0[1], T0[2], T0[3], T0[4], G0[0], G0[1], G0[2], G0[3]);
+      applyA(A, T1[0], T1[1], T1[2], T1[3], T1[4], G1[0], G1[1], G1[2], G1[3]);
+      G0[3] += H.m;
+      const double h0 = ru0 + A.beta * (wv[2] + wv[4]) + wu0, h1 = ru1 + P.dt * wv[3] + wu1;
+      double K0[4], K1[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { K0[j] = i00 * G0[j] + i10 * G1[j]; K1[j] = i10 * G0[j] + i11 * G1[j]; }
+      const double k0 = i00 * h0 + i10 * h1, k1 = i10 * h0 + i11 * h1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { w(r + oKF + j) = K0[j]; w(r + oKF + 4 + j) = K1[j]; }
+      w(r + oKF + 8) = i00; w(r + oKF + 9) = i10; w(r + oKF + 10) = i11; w(r + oKF + 11) = k0; w(r + oKF + 12) = k1;
+      // Y = Pss * Abar (5x4), S = Abar^T Y (4x4, lower)
+      double Y[5][4];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) applyA(A, PS(i, 0), PS(i, 1), PS(i, 2), PS(i, 3), PS(i, 4), Y[i][0], Y[i][1], Y[i][2], Y[i][3]);
+      double Sm[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) applyA(A, Y[0][j], Y[1][j], Y[2][j], Y[3][j], Y[4][j], Sm[0][j], Sm[1][j], Sm[2][j], Sm[3][j]);
+      double aw[4];
+      applyA(A, wv[0], wv[1], wv[2], wv[3], wv[4], aw[0], aw[1], aw[2], aw[3]);
+      const double ac[4] = {A.pp, -1.0, 0.0, A.sed};
+      // r_s,t = grad f_s + lambda_t - A^T lambda_{t+1}
+      double rs[5];
+      rs[0] = lam[0] - ATl[0];
+      rs[1] = lam[1] - ATl[1];
+      rs[2] = lam[2] - ATl[2];
+      rs[3] = gv2 * (s[3] - P.ref_v) + lam[3] - ATl[3];
+      rs[4] = ge2 * s[5] + lam[5] - ATl[5];
+      // new P, p
+      double nss[15];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j)
+          nss[i * (i + 1) / 2 + j] = Sm[i][j] + qc * ac[i] * ac[j] - (G0[i] * K0[j] + G1[i] * K1[j]);
+      nss[0] += q0 + H.xx;
+      nss[2] += q0;
+      nss[5] += q0 + H.pp;
+      nss[8] += H.vp;          // (v,psi)
+      nss[9] += qv;
+      const double qvce = qc * A.vce;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) nss[10 + j] = qvce * ac[j];
+      nss[13] += H.ev;         // (epsi,v)
+      nss[14] = qe + H.ee + qvce * A.vce;
+      double d0 = 0.0, d1 = 0.0;   // coupling with u_{t-1}
+      if (t > 0 && !ls) { d0 = 2.0 * df * P.w_ddelta; d1 = 2.0 * df * P.w_da; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { psu[i][0] = K0[i] * d0; psu[i][1] = K1[i] * d1; }
+      puu00 = -d0 * d0 * i00; puu10 = -d0 * d1 * i10; puu11 = -d1 * d1 * i11;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pv[i] = rs[i] + aw[i] + gc * ac[i] - (G0[i] * k0 + G1[i] * k1);
+      pv[4] = rs[4] + gc * A.vce;
+      pu0 = d0 * k0; pu1 = d1 * k1;
+#pragma unroll
+      for (int i = 0; i < 15; ++i) pss[i] = nss[i];
+      rc_next = gc2 * s[4] + lam[4];
       un0 = u0; un1 = u1;
 #pragma unroll
       for (int k = 0; k < 6; ++k) lamn[k] = lam[k];
@@ -504,64 +564,68 @@ struct Solver {
 
   // ------------------------------------------------------------------------------------------
   // Forward sweep: dx (-> DS, DU), fraction-to-the-boundary steps, directional derivative of the barrier.
-  MPC_HD void forward(bool use_csoc, double dw) {
-    const bool ls = ls_mode;
+  MPC_HD void forward(bool use_csoc) {
+    const bool ls = fl(F_LS);
+    const int bT = oTR + 4 * cur, bC = use_csoc ? (int)oCSOC : oC + 6 * cur;
+    const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df, gc2 = 2.0 * P.w_cte * df;
+    const double tinytol = 10.0 * DBL_EPSILON;
     double ds[6] = {0, 0, 0, 0, 0, 0}, dup0 = 0.0, dup1 = 0.0;
-    double a_pr = 1.0, a_du = 1.0, gbd = 0.0, tiny = 0.0;
+    double a_pr = 1.0, a_du = 1.0, gbd = 0.0;
+    bool nottiny = false;
     double um0 = 0.0, um1 = 0.0;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) w(L.DS + k) = 0.0;
-    (void)dw;
+    for (int k = 0; k < 6; ++k) w(rec(0) + oDS + k) = 0.0;
+    double u0 = w(rec(0) + oU), u1 = w(rec(0) + oU + 1);
     for (int t = 0; t < M; ++t) {
-      const int ko = L.KF + kKF * t;
+      const int r = rec(t), rn = rec(t + 1);
       double K0[4], K1[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { K0[j] = w(ko + j); K1[j] = w(ko + 4 + j); }
-      const double i00 = w(ko + 8), i10 = w(ko + 9), i11 = w(ko + 10), k0 = w(ko + 11), k1 = w(ko + 12);
+      for (int j = 0; j < 4; ++j) { K0[j] = w(r + oKF + j); K1[j] = w(r + oKF + 4 + j); }
+      const double i00 = w(r + oKF + 8), i10 = w(r + oKF + 9), i11 = w(r + oKF + 10), k0 = w(r + oKF + 11), k1 = w(r + oKF + 12);
+      double s[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s[k] = w(r + oS + k);
+      const double sp = w(r + bT), cp = w(r + bT + 1), se = w(r + bT + 2), ce = w(r + bT + 3);
+      double c[6];
+      if (ls) { c[0] = c[1] = c[2] = c[3] = c[4] = c[5] = 0.0; }
+      else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) c[k] = w(rn + bC + k);
+      }
+      double un0 = 0.0, un1 = 0.0;
+      if (t < M - 1) { un0 = w(rn + oU); un1 = w(rn + oU + 1); }
       double d0 = 0.0, d1 = 0.0;
       if (t > 0 && !ls) { d0 = 2.0 * df * P.w_ddelta; d1 = 2.0 * df * P.w_da; }
       const double e0 = d0 * dup0, e1 = d1 * dup1;
       const double du0 = -(K0[0] * ds[0] + K0[1] * ds[1] + K0[2] * ds[2] + K0[3] * ds[3] + k0) + (i00 * e0 + i10 * e1);
       const double du1 = -(K1[0] * ds[0] + K1[1] * ds[1] + K1[2] * ds[2] + K1[3] * ds[3] + k1) + (i10 * e0 + i11 * e1);
-      w(L.DU + 2 * t) = du0; w(L.DU + 2 * t + 1) = du1;
-      double s[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) s[k] = w(L.S + 6 * t + k);
-      const double u0 = w(L.U + 2 * t), u1 = w(L.U + 2 * t + 1);
-      const int to = TRo(cur, t);
-      const double sp = w(to), cp = w(to + 1), se = w(to + 2), ce = w(to + 3);
+      w(r + oDU) = du0; w(r + oDU + 1) = du1;
       double p0, p1, p2, p3;
       poly_eval(cf, s[0], p0, p1, p2, p3);
       const Lin A = make_lin(P, s[3], u0, sp, cp, se, ce, p1, p2);
-      double c[6];
-      if (ls) { c[0] = c[1] = c[2] = c[3] = c[4] = c[5] = 0.0; }
-      else {
-        const int co = use_csoc ? L.CSOC + 6 * (t + 1) : Co(cur, t + 1);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) c[k] = w(co + k);
-      }
       if (!ls) {
         // objective / barrier directional derivative and step bounds for u_t
-        double un0 = 0.0, un1 = 0.0;
-        if (t < M - 1) { un0 = w(L.U + 2 * t + 2); un1 = w(L.U + 2 * t + 3); }
-        const double zl0 = w(L.ZL + 2 * t), zl1 = w(L.ZL + 2 * t + 1), zu0 = w(L.ZU + 2 * t), zu1 = w(L.ZU + 2 * t + 1);
-        const double sl0 = safe_slack(u0 - xL(0), mu, zl0, xL(0)), su0 = safe_slack(xU(0) - u0, mu, zu0, xU(0));
-        const double sl1 = safe_slack(u1 - xL(1), mu, zl1, xL(1)), su1 = safe_slack(xU(1) - u1, mu, zu1, xU(1));
-        gbd += (grad_u(0, t, u0, um0, un0) - mu / sl0 + mu / su0) * du0 + (grad_u(1, t, u1, um1, un1) - mu / sl1 + mu / su1) * du1;
-        gbd += 2.0 * df * (P.w_v * (s[3] - P.ref_v) * ds[3] + P.w_cte * s[4] * ds[4] + P.w_epsi * s[5] * ds[5]);
+        const double zl0 = w(r + oZL), zl1 = w(r + oZL + 1), zu0 = w(r + oZU), zu1 = w(r + oZU + 1);
+        const double sl0 = safe_slack(u0 - P.xl[0], mu, zl0, P.xl[0]), su0 = safe_slack(P.xu[0] - u0, mu, zu0, P.xu[0]);
+        const double sl1 = safe_slack(u1 - P.xl[1], mu, zl1, P.xl[1]), su1 = safe_slack(P.xu[1] - u1, mu, zu1, P.xu[1]);
+        const double isl0 = 1.0 / sl0, isu0 = 1.0 / su0, isl1 = 1.0 / sl1, isu1 = 1.0 / su1;
+        gbd += (grad_u(0, t, u0, um0, un0) - mu * isl0 + mu * isu0) * du0 + (grad_u(1, t, u1, um1, un1) - mu * isl1 + mu * isu1) * du1;
+        gbd += gv2 * (s[3] - P.ref_v) * ds[3] + gc2 * s[4] * ds[4] + ge2 * s[5] * ds[5];
+        // fraction to the boundary: alpha <= tau * slack / |du| (IpDenseVector.cpp:928-970)
         if (du0 < 0.0) a_pr = dmin(a_pr, -tau / du0 * sl0);
         if (du0 > 0.0) a_pr = dmin(a_pr, tau / du0 * su0);
         if (du1 < 0.0) a_pr = dmin(a_pr, -tau / du1 * sl1);
         if (du1 > 0.0) a_pr = dmin(a_pr, tau / du1 * su1);
-        const double dzl0 = (mu - sl0 * zl0 - zl0 * du0) / sl0, dzu0 = (mu - su0 * zu0 + zu0 * du0) / su0;
-        const double dzl1 = (mu - sl1 * zl1 - zl1 * du1) / sl1, dzu1 = (mu - su1 * zu1 + zu1 * du1) / su1;
+        const double dzl0 = (mu - sl0 * zl0 - zl0 * du0) * isl0, dzu0 = (mu - su0 * zu0 + zu0 * du0) * isu0;
+        const double dzl1 = (mu - sl1 * zl1 - zl1 * du1) * isl1, dzu1 = (mu - su1 * zu1 + zu1 * du1) * isu1;
         if (dzl0 < 0.0) a_du = dmin(a_du, -tau / dzl0 * zl0);
         if (dzu0 < 0.0) a_du = dmin(a_du, -tau / dzu0 * zu0);
         if (dzl1 < 0.0) a_du = dmin(a_du, -tau / dzl1 * zl1);
         if (dzu1 < 0.0) a_du = dmin(a_du, -tau / dzu1 * zu1);
-        tiny = dmax(tiny, dmax(fabs(du0) / (fabs(u0) + 1.0), fabs(du1) / (fabs(u1) + 1.0)));
+        // tiny-step test |dx_i| / (|x_i| + 1) <= 10 eps for all i (IpBacktrackingLineSearch.cpp:1145-1200)
+        nottiny = nottiny || fabs(du0) > tinytol * (fabs(u0) + 1.0) || fabs(du1) > tinytol * (fabs(u1) + 1.0);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) tiny = dmax(tiny, fabs(ds[k]) / (fabs(s[k]) + 1.0));
+        for (int k = 0; k < 6; ++k) nottiny = nottiny || fabs(ds[k]) > tinytol * (fabs(s[k]) + 1.0);
       }
       double dn[6];
       dn[0] = ds[0] + A.a1 * ds[2] + A.a3 * ds[3] - c[0];
@@ -571,18 +635,17 @@ struct Solver {
       dn[4] = A.pp * ds[0] - ds[1] + A.sed * ds[3] + A.vce * ds[5] - c[4];
       dn[5] = -A.kap * ds[0] + ds[2] + A.a5 * ds[3] + A.beta * du0 - c[5];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { ds[k] = dn[k]; w(L.DS + 6 * (t + 1) + k) = dn[k]; }
-      dup0 = du0; dup1 = du1; um0 = u0; um1 = u1;
+      for (int k = 0; k < 6; ++k) { ds[k] = dn[k]; w(rn + oDS + k) = dn[k]; }
+      dup0 = du0; dup1 = du1; um0 = u0; um1 = u1; u0 = un0; u1 = un1;
     }
     if (!ls) {
       double s[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { s[k] = w(L.S + 6 * M + k); tiny = dmax(tiny, fabs(ds[k]) / (fabs(s[k]) + 1.0)); }
-      gbd += 2.0 * df * (P.w_v * (s[3] - P.ref_v) * ds[3] + P.w_cte * s[4] * ds[4] + P.w_epsi * s[5] * ds[5]);
+      for (int k = 0; k < 6; ++k) { s[k] = w(rec(M) + oS + k); nottiny = nottiny || fabs(ds[k]) > tinytol * (fabs(s[k]) + 1.0); }
+      gbd += gv2 * (s[3] - P.ref_v) * ds[3] + gc2 * s[4] * ds[4] + ge2 * s[5] * ds[5];
     }
-    fw_alpha_pr = a_pr; fw_alpha_du = a_du; fw_gbd = gbd; fw_tiny = tiny;
+    fw_alpha_pr = a_pr; fw_alpha_du = a_du; fw_gbd = gbd; fw_tiny = !nottiny;
   }
-  double fw_alpha_pr, fw_alpha_du, fw_gbd, fw_tiny;
 
   // ------------------------------------------------------------------------------------------
   // Backward sweep after the line search: dlam from the stationarity rows, then the new iterate
@@ -590,19 +653,22 @@ struct Solver {
   // every norm the convergence test / mu update need at it (IpIpoptCalculatedQuantities.cpp:2672-2832,3279-3306).
   // nbuf = TR/C buffer that holds the accepted trial point.
   MPC_HD void accept(double a, double a_du, double dw, int nbuf) {
-    const bool ls = ls_mode;
+    const bool ls = fl(F_LS), lam_zero = fl(F_LAMZERO);
     const double qv = ls ? 1.0 : 2.0 * P.w_v * df + dw, qe = ls ? 1.0 : 2.0 * P.w_epsi * df + dw,
                  qc = ls ? 1.0 : 2.0 * P.w_cte * df + dw, q0 = ls ? 1.0 : dw;
+    const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df, gc2 = 2.0 * P.w_cte * df;
+    const int bTo = oTR + 4 * cur, bTn = oTR + 4 * nbuf;
     double lp[6], ln[6], lo[6];   // lambda^+_{t+1}, lambda_new_{t+1}, lambda_old_{t+1}
-    double dinf = 0.0, l1 = 0.0, zz1 = 0.0, szmx = 0.0, szmn = 1e300, slog = 0.0, xm = 0.0, dlm = 0.0;
+    double dinf = 0.0, l1 = 0.0, zz1 = 0.0, szmx = 0.0, szmn = 1e300, xm = 0.0, dlm = 0.0;
     {
+      const int r = rec(M);
       double s[6], ds[6], lam[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { s[k] = w(L.S + 6 * M + k); ds[k] = w(L.DS + 6 * M + k); lam[k] = (ls) ? 0.0 : w(L.LAM + 6 * M + k); }
+      for (int k = 0; k < 6; ++k) { s[k] = w(r + oS + k); ds[k] = w(r + oDS + k); lam[k] = (ls) ? 0.0 : w(r + oLAM + k); }
       lp[0] = -q0 * ds[0]; lp[1] = -q0 * ds[1]; lp[2] = -q0 * ds[2];
-      lp[3] = -qv * ds[3] - 2.0 * P.w_v * df * (s[3] - P.ref_v);
-      lp[4] = -qc * ds[4] - 2.0 * P.w_cte * df * s[4];
-      lp[5] = -qe * ds[5] - 2.0 * P.w_epsi * df * s[5];
+      lp[3] = -qv * ds[3] - gv2 * (s[3] - P.ref_v);
+      lp[4] = -qc * ds[4] - gc2 * s[4];
+      lp[5] = -qe * ds[5] - ge2 * s[5];
       double sn[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
@@ -610,46 +676,47 @@ struct Solver {
         dlm = dmax(dlm, fabs(lp[k] - lam[k]));
         ln[k] = lam_zero ? 0.0 : (ls ? lp[k] : lam[k] + a * (lp[k] - lam[k]));
         sn[k] = ls ? s[k] : s[k] + a * ds[k];
-        w(L.LAM + 6 * M + k) = ln[k];
-        if (!ls) w(L.S + 6 * M + k) = sn[k];
+        w(r + oLAM + k) = ln[k];
+        if (!ls) w(r + oS + k) = sn[k];
         l1 += fabs(ln[k]);
         xm = dmax(xm, fabs(sn[k]));
       }
       dinf = dmax(dinf, dmax(fabs(ln[0]), dmax(fabs(ln[1]), fabs(ln[2]))));
-      dinf = dmax(dinf, fabs(2.0 * P.w_v * df * (sn[3] - P.ref_v) + ln[3]));
-      dinf = dmax(dinf, fabs(2.0 * P.w_cte * df * sn[4] + ln[4]));
-      dinf = dmax(dinf, fabs(2.0 * P.w_epsi * df * sn[5] + ln[5]));
+      dinf = dmax(dinf, fabs(gv2 * (sn[3] - P.ref_v) + ln[3]));
+      dinf = dmax(dinf, fabs(gc2 * sn[4] + ln[4]));
+      dinf = dmax(dinf, fabs(ge2 * sn[5] + ln[5]));
     }
     double unn0 = 0.0, unn1 = 0.0;   // u_new at t+1
-    // u_new at t (needed one stage ahead for grad_u): prefetch
     double uc0 = 0.0, uc1 = 0.0, duc0 = 0.0, duc1 = 0.0;
-    if (M > 0) { uc0 = w(L.U + 2 * (M - 1)); uc1 = w(L.U + 2 * (M - 1) + 1); duc0 = w(L.DU + 2 * (M - 1)); duc1 = w(L.DU + 2 * (M - 1) + 1); }
+    if (M > 0) { const int r = rec(M - 1); uc0 = w(r + oU); uc1 = w(r + oU + 1); duc0 = w(r + oDU); duc1 = w(r + oDU + 1); }
     for (int t = M - 1; t >= 0; --t) {
+      const int r = rec(t);
       double s[6], ds[6], lam[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { s[k] = w(L.S + 6 * t + k); ds[k] = w(L.DS + 6 * t + k); lam[k] = ls ? 0.0 : w(L.LAM + 6 * t + k); }
+      for (int k = 0; k < 6; ++k) { s[k] = w(r + oS + k); ds[k] = w(r + oDS + k); lam[k] = ls ? 0.0 : w(r + oLAM + k); }
       const double u0 = uc0, u1 = uc1, du0 = duc0, du1 = duc1;
       double um0 = 0.0, um1 = 0.0, dum0 = 0.0, dum1 = 0.0;
-      if (t > 0) { um0 = w(L.U + 2 * t - 2); um1 = w(L.U + 2 * t - 1); dum0 = w(L.DU + 2 * t - 2); dum1 = w(L.DU + 2 * t - 1); }
+      if (t > 0) { um0 = w(r - kRec + oU); um1 = w(r - kRec + oU + 1); dum0 = w(r - kRec + oDU); dum1 = w(r - kRec + oDU + 1); }
+      const double spo = w(r + bTo), cpo = w(r + bTo + 1), seo = w(r + bTo + 2), ceo = w(r + bTo + 3);
+      const double spn = w(r + bTn), cpn = w(r + bTn + 1), sen = w(r + bTn + 2), cen = w(r + bTn + 3);
+      double zl0 = w(r + oZL), zl1 = w(r + oZL + 1), zu0 = w(r + oZU), zu1 = w(r + oZU + 1);
       // ---- old point: lambda^+_t
       {
-        const int to = TRo(cur, t);
-        const double sp = w(to), cp = w(to + 1), se = w(to + 2), ce = w(to + 3);
         double p0, p1, p2, p3;
         poly_eval(cf, s[0], p0, p1, p2, p3);
-        const Lin A = make_lin(P, s[3], u0, sp, cp, se, ce, p1, p2);
+        const Lin A = make_lin(P, s[3], u0, spo, cpo, seo, ceo, p1, p2);
         Hes H;
         if (ls) { H.xx = H.pp = H.vp = H.ee = H.ev = H.m = 0.0; }
-        else H = make_hes(P, lo, s[3], sp, cp, se, ce, p1, p2, p3);
+        else H = make_hes(P, lo, s[3], spo, cpo, seo, ceo, p1, p2, p3);
         double at[6];
         applyAT6(A, lp, at);
         double nl[6];
         nl[0] = at[0] - (q0 + H.xx) * ds[0];
         nl[1] = at[1] - q0 * ds[1];
         nl[2] = at[2] - ((q0 + H.pp) * ds[2] + H.vp * ds[3]);
-        nl[3] = at[3] - (H.vp * ds[2] + qv * ds[3] + H.ev * ds[5] + H.m * du0) - 2.0 * P.w_v * df * (s[3] - P.ref_v);
-        nl[4] = -qc * ds[4] - 2.0 * P.w_cte * df * s[4];
-        nl[5] = at[5] - ((qe + H.ee) * ds[5] + H.ev * ds[3]) - 2.0 * P.w_epsi * df * s[5];
+        nl[3] = at[3] - (H.vp * ds[2] + qv * ds[3] + H.ev * ds[5] + H.m * du0) - gv2 * (s[3] - P.ref_v);
+        nl[4] = -qc * ds[4] - gc2 * s[4];
+        nl[5] = at[5] - ((qe + H.ee) * ds[5] + H.ev * ds[3]) - ge2 * s[5];
 #pragma unroll
         for (int k = 0; k < 6; ++k) { lp[k] = nl[k]; lo[k] = lam[k]; dlm = dmax(dlm, fabs(nl[k] - lam[k])); }
       }
@@ -659,53 +726,50 @@ struct Solver {
       for (int k = 0; k < 6; ++k) {
         sn[k] = ls ? s[k] : s[k] + a * ds[k];
         lnew[k] = lam_zero ? 0.0 : (ls ? lp[k] : lam[k] + a * (lp[k] - lam[k]));
-        w(L.LAM + 6 * t + k) = lnew[k];
-        if (!ls && t > 0) w(L.S + 6 * t + k) = sn[k];
+        w(r + oLAM + k) = lnew[k];
+        if (!ls && t > 0) w(r + oS + k) = sn[k];
         l1 += fabs(lnew[k]);
         xm = dmax(xm, fabs(sn[k]));
       }
       const double un0 = ls ? u0 : u0 + a * du0, un1 = ls ? u1 : u1 + a * du1;
       const double umn0 = ls ? um0 : um0 + a * dum0, umn1 = ls ? um1 : um1 + a * dum1;
       xm = dmax(xm, dmax(fabs(un0), fabs(un1)));
-      double zl0 = w(L.ZL + 2 * t), zl1 = w(L.ZL + 2 * t + 1), zu0 = w(L.ZU + 2 * t), zu1 = w(L.ZU + 2 * t + 1);
       if (!ls) {
-        const double sl0 = safe_slack(u0 - xL(0), mu, zl0, xL(0)), su0 = safe_slack(xU(0) - u0, mu, zu0, xU(0));
-        const double sl1 = safe_slack(u1 - xL(1), mu, zl1, xL(1)), su1 = safe_slack(xU(1) - u1, mu, zu1, xU(1));
+        const double sl0 = safe_slack(u0 - P.xl[0], mu, zl0, P.xl[0]), su0 = safe_slack(P.xu[0] - u0, mu, zu0, P.xu[0]);
+        const double sl1 = safe_slack(u1 - P.xl[1], mu, zl1, P.xl[1]), su1 = safe_slack(P.xu[1] - u1, mu, zu1, P.xu[1]);
         zl0 += a_du * ((mu - sl0 * zl0 - zl0 * du0) / sl0);
         zu0 += a_du * ((mu - su0 * zu0 + zu0 * du0) / su0);
         zl1 += a_du * ((mu - sl1 * zl1 - zl1 * du1) / sl1);
         zu1 += a_du * ((mu - su1 * zu1 + zu1 * du1) / su1);
       }
-      double nsl0 = safe_slack(un0 - xL(0), mu, zl0, xL(0)), nsu0 = safe_slack(xU(0) - un0, mu, zu0, xU(0));
-      double nsl1 = safe_slack(un1 - xL(1), mu, zl1, xL(1)), nsu1 = safe_slack(xU(1) - un1, mu, zu1, xU(1));
+      const double nsl0 = safe_slack(un0 - P.xl[0], mu, zl0, P.xl[0]), nsu0 = safe_slack(P.xu[0] - un0, mu, zu0, P.xu[0]);
+      const double nsl1 = safe_slack(un1 - P.xl[1], mu, zl1, P.xl[1]), nsu1 = safe_slack(P.xu[1] - un1, mu, zu1, P.xu[1]);
       if (!ls) {   // kappa_sigma = 1e10
-        zl0 = dclamp(zl0, mu / (1e10 * nsl0), 1e10 * mu / nsl0);
-        zu0 = dclamp(zu0, mu / (1e10 * nsu0), 1e10 * mu / nsu0);
-        zl1 = dclamp(zl1, mu / (1e10 * nsl1), 1e10 * mu / nsl1);
-        zu1 = dclamp(zu1, mu / (1e10 * nsu1), 1e10 * mu / nsu1);
-        w(L.ZL + 2 * t) = zl0; w(L.ZL + 2 * t + 1) = zl1; w(L.ZU + 2 * t) = zu0; w(L.ZU + 2 * t + 1) = zu1;
-        w(L.U + 2 * t) = un0; w(L.U + 2 * t + 1) = un1;
+        const double m0 = mu / nsl0, m1 = mu / nsu0, m2 = mu / nsl1, m3 = mu / nsu1;
+        zl0 = dclamp(zl0, 1e-10 * m0, 1e10 * m0);
+        zu0 = dclamp(zu0, 1e-10 * m1, 1e10 * m1);
+        zl1 = dclamp(zl1, 1e-10 * m2, 1e10 * m2);
+        zu1 = dclamp(zu1, 1e-10 * m3, 1e10 * m3);
+        w(r + oZL) = zl0; w(r + oZL + 1) = zl1; w(r + oZU) = zu0; w(r + oZU + 1) = zu1;
+        w(r + oU) = un0; w(r + oU + 1) = un1;
       }
       zz1 += zl0 + zl1 + zu0 + zu1;
       {
         const double c0 = nsl0 * zl0, c1 = nsl1 * zl1, c2 = nsu0 * zu0, c3 = nsu1 * zu1;
         szmx = dmax(szmx, dmax(dmax(c0, c1), dmax(c2, c3)));
         szmn = dmin(szmn, dmin(dmin(c0, c1), dmin(c2, c3)));
-        slog += log(nsl0) + log(nsl1) + log(nsu0) + log(nsu1);
       }
       // grad_x L at the new point
       {
-        const int to = TRo(nbuf, t);
-        const double sp = w(to), cp = w(to + 1), se = w(to + 2), ce = w(to + 3);
         double p0, p1, p2, p3;
         poly_eval(cf, sn[0], p0, p1, p2, p3);
-        const Lin A = make_lin(P, sn[3], un0, sp, cp, se, ce, p1, p2);
+        const Lin A = make_lin(P, sn[3], un0, spn, cpn, sen, cen, p1, p2);
         double at[6];
         applyAT6(A, ln, at);
         dinf = dmax(dinf, dmax(fabs(lnew[0] - at[0]), dmax(fabs(lnew[1] - at[1]), fabs(lnew[2] - at[2]))));
-        dinf = dmax(dinf, fabs(2.0 * P.w_v * df * (sn[3] - P.ref_v) + lnew[3] - at[3]));
-        dinf = dmax(dinf, fabs(2.0 * P.w_cte * df * sn[4] + lnew[4]));
-        dinf = dmax(dinf, fabs(2.0 * P.w_epsi * df * sn[5] + lnew[5] - at[5]));
+        dinf = dmax(dinf, fabs(gv2 * (sn[3] - P.ref_v) + lnew[3] - at[3]));
+        dinf = dmax(dinf, fabs(gc2 * sn[4] + lnew[4]));
+        dinf = dmax(dinf, fabs(ge2 * sn[5] + lnew[5] - at[5]));
         const double g0 = grad_u(0, t, un0, umn0, unn0) - A.beta * (ln[2] + ln[5]) - zl0 + zu0;
         const double g1 = grad_u(1, t, un1, umn1, unn1) - P.dt * ln[3] - zl1 + zu1;
         dinf = dmax(dinf, dmax(fabs(g0), fabs(g1)));
@@ -715,7 +779,7 @@ struct Solver {
       unn0 = un0; unn1 = un1;
       uc0 = um0; uc1 = um1; duc0 = dum0; duc1 = dum1;
     }
-    dualinf = dinf; lam1 = l1; z1 = zz1; sz_max = szmx; sz_min = szmn; sumlog = slog; xmaxabs = xm; dlam_max = dlm;
+    dualinf = dinf; lam1 = l1; z1 = zz1; sz_max = szmx; sz_min = szmn; xmaxabs = xm; dlam_max = dlm;
   }
 
   // ------------------------------------------------------------------------------------------
@@ -723,16 +787,18 @@ struct Solver {
   MPC_HD static bool cmp_le(double lhs, double rhs, double bas) { return lhs - rhs <= 10.0 * DBL_EPSILON * fabs(bas); }
   MPC_HD bool filter_ok(double phi, double th) const {
     bool ok = true;
-    for (int i = 0; i < kMaxFilter; ++i)
-      if (i < nf && !(phi <= fphi[i] || th <= fth[i])) ok = false;
+    for (int i = 0; i < nf; ++i)
+      if (!(phi <= filt(2 * i) || th <= filt(2 * i + 1))) ok = false;
     return ok;
   }
   MPC_HD void filter_add(double phi, double th) {
     int wr = 0;
-    for (int i = 0; i < kMaxFilter; ++i)
-      if (i < nf && !(fphi[i] >= phi && fth[i] >= th)) { fphi[wr] = fphi[i]; fth[wr] = fth[i]; ++wr; }
+    for (int i = 0; i < nf; ++i) {
+      const double a = filt(2 * i), b = filt(2 * i + 1);
+      if (!(a >= phi && b >= th)) { filt(2 * wr) = a; filt(2 * wr + 1) = b; ++wr; }
+    }
     nf = wr;
-    if (nf < kMaxFilter) { fphi[nf] = phi; fth[nf] = th; ++nf; }
+    if (nf < kMaxFilter) { filt(2 * nf) = phi; filt(2 * nf + 1) = th; ++nf; }
   }
   MPC_HD bool is_ftype(double at) const { return ref_gbd < 0.0 && at * pow(-ref_gbd, 2.3) > 1.0 * pow(ref_theta, 1.1); }
   MPC_HD bool armijo(double at, double trial_barr) const { return cmp_le(trial_barr - ref_barr, 1e-8 * at * ref_gbd, ref_barr); }
@@ -775,10 +841,10 @@ struct Solver {
     if (iter >= P.max_iter) { status = kMaxIterExceeded; return false; }
     // IpMonotoneMuUpdate.cpp:132-232
     double Emu = dmax(dualinf / sd, dmax(priminf, dmax(sz_max - mu, mu - sz_min) / sc));
-    bool done = false, tiny = tiny_flag;
-    tiny_flag = false;
+    bool done = false, tiny = fl(F_TINYFLAG);
+    setfl(F_TINYFLAG, false);
     while ((Emu <= 10.0 * mu || tiny) && !done) {
-      const double nm = dmax(dmin(0.2 * mu, pow(mu, 1.5)), mu_min);
+      const double nm = dmax(dmin(0.2 * mu, mu * sqrt(mu)), mu_min);
       const double nt = dmax(0.99, 1.0 - nm);
       const bool changed = nm != mu;
       if (!changed && tiny) { status = kSearchDirectionTooSmall; return false; }
@@ -795,117 +861,193 @@ struct Solver {
   }
 
   // ------------------------------------------------------------------------------------------
-  // One trip through the phase machine.  In the common case a problem runs FACTOR -> FORWARD -> TRIAL ->
-  // ACCEPT (one interior-point iteration) per trip; rare events (inertia correction, backtracking, second
-  // order correction) take extra trips without stalling the other problems of the warp.
-  MPC_HD void trip() {
-    if (phase == PH_FACTOR) {
-      bool ok = factor(dw_curr, in_soc);
-      if (ok) phase = PH_FORWARD;
-      else {   // IpPDPerturbationHandler.cpp:347-391
-        if (dw_curr == 0.0) dw_curr = dw_last == 0.0 ? 1e-4 : dmax(1e-20, dw_last / 3.0);
-        else dw_curr *= (dw_last == 0.0 || 1e5 * dw_last < dw_curr) ? 100.0 : 8.0;
-        if (dw_curr > 1e20) { status = kErrorInStepComputation; phase = PH_DONE; }
-      }
+  // The four passes with the control logic that follows each.  In the common case a problem runs FACTOR ->
+  // FORWARD -> TRIAL -> ACCEPT once per interior-point iteration; rare events (inertia correction, backtracking,
+  // second order correction) take extra rounds without stalling the other problems.
+  MPC_HD void do_factor() {
+    const bool ok = factor(dw_curr, fl(F_INSOC));
+    if (ok) phase = PH_FORWARD;
+    else {   // IpPDPerturbationHandler.cpp:347-391
+      if (dw_curr == 0.0) dw_curr = dw_last == 0.0 ? 1e-4 : dmax(1e-20, dw_last / 3.0);
+      else dw_curr *= (dw_last == 0.0 || 1e5 * dw_last < dw_curr) ? 100.0 : 8.0;
+      if (dw_curr > 1e20) { status = kErrorInStepComputation; phase = PH_DONE; }
     }
-    if (phase == PH_FORWARD) {
-      forward(in_soc, dw_curr);
-      if (ls_mode) { phase = PH_ACCEPT; }
-      else if (in_soc) {
-        alpha = fw_alpha_pr;   // alpha_primal_soc
-        phase = PH_TRIAL;
-      } else if (soc_done) {   // direction restored after a failed SOC: resume backtracking
-        phase = PH_TRIAL;
+  }
+  MPC_HD void do_forward() {
+    forward(fl(F_INSOC));
+    forward_logic();
+  }
+  MPC_HD void forward_logic() {
+    if (fl(F_LS)) { phase = PH_ACCEPT; return; }
+    alpha_du = fw_alpha_du;
+    if (fl(F_INSOC)) {
+      alpha = fw_alpha_pr;   // alpha_primal_soc
+    } else if (fl(F_SOCDONE)) {
+      // direction restored after a failed SOC: resume backtracking with the alpha set in do_trial
+    } else {
+      ref_theta = theta_cur;
+      ref_barr = f_cur - mu * sumlog;
+      ref_gbd = fw_gbd;
+      setfl(F_TINYNOW, fw_tiny);
+      alpha_max = fw_alpha_pr;
+      alpha = alpha_max;
+      n_steps = 0;
+      if (fw_tiny) {
+        if (fl(F_TINYLAST)) setfl(F_TINYFLAG, true);
       } else {
-        alpha_du = fw_alpha_du;
-        ref_theta = theta_cur;
-        ref_barr = f_cur - mu * sumlog;
-        ref_gbd = fw_gbd;
-        tiny_now = fw_tiny <= 10.0 * DBL_EPSILON;
-        alpha_max = fw_alpha_pr;
-        alpha = alpha_max;
-        n_steps = 0;
-        if (tiny_now) {
-          if (tiny_last) tiny_flag = true;
-        } else {
-          double am = 1e-5;   // CalculateAlphaMin IpFilterLSAcceptor.cpp:393-410
-          if (ref_gbd < 0.0) {
-            am = dmin(am, 1e-8 * ref_theta / (-ref_gbd));
-            if (ref_theta <= theta_min) am = dmin(am, 1.0 * pow(ref_theta, 1.1) / pow(-ref_gbd, 2.3));
-          }
-          alpha_min = 0.05 * am;
+        double am = 1e-5;   // CalculateAlphaMin IpFilterLSAcceptor.cpp:393-410
+        if (ref_gbd < 0.0) {
+          am = dmin(am, 1e-8 * ref_theta / (-ref_gbd));
+          if (ref_theta <= theta_min) am = dmin(am, 1.0 * pow(ref_theta, 1.1) / pow(-ref_gbd, 2.3));
         }
-        phase = PH_TRIAL;
+        alpha_min = 0.05 * am;
       }
     }
-    if (phase == PH_TRIAL) {
-      eval_point(alpha, cur ^ 1);
-      const double tbarr = tr_f - mu * tr_sumlog;
-      bool acc;
-      if (tiny_now) acc = true;
-      else {
-        if (!in_soc) alpha_test = alpha;
-        acc = check_accept(alpha_test, tr_theta, tbarr);
-      }
-      if (acc) {
-        if (!tiny_now && (!is_ftype(alpha_test) || !armijo(alpha_test, tbarr)))
-          filter_add(ref_barr - 1e-8 * ref_theta, (1.0 - 1e-5) * ref_theta);
-        phase = PH_ACCEPT;
-      } else if (in_soc) {
-        ++soc_count;
-        if (soc_count < 4 && tr_theta <= 0.99 * theta_soc_old) {   // another correction
-          theta_soc_old = tr_theta;
-          alpha_soc = alpha;
-          build_csoc(alpha_soc);
-          phase = PH_FACTOR;
-        } else {   // give up: restore the Newton direction, continue backtracking
-          in_soc = false; soc_done = true;
-          alpha = 0.5 * alpha_max; n_steps = 1;
-          phase = alpha > alpha_min ? PH_FACTOR : PH_DONE;
-          if (phase == PH_DONE) status = kRestorationFailed;
-        }
-      } else if (!soc_done && alpha == alpha_max && ref_theta <= tr_theta) {   // start SOC (IpFilterLSAcceptor.cpp:473-587)
-        in_soc = true; soc_count = 0;
+    phase = PH_TRIAL;
+  }
+  MPC_HD void do_trial() {
+    eval_point(alpha, cur ^ 1);
+    trial_logic();
+  }
+  MPC_HD void trial_logic() {
+    const double tbarr = tr_f - mu * tr_sumlog;
+    const bool tiny_now = fl(F_TINYNOW), in_soc = fl(F_INSOC);
+    bool acc;
+    if (tiny_now) acc = true;
+    else {
+      if (!in_soc) alpha_test = alpha;
+      acc = check_accept(alpha_test, tr_theta, tbarr);
+    }
+    if (acc) {
+      if (!tiny_now && (!is_ftype(alpha_test) || !armijo(alpha_test, tbarr)))
+        filter_add(ref_barr - 1e-8 * ref_theta, (1.0 - 1e-5) * ref_theta);
+      phase = PH_ACCEPT;
+    } else if (in_soc) {
+      ++soc_count;
+      if (soc_count < 4 && tr_theta <= 0.99 * theta_soc_old) {   // another correction
         theta_soc_old = tr_theta;
         alpha_soc = alpha;
-        init_csoc();
         build_csoc(alpha_soc);
         phase = PH_FACTOR;
-      } else {
-        alpha *= 0.5; ++n_steps;
-        if (!(alpha > alpha_min)) { status = kRestorationFailed; phase = PH_DONE; }
+      } else {   // give up: restore the Newton direction, continue backtracking
+        setfl(F_INSOC, false); setfl(F_SOCDONE, true);
+        alpha = 0.5 * alpha_max; n_steps = 1;
+        phase = alpha > alpha_min ? PH_FACTOR : PH_DONE;
+        if (phase == PH_DONE) status = kRestorationFailed;
       }
-    }
-    if (phase == PH_ACCEPT) {
-      if (ls_mode) {
-        accept(0.0, 0.0, 0.0, cur);
-        if (!lam_zero && dlam_max > 1000.0) { lam_zero = true; }   // constr_mult_init_max: redo with lambda = 0
-        else {
-          ls_mode = false; lam_zero = false;
-          phase = top_of_loop() ? PH_FACTOR : PH_DONE;
-          if (phase == PH_FACTOR) begin_iteration();
-        }
-      } else {
-        accept(alpha, alpha_du, dw_curr, cur ^ 1);
-        cur ^= 1;
-        f_cur = tr_f; theta_cur = tr_theta; priminf = tr_priminf;
-        tiny_last = tiny_now ? dlam_max < 1e-2 : false;
-        in_soc = false; soc_done = false;
-        ++iter;
-        phase = top_of_loop() ? PH_FACTOR : PH_DONE;
-        if (phase == PH_FACTOR) begin_iteration();
-      }
+    } else if (!fl(F_SOCDONE) && alpha == alpha_max && ref_theta <= tr_theta) {   // start SOC (IpFilterLSAcceptor.cpp:473-587)
+      setfl(F_INSOC, true); soc_count = 0;
+      theta_soc_old = tr_theta;
+      alpha_soc = alpha;
+      init_csoc();
+      build_csoc(alpha_soc);
+      phase = PH_FACTOR;
+    } else {
+      alpha *= 0.5; ++n_steps;
+      if (!(alpha > alpha_min)) { status = kRestorationFailed; phase = PH_DONE; }
     }
   }
-  MPC_HD void begin_iteration() {   // PDPerturbationHandler::ConsiderNewSystem
-    if (dw_curr > 0.0) dw_last = dw_curr;
-    dw_curr = 0.0;
+  MPC_HD void do_accept() {
+    accept_pass();
+    accept_logic();
+  }
+  MPC_HD void accept_pass() {
+    if (fl(F_LS)) accept(0.0, 0.0, 0.0, cur);
+    else accept(alpha, alpha_du, dw_curr, cur ^ 1);
+  }
+  MPC_HD void accept_logic() {
+    if (fl(F_LS)) {
+      if (!fl(F_LAMZERO) && dlam_max > 1000.0) { setfl(F_LAMZERO, true); return; }   // constr_mult_init_max: redo with lambda = 0
+      setfl(F_LS, false); setfl(F_LAMZERO, false);
+    } else {
+      cur ^= 1;
+      f_cur = tr_f; theta_cur = tr_theta; priminf = tr_priminf; sumlog = tr_sumlog;
+      setfl(F_TINYLAST, fl(F_TINYNOW) ? dlam_max < 1e-2 : false);
+      setfl(F_INSOC, false); setfl(F_SOCDONE, false);
+      ++iter;
+    }
+    phase = top_of_loop() ? PH_FACTOR : PH_DONE;
+    if (phase == PH_FACTOR) {   // PDPerturbationHandler::ConsiderNewSystem
+      if (dw_curr > 0.0) dw_last = dw_curr;
+      dw_curr = 0.0;
+    }
+  }
+  // ------------------------------------------------------------------------------------------
+  // Per-pass entry points for the per-pass kernels: only the scalars a sweep needs are loaded before it, the
+  // ones its control logic needs are loaded after it (so they are not live across the sweep), and only what may
+  // have changed is stored.  cf must be set by the caller.  The caller has checked load_phase().
+#define LDD(idx, name) name = w(idx)
+#define LDI(idx, name) name = (int)w(idx)
+#define STD_(idx, name) w(idx) = name
+#define STI(idx, name) w(idx) = (double)name
+  MPC_HD void kernel_factor() {
+    LDI(iFLAGS, flags); LDI(iCUR, cur); LDD(dDF, df); LDD(dMU, mu); LDD(dDWC, dw_curr);
+    phase = PH_FACTOR;
+    const bool ok = factor(dw_curr, fl(F_INSOC));
+    if (ok) { w(iPHASE) = (double)PH_FORWARD; return; }
+    LDD(dDWL, dw_last); LDI(iSTATUS, status);
+    if (dw_curr == 0.0) dw_curr = dw_last == 0.0 ? 1e-4 : dmax(1e-20, dw_last / 3.0);
+    else dw_curr *= (dw_last == 0.0 || 1e5 * dw_last < dw_curr) ? 100.0 : 8.0;
+    if (dw_curr > 1e20) { status = kErrorInStepComputation; phase = PH_DONE; }
+    STD_(dDWC, dw_curr); STI(iSTATUS, status); STI(iPHASE, phase);
+  }
+  MPC_HD void kernel_forward() {
+    LDI(iFLAGS, flags); LDI(iCUR, cur); LDD(dDF, df); LDD(dMU, mu); LDD(dTAU, tau);
+    phase = PH_FORWARD;
+    forward(fl(F_INSOC));
+    LDD(dTH, theta_cur); LDD(dF, f_cur); LDD(dSLOG, sumlog); LDD(dTHMIN, theta_min);
+    LDD(dALPHA, alpha); LDD(dAMAX, alpha_max); LDD(dAMIN, alpha_min); LDD(dRTH, ref_theta); LDD(dRBARR, ref_barr);
+    LDD(dRGBD, ref_gbd); LDD(dADU, alpha_du); LDI(iNSTEPS, n_steps);
+    forward_logic();
+    STD_(dADU, alpha_du); STD_(dALPHA, alpha); STD_(dAMAX, alpha_max); STD_(dAMIN, alpha_min); STD_(dRTH, ref_theta);
+    STD_(dRBARR, ref_barr); STD_(dRGBD, ref_gbd); STI(iNSTEPS, n_steps); STI(iFLAGS, flags); STI(iPHASE, phase);
+  }
+  MPC_HD void kernel_trial() {
+    LDI(iFLAGS, flags); LDI(iCUR, cur); LDD(dDF, df); LDD(dMU, mu); LDD(dALPHA, alpha);
+    phase = PH_TRIAL;
+    eval_point(alpha, cur ^ 1);
+    LDD(dRTH, ref_theta); LDD(dRBARR, ref_barr); LDD(dRGBD, ref_gbd); LDD(dTHMAX, theta_max); LDD(dTHMIN, theta_min);
+    LDD(dATEST, alpha_test); LDD(dAMAX, alpha_max); LDD(dAMIN, alpha_min); LDD(dTHSOC, theta_soc_old); LDD(dASOC, alpha_soc);
+    LDI(iSOCCNT, soc_count); LDI(iNSTEPS, n_steps); LDI(iNF, nf); LDI(iSTATUS, status);
+    trial_logic();
+    STD_(dTRF, tr_f); STD_(dTRTH, tr_theta); STD_(dTRPINF, tr_priminf); STD_(dTRSLOG, tr_sumlog); STD_(dTHMAX, theta_max);
+    STD_(dTHMIN, theta_min); STD_(dATEST, alpha_test); STD_(dALPHA, alpha); STD_(dTHSOC, theta_soc_old); STD_(dASOC, alpha_soc);
+    STI(iSOCCNT, soc_count); STI(iNSTEPS, n_steps); STI(iNF, nf); STI(iFLAGS, flags); STI(iSTATUS, status); STI(iPHASE, phase);
+  }
+  MPC_HD void kernel_accept() {
+    LDI(iFLAGS, flags); LDI(iCUR, cur); LDD(dDF, df); LDD(dMU, mu); LDD(dALPHA, alpha); LDD(dADU, alpha_du); LDD(dDWC, dw_curr);
+    phase = PH_ACCEPT;
+    accept_pass();
+    LDD(dTRF, tr_f); LDD(dTRTH, tr_theta); LDD(dTRPINF, tr_priminf); LDD(dTRSLOG, tr_sumlog); LDD(dTAU, tau); LDD(dMUMIN, mu_min);
+    LDD(dCOBJ, curr_obj); LDD(dLOBJ, last_obj); LDD(dDWL, dw_last); LDD(dF, f_cur); LDD(dTH, theta_cur); LDD(dPINF, priminf);
+    LDD(dSLOG, sumlog); LDI(iACCCNT, acceptable_counter); LDI(iITER, iter); LDI(iNF, nf); LDI(iSTATUS, status);
+    accept_logic();
+    STD_(dDINF, dualinf); STD_(dLAM1, lam1); STD_(dZ1, z1); STD_(dSZMAX, sz_max); STD_(dSZMIN, sz_min); STD_(dXMAX, xmaxabs);
+    STD_(dDLMAX, dlam_max); STD_(dF, f_cur); STD_(dTH, theta_cur); STD_(dPINF, priminf); STD_(dSLOG, sumlog); STD_(dMU, mu);
+    STD_(dTAU, tau); STD_(dCOBJ, curr_obj); STD_(dLOBJ, last_obj); STD_(dDWC, dw_curr); STD_(dDWL, dw_last);
+    STI(iACCCNT, acceptable_counter); STI(iITER, iter); STI(iNF, nf); STI(iCUR, cur); STI(iFLAGS, flags); STI(iSTATUS, status);
+    STI(iPHASE, phase);
+  }
+#undef LDD
+#undef LDI
+#undef STD_
+#undef STI
+
+  MPC_HD void trip() {
+    if (phase == PH_FACTOR) do_factor();
+    if (phase == PH_FORWARD) do_forward();
+    if (phase == PH_TRIAL) do_trial();
+    if (phase == PH_ACCEPT) do_accept();
   }
   MPC_HD void init_csoc() {
-    for (int i = 6; i < 6 * N; ++i) w(L.CSOC + i) = w(L.C + cur * 6 * N + i);
+    for (int t = 1; t < N; ++t)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) w(rec(t) + oCSOC + k) = w(rec(t) + oC + 6 * cur + k);
   }
   MPC_HD void build_csoc(double a) {   // c_soc = c(trial) + alpha_soc * c_soc
-    for (int i = 6; i < 6 * N; ++i) w(L.CSOC + i) = w(L.C + (cur ^ 1) * 6 * N + i) + a * w(L.CSOC + i);
+    for (int t = 1; t < N; ++t)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) w(rec(t) + oCSOC + k) = w(rec(t) + oC + 6 * (cur ^ 1) + k) + a * w(rec(t) + oCSOC + k);
   }
 
   // ------------------------------------------------------------------------------------------
@@ -913,17 +1055,17 @@ struct Solver {
   // traj (optional): full variable vector in the reference layout (MPC.cpp:36-43), element i at traj[i*tstride].
   MPC_HD void finish(Result& R, double* traj, size_t tstride) {
     R.status = status; R.iters = iter; R.obj = f_cur / df;
-    R.out8[0] = w(L.S + 6 + 0); R.out8[1] = w(L.S + 6 + 1); R.out8[2] = w(L.S + 6 + 2); R.out8[3] = w(L.S + 6 + 3);
-    R.out8[4] = w(L.S + 6 + 4); R.out8[5] = w(L.S + 6 + 5);
-    R.out8[6] = dclamp(w(L.U + 0), -bnd(0), bnd(0));
-    R.out8[7] = dclamp(w(L.U + 1), -bnd(1), bnd(1));
+#pragma unroll
+    for (int k = 0; k < 6; ++k) R.out8[k] = w(rec(1) + oS + k);
+    R.out8[6] = dclamp(w(rec(0) + oU + 0), -P.ob[0], P.ob[0]);
+    R.out8[7] = dclamp(w(rec(0) + oU + 1), -P.ob[1], P.ob[1]);
     if (traj) {
       for (int t = 0; t < N; ++t)
 #pragma unroll
-        for (int k = 0; k < 6; ++k) traj[(size_t)(k * N + t) * tstride] = w(L.S + 6 * t + k);
+        for (int k = 0; k < 6; ++k) traj[(size_t)(k * N + t) * tstride] = w(rec(t) + oS + k);
       for (int t = 0; t < M; ++t) {
-        traj[(size_t)(6 * N + t) * tstride] = dclamp(w(L.U + 2 * t), -bnd(0), bnd(0));
-        traj[(size_t)(6 * N + M + t) * tstride] = dclamp(w(L.U + 2 * t + 1), -bnd(1), bnd(1));
+        traj[(size_t)(6 * N + t) * tstride] = dclamp(w(rec(t) + oU), -P.ob[0], P.ob[0]);
+        traj[(size_t)(6 * N + M + t) * tstride] = dclamp(w(rec(t) + oU + 1), -P.ob[1], P.ob[1]);
       }
     }
   }

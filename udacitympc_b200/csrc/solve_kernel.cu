@@ -1,57 +1,169 @@
-// Fused interior-point solve kernel (K1 derivative evaluation + K2 Riccati KKT solve + K3 barrier / line-search /
-// filter / convergence logic) for sm_100a.  One problem per thread, all per-problem vectors in a warp-interleaved
-// HBM workspace (every workspace access of a warp is one coalesced 256-byte row), the 7x7 Riccati blocks in
-// registers.  Replaces CppAD::ipopt::solve at /root/reference/mpc_to_line/solution/MPC.cpp:241-243.
+// Interior-point solve kernels for sm_100a (K1 derivative evaluation, K2 Riccati KKT solve, K3 barrier / line
+// search / filter / convergence logic).  One problem per thread; every per-problem vector lives in a
+// warp-interleaved HBM workspace (each workspace access of a warp is one coalesced 256-byte row) and the 7x7
+// Riccati blocks live in registers.  Replaces CppAD::ipopt::solve at
+// /root/reference/mpc_to_line/solution/MPC.cpp:241-243.
+//
+// Two execution modes share the same pass code (mpc_core.cuh):
+//   per-pass kernels  init | factor | forward | trial | accept, launched round after round on one stream.  Each
+//                     kernel has its own register budget (the Riccati factorisation needs ~250 registers, the
+//                     other sweeps far fewer and run at 3-4x the occupancy) and a small instruction footprint.
+//   fused kernel      one launch loops the four passes per thread until its problem is done.  Used to finish
+//                     stragglers after the fixed number of rounds, and for tiny batches (latency).
 #include "kernels.h"
 
 namespace b200mpc {
 
 constexpr int kBlock = 64;
+// resident blocks per SM the light sweeps are compiled for (register cap = 65536 / (64 * blocks))
+#ifndef MPC_FWD_BLOCKS
+#define MPC_FWD_BLOCKS 8
+#endif
+#ifndef MPC_TRIAL_BLOCKS
+#define MPC_TRIAL_BLOCKS 8
+#endif
+#ifndef MPC_ACCEPT_BLOCKS
+#define MPC_ACCEPT_BLOCKS 8
+#endif
+constexpr int kFwdBlocks = MPC_FWD_BLOCKS, kTrialBlocks = MPC_TRIAL_BLOCKS, kAcceptBlocks = MPC_ACCEPT_BLOCKS;
 
 size_t solve_workspace_doubles(int N, int B) {
-  Layout L(N);
   size_t groups = ((size_t)B + 31) / 32;
-  return groups * (size_t)L.total * 32;
+  return groups * (size_t)workspace_doubles_per_problem(N) * 32;
 }
 
-__global__ void __launch_bounds__(kBlock) mpc_solve_kernel(const __grid_constant__ Params P, int B, int steps,
-                                                           const double* __restrict__ state6,
-                                                           const double* __restrict__ coeffs, int ncoef,
-                                                           double* __restrict__ ws, double* __restrict__ out8,
-                                                           double* __restrict__ traj, double* __restrict__ obj,
-                                                           int* __restrict__ status, int* __restrict__ iters) {
+struct SolveArgs {
+  int B, steps, step, ncoef;
+  const double* state6;   // [6][B]
+  const double* coeffs;   // [ncoef][B]
+  double* ws;
+  double* out8;           // [steps][8][B]
+  double* traj;           // [8N-2][B] or null (last step)
+  double* obj;            // [steps][B] or null
+  int* status;            // [B] or null (last step)
+  int* iters;             // [steps][B] or null
+};
+
+__device__ __forceinline__ double* problem_base(const Params& P, const SolveArgs& A, int b) {
+  return A.ws + (size_t)(b >> 5) * (size_t)workspace_doubles_per_problem(P.N) * 32 + (b & 31);
+}
+__device__ __forceinline__ void load_coeffs(const SolveArgs& A, int b, double* cf) {
+#pragma unroll
+  for (int i = 0; i < kMaxCoef; ++i) cf[i] = i < A.ncoef ? A.coeffs[(size_t)i * A.B + b] : 0.0;
+}
+// initial state of closed-loop step `step`: the caller's state for step 0, else the previous step's out8[0..5]
+// (solution/main.cpp:66)
+__device__ __forceinline__ void load_state6(const SolveArgs& A, int b, double* s0) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+    s0[k] = A.step == 0 ? A.state6[(size_t)k * A.B + b] : A.out8[((size_t)(A.step - 1) * 8 + k) * A.B + b];
+}
+__device__ __forceinline__ void write_result(const Params& P, const SolveArgs& A, int b, Solver<32>& S) {
+  Result R;
+  S.finish(R, (A.traj && A.step == A.steps - 1) ? A.traj + b : nullptr, (size_t)A.B);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) A.out8[((size_t)A.step * 8 + k) * A.B + b] = R.out8[k];
+  if (A.obj) A.obj[(size_t)A.step * A.B + b] = R.obj;
+  if (A.iters) A.iters[(size_t)A.step * A.B + b] = R.iters;
+  if (A.status && A.step == A.steps - 1) A.status[b] = R.status;
+}
+
+// ---- per-pass kernels ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) mpc_init_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const Layout L(P.N);
-  double* base = ws + (size_t)(b >> 5) * (size_t)L.total * 32 + (b & 31);
-  Solver<32> S(P, base);
+  if (b >= A.B) return;
+  Solver<32> S(P, problem_base(P, A, b));
   double s0[6], cf[kMaxCoef];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) s0[k] = state6[(size_t)k * B + b];
-#pragma unroll
-  for (int i = 0; i < kMaxCoef; ++i) cf[i] = i < ncoef ? coeffs[(size_t)i * B + b] : 0.0;
-  for (int step = 0; step < steps; ++step) {
-    S.init(s0, cf, ncoef);
-    while (S.phase != PH_DONE) S.trip();
-    Result R;
-    S.finish(R, (traj && step == steps - 1) ? traj + b : nullptr, (size_t)B);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) out8[((size_t)step * 8 + k) * B + b] = R.out8[k];
-    if (obj) obj[(size_t)step * B + b] = R.obj;
-    if (iters) iters[(size_t)step * B + b] = R.iters;
-    if (status && step == steps - 1) status[b] = R.status;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) s0[k] = R.out8[k];   // main.cpp:66 feeds vars[0..5] back
+  load_state6(A, b, s0);
+  load_coeffs(A, b, cf);
+  S.init(s0, cf, A.ncoef);
+  S.store_state();
+}
+
+__global__ void __launch_bounds__(kBlock) mpc_factor_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.B) return;
+  Solver<32> S(P, problem_base(P, A, b));
+  if (S.load_phase() != PH_FACTOR) return;
+  load_coeffs(A, b, S.cf);
+  S.kernel_factor();
+}
+
+__global__ void __launch_bounds__(kBlock, kFwdBlocks) mpc_forward_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.B) return;
+  Solver<32> S(P, problem_base(P, A, b));
+  if (S.load_phase() != PH_FORWARD) return;
+  load_coeffs(A, b, S.cf);
+  S.kernel_forward();
+}
+
+__global__ void __launch_bounds__(kBlock, kTrialBlocks) mpc_trial_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.B) return;
+  Solver<32> S(P, problem_base(P, A, b));
+  if (S.load_phase() != PH_TRIAL) return;
+  load_coeffs(A, b, S.cf);
+  S.kernel_trial();
+}
+
+__global__ void __launch_bounds__(kBlock, kAcceptBlocks) mpc_accept_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.B) return;
+  Solver<32> S(P, problem_base(P, A, b));
+  if (S.load_phase() != PH_ACCEPT) return;
+  load_coeffs(A, b, S.cf);
+  S.kernel_accept();
+  if (S.phase == PH_DONE) write_result(P, A, b, S);
+}
+
+// ---- fused kernel: finishes whatever is still active (fresh == 1: starts from the inputs) ---------------------
+__global__ void __launch_bounds__(kBlock) mpc_fused_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A, int fresh) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.B) return;
+  Solver<32> S(P, problem_base(P, A, b));
+  load_coeffs(A, b, S.cf);
+  if (fresh) {
+    double s0[6];
+    load_state6(A, b, s0);
+    S.init(s0, S.cf, kMaxCoef);
+  } else {
+    if (S.load_phase() == PH_DONE) return;
+    S.load_state();
   }
+  while (S.phase != PH_DONE) S.trip();
+  S.store_state();
+  write_result(P, A, b, S);
 }
 
 cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6, const double* coeffs, int ncoef,
                          double* ws, double* out8, double* traj, double* obj, int* status, int* iters,
-                         cudaStream_t stream) {
+                         const SolveConfig& cfg, cudaStream_t stream, long long* n_launches) {
   if (B <= 0) return cudaSuccess;
   const int grid = (B + kBlock - 1) / kBlock;
-  mpc_solve_kernel<<<grid, kBlock, 0, stream>>>(P, B, steps, state6, coeffs, ncoef, ws, out8, traj, obj, status, iters);
-  return cudaGetLastError();
+  SolveArgs A{B, steps, 0, ncoef, state6, coeffs, ws, out8, traj, obj, status, iters};
+  long long n = 0;
+  for (int step = 0; step < steps; ++step) {
+    A.step = step;
+    if (cfg.mode == kModeFused || B < cfg.fused_below) {
+      mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 1);
+      ++n;
+    } else {
+      mpc_init_kernel<<<grid, kBlock, 0, stream>>>(P, A);
+      for (int r = 0; r < cfg.rounds; ++r) {
+        mpc_factor_kernel<<<grid, kBlock, 0, stream>>>(P, A);
+        mpc_forward_kernel<<<grid, kBlock, 0, stream>>>(P, A);
+        mpc_trial_kernel<<<grid, kBlock, 0, stream>>>(P, A);
+        mpc_accept_kernel<<<grid, kBlock, 0, stream>>>(P, A);
+      }
+      mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 0);
+      n += 2 + 4LL * cfg.rounds;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  if (n_launches) *n_launches += n;
+  return cudaSuccess;
 }
 
 // ---------------------------------------------------------------------------------------------
