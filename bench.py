@@ -189,25 +189,31 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     B, K, W = args.batch, args.steps, args.warmup
 
-    mpc = mpcmod.MPC(device=local)
-    mpc.set_solver_mode({"perpass": 0, "fused": 1}[args.mode], args.rounds, -1)
+    S = max(1, args.streams)
+    mpcs = [mpcmod.MPC(device=local) for _ in range(S)]
+    for m in mpcs:
+        m.set_solver_mode({"perpass": 0, "fused": 1}[args.mode], args.rounds, -1)
+    mpc = mpcs[0]
     nsets = 2
     sets = [make_workload(args.workload, B, seed_shift=rank * nsets + s, mpc=mpc) for s in range(nsets)]
     ncoef = sets[0][1].shape[1]
-    # device-resident, field-major inputs and outputs
+    # device-resident, field-major inputs and outputs (one output set per stream)
     d_in = [(torch.from_numpy(np.ascontiguousarray(st.T)).to(dev), torch.from_numpy(np.ascontiguousarray(cf.T)).to(dev))
             for st, cf in sets]
-    d_out8 = torch.empty((8, B), dtype=torch.float64, device=dev)
-    d_obj = torch.empty(B, dtype=torch.float64, device=dev)
-    d_status = torch.empty(B, dtype=torch.int32, device=dev)
-    d_iters = torch.empty(B, dtype=torch.int32, device=dev)
-    stream = torch.cuda.Stream(device=dev)   # a real (non-default) stream: kernels and timing events share it
+    d_out = [dict(out8=torch.empty((8, B), dtype=torch.float64, device=dev), obj=torch.empty(B, dtype=torch.float64, device=dev),
+                  status=torch.empty(B, dtype=torch.int32, device=dev), iters=torch.empty(B, dtype=torch.int32, device=dev))
+             for _ in range(S)]
+    # real (non-default) streams: kernels and timing events share them.  With S > 1 consecutive steps alternate
+    # between S solver handles / streams so that the thin tail of one batch (few problems still iterating)
+    # overlaps the bulk of the next.
+    streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     torch.cuda.synchronize()
 
     def dev_step(i):
         st, cf = d_in[i % nsets]
-        mpc.solve_batch_device(B, st.data_ptr(), cf.data_ptr(), ncoef, d_out8.data_ptr(), 0, d_obj.data_ptr(),
-                               d_status.data_ptr(), d_iters.data_ptr(), stream.cuda_stream)
+        o = d_out[i % S]
+        mpcs[i % S].solve_batch_device(B, st.data_ptr(), cf.data_ptr(), ncoef, o["out8"].data_ptr(), 0, o["obj"].data_ptr(),
+                                       o["status"].data_ptr(), o["iters"].data_ptr(), streams[i % S].cuda_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -216,32 +222,42 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     fp64_peak = mpc.fp64_peak_tflops()
-    for i in range(W):
+    for i in range(max(W, S)):
         dev_step(i)
     barrier()
-    mpc.kernel_time_ms(reset=True)
-    launches0 = mpc.launch_count()
+    for m in mpcs:
+        m.kernel_time_ms(reset=True)
+    launches0 = sum(m.launch_count() for m in mpcs)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tot_iters = 0
-    e0.record(stream)
+    e0.record(streams[0])
+    for s_ in streams[1:]:
+        s_.wait_event(e0)
     for i in range(K):
         dev_step(i)
-    e1.record(stream)
+    for s_ in streams[1:]:
+        ev = torch.cuda.Event()
+        ev.record(s_)
+        streams[0].wait_event(ev)
+    e1.record(streams[0])
     barrier()
     ms_total = e0.elapsed_time(e1)
-    kern_ms, kern_n = mpc.kernel_time_ms(reset=True)
-    launches = mpc.launch_count() - launches0
+    kern = [m.kernel_time_ms(reset=True) for m in mpcs]
+    kern_ms, kern_n = sum(k[0] for k in kern), sum(k[1] for k in kern)
+    launches = sum(m.launch_count() for m in mpcs) - launches0
     # mean iterations of the two input sets (for the algorithmic FLOP count)
     iters_mean = []
     ok_frac = []
     for s in range(nsets):
-        dev_step(s)
+        st, cf = d_in[s]
+        o = d_out[0]
+        mpc.solve_batch_device(B, st.data_ptr(), cf.data_ptr(), ncoef, o["out8"].data_ptr(), 0, o["obj"].data_ptr(),
+                               o["status"].data_ptr(), o["iters"].data_ptr(), streams[0].cuda_stream)
         torch.cuda.synchronize()
-        iters_mean.append(float(d_iters.double().mean().item()))
-        ok_frac.append(float((d_status == 0).double().mean().item()))
+        iters_mean.append(float(o["iters"].double().mean().item()))
+        ok_frac.append(float((o["status"] == 0).double().mean().item()))
     mpc.kernel_time_ms(reset=True)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -249,36 +265,43 @@ def run_ours(args):
     ms_total = float(t.item())
     value = world * B * K / (ms_total * 1e-3)
 
-    # ---- e2e: host buffers (pinned), H2D + D2H inside the timed region, through the host-buffer C-ABI call
-    pin = [(torch.from_numpy(st).pin_memory(), torch.from_numpy(cf).pin_memory()) for st, cf in sets]
-    out8_h = torch.empty((B, 8), dtype=torch.float64).pin_memory()
-    obj_h = torch.empty(B, dtype=torch.float64).pin_memory()
-    st_h = torch.empty(B, dtype=torch.int32).pin_memory()
-    it_h = torch.empty(B, dtype=torch.int32).pin_memory()
-    lib = mpcmod.load_library()
+    # ---- e2e: host buffers (pinned), H2D + D2H inside the timed region, through the host-buffer C-ABI call;
+    # S host threads, one per solver handle (the call blocks until its results are in the caller's buffers)
     import ctypes
+    from concurrent.futures import ThreadPoolExecutor
+    pin = [(torch.from_numpy(st).pin_memory(), torch.from_numpy(cf).pin_memory()) for st, cf in sets]
+    hout = [dict(out8=torch.empty((B, 8), dtype=torch.float64).pin_memory(), obj=torch.empty(B, dtype=torch.float64).pin_memory(),
+                 status=torch.empty(B, dtype=torch.int32).pin_memory(), iters=torch.empty(B, dtype=torch.int32).pin_memory())
+            for _ in range(S)]
+    lib = mpcmod.load_library()
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
 
-    def host_step(i):
+    def host_step(i, k=None):
+        k = i % S if k is None else k
         st, cf = pin[i % nsets]
-        rc = lib.b200mpc_solve_batch(mpc.handle, B, ctypes.cast(st.data_ptr(), dp), ctypes.cast(cf.data_ptr(), dp), ncoef,
-                                     ctypes.cast(out8_h.data_ptr(), dp), None, ctypes.cast(obj_h.data_ptr(), dp),
-                                     ctypes.cast(st_h.data_ptr(), ip), ctypes.cast(it_h.data_ptr(), ip))
+        o = hout[k]
+        rc = lib.b200mpc_solve_batch(mpcs[k].handle, B, ctypes.cast(st.data_ptr(), dp), ctypes.cast(cf.data_ptr(), dp), ncoef,
+                                     ctypes.cast(o["out8"].data_ptr(), dp), None, ctypes.cast(o["obj"].data_ptr(), dp),
+                                     ctypes.cast(o["status"].data_ptr(), ip), ctypes.cast(o["iters"].data_ptr(), ip))
         if rc:
             raise RuntimeError(lib.b200mpc_last_error().decode())
+
+    def worker(k, n):
+        for i in range(k, n, S):
+            host_step(i, k)
 
     for i in range(max(3, W)):
         host_step(i)
     barrier()
-    t0 = time.perf_counter()
-    for i in range(K):
-        host_step(i)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    with ThreadPoolExecutor(S) as ex:
+        t0 = time.perf_counter()
+        list(ex.map(lambda k: worker(k, K), range(S)))
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
     lat = []
-    for i in range(max(K, args.latency_reps)):
+    for i in range(max(K, args.latency_reps)):   # unloaded latency of one call
         a = time.perf_counter()
-        host_step(i)
+        host_step(i, 0)
         lat.append(time.perf_counter() - a)
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     p99 = torch.tensor([float(np.percentile(lat, 99))], dtype=torch.float64, device=dev)
@@ -286,13 +309,17 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(p99, op=dist.ReduceOp.MAX)
     e2e_value = world * B * K / float(t.item())
-    mpc.kernel_time_ms(reset=True)
+    for m in mpcs:
+        m.kernel_time_ms(reset=True)
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
         mean_it = float(np.mean(iters_mean))
         flop_per_launch = f_iter(HORIZON) * mean_it * B
-        avg_kernel_ms = kern_ms / max(1, kern_n)
+        # device time of the solver kernels per step: with one stream, the first-to-last-kernel interval of each
+        # step (CUDA events inside the C ABI); with overlapped streams the intervals overlap, so the per-step share of
+        # the timed region is used instead
+        avg_kernel_ms = kern_ms / max(1, kern_n) if S == 1 else ms_total / K
         achieved = flop_per_launch / (avg_kernel_ms * 1e-3) / 1e12
         peaks = {}
         try:
@@ -311,7 +338,7 @@ def run_ours(args):
                           traffic=None,
                           kernel=("mpc_{init,factor,forward,trial,accept,fused}_kernel: all solver kernels of one step, first to last"
                                   if args.mode == "perpass" else "mpc_fused_kernel"),
-                          avg_kernel_ms=avg_kernel_ms, launches_timed=kern_n, solver_mode=args.mode,
+                          avg_kernel_ms=avg_kernel_ms, launches_timed=kern_n, solver_mode=args.mode, streams=S,
                           flop_per_launch=flop_per_launch, mean_ip_iters=mean_it,
                           peak_source="DFMA microbenchmark in this run (b200mpc_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                           hbm_peak_gbs=peaks.get("hbm_gbs"), algorithmic_io_bytes_per_solve=(6 + ncoef + 8 + 2) * 8,
@@ -322,7 +349,8 @@ def run_ours(args):
             st, cf = sets[0]
             line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate(st[:4096], cf[:4096], args.cpu_per_core).items()}
         print(json.dumps(line))
-    mpc.close()
+    for m in mpcs:
+        m.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -338,6 +366,7 @@ def main():
     ap.add_argument("--latency-reps", type=int, default=100)
     ap.add_argument("--cpu-per-core", type=int, default=150, help="cpu_baseline: solves per host core in the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=3, help="solver handles / CUDA streams consecutive steps alternate between")
     ap.add_argument("--mode", default="perpass", choices=["perpass", "fused"], help="solver execution mode (include/b200mpc.h)")
     ap.add_argument("--rounds", type=int, default=0, help="per-pass mode: rounds before the fused finisher (0 = library default)")
     args = ap.parse_args()

@@ -54,7 +54,8 @@ _lib_lock = threading.Lock()
 
 
 def lib_path():
-    return os.path.join(_PKG, "lib", "libb200mpc.so")
+    """In-tree library; B200MPC_LIB selects another build of the same library (kernel tuning experiments)."""
+    return os.environ.get("B200MPC_LIB") or os.path.join(_PKG, "lib", "libb200mpc.so")
 
 
 def load_library():

@@ -117,10 +117,29 @@ static_assert(kNumScal <= kRec, "scalar record must fit one stage record");
 
 MPC_HD int workspace_doubles_per_problem(int N) { return kRec * (N + 1); }
 
+// MPC_PREFETCH: 0 = off, 1 = prefetch.global.L1, 2 = prefetch.global.L2 (device only)
+#ifndef MPC_PREFETCH
+#define MPC_PREFETCH 1
+#endif
 template <int LANES>
 struct Ws {
   double* b;
   MPC_HD double& operator()(int i) const { return b[(size_t)i * LANES]; }
+  // hint: rows [i, i+n) of this problem group will be read soon (each row of a warp is one 256-byte line pair)
+  MPC_HD void prefetch(int i, int n) const {
+#if defined(__CUDA_ARCH__) && MPC_PREFETCH
+#pragma unroll
+    for (int k = 0; k < n; ++k) {
+#if MPC_PREFETCH == 1
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(b + (size_t)(i + k) * LANES));
+#else
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (size_t)(i + k) * LANES));
+#endif
+    }
+#else
+    (void)i; (void)n;
+#endif
+  }
 };
 
 MPC_HD double dmax(double a, double b) { return a > b ? a : b; }
@@ -357,6 +376,10 @@ struct Solver {
     const int bT = oTR + 4 * buf, bC = oC + 6 * buf;
     for (int t = 0; t < M; ++t) {
       const int r = rec(t), rn = rec(t + 1);
+      if (t + 1 < M) {   // next stage's rows
+        w.prefetch(rn + oU, 2); w.prefetch(rn + kRec + oS, 6);
+        if (step) { w.prefetch(rn + oDU, 2); w.prefetch(rn + kRec + oDS, 6); }
+      }
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         un[j] = w(r + oU + j);
@@ -434,6 +457,10 @@ struct Solver {
     bool ok = true;
     for (int t = M - 1; t >= 0; --t) {
       const int r = rec(t), rn = rec(t + 1);
+      if (t > 0) {   // rows of stage t-1: S,U,LAM,ZL,ZU are contiguous (18 rows), then trig and the residual of rows t
+        w.prefetch(r - kRec + oS, 18); w.prefetch(r - kRec + bT, 4);
+        if (!ls) w.prefetch(r + bC, 6);
+      }
       double s[6], lam[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) { s[k] = w(r + oS + k); lam[k] = ls ? 0.0 : w(r + oLAM + k); }
@@ -578,6 +605,10 @@ struct Solver {
     double u0 = w(rec(0) + oU), u1 = w(rec(0) + oU + 1);
     for (int t = 0; t < M; ++t) {
       const int r = rec(t), rn = rec(t + 1);
+      if (t + 1 < M) {
+        w.prefetch(rn + oKF, 13); w.prefetch(rn + oS, 6); w.prefetch(rn + bT, 4); w.prefetch(rn + kRec + oU, 2);
+        if (!ls) { w.prefetch(rn + oZL, 4); w.prefetch(rn + kRec + bC, 6); }
+      }
       double K0[4], K1[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) { K0[j] = w(r + oKF + j); K1[j] = w(r + oKF + 4 + j); }
@@ -691,6 +722,7 @@ struct Solver {
     if (M > 0) { const int r = rec(M - 1); uc0 = w(r + oU); uc1 = w(r + oU + 1); duc0 = w(r + oDU); duc1 = w(r + oDU + 1); }
     for (int t = M - 1; t >= 0; --t) {
       const int r = rec(t);
+      if (t > 0) w.prefetch(r - kRec + oS, 34);   // S,U,LAM,ZL,ZU,DS,DU and both trig buffers of stage t-1 are contiguous
       double s[6], ds[6], lam[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) { s[k] = w(r + oS + k); ds[k] = w(r + oDS + k); lam[k] = ls ? 0.0 : w(r + oLAM + k); }
