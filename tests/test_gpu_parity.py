@@ -228,3 +228,26 @@ def test_device_pointer_entry_and_multi_handle(mpc):
 def test_fp64_peak_is_plausible(mpc):
     tf = mpc.fp64_peak_tflops()
     assert 5.0 < tf < 80.0, tf
+
+
+def test_cpp_drop_in_closed_loop(tmp_path):
+    """examples/mpc_to_line_main.cpp = the reference's solution/main.cpp loop on the C++ drop-in class
+    (include/b200mpc/MPC.h): compiled with g++ against libb200mpc.so, its printed trace must match the golden one."""
+    import os
+    import re
+    import subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "mpc_to_line")
+    libdir = os.path.join(ROOT, "udacitympc_b200", "lib")
+    subprocess.run(["g++", "-std=c++11", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "mpc_to_line_main.cpp"),
+                    "-L" + libdir, "-lb200mpc", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    out = subprocess.run([exe, str(tmp_path / "trace.csv")], check=True, capture_output=True, text=True).stdout
+    g = golden("config1_closed_loop.npz")
+    costs = [float(v) for v in re.findall(r"^Cost (\S+)$", out, flags=re.M)]
+    assert len(costs) == 50
+    np.testing.assert_allclose(costs, g["cost"], rtol=1e-5)   # iostream prints 6 significant digits
+    for name, col in (("x", 0), ("y", 1), ("psi", 2), ("v", 3), ("cte", 4), ("epsi", 5), ("delta", 6), ("a", 7)):
+        vals = [float(v) for v in re.findall(rf"^{name} = (\S+)$", out, flags=re.M)]
+        assert len(vals) == 50
+        np.testing.assert_allclose(vals, g["out8"][:, col], rtol=1e-5, atol=2e-6)
+    assert (tmp_path / "trace.csv").read_text().count("\n") == 51
