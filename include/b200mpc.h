@@ -125,7 +125,7 @@ int b200mpc_rollout_batch_device(b200mpc_handle* h, int B, int H, const double* 
                                  double dt, double Lf, double* d_out, void* stream);
 
 /* Execution mode of the solver (tuning; results do not depend on it).
- *   mode 0 (default)  per-pass kernels: init, then `rounds` rounds of (factor, forward, trial, accept) launched back to
+ *   mode 0 (default)  per-pass kernels: init, then `rounds` rounds of (factor, forward, step) launched back to
  *                     back on the stream, then one fused launch that finishes any problem still iterating
  *   mode 1            the fused kernel alone (one launch per solve; lowest latency for small batches)
  * rounds <= 0 / fused_below < 0 keep the current value.  Batches smaller than fused_below always use mode 1. */

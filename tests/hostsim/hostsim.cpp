@@ -34,6 +34,7 @@ int hostsim_solve_mode(const hostsim_params* hp, const double* state6, const dou
   int rows = 0, trips = 0, last_iter = -1;
   Result R;
   double df = 1.0;
+  int cur = 0;
   auto log_row = [&](Solver<1>& S) {
     if (trace && S.iter != last_iter && rows < trace_cap) {
       double* r = trace + 8 * rows++;
@@ -47,22 +48,20 @@ int hostsim_solve_mode(const hostsim_params* hp, const double* state6, const dou
     S.init(state6, coeffs, ncoef);
     while (S.phase != PH_DONE && trips < 100000) { S.trip(); ++trips; log_row(S); }
     S.finish(R, x_out, 1);
-    df = S.df;
+    df = S.df; cur = S.cur;
   } else {
     { Solver<1> S(P, ws.data()); S.init(state6, coeffs, ncoef); S.store_state(); }
     int phase = PH_FACTOR;
     while (phase != PH_DONE && trips < 400000) {
-      for (int k = 0; k < 4; ++k) {   // the four kernels of one round
+      for (int k = 0; k < 3; ++k) {   // the three kernels of one round
         Solver<1> S(P, ws.data());
         if (S.load_phase() != k) continue;
         S.set_coeffs(coeffs, ncoef);
         if (k == PH_FACTOR) S.kernel_factor();
         else if (k == PH_FORWARD) S.kernel_forward();
-        else if (k == PH_TRIAL) S.kernel_trial();
-        else S.kernel_accept();
+        else S.kernel_step();
         phase = S.load_phase();
-        if (k == PH_ACCEPT) S.load_state();
-        if (k == PH_ACCEPT) log_row(S);
+        if (k == PH_STEP) { S.load_state(); log_row(S); }
       }
       ++trips;
     }
@@ -70,11 +69,11 @@ int hostsim_solve_mode(const hostsim_params* hp, const double* state6, const dou
     S.set_coeffs(coeffs, ncoef);
     S.load_state();
     S.finish(R, x_out, 1);
-    df = S.df;
+    df = S.df; cur = S.cur;
   }
   for (int i = 0; i < 8; ++i) out8[i] = R.out8[i];
   *obj = R.obj; *iters = R.iters;
-  if (lam_out) for (int t = 0; t < P.N; ++t) for (int k = 0; k < 6; ++k) lam_out[k * P.N + t] = ws[(size_t)(t + 1) * kRec + oLAM + k] / df;
+  if (lam_out) for (int t = 0; t < P.N; ++t) for (int k = 0; k < 6; ++k) lam_out[k * P.N + t] = ws[(size_t)(t + 1) * kRec + kX * cur + xLAM + k] / df;
   if (trace_rows) *trace_rows = rows;
   return R.status;
 }

@@ -16,7 +16,7 @@ size_t solve_workspace_doubles(int N, int B);
 enum SolveMode { kModePerPass = 0, kModeFused = 1 };
 struct SolveConfig {
   int mode = kModePerPass;
-  int rounds = 24;        // per-pass mode: rounds of (factor, forward, trial, accept) before the fused finisher
+  int rounds = 24;        // per-pass mode: rounds of (factor, forward, step) before the fused finisher
   int fused_below = 2048; // batches smaller than this use the fused kernel alone (launch latency dominates)
 };
 cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6, const double* coeffs, int ncoef,

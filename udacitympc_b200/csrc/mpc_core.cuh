@@ -26,14 +26,17 @@
 // folded into stage t as a quadratic on a linear output; the (u_{t+1},u_t) smoothness coupling is carried by
 // augmenting the recursion state with the previous control: xi_t = (x,y,psi,v,epsi | delta_{t-1},a_{t-1}) in R^7.
 //
-// Execution structure.  One interior-point iteration = four sweeps over the horizon ("passes"):
+// Execution structure.  One interior-point iteration = three sweeps over the horizon ("passes"):
 //   FACTOR  (backward)  K1 derivative blocks + K2 Riccati factorisation and feed-forward
 //   FORWARD (forward)   K2 back-substitution: dx, fraction-to-the-boundary step sizes, barrier slope
-//   TRIAL   (forward)   K1 residuals/objective at the trial point + K3 filter / Armijo acceptance
-//   ACCEPT  (backward)  K2 multiplier recovery + K3 step, kappa_sigma reset, error norms, mu update, convergence
+//   STEP    (backward)  K1 residuals/objective/barrier at the trial point x + alpha dx, K2 multiplier recovery, the
+//                       trial iterate (x, lambda, z with the kappa_sigma reset) and every error norm at it, then
+//                       K3: filter / Armijo acceptance, mu update, convergence test.  The trial iterate is written
+//                       to the second copy of the iterate arrays and becomes current only if it is accepted
+//                       (first trial accepted in >99% of iterations), so a rejection costs nothing extra.
 // Every pass touches the per-problem workspace once per stage.  A problem's scalar algorithm state lives in the
-// same workspace (record -1), so each pass can run as its own kernel (high occupancy for the light passes) or all
-// four can be looped inside one kernel.
+// same workspace (record 0), so each pass can run as its own kernel (its own register budget and occupancy) or
+// all three can be looped inside one kernel.
 #pragma once
 #include <float.h>
 #include <math.h>
@@ -95,17 +98,19 @@ constexpr int kMaxFilter = 8;
 // Element i of the problem owned by lane l of a 32-problem group lives at group_base[i*LANES + l] (LANES = 32 on
 // the device: every access of a warp is one coalesced 256-byte row).  Record 0 holds the scalar state, records
 // 1..N the per-stage data of time t = 0..N-1 at fixed offsets.
+// The iterate block X = {S, U, LAM, ZL, ZU, TR, C} exists twice (current / trial); buffer b starts at 28*b.
 enum StageOff {
-  oS = 0,      // state s_t (6)
-  oU = 6,      // control u_t (2)
-  oLAM = 8,    // multipliers of the rows of time t (6)
-  oZL = 14, oZU = 16,   // bound multipliers of u_t (2+2)
-  oDS = 18, oDU = 24,   // search direction (6+2)
-  oTR = 26,    // sin/cos(psi_t), sin/cos(epsi_t): two buffers of 4 (current / trial)
-  oC = 34,     // constraint residual of the rows of time t: two buffers of 6
-  oCSOC = 46,  // second-order-correction right-hand side (6)
-  oKF = 52,    // Riccati factors of stage t: K (2x4), Lambda^-1 (3), k (2)
-  kRec = 65
+  xS = 0,      // state s_t (6)
+  xU = 6,      // control u_t (2)
+  xLAM = 8,    // multipliers of the rows of time t (6)
+  xZL = 14, xZU = 16,   // bound multipliers of u_t (2+2)
+  xTR = 18,    // sin/cos(psi_t), sin/cos(epsi_t) (4)
+  xC = 22,     // constraint residual of the rows of time t (6)
+  kX = 28,
+  oDS = 56, oDU = 62,   // search direction (6+2)
+  oCSOC = 64,  // second-order-correction right-hand side (6)
+  oKF = 70,    // Riccati factors of stage t: K (2x4), Lambda^-1 (3), k (2)
+  kRec = 83
 };
 enum ScalarD {
   dDF, dMU, dTAU, dMUMIN, dDWC, dDWL, dTHMAX, dTHMIN, dF, dTH, dPINF, dDINF, dLAM1, dZ1, dSZMAX, dSZMIN, dSLOG, dXMAX,
@@ -241,7 +246,7 @@ struct Result {
   double out8[8];
 };
 
-enum Phase { PH_FACTOR = 0, PH_FORWARD = 1, PH_TRIAL = 2, PH_ACCEPT = 3, PH_DONE = 4 };
+enum Phase { PH_FACTOR = 0, PH_FORWARD = 1, PH_STEP = 2, PH_DONE = 3 };
 enum Flags { F_INSOC = 1, F_SOCDONE = 2, F_LS = 4, F_LAMZERO = 8, F_TINYLAST = 16, F_TINYFLAG = 32, F_TINYNOW = 64 };
 
 // The per-problem solver.  All "passes" are loops over the horizon that touch the workspace once per stage.
@@ -320,22 +325,26 @@ struct Solver {
     const double nd = (t > 0 ? 1.0 : 0.0) + (t < M - 1 ? 1.0 : 0.0);
     return 2.0 * df * (wq + nd * wd);
   }
+  // constraint residual of the rows of time t+1 (MPC.cpp:130-137): sn - F(s, u)
+  MPC_HD void residual(const double* s, const double* u, const double* sn, double sp, double cp, double se, double p0,
+                       double psides, double* c) const {
+    const double vd = s[3] * u[0] * P.dtLf;
+    c[0] = sn[0] - (s[0] + s[3] * cp * P.dt);
+    c[1] = sn[1] - (s[1] + s[3] * sp * P.dt);
+    c[2] = sn[2] - (s[2] + vd);
+    c[3] = sn[3] - (s[3] + u[1] * P.dt);
+    c[4] = sn[4] - ((p0 - s[1]) + (s[3] * se * P.dt));
+    c[5] = sn[5] - ((s[2] - psides) + vd);
+  }
+  MPC_HD double state_cost(const double* s) const {
+    return P.w_cte * (s[4] * s[4]) + P.w_epsi * (s[5] * s[5]) + P.w_v * ((s[3] - P.ref_v) * (s[3] - P.ref_v));
+  }
 
   // ------------------------------------------------------------------------------------------
   // start point, bounds, scaling, z, mu  (MPC.cpp:167-203; IpGradientScaling.cpp:99-116;
-  // IpDefaultIterateInitializer.cpp:230-266, 469-649)
+  // IpDefaultIterateInitializer.cpp:230-266, 469-649), residuals / objective / barrier at the start point
   MPC_HD void init(const double* s0, const double* coef, int ncoef) {
     set_coeffs(coef, ncoef);
-    for (int t = 0; t < N; ++t) {
-      const int r = rec(t);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) { w(r + oS + k) = t == 0 ? s0[k] : 0.0; w(r + oLAM + k) = 0.0; }
-      if (t < M) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) { w(r + oU + j) = P.u_init[j]; w(r + oZL + j) = 1.0; w(r + oZU + j) = 1.0; }
-      }
-    }
-    // gradient of f at the user's start point: states zero except t=0, controls zero
     double gmax = dmax(fabs(2.0 * P.w_cte * s0[4]), fabs(2.0 * P.w_epsi * s0[5]));
     gmax = dmax(gmax, fabs(2.0 * P.w_v * (s0[3] - P.ref_v)));
     if (N > 1) gmax = dmax(gmax, fabs(2.0 * P.w_v * (0.0 - P.ref_v)));
@@ -358,69 +367,35 @@ struct Solver {
     theta_soc_old = alpha_soc = 0.0;
     n_steps = soc_count = 0;
     dualinf = lam1 = z1 = sz_max = sz_min = xmaxabs = 0.0;
-    // residuals / trig at the start point, then least-square multipliers through the same passes
-    eval_point(0.0, cur);
-    f_cur = tr_f; theta_cur = tr_theta; priminf = tr_priminf; sumlog = tr_sumlog;
-    phase = PH_FACTOR;
-  }
-
-  // ------------------------------------------------------------------------------------------
-  // f, c, trig at x + a*dx  -> TR[buf], C[buf]; scalars tr_*  (MPC.cpp:57-138)
-  MPC_HD void eval_point(double a, int buf) {
-    double s[6], sn[6], u[2], un[2];
-    const bool step = a != 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) s[k] = w(rec(0) + oS + k);   // ds_0 = 0
+    tr_f = tr_theta = tr_priminf = tr_sumlog = 0.0;
+    // states are zero except t = 0, controls at their (pushed) start value, z = 1, lambda = 0
+    double s[6], sn[6], u[2];
+    u[0] = P.u_init[0]; u[1] = P.u_init[1];
     double f = 0.0, th = 0.0, cm = 0.0, sl = 0.0;
-    u[0] = u[1] = 0.0;
-    const int bT = oTR + 4 * buf, bC = oC + 6 * buf;
-    for (int t = 0; t < M; ++t) {
-      const int r = rec(t), rn = rec(t + 1);
-      if (t + 1 < M) {   // next stage's rows
-        w.prefetch(rn + oU, 2); w.prefetch(rn + kRec + oS, 6);
-        if (step) { w.prefetch(rn + oDU, 2); w.prefetch(rn + kRec + oDS, 6); }
+    const double q = (u[0] - P.xl[0]) * (P.xu[0] - u[0]) * ((u[1] - P.xl[1]) * (P.xu[1] - u[1]));
+    const double lq = log(q);
+    for (int t = 0; t < N; ++t) {
+      const int r = rec(t);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { s[k] = t == 0 ? s0[k] : 0.0; sn[k] = 0.0; w(r + xS + k) = s[k]; w(r + xLAM + k) = 0.0; }
+      f += state_cost(s);
+      if (t < M) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { w(r + xU + j) = u[j]; w(r + xZL + j) = 1.0; w(r + xZU + j) = 1.0; }
+        double sp, cp, se, ce, p0, p1, p2, p3, c[6];
+        sincos(s[2], &sp, &cp);
+        sincos(s[5], &se, &ce);
+        poly_eval(cf, s[0], p0, p1, p2, p3);
+        residual(s, u, sn, sp, cp, se, p0, atan(p1), c);
+        w(r + xTR) = sp; w(r + xTR + 1) = cp; w(r + xTR + 2) = se; w(r + xTR + 3) = ce;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { w(r + kRec + xC + k) = c[k]; th += fabs(c[k]); cm = dmax(cm, fabs(c[k])); }
+        f += P.w_delta * (u[0] * u[0]) + P.w_a * (u[1] * u[1]);
+        sl += lq;
       }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        un[j] = w(r + oU + j);
-        if (step) un[j] += a * w(r + oDU + j);
-      }
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        sn[k] = w(rn + oS + k);
-        if (step) sn[k] += a * w(rn + oDS + k);
-      }
-      const double zl0 = w(r + oZL), zl1 = w(r + oZL + 1), zu0 = w(r + oZU), zu1 = w(r + oZU + 1);
-      double sp, cp, se, ce, p0, p1, p2, p3;
-      sincos(s[2], &sp, &cp);
-      sincos(s[5], &se, &ce);
-      poly_eval(cf, s[0], p0, p1, p2, p3);
-      const double psides = atan(p1);
-      const double vd = s[3] * un[0] * P.dtLf;
-      double c[6];
-      c[0] = sn[0] - (s[0] + s[3] * cp * P.dt);
-      c[1] = sn[1] - (s[1] + s[3] * sp * P.dt);
-      c[2] = sn[2] - (s[2] + vd);
-      c[3] = sn[3] - (s[3] + un[1] * P.dt);
-      c[4] = sn[4] - ((p0 - s[1]) + (s[3] * se * P.dt));
-      c[5] = sn[5] - ((s[2] - psides) + vd);
-      w(r + bT + 0) = sp; w(r + bT + 1) = cp; w(r + bT + 2) = se; w(r + bT + 3) = ce;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) { w(rn + bC + k) = c[k]; th += fabs(c[k]); cm = dmax(cm, fabs(c[k])); }
-      // cost of time t
-      f += P.w_cte * (s[4] * s[4]) + P.w_epsi * (s[5] * s[5]) + P.w_v * ((s[3] - P.ref_v) * (s[3] - P.ref_v));
-      f += P.w_delta * (un[0] * un[0]) + P.w_a * (un[1] * un[1]);
-      if (t > 0) f += P.w_ddelta * ((un[0] - u[0]) * (un[0] - u[0])) + P.w_da * ((un[1] - u[1]) * (un[1] - u[1]));
-      // log-barrier of the four slacks of u_t: one log of their product
-      const double q0 = safe_slack(un[0] - P.xl[0], mu, zl0, P.xl[0]) * safe_slack(P.xu[0] - un[0], mu, zu0, P.xu[0]);
-      const double q1 = safe_slack(un[1] - P.xl[1], mu, zl1, P.xl[1]) * safe_slack(P.xu[1] - un[1], mu, zu1, P.xu[1]);
-      sl += log(q0 * q1);
-      u[0] = un[0]; u[1] = un[1];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) s[k] = sn[k];
     }
-    f += P.w_cte * (s[4] * s[4]) + P.w_epsi * (s[5] * s[5]) + P.w_v * ((s[3] - P.ref_v) * (s[3] - P.ref_v));
-    tr_f = df * f; tr_theta = th; tr_priminf = cm; tr_sumlog = sl;
+    f_cur = df * f; theta_cur = th; priminf = cm; sumlog = sl;
+    phase = PH_FACTOR;
   }
 
   // ------------------------------------------------------------------------------------------
@@ -431,7 +406,7 @@ struct Solver {
     const double qv = ls ? 1.0 : 2.0 * P.w_v * df + dw, qe = ls ? 1.0 : 2.0 * P.w_epsi * df + dw,
                  qc = ls ? 1.0 : 2.0 * P.w_cte * df + dw, q0 = ls ? 1.0 : dw;
     const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df, gc2 = 2.0 * P.w_cte * df;
-    const int bT = oTR + 4 * cur, bC = use_csoc ? (int)oCSOC : oC + 6 * cur;
+    const int bX = kX * cur, bC = use_csoc ? (int)oCSOC : bX + xC;
     double pss[15], psu[4][2], puu00 = 0.0, puu10 = 0.0, puu11 = 0.0, pv[5], pu0 = 0.0, pu1 = 0.0;
 #pragma unroll
     for (int i = 0; i < 15; ++i) pss[i] = 0.0;
@@ -440,10 +415,10 @@ struct Solver {
     double lamn[6];   // lambda_{t+1}
     double rc_next;
     {
-      const int r = rec(M);
+      const int r = rec(M) + bX;
       double sT[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { lamn[k] = ls ? 0.0 : w(r + oLAM + k); sT[k] = w(r + oS + k); }
+      for (int k = 0; k < 6; ++k) { lamn[k] = ls ? 0.0 : w(r + xLAM + k); sT[k] = w(r + xS + k); }
       PS(0, 0) = q0; PS(1, 1) = q0; PS(2, 2) = q0; PS(3, 3) = qv; PS(4, 4) = qe;
       // r_s at the terminal time: grad f + lambda
       pv[0] = lamn[0]; pv[1] = lamn[1]; pv[2] = lamn[2];
@@ -452,23 +427,21 @@ struct Solver {
       rc_next = gc2 * sT[4] + lamn[4];   // grad L wrt cte_{t+1}
     }
     double un0 = 0.0, un1 = 0.0;         // u_{t+1}
-    double d0n = 0.0, d1n = 0.0;         // unused at the last stage
-    (void)d0n; (void)d1n;
     bool ok = true;
     for (int t = M - 1; t >= 0; --t) {
-      const int r = rec(t), rn = rec(t + 1);
-      if (t > 0) {   // rows of stage t-1: S,U,LAM,ZL,ZU are contiguous (18 rows), then trig and the residual of rows t
-        w.prefetch(r - kRec + oS, 18); w.prefetch(r - kRec + bT, 4);
-        if (!ls) w.prefetch(r + bC, 6);
+      const int r = rec(t) + bX, rn = rec(t + 1);
+      if (t > 0) {   // rows of stage t-1: S,U,LAM,ZL,ZU,TR are contiguous (22 rows), then the residual of rows t
+        w.prefetch(r - kRec + xS, 22);
+        if (!ls) w.prefetch(rec(t) + bC, 6);
       }
       double s[6], lam[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { s[k] = w(r + oS + k); lam[k] = ls ? 0.0 : w(r + oLAM + k); }
-      const double u0 = w(r + oU), u1 = w(r + oU + 1);
+      for (int k = 0; k < 6; ++k) { s[k] = w(r + xS + k); lam[k] = ls ? 0.0 : w(r + xLAM + k); }
+      const double u0 = w(r + xU), u1 = w(r + xU + 1);
       double um0 = 0.0, um1 = 0.0;
-      if (t > 0) { um0 = w(r - kRec + oU); um1 = w(r - kRec + oU + 1); }
-      const double sp = w(r + bT), cp = w(r + bT + 1), se = w(r + bT + 2), ce = w(r + bT + 3);
-      const double zl0 = w(r + oZL), zl1 = w(r + oZL + 1), zu0 = w(r + oZU), zu1 = w(r + oZU + 1);
+      if (t > 0) { um0 = w(r - kRec + xU); um1 = w(r - kRec + xU + 1); }
+      const double sp = w(r + xTR), cp = w(r + xTR + 1), se = w(r + xTR + 2), ce = w(r + xTR + 3);
+      const double zl0 = w(r + xZL), zl1 = w(r + xZL + 1), zu0 = w(r + xZU), zu1 = w(r + xZU + 1);
       // constraint right-hand side of rows t+1
       double rb[5], cc;
       if (ls) { rb[0] = rb[1] = rb[2] = rb[3] = rb[4] = 0.0; cc = 0.0; }
@@ -533,9 +506,12 @@ struct Solver {
 #pragma unroll
       for (int j = 0; j < 4; ++j) { K0[j] = i00 * G0[j] + i10 * G1[j]; K1[j] = i10 * G0[j] + i11 * G1[j]; }
       const double k0 = i00 * h0 + i10 * h1, k1 = i10 * h0 + i11 * h1;
+      {
+        const int ko = rec(t) + oKF;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { w(r + oKF + j) = K0[j]; w(r + oKF + 4 + j) = K1[j]; }
-      w(r + oKF + 8) = i00; w(r + oKF + 9) = i10; w(r + oKF + 10) = i11; w(r + oKF + 11) = k0; w(r + oKF + 12) = k1;
+        for (int j = 0; j < 4; ++j) { w(ko + j) = K0[j]; w(ko + 4 + j) = K1[j]; }
+        w(ko + 8) = i00; w(ko + 9) = i10; w(ko + 10) = i11; w(ko + 11) = k0; w(ko + 12) = k1;
+      }
       // Y = Pss * Abar (5x4), S = Abar^T Y (4x4, lower)
       double Y[5][4];
 #pragma unroll
@@ -593,7 +569,7 @@ struct Solver {
   // Forward sweep: dx (-> DS, DU), fraction-to-the-boundary steps, directional derivative of the barrier.
   MPC_HD void forward(bool use_csoc) {
     const bool ls = fl(F_LS);
-    const int bT = oTR + 4 * cur, bC = use_csoc ? (int)oCSOC : oC + 6 * cur;
+    const int bX = kX * cur, bC = use_csoc ? (int)oCSOC : bX + xC;
     const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df, gc2 = 2.0 * P.w_cte * df;
     const double tinytol = 10.0 * DBL_EPSILON;
     double ds[6] = {0, 0, 0, 0, 0, 0}, dup0 = 0.0, dup1 = 0.0;
@@ -602,21 +578,22 @@ struct Solver {
     double um0 = 0.0, um1 = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) w(rec(0) + oDS + k) = 0.0;
-    double u0 = w(rec(0) + oU), u1 = w(rec(0) + oU + 1);
+    double u0 = w(rec(0) + bX + xU), u1 = w(rec(0) + bX + xU + 1);
     for (int t = 0; t < M; ++t) {
-      const int r = rec(t), rn = rec(t + 1);
+      const int r = rec(t) + bX, rn = rec(t + 1);
       if (t + 1 < M) {
-        w.prefetch(rn + oKF, 13); w.prefetch(rn + oS, 6); w.prefetch(rn + bT, 4); w.prefetch(rn + kRec + oU, 2);
-        if (!ls) { w.prefetch(rn + oZL, 4); w.prefetch(rn + kRec + bC, 6); }
+        w.prefetch(rn + oKF, 13); w.prefetch(rn + bX + xS, 6); w.prefetch(rn + bX + xTR, 4); w.prefetch(rn + kRec + bX + xU, 2);
+        if (!ls) { w.prefetch(rn + bX + xZL, 4); w.prefetch(rn + kRec + bC, 6); }
       }
+      const int ko = rec(t) + oKF;
       double K0[4], K1[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { K0[j] = w(r + oKF + j); K1[j] = w(r + oKF + 4 + j); }
-      const double i00 = w(r + oKF + 8), i10 = w(r + oKF + 9), i11 = w(r + oKF + 10), k0 = w(r + oKF + 11), k1 = w(r + oKF + 12);
+      for (int j = 0; j < 4; ++j) { K0[j] = w(ko + j); K1[j] = w(ko + 4 + j); }
+      const double i00 = w(ko + 8), i10 = w(ko + 9), i11 = w(ko + 10), k0 = w(ko + 11), k1 = w(ko + 12);
       double s[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) s[k] = w(r + oS + k);
-      const double sp = w(r + bT), cp = w(r + bT + 1), se = w(r + bT + 2), ce = w(r + bT + 3);
+      for (int k = 0; k < 6; ++k) s[k] = w(r + xS + k);
+      const double sp = w(r + xTR), cp = w(r + xTR + 1), se = w(r + xTR + 2), ce = w(r + xTR + 3);
       double c[6];
       if (ls) { c[0] = c[1] = c[2] = c[3] = c[4] = c[5] = 0.0; }
       else {
@@ -624,19 +601,19 @@ struct Solver {
         for (int k = 0; k < 6; ++k) c[k] = w(rn + bC + k);
       }
       double un0 = 0.0, un1 = 0.0;
-      if (t < M - 1) { un0 = w(rn + oU); un1 = w(rn + oU + 1); }
+      if (t < M - 1) { un0 = w(rn + bX + xU); un1 = w(rn + bX + xU + 1); }
       double d0 = 0.0, d1 = 0.0;
       if (t > 0 && !ls) { d0 = 2.0 * df * P.w_ddelta; d1 = 2.0 * df * P.w_da; }
       const double e0 = d0 * dup0, e1 = d1 * dup1;
       const double du0 = -(K0[0] * ds[0] + K0[1] * ds[1] + K0[2] * ds[2] + K0[3] * ds[3] + k0) + (i00 * e0 + i10 * e1);
       const double du1 = -(K1[0] * ds[0] + K1[1] * ds[1] + K1[2] * ds[2] + K1[3] * ds[3] + k1) + (i10 * e0 + i11 * e1);
-      w(r + oDU) = du0; w(r + oDU + 1) = du1;
+      w(rec(t) + oDU) = du0; w(rec(t) + oDU + 1) = du1;
       double p0, p1, p2, p3;
       poly_eval(cf, s[0], p0, p1, p2, p3);
       const Lin A = make_lin(P, s[3], u0, sp, cp, se, ce, p1, p2);
       if (!ls) {
         // objective / barrier directional derivative and step bounds for u_t
-        const double zl0 = w(r + oZL), zl1 = w(r + oZL + 1), zu0 = w(r + oZU), zu1 = w(r + oZU + 1);
+        const double zl0 = w(r + xZL), zl1 = w(r + xZL + 1), zu0 = w(r + xZU), zu1 = w(r + xZU + 1);
         const double sl0 = safe_slack(u0 - P.xl[0], mu, zl0, P.xl[0]), su0 = safe_slack(P.xu[0] - u0, mu, zu0, P.xu[0]);
         const double sl1 = safe_slack(u1 - P.xl[1], mu, zl1, P.xl[1]), su1 = safe_slack(P.xu[1] - u1, mu, zu1, P.xu[1]);
         const double isl0 = 1.0 / sl0, isu0 = 1.0 / su0, isl1 = 1.0 / sl1, isu1 = 1.0 / su1;
@@ -672,74 +649,152 @@ struct Solver {
     if (!ls) {
       double s[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { s[k] = w(rec(M) + oS + k); nottiny = nottiny || fabs(ds[k]) > tinytol * (fabs(s[k]) + 1.0); }
+      for (int k = 0; k < 6; ++k) { s[k] = w(rec(M) + bX + xS + k); nottiny = nottiny || fabs(ds[k]) > tinytol * (fabs(s[k]) + 1.0); }
       gbd += gv2 * (s[3] - P.ref_v) * ds[3] + gc2 * s[4] * ds[4] + ge2 * s[5] * ds[5];
     }
     fw_alpha_pr = a_pr; fw_alpha_du = a_du; fw_gbd = gbd; fw_tiny = !nottiny;
   }
 
   // ------------------------------------------------------------------------------------------
-  // Backward sweep after the line search: dlam from the stationarity rows, then the new iterate
-  // (x += a dx, lam += a dlam, z += a_du dz with the kappa_sigma safeguard, IpIpoptAlg.cpp:880-951) and
-  // every norm the convergence test / mu update need at it (IpIpoptCalculatedQuantities.cpp:2672-2832,3279-3306).
-  // nbuf = TR/C buffer that holds the accepted trial point.
-  MPC_HD void accept(double a, double a_du, double dw, int nbuf) {
-    const bool ls = fl(F_LS), lam_zero = fl(F_LAMZERO);
-    const double qv = ls ? 1.0 : 2.0 * P.w_v * df + dw, qe = ls ? 1.0 : 2.0 * P.w_epsi * df + dw,
-                 qc = ls ? 1.0 : 2.0 * P.w_cte * df + dw, q0 = ls ? 1.0 : dw;
+  // Least-square multiplier initialisation (IpLeastSquareMults.cpp:40-94): lambda from the stationarity rows of the
+  // H = I system solved by factor()/forward() in F_LS mode; x, z unchanged.  Also every norm the convergence
+  // test / mu update need at the start point.  zero = discard the estimate (||lambda||_inf > 1000).
+  MPC_HD void accept_ls(bool zero) {
     const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df, gc2 = 2.0 * P.w_cte * df;
-    const int bTo = oTR + 4 * cur, bTn = oTR + 4 * nbuf;
-    double lp[6], ln[6], lo[6];   // lambda^+_{t+1}, lambda_new_{t+1}, lambda_old_{t+1}
+    const int bX = kX * cur;
+    double lp[6], ln[6];
     double dinf = 0.0, l1 = 0.0, zz1 = 0.0, szmx = 0.0, szmn = 1e300, xm = 0.0, dlm = 0.0;
+    {
+      const int r = rec(M) + bX;
+      double s[6], ds[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { s[k] = w(r + xS + k); ds[k] = w(rec(M) + oDS + k); xm = dmax(xm, fabs(s[k])); }
+      lp[0] = -ds[0]; lp[1] = -ds[1]; lp[2] = -ds[2];
+      lp[3] = -ds[3] - gv2 * (s[3] - P.ref_v);
+      lp[4] = -ds[4] - gc2 * s[4];
+      lp[5] = -ds[5] - ge2 * s[5];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { dlm = dmax(dlm, fabs(lp[k])); ln[k] = zero ? 0.0 : lp[k]; w(r + xLAM + k) = ln[k]; l1 += fabs(ln[k]); }
+      dinf = dmax(dinf, dmax(fabs(ln[0]), dmax(fabs(ln[1]), fabs(ln[2]))));
+      dinf = dmax(dinf, fabs(gv2 * (s[3] - P.ref_v) + ln[3]));
+      dinf = dmax(dinf, fabs(gc2 * s[4] + ln[4]));
+      dinf = dmax(dinf, fabs(ge2 * s[5] + ln[5]));
+    }
+    double un0 = 0.0, un1 = 0.0;
+    for (int t = M - 1; t >= 0; --t) {
+      const int r = rec(t) + bX;
+      double s[6], ds[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { s[k] = w(r + xS + k); ds[k] = w(rec(t) + oDS + k); xm = dmax(xm, fabs(s[k])); }
+      const double u0 = w(r + xU), u1 = w(r + xU + 1);
+      double um0 = 0.0, um1 = 0.0;
+      if (t > 0) { um0 = w(r - kRec + xU); um1 = w(r - kRec + xU + 1); }
+      const double sp = w(r + xTR), cp = w(r + xTR + 1), se = w(r + xTR + 2), ce = w(r + xTR + 3);
+      const double zl0 = w(r + xZL), zl1 = w(r + xZL + 1), zu0 = w(r + xZU), zu1 = w(r + xZU + 1);
+      double p0, p1, p2, p3;
+      poly_eval(cf, s[0], p0, p1, p2, p3);
+      const Lin A = make_lin(P, s[3], u0, sp, cp, se, ce, p1, p2);
+      double at[6], nl[6];
+      applyAT6(A, lp, at);
+      nl[0] = at[0] - ds[0];
+      nl[1] = at[1] - ds[1];
+      nl[2] = at[2] - ds[2];
+      nl[3] = at[3] - ds[3] - gv2 * (s[3] - P.ref_v);
+      nl[4] = -ds[4] - gc2 * s[4];
+      nl[5] = at[5] - ds[5] - ge2 * s[5];
+      double atn[6];
+      applyAT6(A, ln, atn);
+      double lnew[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        lp[k] = nl[k]; dlm = dmax(dlm, fabs(nl[k]));
+        lnew[k] = zero ? 0.0 : nl[k];
+        w(r + xLAM + k) = lnew[k];
+        l1 += fabs(lnew[k]);
+      }
+      xm = dmax(xm, dmax(fabs(u0), fabs(u1)));
+      const double sl0 = safe_slack(u0 - P.xl[0], mu, zl0, P.xl[0]), su0 = safe_slack(P.xu[0] - u0, mu, zu0, P.xu[0]);
+      const double sl1 = safe_slack(u1 - P.xl[1], mu, zl1, P.xl[1]), su1 = safe_slack(P.xu[1] - u1, mu, zu1, P.xu[1]);
+      zz1 += zl0 + zl1 + zu0 + zu1;
+      const double c0 = sl0 * zl0, c1 = sl1 * zl1, c2 = su0 * zu0, c3 = su1 * zu1;
+      szmx = dmax(szmx, dmax(dmax(c0, c1), dmax(c2, c3)));
+      szmn = dmin(szmn, dmin(dmin(c0, c1), dmin(c2, c3)));
+      dinf = dmax(dinf, dmax(fabs(lnew[0] - atn[0]), dmax(fabs(lnew[1] - atn[1]), fabs(lnew[2] - atn[2]))));
+      dinf = dmax(dinf, fabs(gv2 * (s[3] - P.ref_v) + lnew[3] - atn[3]));
+      dinf = dmax(dinf, fabs(gc2 * s[4] + lnew[4]));
+      dinf = dmax(dinf, fabs(ge2 * s[5] + lnew[5] - atn[5]));
+      const double g0 = grad_u(0, t, u0, um0, un0) - A.beta * (ln[2] + ln[5]) - zl0 + zu0;
+      const double g1 = grad_u(1, t, u1, um1, un1) - P.dt * ln[3] - zl1 + zu1;
+      dinf = dmax(dinf, dmax(fabs(g0), fabs(g1)));
+#pragma unroll
+      for (int k = 0; k < 6; ++k) ln[k] = lnew[k];
+      un0 = u0; un1 = u1;
+    }
+    dualinf = dinf; lam1 = l1; z1 = zz1; sz_max = szmx; sz_min = szmn; xmaxabs = xm; dlam_max = dlm;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // The fused STEP sweep (backward).  For the trial step sizes (a for x and lambda, a_du for z) it computes, stage by
+  // stage: the trial point x + a dx with its trig values, constraint residuals, objective and log-barrier
+  // (MPC.cpp:57-138; what Ipopt evaluates in the line search), dlam from the stationarity rows of the CURRENT
+  // linearisation, the trial multipliers lambda + a dlam and z + a_du dz with the kappa_sigma reset
+  // (IpIpoptAlg.cpp:880-951), and every norm the convergence test / mu update need at the trial iterate
+  // (IpIpoptCalculatedQuantities.cpp:2672-2832, 3279-3306).  Everything is written to the OTHER copy of the iterate
+  // block; the caller flips `cur` if the trial point is accepted.
+  MPC_HD void step_sweep(double a, double a_du, double dw) {
+    const double qv = 2.0 * P.w_v * df + dw, qe = 2.0 * P.w_epsi * df + dw, qc = 2.0 * P.w_cte * df + dw, q0 = dw;
+    const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df, gc2 = 2.0 * P.w_cte * df;
+    const int bO = kX * cur, bN = kX * (cur ^ 1);
+    double lp[6], lo[6], ln[6];   // lambda^+_{t+1}, lambda_old_{t+1}, lambda_new_{t+1}
+    double snn[6];                // s_new at t+1
+    double dinf = 0.0, l1 = 0.0, zz1 = 0.0, szmx = 0.0, szmn = 1e300, xm = 0.0, dlm = 0.0;
+    double f = 0.0, th = 0.0, cm = 0.0, slog = 0.0;
     {
       const int r = rec(M);
       double s[6], ds[6], lam[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { s[k] = w(r + oS + k); ds[k] = w(r + oDS + k); lam[k] = (ls) ? 0.0 : w(r + oLAM + k); }
+      for (int k = 0; k < 6; ++k) { s[k] = w(r + bO + xS + k); ds[k] = w(r + oDS + k); lam[k] = w(r + bO + xLAM + k); }
       lp[0] = -q0 * ds[0]; lp[1] = -q0 * ds[1]; lp[2] = -q0 * ds[2];
       lp[3] = -qv * ds[3] - gv2 * (s[3] - P.ref_v);
       lp[4] = -qc * ds[4] - gc2 * s[4];
       lp[5] = -qe * ds[5] - ge2 * s[5];
-      double sn[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         lo[k] = lam[k];
         dlm = dmax(dlm, fabs(lp[k] - lam[k]));
-        ln[k] = lam_zero ? 0.0 : (ls ? lp[k] : lam[k] + a * (lp[k] - lam[k]));
-        sn[k] = ls ? s[k] : s[k] + a * ds[k];
-        w(r + oLAM + k) = ln[k];
-        if (!ls) w(r + oS + k) = sn[k];
+        ln[k] = lam[k] + a * (lp[k] - lam[k]);
+        snn[k] = s[k] + a * ds[k];
+        w(r + bN + xLAM + k) = ln[k];
+        w(r + bN + xS + k) = snn[k];
         l1 += fabs(ln[k]);
-        xm = dmax(xm, fabs(sn[k]));
+        xm = dmax(xm, fabs(snn[k]));
       }
+      f += state_cost(snn);
       dinf = dmax(dinf, dmax(fabs(ln[0]), dmax(fabs(ln[1]), fabs(ln[2]))));
-      dinf = dmax(dinf, fabs(gv2 * (sn[3] - P.ref_v) + ln[3]));
-      dinf = dmax(dinf, fabs(gc2 * sn[4] + ln[4]));
-      dinf = dmax(dinf, fabs(ge2 * sn[5] + ln[5]));
+      dinf = dmax(dinf, fabs(gv2 * (snn[3] - P.ref_v) + ln[3]));
+      dinf = dmax(dinf, fabs(gc2 * snn[4] + ln[4]));
+      dinf = dmax(dinf, fabs(ge2 * snn[5] + ln[5]));
     }
     double unn0 = 0.0, unn1 = 0.0;   // u_new at t+1
     double uc0 = 0.0, uc1 = 0.0, duc0 = 0.0, duc1 = 0.0;
-    if (M > 0) { const int r = rec(M - 1); uc0 = w(r + oU); uc1 = w(r + oU + 1); duc0 = w(r + oDU); duc1 = w(r + oDU + 1); }
+    { const int r = rec(M - 1); uc0 = w(r + bO + xU); uc1 = w(r + bO + xU + 1); duc0 = w(r + oDU); duc1 = w(r + oDU + 1); }
     for (int t = M - 1; t >= 0; --t) {
       const int r = rec(t);
-      if (t > 0) w.prefetch(r - kRec + oS, 34);   // S,U,LAM,ZL,ZU,DS,DU and both trig buffers of stage t-1 are contiguous
+      if (t > 0) { w.prefetch(r - kRec + bO + xS, 22); w.prefetch(r - kRec + oDS, 8); }
       double s[6], ds[6], lam[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { s[k] = w(r + oS + k); ds[k] = w(r + oDS + k); lam[k] = ls ? 0.0 : w(r + oLAM + k); }
+      for (int k = 0; k < 6; ++k) { s[k] = w(r + bO + xS + k); ds[k] = w(r + oDS + k); lam[k] = w(r + bO + xLAM + k); }
       const double u0 = uc0, u1 = uc1, du0 = duc0, du1 = duc1;
       double um0 = 0.0, um1 = 0.0, dum0 = 0.0, dum1 = 0.0;
-      if (t > 0) { um0 = w(r - kRec + oU); um1 = w(r - kRec + oU + 1); dum0 = w(r - kRec + oDU); dum1 = w(r - kRec + oDU + 1); }
-      const double spo = w(r + bTo), cpo = w(r + bTo + 1), seo = w(r + bTo + 2), ceo = w(r + bTo + 3);
-      const double spn = w(r + bTn), cpn = w(r + bTn + 1), sen = w(r + bTn + 2), cen = w(r + bTn + 3);
-      double zl0 = w(r + oZL), zl1 = w(r + oZL + 1), zu0 = w(r + oZU), zu1 = w(r + oZU + 1);
-      // ---- old point: lambda^+_t
+      if (t > 0) { um0 = w(r - kRec + bO + xU); um1 = w(r - kRec + bO + xU + 1); dum0 = w(r - kRec + oDU); dum1 = w(r - kRec + oDU + 1); }
+      double zl0 = w(r + bO + xZL), zl1 = w(r + bO + xZL + 1), zu0 = w(r + bO + xZU), zu1 = w(r + bO + xZU + 1);
+      // ---- current point: lambda^+_t from the stationarity rows
       {
+        const double spo = w(r + bO + xTR), cpo = w(r + bO + xTR + 1), seo = w(r + bO + xTR + 2), ceo = w(r + bO + xTR + 3);
         double p0, p1, p2, p3;
         poly_eval(cf, s[0], p0, p1, p2, p3);
         const Lin A = make_lin(P, s[3], u0, spo, cpo, seo, ceo, p1, p2);
-        Hes H;
-        if (ls) { H.xx = H.pp = H.vp = H.ee = H.ev = H.m = 0.0; }
-        else H = make_hes(P, lo, s[3], spo, cpo, seo, ceo, p1, p2, p3);
+        const Hes H = make_hes(P, lo, s[3], spo, cpo, seo, ceo, p1, p2, p3);
         double at[6];
         applyAT6(A, lp, at);
         double nl[6];
@@ -752,38 +807,42 @@ struct Solver {
 #pragma unroll
         for (int k = 0; k < 6; ++k) { lp[k] = nl[k]; lo[k] = lam[k]; dlm = dmax(dlm, fabs(nl[k] - lam[k])); }
       }
-      // ---- new point
-      double sn[6], lnew[6];
+      // ---- trial point
+      double sn[6], lnew[6], un[2];
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
-        sn[k] = ls ? s[k] : s[k] + a * ds[k];
-        lnew[k] = lam_zero ? 0.0 : (ls ? lp[k] : lam[k] + a * (lp[k] - lam[k]));
-        w(r + oLAM + k) = lnew[k];
-        if (!ls && t > 0) w(r + oS + k) = sn[k];
+        sn[k] = s[k] + a * ds[k];
+        lnew[k] = lam[k] + a * (lp[k] - lam[k]);
+        w(r + bN + xLAM + k) = lnew[k];
+        w(r + bN + xS + k) = sn[k];
         l1 += fabs(lnew[k]);
         xm = dmax(xm, fabs(sn[k]));
       }
-      const double un0 = ls ? u0 : u0 + a * du0, un1 = ls ? u1 : u1 + a * du1;
-      const double umn0 = ls ? um0 : um0 + a * dum0, umn1 = ls ? um1 : um1 + a * dum1;
-      xm = dmax(xm, dmax(fabs(un0), fabs(un1)));
-      if (!ls) {
+      un[0] = u0 + a * du0; un[1] = u1 + a * du1;
+      const double umn0 = um0 + a * dum0, umn1 = um1 + a * dum1;
+      xm = dmax(xm, dmax(fabs(un[0]), fabs(un[1])));
+      w(r + bN + xU) = un[0]; w(r + bN + xU + 1) = un[1];
+      {
         const double sl0 = safe_slack(u0 - P.xl[0], mu, zl0, P.xl[0]), su0 = safe_slack(P.xu[0] - u0, mu, zu0, P.xu[0]);
         const double sl1 = safe_slack(u1 - P.xl[1], mu, zl1, P.xl[1]), su1 = safe_slack(P.xu[1] - u1, mu, zu1, P.xu[1]);
+        // the barrier of the trial point is evaluated with the current z (only matters in the slack safeguard)
+        const double b0 = safe_slack(un[0] - P.xl[0], mu, zl0, P.xl[0]) * safe_slack(P.xu[0] - un[0], mu, zu0, P.xu[0]);
+        const double b1 = safe_slack(un[1] - P.xl[1], mu, zl1, P.xl[1]) * safe_slack(P.xu[1] - un[1], mu, zu1, P.xu[1]);
+        slog += log(b0 * b1);
         zl0 += a_du * ((mu - sl0 * zl0 - zl0 * du0) / sl0);
         zu0 += a_du * ((mu - su0 * zu0 + zu0 * du0) / su0);
         zl1 += a_du * ((mu - sl1 * zl1 - zl1 * du1) / sl1);
         zu1 += a_du * ((mu - su1 * zu1 + zu1 * du1) / su1);
       }
-      const double nsl0 = safe_slack(un0 - P.xl[0], mu, zl0, P.xl[0]), nsu0 = safe_slack(P.xu[0] - un0, mu, zu0, P.xu[0]);
-      const double nsl1 = safe_slack(un1 - P.xl[1], mu, zl1, P.xl[1]), nsu1 = safe_slack(P.xu[1] - un1, mu, zu1, P.xu[1]);
-      if (!ls) {   // kappa_sigma = 1e10
+      const double nsl0 = safe_slack(un[0] - P.xl[0], mu, zl0, P.xl[0]), nsu0 = safe_slack(P.xu[0] - un[0], mu, zu0, P.xu[0]);
+      const double nsl1 = safe_slack(un[1] - P.xl[1], mu, zl1, P.xl[1]), nsu1 = safe_slack(P.xu[1] - un[1], mu, zu1, P.xu[1]);
+      {   // kappa_sigma = 1e10
         const double m0 = mu / nsl0, m1 = mu / nsu0, m2 = mu / nsl1, m3 = mu / nsu1;
         zl0 = dclamp(zl0, 1e-10 * m0, 1e10 * m0);
         zu0 = dclamp(zu0, 1e-10 * m1, 1e10 * m1);
         zl1 = dclamp(zl1, 1e-10 * m2, 1e10 * m2);
         zu1 = dclamp(zu1, 1e-10 * m3, 1e10 * m3);
-        w(r + oZL) = zl0; w(r + oZL + 1) = zl1; w(r + oZU) = zu0; w(r + oZU + 1) = zu1;
-        w(r + oU) = un0; w(r + oU + 1) = un1;
+        w(r + bN + xZL) = zl0; w(r + bN + xZL + 1) = zl1; w(r + bN + xZU) = zu0; w(r + bN + xZU + 1) = zu1;
       }
       zz1 += zl0 + zl1 + zu0 + zu1;
       {
@@ -791,27 +850,36 @@ struct Solver {
         szmx = dmax(szmx, dmax(dmax(c0, c1), dmax(c2, c3)));
         szmn = dmin(szmn, dmin(dmin(c0, c1), dmin(c2, c3)));
       }
-      // grad_x L at the new point
+      // residuals, objective and grad_x L at the trial point
       {
-        double p0, p1, p2, p3;
+        double spn, cpn, sen, cen, p0, p1, p2, p3, c[6];
+        sincos(sn[2], &spn, &cpn);
+        sincos(sn[5], &sen, &cen);
         poly_eval(cf, sn[0], p0, p1, p2, p3);
-        const Lin A = make_lin(P, sn[3], un0, spn, cpn, sen, cen, p1, p2);
+        residual(sn, un, snn, spn, cpn, sen, p0, atan(p1), c);
+        w(r + bN + xTR) = spn; w(r + bN + xTR + 1) = cpn; w(r + bN + xTR + 2) = sen; w(r + bN + xTR + 3) = cen;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { w(r + kRec + bN + xC + k) = c[k]; th += fabs(c[k]); cm = dmax(cm, fabs(c[k])); }
+        f += state_cost(sn) + P.w_delta * (un[0] * un[0]) + P.w_a * (un[1] * un[1]);
+        if (t > 0) f += P.w_ddelta * ((un[0] - umn0) * (un[0] - umn0)) + P.w_da * ((un[1] - umn1) * (un[1] - umn1));
+        const Lin A = make_lin(P, sn[3], un[0], spn, cpn, sen, cen, p1, p2);
         double at[6];
         applyAT6(A, ln, at);
         dinf = dmax(dinf, dmax(fabs(lnew[0] - at[0]), dmax(fabs(lnew[1] - at[1]), fabs(lnew[2] - at[2]))));
         dinf = dmax(dinf, fabs(gv2 * (sn[3] - P.ref_v) + lnew[3] - at[3]));
         dinf = dmax(dinf, fabs(gc2 * sn[4] + lnew[4]));
         dinf = dmax(dinf, fabs(ge2 * sn[5] + lnew[5] - at[5]));
-        const double g0 = grad_u(0, t, un0, umn0, unn0) - A.beta * (ln[2] + ln[5]) - zl0 + zu0;
-        const double g1 = grad_u(1, t, un1, umn1, unn1) - P.dt * ln[3] - zl1 + zu1;
+        const double g0 = grad_u(0, t, un[0], umn0, unn0) - A.beta * (ln[2] + ln[5]) - zl0 + zu0;
+        const double g1 = grad_u(1, t, un[1], umn1, unn1) - P.dt * ln[3] - zl1 + zu1;
         dinf = dmax(dinf, dmax(fabs(g0), fabs(g1)));
       }
 #pragma unroll
-      for (int k = 0; k < 6; ++k) ln[k] = lnew[k];
-      unn0 = un0; unn1 = un1;
+      for (int k = 0; k < 6; ++k) { ln[k] = lnew[k]; snn[k] = sn[k]; }
+      unn0 = un[0]; unn1 = un[1];
       uc0 = um0; uc1 = um1; duc0 = dum0; duc1 = dum1;
     }
     dualinf = dinf; lam1 = l1; z1 = zz1; sz_max = szmx; sz_min = szmn; xmaxabs = xm; dlam_max = dlm;
+    tr_f = df * f; tr_theta = th; tr_priminf = cm; tr_sumlog = slog;
   }
 
   // ------------------------------------------------------------------------------------------
@@ -893,29 +961,31 @@ struct Solver {
   }
 
   // ------------------------------------------------------------------------------------------
-  // The four passes with the control logic that follows each.  In the common case a problem runs FACTOR ->
-  // FORWARD -> TRIAL -> ACCEPT once per interior-point iteration; rare events (inertia correction, backtracking,
-  // second order correction) take extra rounds without stalling the other problems.
+  // The three passes with the control logic that follows each.  In the common case a problem runs FACTOR ->
+  // FORWARD -> STEP once per interior-point iteration; rare events (inertia correction, backtracking, second order
+  // correction) take extra rounds without stalling the other problems.
   MPC_HD void do_factor() {
     const bool ok = factor(dw_curr, fl(F_INSOC));
     if (ok) phase = PH_FORWARD;
-    else {   // IpPDPerturbationHandler.cpp:347-391
-      if (dw_curr == 0.0) dw_curr = dw_last == 0.0 ? 1e-4 : dmax(1e-20, dw_last / 3.0);
-      else dw_curr *= (dw_last == 0.0 || 1e5 * dw_last < dw_curr) ? 100.0 : 8.0;
-      if (dw_curr > 1e20) { status = kErrorInStepComputation; phase = PH_DONE; }
-    }
+    else factor_failed();
+  }
+  MPC_HD void factor_failed() {   // IpPDPerturbationHandler.cpp:347-391
+    if (dw_curr == 0.0) dw_curr = dw_last == 0.0 ? 1e-4 : dmax(1e-20, dw_last / 3.0);
+    else dw_curr *= (dw_last == 0.0 || 1e5 * dw_last < dw_curr) ? 100.0 : 8.0;
+    if (dw_curr > 1e20) { status = kErrorInStepComputation; phase = PH_DONE; }
   }
   MPC_HD void do_forward() {
     forward(fl(F_INSOC));
     forward_logic();
   }
   MPC_HD void forward_logic() {
-    if (fl(F_LS)) { phase = PH_ACCEPT; return; }
+    phase = PH_STEP;
+    if (fl(F_LS)) return;
     alpha_du = fw_alpha_du;
     if (fl(F_INSOC)) {
       alpha = fw_alpha_pr;   // alpha_primal_soc
     } else if (fl(F_SOCDONE)) {
-      // direction restored after a failed SOC: resume backtracking with the alpha set in do_trial
+      // direction restored after a failed SOC: resume backtracking with the alpha set in step_logic
     } else {
       ref_theta = theta_cur;
       ref_barr = f_cur - mu * sumlog;
@@ -935,66 +1005,62 @@ struct Solver {
         alpha_min = 0.05 * am;
       }
     }
-    phase = PH_TRIAL;
   }
-  MPC_HD void do_trial() {
-    eval_point(alpha, cur ^ 1);
-    trial_logic();
+  MPC_HD void do_step() {
+    step_pass();
+    step_logic();
   }
-  MPC_HD void trial_logic() {
-    const double tbarr = tr_f - mu * tr_sumlog;
-    const bool tiny_now = fl(F_TINYNOW), in_soc = fl(F_INSOC);
-    bool acc;
-    if (tiny_now) acc = true;
-    else {
-      if (!in_soc) alpha_test = alpha;
-      acc = check_accept(alpha_test, tr_theta, tbarr);
-    }
-    if (acc) {
-      if (!tiny_now && (!is_ftype(alpha_test) || !armijo(alpha_test, tbarr)))
-        filter_add(ref_barr - 1e-8 * ref_theta, (1.0 - 1e-5) * ref_theta);
-      phase = PH_ACCEPT;
-    } else if (in_soc) {
-      ++soc_count;
-      if (soc_count < 4 && tr_theta <= 0.99 * theta_soc_old) {   // another correction
-        theta_soc_old = tr_theta;
-        alpha_soc = alpha;
-        build_csoc(alpha_soc);
-        phase = PH_FACTOR;
-      } else {   // give up: restore the Newton direction, continue backtracking
-        setfl(F_INSOC, false); setfl(F_SOCDONE, true);
-        alpha = 0.5 * alpha_max; n_steps = 1;
-        phase = alpha > alpha_min ? PH_FACTOR : PH_DONE;
-        if (phase == PH_DONE) status = kRestorationFailed;
-      }
-    } else if (!fl(F_SOCDONE) && alpha == alpha_max && ref_theta <= tr_theta) {   // start SOC (IpFilterLSAcceptor.cpp:473-587)
-      setfl(F_INSOC, true); soc_count = 0;
-      theta_soc_old = tr_theta;
-      alpha_soc = alpha;
-      init_csoc();
-      build_csoc(alpha_soc);
-      phase = PH_FACTOR;
-    } else {
-      alpha *= 0.5; ++n_steps;
-      if (!(alpha > alpha_min)) { status = kRestorationFailed; phase = PH_DONE; }
-    }
+  MPC_HD void step_pass() {
+    if (fl(F_LS)) accept_ls(fl(F_LAMZERO));
+    else step_sweep(alpha, alpha_du, dw_curr);
   }
-  MPC_HD void do_accept() {
-    accept_pass();
-    accept_logic();
-  }
-  MPC_HD void accept_pass() {
-    if (fl(F_LS)) accept(0.0, 0.0, 0.0, cur);
-    else accept(alpha, alpha_du, dw_curr, cur ^ 1);
-  }
-  MPC_HD void accept_logic() {
+  MPC_HD void step_logic() {
     if (fl(F_LS)) {
       if (!fl(F_LAMZERO) && dlam_max > 1000.0) { setfl(F_LAMZERO, true); return; }   // constr_mult_init_max: redo with lambda = 0
       setfl(F_LS, false); setfl(F_LAMZERO, false);
     } else {
+      // ---- line search decision on the trial point (IpBacktrackingLineSearch.cpp:637-797)
+      const double tbarr = tr_f - mu * tr_sumlog;
+      const bool tiny_now = fl(F_TINYNOW), in_soc = fl(F_INSOC);
+      bool acc;
+      if (tiny_now) acc = true;
+      else {
+        if (!in_soc) alpha_test = alpha;
+        acc = check_accept(alpha_test, tr_theta, tbarr);
+      }
+      if (!acc) {
+        if (in_soc) {
+          ++soc_count;
+          if (soc_count < 4 && tr_theta <= 0.99 * theta_soc_old) {   // another correction
+            theta_soc_old = tr_theta;
+            alpha_soc = alpha;
+            build_csoc(alpha_soc);
+            phase = PH_FACTOR;
+          } else {   // give up: restore the Newton direction, continue backtracking
+            setfl(F_INSOC, false); setfl(F_SOCDONE, true);
+            alpha = 0.5 * alpha_max; n_steps = 1;
+            phase = alpha > alpha_min ? PH_FACTOR : PH_DONE;
+            if (phase == PH_DONE) status = kRestorationFailed;
+          }
+        } else if (!fl(F_SOCDONE) && alpha == alpha_max && ref_theta <= tr_theta) {   // start SOC (IpFilterLSAcceptor.cpp:473-587)
+          setfl(F_INSOC, true); soc_count = 0;
+          theta_soc_old = tr_theta;
+          alpha_soc = alpha;
+          init_csoc();
+          build_csoc(alpha_soc);
+          phase = PH_FACTOR;
+        } else {
+          alpha *= 0.5; ++n_steps;
+          if (!(alpha > alpha_min)) { status = kRestorationFailed; phase = PH_DONE; }
+        }
+        return;
+      }
+      if (!tiny_now && (!is_ftype(alpha_test) || !armijo(alpha_test, tbarr)))
+        filter_add(ref_barr - 1e-8 * ref_theta, (1.0 - 1e-5) * ref_theta);
+      // ---- accept: the trial copy becomes the current iterate
       cur ^= 1;
       f_cur = tr_f; theta_cur = tr_theta; priminf = tr_priminf; sumlog = tr_sumlog;
-      setfl(F_TINYLAST, fl(F_TINYNOW) ? dlam_max < 1e-2 : false);
+      setfl(F_TINYLAST, tiny_now ? dlam_max < 1e-2 : false);
       setfl(F_INSOC, false); setfl(F_SOCDONE, false);
       ++iter;
     }
@@ -1004,6 +1070,17 @@ struct Solver {
       dw_curr = 0.0;
     }
   }
+  MPC_HD void init_csoc() {
+    for (int t = 1; t < N; ++t)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) w(rec(t) + oCSOC + k) = w(rec(t) + kX * cur + xC + k);
+  }
+  MPC_HD void build_csoc(double a) {   // c_soc = c(trial) + alpha_soc * c_soc
+    for (int t = 1; t < N; ++t)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) w(rec(t) + oCSOC + k) = w(rec(t) + kX * (cur ^ 1) + xC + k) + a * w(rec(t) + oCSOC + k);
+  }
+
   // ------------------------------------------------------------------------------------------
   // Per-pass entry points for the per-pass kernels: only the scalars a sweep needs are loaded before it, the
   // ones its control logic needs are loaded after it (so they are not live across the sweep), and only what may
@@ -1018,9 +1095,7 @@ struct Solver {
     const bool ok = factor(dw_curr, fl(F_INSOC));
     if (ok) { w(iPHASE) = (double)PH_FORWARD; return; }
     LDD(dDWL, dw_last); LDI(iSTATUS, status);
-    if (dw_curr == 0.0) dw_curr = dw_last == 0.0 ? 1e-4 : dmax(1e-20, dw_last / 3.0);
-    else dw_curr *= (dw_last == 0.0 || 1e5 * dw_last < dw_curr) ? 100.0 : 8.0;
-    if (dw_curr > 1e20) { status = kErrorInStepComputation; phase = PH_DONE; }
+    factor_failed();
     STD_(dDWC, dw_curr); STI(iSTATUS, status); STI(iPHASE, phase);
   }
   MPC_HD void kernel_forward() {
@@ -1034,31 +1109,22 @@ struct Solver {
     STD_(dADU, alpha_du); STD_(dALPHA, alpha); STD_(dAMAX, alpha_max); STD_(dAMIN, alpha_min); STD_(dRTH, ref_theta);
     STD_(dRBARR, ref_barr); STD_(dRGBD, ref_gbd); STI(iNSTEPS, n_steps); STI(iFLAGS, flags); STI(iPHASE, phase);
   }
-  MPC_HD void kernel_trial() {
-    LDI(iFLAGS, flags); LDI(iCUR, cur); LDD(dDF, df); LDD(dMU, mu); LDD(dALPHA, alpha);
-    phase = PH_TRIAL;
-    eval_point(alpha, cur ^ 1);
+  MPC_HD void kernel_step() {
+    LDI(iFLAGS, flags); LDI(iCUR, cur); LDD(dDF, df); LDD(dMU, mu); LDD(dALPHA, alpha); LDD(dADU, alpha_du); LDD(dDWC, dw_curr);
+    phase = PH_STEP;
+    step_pass();
     LDD(dRTH, ref_theta); LDD(dRBARR, ref_barr); LDD(dRGBD, ref_gbd); LDD(dTHMAX, theta_max); LDD(dTHMIN, theta_min);
     LDD(dATEST, alpha_test); LDD(dAMAX, alpha_max); LDD(dAMIN, alpha_min); LDD(dTHSOC, theta_soc_old); LDD(dASOC, alpha_soc);
-    LDI(iSOCCNT, soc_count); LDI(iNSTEPS, n_steps); LDI(iNF, nf); LDI(iSTATUS, status);
-    trial_logic();
-    STD_(dTRF, tr_f); STD_(dTRTH, tr_theta); STD_(dTRPINF, tr_priminf); STD_(dTRSLOG, tr_sumlog); STD_(dTHMAX, theta_max);
-    STD_(dTHMIN, theta_min); STD_(dATEST, alpha_test); STD_(dALPHA, alpha); STD_(dTHSOC, theta_soc_old); STD_(dASOC, alpha_soc);
-    STI(iSOCCNT, soc_count); STI(iNSTEPS, n_steps); STI(iNF, nf); STI(iFLAGS, flags); STI(iSTATUS, status); STI(iPHASE, phase);
-  }
-  MPC_HD void kernel_accept() {
-    LDI(iFLAGS, flags); LDI(iCUR, cur); LDD(dDF, df); LDD(dMU, mu); LDD(dALPHA, alpha); LDD(dADU, alpha_du); LDD(dDWC, dw_curr);
-    phase = PH_ACCEPT;
-    accept_pass();
-    LDD(dTRF, tr_f); LDD(dTRTH, tr_theta); LDD(dTRPINF, tr_priminf); LDD(dTRSLOG, tr_sumlog); LDD(dTAU, tau); LDD(dMUMIN, mu_min);
-    LDD(dCOBJ, curr_obj); LDD(dLOBJ, last_obj); LDD(dDWL, dw_last); LDD(dF, f_cur); LDD(dTH, theta_cur); LDD(dPINF, priminf);
-    LDD(dSLOG, sumlog); LDI(iACCCNT, acceptable_counter); LDI(iITER, iter); LDI(iNF, nf); LDI(iSTATUS, status);
-    accept_logic();
-    STD_(dDINF, dualinf); STD_(dLAM1, lam1); STD_(dZ1, z1); STD_(dSZMAX, sz_max); STD_(dSZMIN, sz_min); STD_(dXMAX, xmaxabs);
-    STD_(dDLMAX, dlam_max); STD_(dF, f_cur); STD_(dTH, theta_cur); STD_(dPINF, priminf); STD_(dSLOG, sumlog); STD_(dMU, mu);
+    LDD(dTAU, tau); LDD(dMUMIN, mu_min); LDD(dCOBJ, curr_obj); LDD(dLOBJ, last_obj); LDD(dDWL, dw_last);
+    LDD(dF, f_cur); LDD(dTH, theta_cur); LDD(dPINF, priminf); LDD(dSLOG, sumlog);
+    LDI(iSOCCNT, soc_count); LDI(iNSTEPS, n_steps); LDI(iNF, nf); LDI(iSTATUS, status); LDI(iACCCNT, acceptable_counter);
+    LDI(iITER, iter);
+    step_logic();
+    STD_(dTHMAX, theta_max); STD_(dTHMIN, theta_min); STD_(dATEST, alpha_test); STD_(dALPHA, alpha); STD_(dTHSOC, theta_soc_old);
+    STD_(dASOC, alpha_soc); STD_(dF, f_cur); STD_(dTH, theta_cur); STD_(dPINF, priminf); STD_(dSLOG, sumlog); STD_(dMU, mu);
     STD_(dTAU, tau); STD_(dCOBJ, curr_obj); STD_(dLOBJ, last_obj); STD_(dDWC, dw_curr); STD_(dDWL, dw_last);
-    STI(iACCCNT, acceptable_counter); STI(iITER, iter); STI(iNF, nf); STI(iCUR, cur); STI(iFLAGS, flags); STI(iSTATUS, status);
-    STI(iPHASE, phase);
+    STI(iSOCCNT, soc_count); STI(iNSTEPS, n_steps); STI(iNF, nf); STI(iACCCNT, acceptable_counter); STI(iITER, iter);
+    STI(iCUR, cur); STI(iFLAGS, flags); STI(iSTATUS, status); STI(iPHASE, phase);
   }
 #undef LDD
 #undef LDI
@@ -1068,36 +1134,26 @@ struct Solver {
   MPC_HD void trip() {
     if (phase == PH_FACTOR) do_factor();
     if (phase == PH_FORWARD) do_forward();
-    if (phase == PH_TRIAL) do_trial();
-    if (phase == PH_ACCEPT) do_accept();
-  }
-  MPC_HD void init_csoc() {
-    for (int t = 1; t < N; ++t)
-#pragma unroll
-      for (int k = 0; k < 6; ++k) w(rec(t) + oCSOC + k) = w(rec(t) + oC + 6 * cur + k);
-  }
-  MPC_HD void build_csoc(double a) {   // c_soc = c(trial) + alpha_soc * c_soc
-    for (int t = 1; t < N; ++t)
-#pragma unroll
-      for (int k = 0; k < 6; ++k) w(rec(t) + oCSOC + k) = w(rec(t) + oC + 6 * (cur ^ 1) + k) + a * w(rec(t) + oCSOC + k);
+    if (phase == PH_STEP) do_step();
   }
 
   // ------------------------------------------------------------------------------------------
   // finalize: honor_original_bounds (IpOrigIpoptNLP.cpp:875-883), unscaled objective, MPC.cpp:253-256.
   // traj (optional): full variable vector in the reference layout (MPC.cpp:36-43), element i at traj[i*tstride].
   MPC_HD void finish(Result& R, double* traj, size_t tstride) {
+    const int bX = kX * cur;
     R.status = status; R.iters = iter; R.obj = f_cur / df;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) R.out8[k] = w(rec(1) + oS + k);
-    R.out8[6] = dclamp(w(rec(0) + oU + 0), -P.ob[0], P.ob[0]);
-    R.out8[7] = dclamp(w(rec(0) + oU + 1), -P.ob[1], P.ob[1]);
+    for (int k = 0; k < 6; ++k) R.out8[k] = w(rec(1) + bX + xS + k);
+    R.out8[6] = dclamp(w(rec(0) + bX + xU + 0), -P.ob[0], P.ob[0]);
+    R.out8[7] = dclamp(w(rec(0) + bX + xU + 1), -P.ob[1], P.ob[1]);
     if (traj) {
       for (int t = 0; t < N; ++t)
 #pragma unroll
-        for (int k = 0; k < 6; ++k) traj[(size_t)(k * N + t) * tstride] = w(rec(t) + oS + k);
+        for (int k = 0; k < 6; ++k) traj[(size_t)(k * N + t) * tstride] = w(rec(t) + bX + xS + k);
       for (int t = 0; t < M; ++t) {
-        traj[(size_t)(6 * N + t) * tstride] = dclamp(w(rec(t) + oU), -P.ob[0], P.ob[0]);
-        traj[(size_t)(6 * N + M + t) * tstride] = dclamp(w(rec(t) + oU + 1), -P.ob[1], P.ob[1]);
+        traj[(size_t)(6 * N + t) * tstride] = dclamp(w(rec(t) + bX + xU), -P.ob[0], P.ob[0]);
+        traj[(size_t)(6 * N + M + t) * tstride] = dclamp(w(rec(t) + bX + xU + 1), -P.ob[1], P.ob[1]);
       }
     }
   }

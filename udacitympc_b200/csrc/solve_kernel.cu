@@ -5,10 +5,10 @@
 // /root/reference/mpc_to_line/solution/MPC.cpp:241-243.
 //
 // Two execution modes share the same pass code (mpc_core.cuh):
-//   per-pass kernels  init | factor | forward | trial | accept, launched round after round on one stream.  Each
+//   per-pass kernels  init | factor | forward | step, launched round after round on one stream.  Each
 //                     kernel has its own register budget (the Riccati factorisation needs ~250 registers, the
 //                     other sweeps far fewer and run at 3-4x the occupancy) and a small instruction footprint.
-//   fused kernel      one launch loops the four passes per thread until its problem is done.  Used to finish
+//   fused kernel      one launch loops the three passes per thread until its problem is done.  Used to finish
 //                     stragglers after the fixed number of rounds, and for tiny batches (latency).
 #include "kernels.h"
 
@@ -19,13 +19,10 @@ constexpr int kBlock = 64;
 #ifndef MPC_FWD_BLOCKS
 #define MPC_FWD_BLOCKS 8
 #endif
-#ifndef MPC_TRIAL_BLOCKS
-#define MPC_TRIAL_BLOCKS 8
+#ifndef MPC_STEP_BLOCKS
+#define MPC_STEP_BLOCKS 4
 #endif
-#ifndef MPC_ACCEPT_BLOCKS
-#define MPC_ACCEPT_BLOCKS 8
-#endif
-constexpr int kFwdBlocks = MPC_FWD_BLOCKS, kTrialBlocks = MPC_TRIAL_BLOCKS, kAcceptBlocks = MPC_ACCEPT_BLOCKS;
+constexpr int kFwdBlocks = MPC_FWD_BLOCKS, kStepBlocks = MPC_STEP_BLOCKS;
 
 size_t solve_workspace_doubles(int N, int B) {
   size_t groups = ((size_t)B + 31) / 32;
@@ -98,22 +95,13 @@ __global__ void __launch_bounds__(kBlock, kFwdBlocks) mpc_forward_kernel(const _
   S.kernel_forward();
 }
 
-__global__ void __launch_bounds__(kBlock, kTrialBlocks) mpc_trial_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
+__global__ void __launch_bounds__(kBlock, kStepBlocks) mpc_step_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= A.B) return;
   Solver<32> S(P, problem_base(P, A, b));
-  if (S.load_phase() != PH_TRIAL) return;
+  if (S.load_phase() != PH_STEP) return;
   load_coeffs(A, b, S.cf);
-  S.kernel_trial();
-}
-
-__global__ void __launch_bounds__(kBlock, kAcceptBlocks) mpc_accept_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= A.B) return;
-  Solver<32> S(P, problem_base(P, A, b));
-  if (S.load_phase() != PH_ACCEPT) return;
-  load_coeffs(A, b, S.cf);
-  S.kernel_accept();
+  S.kernel_step();
   if (S.phase == PH_DONE) write_result(P, A, b, S);
 }
 
@@ -153,11 +141,10 @@ cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6
       for (int r = 0; r < cfg.rounds; ++r) {
         mpc_factor_kernel<<<grid, kBlock, 0, stream>>>(P, A);
         mpc_forward_kernel<<<grid, kBlock, 0, stream>>>(P, A);
-        mpc_trial_kernel<<<grid, kBlock, 0, stream>>>(P, A);
-        mpc_accept_kernel<<<grid, kBlock, 0, stream>>>(P, A);
+        mpc_step_kernel<<<grid, kBlock, 0, stream>>>(P, A);
       }
       mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 0);
-      n += 2 + 4LL * cfg.rounds;
+      n += 2 + 3LL * cfg.rounds;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
