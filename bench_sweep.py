@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""bench_sweep.py -- BASELINE.json configs[4]: horizon / batch sweep (N in 10..100, batch 1K..1M), degree-3 reference
+from roadmap windows, one B200.  Device-resident inputs, CUDA events.  For every point: solves/s, mean / max
+interior-point iterations and the status histogram (status -2 = the line search failed and Ipopt would have entered
+its restoration phase, which is not implemented; such problems are reported, never hidden).
+`python bench_sweep.py > profiles/r1_sweep.json`"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--horizons", default="10,25,50,100")
+    ap.add_argument("--batches", default="1024,16384,65536,262144,1048576")
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    import udacitympc_b200 as mp
+    from udacitympc_b200 import synth
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    Bmax = max(int(b) for b in args.batches.split(","))
+    nb = min(Bmax, 262144)
+    with mp.MPC(device=0) as m0:
+        xs, ys = synth.roadmap_windows(nb)
+        fit = mp.polyfit_batch(xs, ys, 3, mpc=m0)
+    st = synth.roadmap_problems(nb, fit)
+    rows = []
+    for N in [int(n) for n in args.horizons.split(",")]:
+        for B in [int(b) for b in args.batches.split(",")]:
+            if B * 83 * (N + 1) * 8 > 60e9:
+                continue
+            t = (B + nb - 1) // nb
+            st_d = torch.from_numpy(np.ascontiguousarray(np.tile(st, (t, 1))[:B].T)).to(dev)
+            cf_d = torch.from_numpy(np.ascontiguousarray(np.tile(fit, (t, 1))[:B].T)).to(dev)
+            out8 = torch.empty((8, B), dtype=torch.float64, device=dev)
+            status = torch.empty(B, dtype=torch.int32, device=dev)
+            iters = torch.empty(B, dtype=torch.int32, device=dev)
+            with mp.MPC(device=0, N=N) as m:
+                m.set_solver_mode(0, max(24, N + 10), -1)
+
+                def step():
+                    m.solve_batch_device(B, st_d.data_ptr(), cf_d.data_ptr(), 4, out8.data_ptr(), 0, 0, status.data_ptr(),
+                                         iters.data_ptr(), stream.cuda_stream)
+                step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(args.reps):
+                    step()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / args.reps
+            sc = status.cpu().numpy()
+            it = iters.cpu().numpy()
+            hist = {int(k): int(v) for k, v in zip(*np.unique(sc, return_counts=True))}
+            rows.append(dict(N=N, batch=B, ms_per_batch=ms, solves_per_s=B / (ms * 1e-3), mean_iters=float(it.mean()),
+                             max_iters=int(it.max()), status_hist=hist, solved_fraction=float((sc == 0).mean())))
+            print(json.dumps(rows[-1]), file=sys.stderr)
+            del st_d, cf_d, out8
+            torch.cuda.empty_cache()
+    print(json.dumps(dict(workload="degree-3 reference from roadmap windows (SURVEY 8d config 5), dt=0.05", rows=rows), indent=1))
+
+
+if __name__ == "__main__":
+    main()
