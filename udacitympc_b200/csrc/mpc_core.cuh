@@ -122,6 +122,15 @@ static_assert(kNumScal <= kRec, "scalar record must fit one stage record");
 
 MPC_HD int workspace_doubles_per_problem(int N) { return kRec * (N + 1); }
 
+// HBM traffic vs recomputation (the solver kernels are HBM-bound with FP64 issue slots to spare):
+//   MPC_STORE_TRIG 0: sin/cos(psi_t), sin/cos(epsi_t) are recomputed by every sweep instead of stored (16 doubles/stage/iter)
+//   MPC_STORE_C    0: the constraint residuals are recomputed from the iterate instead of stored (18 doubles/stage/iter)
+#ifndef MPC_STORE_TRIG
+#define MPC_STORE_TRIG 1
+#endif
+#ifndef MPC_STORE_C
+#define MPC_STORE_C 0
+#endif
 // MPC_PREFETCH: 0 = off, 1 = prefetch.global.L1, 2 = prefetch.global.L2 (device only)
 #ifndef MPC_PREFETCH
 #define MPC_PREFETCH 1
@@ -336,6 +345,31 @@ struct Solver {
     c[4] = sn[4] - ((p0 - s[1]) + (s[3] * se * P.dt));
     c[5] = sn[5] - ((s[2] - psides) + vd);
   }
+  // sin/cos of psi_t and epsi_t of the iterate copy starting at row r (stored or recomputed)
+  MPC_HD void trig_of(int r, const double* s, double& sp, double& cp, double& se, double& ce) const {
+#if MPC_STORE_TRIG
+    (void)s;
+    sp = w(r + xTR); cp = w(r + xTR + 1); se = w(r + xTR + 2); ce = w(r + xTR + 3);
+#else
+    (void)r;
+    sincos(s[2], &sp, &cp);
+    sincos(s[5], &se, &ce);
+#endif
+  }
+  // constraint residual of the rows of time t+1 at the iterate copy `buf` (rare paths only)
+  MPC_HD void residual_at(int buf, int t, double* c) const {
+#if MPC_STORE_C
+    for (int k = 0; k < 6; ++k) c[k] = w(rec(t + 1) + kX * buf + xC + k);
+#else
+    const int r = rec(t) + kX * buf;
+    double s[6], sn[6], u[2], sp, cp, se, ce, p0, p1, p2, p3;
+    for (int k = 0; k < 6; ++k) { s[k] = w(r + xS + k); sn[k] = w(r + kRec + xS + k); }
+    u[0] = w(r + xU); u[1] = w(r + xU + 1);
+    trig_of(r, s, sp, cp, se, ce);
+    poly_eval(cf, s[0], p0, p1, p2, p3);
+    residual(s, u, sn, sp, cp, se, p0, atan(p1), c);
+#endif
+  }
   MPC_HD double state_cost(const double* s) const {
     return P.w_cte * (s[4] * s[4]) + P.w_epsi * (s[5] * s[5]) + P.w_v * ((s[3] - P.ref_v) * (s[3] - P.ref_v));
   }
@@ -387,9 +421,16 @@ struct Solver {
         sincos(s[5], &se, &ce);
         poly_eval(cf, s[0], p0, p1, p2, p3);
         residual(s, u, sn, sp, cp, se, p0, atan(p1), c);
+#if MPC_STORE_TRIG
         w(r + xTR) = sp; w(r + xTR + 1) = cp; w(r + xTR + 2) = se; w(r + xTR + 3) = ce;
+#endif
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { w(r + kRec + xC + k) = c[k]; th += fabs(c[k]); cm = dmax(cm, fabs(c[k])); }
+        for (int k = 0; k < 6; ++k) {
+#if MPC_STORE_C
+          w(r + kRec + xC + k) = c[k];
+#endif
+          th += fabs(c[k]); cm = dmax(cm, fabs(c[k]));
+        }
         f += P.w_delta * (u[0] * u[0]) + P.w_a * (u[1] * u[1]);
         sl += lq;
       }
@@ -414,9 +455,9 @@ struct Solver {
     for (int i = 0; i < 4; ++i) psu[i][0] = psu[i][1] = 0.0;
     double lamn[6];   // lambda_{t+1}
     double rc_next;
+    double sT[6];     // s_{t+1}
     {
       const int r = rec(M) + bX;
-      double sT[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) { lamn[k] = ls ? 0.0 : w(r + xLAM + k); sT[k] = w(r + xS + k); }
       PS(0, 0) = q0; PS(1, 1) = q0; PS(2, 2) = q0; PS(3, 3) = qv; PS(4, 4) = qe;
@@ -430,9 +471,9 @@ struct Solver {
     bool ok = true;
     for (int t = M - 1; t >= 0; --t) {
       const int r = rec(t) + bX, rn = rec(t + 1);
-      if (t > 0) {   // rows of stage t-1: S,U,LAM,ZL,ZU,TR are contiguous (22 rows), then the residual of rows t
-        w.prefetch(r - kRec + xS, 22);
-        if (!ls) w.prefetch(rec(t) + bC, 6);
+      if (t > 0) {   // rows of stage t-1: S,U,LAM,ZL,ZU(,TR) are contiguous, then the residual of rows t
+        w.prefetch(r - kRec + xS, MPC_STORE_TRIG ? 22 : 18);
+        if (!ls && (MPC_STORE_C || use_csoc)) w.prefetch(rec(t) + bC, 6);
       }
       double s[6], lam[6];
 #pragma unroll
@@ -440,17 +481,23 @@ struct Solver {
       const double u0 = w(r + xU), u1 = w(r + xU + 1);
       double um0 = 0.0, um1 = 0.0;
       if (t > 0) { um0 = w(r - kRec + xU); um1 = w(r - kRec + xU + 1); }
-      const double sp = w(r + xTR), cp = w(r + xTR + 1), se = w(r + xTR + 2), ce = w(r + xTR + 3);
+      double sp, cp, se, ce;
+      trig_of(r, s, sp, cp, se, ce);
       const double zl0 = w(r + xZL), zl1 = w(r + xZL + 1), zu0 = w(r + xZU), zu1 = w(r + xZU + 1);
+      double p0, p1, p2, p3;
+      poly_eval(cf, s[0], p0, p1, p2, p3);
       // constraint right-hand side of rows t+1
       double rb[5], cc;
       if (ls) { rb[0] = rb[1] = rb[2] = rb[3] = rb[4] = 0.0; cc = 0.0; }
-      else {
+      else if (MPC_STORE_C || use_csoc) {
         rb[0] = -w(rn + bC); rb[1] = -w(rn + bC + 1); rb[2] = -w(rn + bC + 2); rb[3] = -w(rn + bC + 3);
         cc = w(rn + bC + 4); rb[4] = -w(rn + bC + 5);
+      } else {
+        double c[6];
+        const double uu[2] = {u0, u1};
+        residual(s, uu, sT, sp, cp, se, p0, atan(p1), c);
+        rb[0] = -c[0]; rb[1] = -c[1]; rb[2] = -c[2]; rb[3] = -c[3]; cc = c[4]; rb[4] = -c[5];
       }
-      double p0, p1, p2, p3;
-      poly_eval(cf, s[0], p0, p1, p2, p3);
       const Lin A = make_lin(P, s[3], u0, sp, cp, se, ce, p1, p2);
       Hes H;
       if (ls) { H.xx = H.pp = H.vp = H.ee = H.ev = H.m = 0.0; }
@@ -560,7 +607,7 @@ struct Solver {
       rc_next = gc2 * s[4] + lam[4];
       un0 = u0; un1 = u1;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) lamn[k] = lam[k];
+      for (int k = 0; k < 6; ++k) { lamn[k] = lam[k]; sT[k] = s[k]; }
     }
     return ok;
   }
@@ -579,26 +626,35 @@ struct Solver {
 #pragma unroll
     for (int k = 0; k < 6; ++k) w(rec(0) + oDS + k) = 0.0;
     double u0 = w(rec(0) + bX + xU), u1 = w(rec(0) + bX + xU + 1);
+    double s[6], snx[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s[k] = w(rec(0) + bX + xS + k);
     for (int t = 0; t < M; ++t) {
       const int r = rec(t) + bX, rn = rec(t + 1);
       if (t + 1 < M) {
-        w.prefetch(rn + oKF, 13); w.prefetch(rn + bX + xS, 6); w.prefetch(rn + bX + xTR, 4); w.prefetch(rn + kRec + bX + xU, 2);
-        if (!ls) { w.prefetch(rn + bX + xZL, 4); w.prefetch(rn + kRec + bC, 6); }
+        w.prefetch(rn + oKF, 13); w.prefetch(rn + kRec + bX + xS, 8);
+        if (MPC_STORE_TRIG) w.prefetch(rn + bX + xTR, 4);
+        if (!ls) { w.prefetch(rn + bX + xZL, 4); if (MPC_STORE_C || use_csoc) w.prefetch(rn + kRec + bC, 6); }
       }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) snx[k] = w(rn + bX + xS + k);
       const int ko = rec(t) + oKF;
       double K0[4], K1[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) { K0[j] = w(ko + j); K1[j] = w(ko + 4 + j); }
       const double i00 = w(ko + 8), i10 = w(ko + 9), i11 = w(ko + 10), k0 = w(ko + 11), k1 = w(ko + 12);
-      double s[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) s[k] = w(r + xS + k);
-      const double sp = w(r + xTR), cp = w(r + xTR + 1), se = w(r + xTR + 2), ce = w(r + xTR + 3);
+      double sp, cp, se, ce;
+      trig_of(r, s, sp, cp, se, ce);
+      double p0, p1, p2, p3;
+      poly_eval(cf, s[0], p0, p1, p2, p3);
       double c[6];
       if (ls) { c[0] = c[1] = c[2] = c[3] = c[4] = c[5] = 0.0; }
-      else {
+      else if (MPC_STORE_C || use_csoc) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) c[k] = w(rn + bC + k);
+      } else {
+        const double uu[2] = {u0, u1};
+        residual(s, uu, snx, sp, cp, se, p0, atan(p1), c);
       }
       double un0 = 0.0, un1 = 0.0;
       if (t < M - 1) { un0 = w(rn + bX + xU); un1 = w(rn + bX + xU + 1); }
@@ -608,8 +664,6 @@ struct Solver {
       const double du0 = -(K0[0] * ds[0] + K0[1] * ds[1] + K0[2] * ds[2] + K0[3] * ds[3] + k0) + (i00 * e0 + i10 * e1);
       const double du1 = -(K1[0] * ds[0] + K1[1] * ds[1] + K1[2] * ds[2] + K1[3] * ds[3] + k1) + (i10 * e0 + i11 * e1);
       w(rec(t) + oDU) = du0; w(rec(t) + oDU + 1) = du1;
-      double p0, p1, p2, p3;
-      poly_eval(cf, s[0], p0, p1, p2, p3);
       const Lin A = make_lin(P, s[3], u0, sp, cp, se, ce, p1, p2);
       if (!ls) {
         // objective / barrier directional derivative and step bounds for u_t
@@ -643,13 +697,12 @@ struct Solver {
       dn[4] = A.pp * ds[0] - ds[1] + A.sed * ds[3] + A.vce * ds[5] - c[4];
       dn[5] = -A.kap * ds[0] + ds[2] + A.a5 * ds[3] + A.beta * du0 - c[5];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { ds[k] = dn[k]; w(rn + oDS + k) = dn[k]; }
+      for (int k = 0; k < 6; ++k) { ds[k] = dn[k]; w(rn + oDS + k) = dn[k]; s[k] = snx[k]; }
       dup0 = du0; dup1 = du1; um0 = u0; um1 = u1; u0 = un0; u1 = un1;
     }
     if (!ls) {
-      double s[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { s[k] = w(rec(M) + bX + xS + k); nottiny = nottiny || fabs(ds[k]) > tinytol * (fabs(s[k]) + 1.0); }
+      for (int k = 0; k < 6; ++k) nottiny = nottiny || fabs(ds[k]) > tinytol * (fabs(s[k]) + 1.0);
       gbd += gv2 * (s[3] - P.ref_v) * ds[3] + gc2 * s[4] * ds[4] + ge2 * s[5] * ds[5];
     }
     fw_alpha_pr = a_pr; fw_alpha_du = a_du; fw_gbd = gbd; fw_tiny = !nottiny;
@@ -689,7 +742,8 @@ struct Solver {
       const double u0 = w(r + xU), u1 = w(r + xU + 1);
       double um0 = 0.0, um1 = 0.0;
       if (t > 0) { um0 = w(r - kRec + xU); um1 = w(r - kRec + xU + 1); }
-      const double sp = w(r + xTR), cp = w(r + xTR + 1), se = w(r + xTR + 2), ce = w(r + xTR + 3);
+      double sp, cp, se, ce;
+      trig_of(r, s, sp, cp, se, ce);
       const double zl0 = w(r + xZL), zl1 = w(r + xZL + 1), zu0 = w(r + xZU), zu1 = w(r + xZU + 1);
       double p0, p1, p2, p3;
       poly_eval(cf, s[0], p0, p1, p2, p3);
@@ -780,7 +834,7 @@ struct Solver {
     { const int r = rec(M - 1); uc0 = w(r + bO + xU); uc1 = w(r + bO + xU + 1); duc0 = w(r + oDU); duc1 = w(r + oDU + 1); }
     for (int t = M - 1; t >= 0; --t) {
       const int r = rec(t);
-      if (t > 0) { w.prefetch(r - kRec + bO + xS, 22); w.prefetch(r - kRec + oDS, 8); }
+      if (t > 0) { w.prefetch(r - kRec + bO + xS, MPC_STORE_TRIG ? 22 : 18); w.prefetch(r - kRec + oDS, 8); }
       double s[6], ds[6], lam[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) { s[k] = w(r + bO + xS + k); ds[k] = w(r + oDS + k); lam[k] = w(r + bO + xLAM + k); }
@@ -790,7 +844,8 @@ struct Solver {
       double zl0 = w(r + bO + xZL), zl1 = w(r + bO + xZL + 1), zu0 = w(r + bO + xZU), zu1 = w(r + bO + xZU + 1);
       // ---- current point: lambda^+_t from the stationarity rows
       {
-        const double spo = w(r + bO + xTR), cpo = w(r + bO + xTR + 1), seo = w(r + bO + xTR + 2), ceo = w(r + bO + xTR + 3);
+        double spo, cpo, seo, ceo;
+        trig_of(r + bO, s, spo, cpo, seo, ceo);
         double p0, p1, p2, p3;
         poly_eval(cf, s[0], p0, p1, p2, p3);
         const Lin A = make_lin(P, s[3], u0, spo, cpo, seo, ceo, p1, p2);
@@ -857,9 +912,16 @@ struct Solver {
         sincos(sn[5], &sen, &cen);
         poly_eval(cf, sn[0], p0, p1, p2, p3);
         residual(sn, un, snn, spn, cpn, sen, p0, atan(p1), c);
+#if MPC_STORE_TRIG
         w(r + bN + xTR) = spn; w(r + bN + xTR + 1) = cpn; w(r + bN + xTR + 2) = sen; w(r + bN + xTR + 3) = cen;
+#endif
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { w(r + kRec + bN + xC + k) = c[k]; th += fabs(c[k]); cm = dmax(cm, fabs(c[k])); }
+        for (int k = 0; k < 6; ++k) {
+#if MPC_STORE_C
+          w(r + kRec + bN + xC + k) = c[k];
+#endif
+          th += fabs(c[k]); cm = dmax(cm, fabs(c[k]));
+        }
         f += state_cost(sn) + P.w_delta * (un[0] * un[0]) + P.w_a * (un[1] * un[1]);
         if (t > 0) f += P.w_ddelta * ((un[0] - umn0) * (un[0] - umn0)) + P.w_da * ((un[1] - umn1) * (un[1] - umn1));
         const Lin A = make_lin(P, sn[3], un[0], spn, cpn, sen, cen, p1, p2);
@@ -1071,14 +1133,18 @@ struct Solver {
     }
   }
   MPC_HD void init_csoc() {
-    for (int t = 1; t < N; ++t)
-#pragma unroll
-      for (int k = 0; k < 6; ++k) w(rec(t) + oCSOC + k) = w(rec(t) + kX * cur + xC + k);
+    for (int t = 0; t < M; ++t) {
+      double c[6];
+      residual_at(cur, t, c);
+      for (int k = 0; k < 6; ++k) w(rec(t + 1) + oCSOC + k) = c[k];
+    }
   }
   MPC_HD void build_csoc(double a) {   // c_soc = c(trial) + alpha_soc * c_soc
-    for (int t = 1; t < N; ++t)
-#pragma unroll
-      for (int k = 0; k < 6; ++k) w(rec(t) + oCSOC + k) = w(rec(t) + kX * (cur ^ 1) + xC + k) + a * w(rec(t) + oCSOC + k);
+    for (int t = 0; t < M; ++t) {
+      double c[6];
+      residual_at(cur ^ 1, t, c);
+      for (int k = 0; k < 6; ++k) w(rec(t + 1) + oCSOC + k) = c[k] + a * w(rec(t + 1) + oCSOC + k);
+    }
   }
 
   // ------------------------------------------------------------------------------------------
