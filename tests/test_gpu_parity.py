@@ -103,6 +103,14 @@ def test_weights_and_scaling_vs_port(mpc):
         o = ob.port_solve(g["states"][b], g["coeffs"][b], params=ob.default_params(**kw))
         assert r["status"][b] == o["status"] and r["iters"][b] == o["iters"]
         np.testing.assert_allclose(r["traj"][b], o["x"], rtol=0, atol=1e-8)
+    with mp.MPC(ref_v=6.0) as m:   # small gradients: the least-square multiplier estimate is kept (<= 1000)
+        st6 = g["states"][:8].copy()
+        st6[:, 3] = 5.0 + 0.2 * np.arange(8)
+        r = m.solve_batch(st6, g["coeffs"][:8], want_traj=True)
+        for b in range(8):
+            o = ob.port_solve(st6[b], g["coeffs"][b], params=ob.default_params(ref_v=6.0))
+            assert r["status"][b] == o["status"] and r["iters"][b] == o["iters"]
+            np.testing.assert_allclose(r["traj"][b], o["x"], rtol=0, atol=1e-8)
     st = np.array([[0.0, 70.0, 0.1, 12.0, -71.0, 0.1]])   # objective scaling branch (IpGradientScaling.cpp:99-116)
     r = mpc.solve_batch(st, np.array([[-1.0, 0.0]]), want_traj=True)
     o = ob.port_solve(st[0], [-1.0, 0.0])

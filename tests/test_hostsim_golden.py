@@ -121,3 +121,18 @@ def test_per_pass_state_persistence(hostsim):
             assert a["status"] == c["status"] and a["iters"] == c["iters"]
             np.testing.assert_array_equal(a["x"], c["x"])
             assert a["obj"] == c["obj"]
+
+
+def test_least_square_multiplier_estimate_is_kept_when_small(hostsim):
+    """With a small reference speed the least-square multiplier estimate stays below constr_mult_init_max = 1000 and
+    Ipopt keeps it (IpDefaultIterateInitializer.cpp:651-718); with the reference's ref_v = 40 it is discarded."""
+    import oracle_bindings as ob
+    g = golden("line_256.npz")
+    for b in range(6):
+        st = g["states"][b].copy()
+        st[3] = 5.0 + 0.2 * b
+        for mode in (0, 1):
+            r = hostsim.solve(st, g["coeffs"][b], mode=mode, ref_v=6.0)
+            o = ob.port_solve(st, g["coeffs"][b], params=ob.default_params(ref_v=6.0))
+            assert r["status"] == o["status"] and r["iters"] == o["iters"]
+            np.testing.assert_allclose(r["x"], o["x"], rtol=0, atol=1e-8)

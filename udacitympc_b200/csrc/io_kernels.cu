@@ -107,8 +107,9 @@ __device__ __forceinline__ void polyfit_regs(const double* xs, const double* ys,
     } else {
       beta = sqrt(c0 * c0 + tail);
       if (c0 >= 0.0) beta = -beta;
+      const double inv = 1.0 / (c0 - beta);   // Eigen divides element-wise; one reciprocal differs by <= 1 ulp
 #pragma unroll
-      for (int i = 1; i < rr; ++i) A[k][k + i] = A[k][k + i] / (c0 - beta);
+      for (int i = 1; i < rr; ++i) A[k][k + i] = A[k][k + i] * inv;
       tau = (beta - c0) / beta;
     }
     h[k] = tau; A[k][k] = beta;

@@ -256,7 +256,7 @@ struct Result {
 };
 
 enum Phase { PH_FACTOR = 0, PH_FORWARD = 1, PH_STEP = 2, PH_DONE = 3 };
-enum Flags { F_INSOC = 1, F_SOCDONE = 2, F_LS = 4, F_LAMZERO = 8, F_TINYLAST = 16, F_TINYFLAG = 32, F_TINYNOW = 64 };
+enum Flags { F_INSOC = 1, F_SOCDONE = 2, F_LS = 4, F_LSKEEP = 8, F_TINYLAST = 16, F_TINYFLAG = 32, F_TINYNOW = 64 };
 
 // The per-problem solver.  All "passes" are loops over the horizon that touch the workspace once per stage.
 template <int LANES>
@@ -711,7 +711,9 @@ struct Solver {
   // ------------------------------------------------------------------------------------------
   // Least-square multiplier initialisation (IpLeastSquareMults.cpp:40-94): lambda from the stationarity rows of the
   // H = I system solved by factor()/forward() in F_LS mode; x, z unchanged.  Also every norm the convergence
-  // test / mu update need at the start point.  zero = discard the estimate (||lambda||_inf > 1000).
+  // test / mu update need at the start point.  The first pass (zero = true) only measures ||lambda_LS||_inf and
+  // evaluates the norms for lambda = 0 (what Ipopt falls back to when the estimate exceeds constr_mult_init_max =
+  // 1000, the common case here) without storing anything; a second pass (zero = false) stores the estimate.
   MPC_HD void accept_ls(bool zero) {
     const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df, gc2 = 2.0 * P.w_cte * df;
     const int bX = kX * cur;
@@ -727,7 +729,11 @@ struct Solver {
       lp[4] = -ds[4] - gc2 * s[4];
       lp[5] = -ds[5] - ge2 * s[5];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { dlm = dmax(dlm, fabs(lp[k])); ln[k] = zero ? 0.0 : lp[k]; w(r + xLAM + k) = ln[k]; l1 += fabs(ln[k]); }
+      for (int k = 0; k < 6; ++k) {
+        dlm = dmax(dlm, fabs(lp[k])); ln[k] = zero ? 0.0 : lp[k];
+        if (!zero) w(r + xLAM + k) = ln[k];   // lambda is already zero from init()
+        l1 += fabs(ln[k]);
+      }
       dinf = dmax(dinf, dmax(fabs(ln[0]), dmax(fabs(ln[1]), fabs(ln[2]))));
       dinf = dmax(dinf, fabs(gv2 * (s[3] - P.ref_v) + ln[3]));
       dinf = dmax(dinf, fabs(gc2 * s[4] + ln[4]));
@@ -763,7 +769,7 @@ struct Solver {
       for (int k = 0; k < 6; ++k) {
         lp[k] = nl[k]; dlm = dmax(dlm, fabs(nl[k]));
         lnew[k] = zero ? 0.0 : nl[k];
-        w(r + xLAM + k) = lnew[k];
+        if (!zero) w(r + xLAM + k) = lnew[k];
         l1 += fabs(lnew[k]);
       }
       xm = dmax(xm, dmax(fabs(u0), fabs(u1)));
@@ -1073,13 +1079,13 @@ struct Solver {
     step_logic();
   }
   MPC_HD void step_pass() {
-    if (fl(F_LS)) accept_ls(fl(F_LAMZERO));
+    if (fl(F_LS)) accept_ls(!fl(F_LSKEEP));
     else step_sweep(alpha, alpha_du, dw_curr);
   }
   MPC_HD void step_logic() {
     if (fl(F_LS)) {
-      if (!fl(F_LAMZERO) && dlam_max > 1000.0) { setfl(F_LAMZERO, true); return; }   // constr_mult_init_max: redo with lambda = 0
-      setfl(F_LS, false); setfl(F_LAMZERO, false);
+      if (!fl(F_LSKEEP) && dlam_max <= 1000.0) { setfl(F_LSKEEP, true); return; }   // estimate within constr_mult_init_max: store it
+      setfl(F_LS, false); setfl(F_LSKEEP, false);
     } else {
       // ---- line search decision on the trial point (IpBacktrackingLineSearch.cpp:637-797)
       const double tbarr = tr_f - mu * tr_sumlog;
