@@ -231,8 +231,7 @@ def run_ours(args):
         m.kernel_time_ms(reset=True)
     launches0 = sum(m.launch_count() for m in mpcs)
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(streams[0])
     for s_ in streams[1:]:
@@ -262,7 +261,11 @@ def run_ours(args):
         ok_frac.append(float((o["status"] == 0).double().mean().item()))
     mpc.kernel_time_ms(reset=True)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    per_rank_ms = [ms_total / K]
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank_ms = [float(x.item()) / K for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     value = world * B * K / (ms_total * 1e-3)
@@ -313,7 +316,13 @@ def run_ours(args):
     e2e_value = world * B * K / float(t.item())
     for m in mpcs:
         m.kernel_time_ms(reset=True)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
+    per_rank_mhz = [clocks.get("sm_mhz") or 0.0]
+    if world > 1:
+        c = torch.tensor([clocks.get("sm_mhz") or 0.0], dtype=torch.float64, device=dev)
+        allc = [torch.zeros_like(c) for _ in range(world)]
+        dist.all_gather(allc, c)
+        per_rank_mhz = [float(x.item()) for x in allc]
 
     if rank == 0:
         mean_it = float(np.mean(iters_mean))
@@ -335,10 +344,10 @@ def run_ours(args):
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=B * (6 + ncoef) * 8, d2h_bytes_per_step=B * (8 + 1) * 8 + 2 * B * 4,
                      p99_batch_latency_ms=1e3 * float(p99.item()), latency_reps=len(lat)),
             gpu_launches=int(launches),
-            clocks=clocks,
+            clocks=clocks, per_rank_ms_per_step=per_rank_ms, per_rank_sm_mhz=per_rank_mhz,
             roofline=dict(bound="fp64", achieved=achieved, peak=fp64_peak, unit="TFLOP/s", frac=achieved / fp64_peak if fp64_peak else None,
                           traffic=None,
-                          kernel=("mpc_{init,factor,forward,trial,accept,fused}_kernel: all solver kernels of one step, first to last"
+                          kernel=("mpc_{init,factor,forward,step,fused}_kernel: all solver kernels of one step (one CUDA graph), first to last"
                                   if args.mode == "perpass" else "mpc_fused_kernel"),
                           avg_kernel_ms=avg_kernel_ms, launches_timed=kern_n, solver_mode=args.mode, streams=S,
                           flop_per_launch=flop_per_launch, mean_ip_iters=mean_it,

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -48,6 +49,15 @@ struct b200mpc_handle {
   DevBuf ws, in_aos, st_soa, cf_soa, out_soa, out_aos, traj_soa, traj_aos, obj, status, iters, misc0, misc1, misc2, misc3;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;   // around every solver-kernel launch
   long long launches = 0;
+  // CUDA graphs of whole solves (init + rounds x (factor, forward, step) + finisher), keyed by every launch argument
+  struct GraphEntry {
+    int B, steps, ncoef, mode, rounds, fused_below;
+    const void *st, *cf, *ws, *out8, *traj, *obj, *status, *iters;
+    cudaGraphExec_t exec;
+    long long n_kernels;
+  };
+  std::vector<GraphEntry> graphs;
+  bool use_graphs = true;
 };
 
 namespace {
@@ -80,7 +90,44 @@ int timed_solve(b200mpc_handle* h, int B, int steps, const double* st, const dou
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, s));
   }
-  CU(launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, &h->launches));
+  // One solve is ~75 dependent launches; replaying a captured graph keeps the host out of the inner loop (several
+  // ranks / streams per host otherwise become launch-bound).  The legacy default stream cannot be captured.
+  bool done = false;
+  if (h->use_graphs && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) {
+    b200mpc_handle::GraphEntry key{B, steps, ncoef, h->cfg.mode, h->cfg.rounds, h->cfg.fused_below, st, cf, h->ws.p, out8, traj, obj, status, iters, nullptr, 0};
+    b200mpc_handle::GraphEntry* hit = nullptr;
+    for (auto& g : h->graphs)
+      if (g.B == key.B && g.steps == key.steps && g.ncoef == key.ncoef && g.mode == key.mode && g.rounds == key.rounds &&
+          g.fused_below == key.fused_below && g.st == key.st && g.cf == key.cf && g.ws == key.ws && g.out8 == key.out8 &&
+          g.traj == key.traj && g.obj == key.obj && g.status == key.status && g.iters == key.iters)
+        hit = &g;
+    if (!hit) {
+      cudaGraph_t graph = nullptr;
+      long long n = 0;
+      if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+        cudaError_t le = launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, &n);
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (le == cudaSuccess && ce == cudaSuccess && graph) {
+          cudaGraphExec_t exec = nullptr;
+          if (cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+            if (h->graphs.size() >= 16) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+            key.exec = exec; key.n_kernels = n;
+            h->graphs.push_back(key);
+            hit = &h->graphs.back();
+          }
+        }
+        if (graph) cudaGraphDestroy(graph);
+      }
+      cudaGetLastError();   // a failed capture falls back to plain launches below
+    }
+    if (hit) {
+      CU(cudaGraphLaunch(hit->exec, s));
+      h->launches += hit->n_kernels;
+      done = true;
+    }
+  }
+  if (!done)
+    CU(launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, &h->launches));
   if (rec) {
     CU(cudaEventRecord(e1, s));
     h->timing.emplace_back(e0, e1);
@@ -117,6 +164,7 @@ int b200mpc_create(const b200mpc_params* p, int device, b200mpc_handle** out) {
   if (!h) return fail(B200MPC_ERR_NOMEM, "out of host memory");
   h->P = to_core(*p);
   h->device = device;
+  if (const char* e = getenv("B200MPC_NO_GRAPHS")) h->use_graphs = !(e[0] == '1');
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
   *out = h;
@@ -128,6 +176,7 @@ void b200mpc_destroy(b200mpc_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& ev : h->timing) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
   DevBuf* bufs[] = {&h->ws, &h->in_aos, &h->st_soa, &h->cf_soa, &h->out_soa, &h->out_aos, &h->traj_soa, &h->traj_aos,
                     &h->obj, &h->status, &h->iters, &h->misc0, &h->misc1, &h->misc2, &h->misc3};
   for (DevBuf* b : bufs) b->release();
