@@ -291,16 +291,18 @@ def run_ours(args):
         if rc:
             raise RuntimeError(lib.b200mpc_last_error().decode())
 
+    T = min(S, 3)   # host threads of the end-to-end leg (one solver handle each)
+
     def worker(k, n):
-        for i in range(k, n, S):
+        for i in range(k, n, T):
             host_step(i, k)
 
     for i in range(max(3, W)):
         host_step(i)
     barrier()
-    with ThreadPoolExecutor(S) as ex:
+    with ThreadPoolExecutor(T) as ex:
         t0 = time.perf_counter()
-        list(ex.map(lambda k: worker(k, K), range(S)))
+        list(ex.map(lambda k: worker(k, K), range(T)))
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
     lat = []
@@ -349,7 +351,7 @@ def run_ours(args):
                           traffic=None,
                           kernel=("mpc_{init,factor,forward,step,fused}_kernel: all solver kernels of one step (one CUDA graph), first to last"
                                   if args.mode == "perpass" else "mpc_fused_kernel"),
-                          avg_kernel_ms=avg_kernel_ms, launches_timed=kern_n, solver_mode=args.mode, streams=S,
+                          avg_kernel_ms=avg_kernel_ms, launches_timed=kern_n, solver_mode=args.mode, streams=S, e2e_host_threads=min(S, 3),
                           flop_per_launch=flop_per_launch, mean_ip_iters=mean_it,
                           peak_source="DFMA microbenchmark in this run (b200mpc_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                           hbm_peak_gbs=peaks.get("hbm_gbs"), algorithmic_io_bytes_per_solve=(6 + ncoef + 8 + 2) * 8,
@@ -377,7 +379,7 @@ def main():
     ap.add_argument("--latency-reps", type=int, default=100)
     ap.add_argument("--cpu-per-core", type=int, default=150, help="cpu_baseline: solves per host core in the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=3, help="solver handles / CUDA streams consecutive steps alternate between")
+    ap.add_argument("--streams", type=int, default=6, help="solver handles / CUDA streams consecutive steps alternate between")
     ap.add_argument("--mode", default="perpass", choices=["perpass", "fused"], help="solver execution mode (include/b200mpc.h)")
     ap.add_argument("--rounds", type=int, default=0, help="per-pass mode: rounds before the fused finisher (0 = library default)")
     args = ap.parse_args()

@@ -14,7 +14,10 @@
 
 namespace b200mpc {
 
-constexpr int kBlock = 64;
+#ifndef MPC_BLOCK
+#define MPC_BLOCK 64
+#endif
+constexpr int kBlock = MPC_BLOCK;
 // resident blocks per SM the light sweeps are compiled for (register cap = 65536 / (64 * blocks))
 #ifndef MPC_FWD_BLOCKS
 #define MPC_FWD_BLOCKS 8
