@@ -37,6 +37,31 @@ def f_iter(N):
     return (N - 1) * (2421 + 150) + 20 * N
 
 
+def profiled_traffic_bytes():
+    """DRAM bytes (read + write) of all solver kernels of ONE step, from the committed ncu launch list of this same
+    command (profiles/r1_final_launches_time_dram.csv: one init ... next init).  None if the file is missing."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1_final_launches_time_dram.csv")
+    try:
+        rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+        hdr = rows[0]
+        ik, iv, im, iu, iid = (hdr.index(c) for c in ("Kernel Name", "Metric Value", "Metric Name", "Metric Unit", "ID"))
+        per = {}
+        for r in rows[1:]:
+            if "dram__bytes" not in r[im]:
+                continue
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[iu], 1.0)
+            d = per.setdefault(int(r[iid]), [r[ik], 0.0])
+            d[1] += float(r[iv].replace(",", "")) * scale
+        seq = [per[k] for k in sorted(per)]
+        starts = [i for i, (k, _) in enumerate(seq) if "mpc_init_kernel" in k]
+        if len(starts) < 2:
+            return None
+        return float(sum(b for k, b in seq[starts[0]:starts[1]] if "mpc_" in k))
+    except Exception:
+        return None
+
+
 def make_workload(kind, B, seed_shift=0, mpc=None):
     """Returns (states (B,6), coeffs (B,ncoef)).  Degree-3 coefficients come from the GPU polyfit when a handle is
     given (that is the product path); the CPU-only reference arm uses numpy's QR for its own inputs."""
@@ -348,7 +373,8 @@ def run_ours(args):
             gpu_launches=int(launches),
             clocks=clocks, per_rank_ms_per_step=per_rank_ms, per_rank_sm_mhz=per_rank_mhz,
             roofline=dict(bound="fp64", achieved=achieved, peak=fp64_peak, unit="TFLOP/s", frac=achieved / fp64_peak if fp64_peak else None,
-                          traffic=None,
+                          traffic=profiled_traffic_bytes(), traffic_unit="bytes of DRAM read+write per step (ncu, profiles/r1_final_launches_time_dram.csv)",
+                          hbm_achieved_gbs=(profiled_traffic_bytes() or 0.0) / (avg_kernel_ms * 1e-3) / 1e9 if profiled_traffic_bytes() else None,
                           kernel=("mpc_{init,factor,forward,step,fused}_kernel: all solver kernels of one step (one CUDA graph), first to last"
                                   if args.mode == "perpass" else "mpc_fused_kernel"),
                           avg_kernel_ms=avg_kernel_ms, launches_timed=kern_n, solver_mode=args.mode, streams=S, e2e_host_threads=min(S, 3),
