@@ -114,5 +114,28 @@ def main():
     print("golden fixtures written to", HERE)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--config3" not in sys.argv:
     main()
+
+
+def config3():
+    """BASELINE configs[2]: 4096 randomized degree-1 problems, solved by the reference binaries
+    on all cores.  Only the returned 8-vector, objective, status and iteration count are stored (the full 198-vector
+    of the first 256 problems is in line_256.npz)."""
+    import multiprocessing as mp
+    from udacitympc_b200 import synth
+    st, cf = synth.line_problems(4096)
+    with mp.get_context("fork").Pool(os.cpu_count()) as pool:
+        res = pool.map(_solve_one, [(st[b], cf[b]) for b in range(4096)], chunksize=64)
+    np.savez_compressed(os.path.join(HERE, "config3_line_4096.npz"), out8=np.array([r[0] for r in res]),
+                        obj=np.array([r[1] for r in res]), status=np.array([r[2] for r in res], dtype=np.int32),
+                        iters=np.array([r[3] for r in res], dtype=np.int32), used_restoration=np.array([r[4] for r in res], dtype=np.int32))
+
+
+def _solve_one(a):
+    r = ob.ref_solve(a[0], a[1], trace=True)
+    return r["out8"], r["obj"], r["status"], r["iters"], int((r["trace"][:, 9] >= 100).any())
+
+
+if __name__ == "__main__" and "--config3" in sys.argv:
+    config3()

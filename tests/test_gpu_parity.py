@@ -259,3 +259,16 @@ def test_cpp_drop_in_closed_loop(tmp_path):
         assert len(vals) == 50
         np.testing.assert_allclose(vals, g["out8"][:, col], rtol=1e-5, atol=2e-6)
     assert (tmp_path / "trace.csv").read_text().count("\n") == 51
+
+
+def test_config3_4096_line_problems_vs_reference(mpc):
+    """BASELINE configs[2]: 4096 randomized degree-1 problems, every one against the reference binaries' answer."""
+    g = golden("config3_line_4096.npz")
+    st, cf = synth.line_problems(4096)
+    r = mpc.solve_batch(st, cf)
+    assert (r["status"] == g["status"]).all() and (g["status"] == 0).all()
+    np.testing.assert_allclose(r["out8"][:, 6:], g["out8"][:, 6:], rtol=0, atol=TOL_ACT)
+    np.testing.assert_allclose(r["out8"], g["out8"], rtol=0, atol=TOL_TRAJ)
+    assert (np.abs(r["cost"] - g["obj"]) <= TOL_OBJ * np.abs(g["obj"])).all()
+    np.testing.assert_allclose(r["out8"], g["out8"], rtol=0, atol=1e-8)
+    assert (r["iters"] == g["iters"]).mean() >= 0.995

@@ -136,3 +136,14 @@ def test_least_square_multiplier_estimate_is_kept_when_small(hostsim):
             o = ob.port_solve(st, g["coeffs"][b], params=ob.default_params(ref_v=6.0))
             assert r["status"] == o["status"] and r["iters"] == o["iters"]
             np.testing.assert_allclose(r["x"], o["x"], rtol=0, atol=1e-8)
+
+
+def test_config3_sample(hostsim):
+    from udacitympc_b200 import synth
+    g = golden("config3_line_4096.npz")
+    st, cf = synth.line_problems(4096)
+    for b in range(0, 4096, 16):
+        r = hostsim.solve(st[b], cf[b])
+        assert r["status"] == g["status"][b] and r["iters"] == g["iters"][b]
+        np.testing.assert_allclose(r["out8"], g["out8"][b], rtol=0, atol=1e-8)
+        assert abs(r["obj"] - g["obj"][b]) <= TOL_OBJ * abs(g["obj"][b])
