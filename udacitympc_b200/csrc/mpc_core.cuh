@@ -137,17 +137,21 @@ MPC_HD int workspace_doubles_per_problem(int N) { return kRec * (N + 1); }
 #endif
 template <int LANES>
 struct Ws {
-  double* b;
+  double* b;   // base of this problem: group base + lane
+  int lane;    // lane of this problem inside its group (0 on the host)
   MPC_HD double& operator()(int i) const { return b[(size_t)i * LANES]; }
-  // hint: rows [i, i+n) of this problem group will be read soon (each row of a warp is one 256-byte line pair)
+  // hint: rows [i, i+n) (n <= LANES) of this problem group will be read soon.  Each row of a warp is one 256-byte
+  // pair of 128-byte lines; lane l touches both lines of row i+l, so two instructions cover up to 32 rows.
   MPC_HD void prefetch(int i, int n) const {
 #if defined(__CUDA_ARCH__) && MPC_PREFETCH
-#pragma unroll
-    for (int k = 0; k < n; ++k) {
+    if (lane < n) {
+      const double* row = b - lane + (size_t)(i + lane) * LANES;
 #if MPC_PREFETCH == 1
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(b + (size_t)(i + k) * LANES));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 16));
 #else
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (size_t)(i + k) * LANES));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 16));
 #endif
     }
 #else
@@ -279,7 +283,7 @@ struct Solver {
   double fw_alpha_pr, fw_alpha_du, fw_gbd;
   bool fw_tiny;
 
-  MPC_HD Solver(const Params& p, double* base) : P(p), w{base}, N(p.N), M(p.N - 1) {}
+  MPC_HD Solver(const Params& p, double* base, int lane = 0) : P(p), w{base, lane}, N(p.N), M(p.N - 1) {}
 
   MPC_HD bool fl(int f) const { return (flags & f) != 0; }
   MPC_HD void setfl(int f, bool v) { flags = v ? (flags | f) : (flags & ~f); }
@@ -633,8 +637,8 @@ struct Solver {
       const int r = rec(t) + bX, rn = rec(t + 1);
       if (t + 1 < M) {
         w.prefetch(rn + oKF, 13); w.prefetch(rn + kRec + bX + xS, 8);
-        if (MPC_STORE_TRIG) w.prefetch(rn + bX + xTR, 4);
-        if (!ls) { w.prefetch(rn + bX + xZL, 4); if (MPC_STORE_C || use_csoc) w.prefetch(rn + kRec + bC, 6); }
+        w.prefetch(rn + bX + xZL, MPC_STORE_TRIG ? 8 : 4);   // ZL, ZU and the trig values are contiguous
+        if (!ls && (MPC_STORE_C || use_csoc)) w.prefetch(rn + kRec + bC, 6);
       }
 #pragma unroll
       for (int k = 0; k < 6; ++k) snx[k] = w(rn + bX + xS + k);

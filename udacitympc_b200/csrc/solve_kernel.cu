@@ -72,7 +72,7 @@ __device__ __forceinline__ void write_result(const Params& P, const SolveArgs& A
 __global__ void __launch_bounds__(kBlock) mpc_init_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= A.B) return;
-  Solver<32> S(P, problem_base(P, A, b));
+  Solver<32> S(P, problem_base(P, A, b), b & 31);
   double s0[6], cf[kMaxCoef];
   load_state6(A, b, s0);
   load_coeffs(A, b, cf);
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kBlock) mpc_init_kernel(const __grid_constant_
 __global__ void __launch_bounds__(kBlock) mpc_factor_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= A.B) return;
-  Solver<32> S(P, problem_base(P, A, b));
+  Solver<32> S(P, problem_base(P, A, b), b & 31);
   if (S.load_phase() != PH_FACTOR) return;
   load_coeffs(A, b, S.cf);
   S.kernel_factor();
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kBlock) mpc_factor_kernel(const __grid_constan
 __global__ void __launch_bounds__(kBlock, kFwdBlocks) mpc_forward_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= A.B) return;
-  Solver<32> S(P, problem_base(P, A, b));
+  Solver<32> S(P, problem_base(P, A, b), b & 31);
   if (S.load_phase() != PH_FORWARD) return;
   load_coeffs(A, b, S.cf);
   S.kernel_forward();
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kBlock, kFwdBlocks) mpc_forward_kernel(const _
 __global__ void __launch_bounds__(kBlock, kStepBlocks) mpc_step_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= A.B) return;
-  Solver<32> S(P, problem_base(P, A, b));
+  Solver<32> S(P, problem_base(P, A, b), b & 31);
   if (S.load_phase() != PH_STEP) return;
   load_coeffs(A, b, S.cf);
   S.kernel_step();
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kBlock, kStepBlocks) mpc_step_kernel(const __g
 __global__ void __launch_bounds__(kBlock) mpc_fused_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A, int fresh) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= A.B) return;
-  Solver<32> S(P, problem_base(P, A, b));
+  Solver<32> S(P, problem_base(P, A, b), b & 31);
   load_coeffs(A, b, S.cf);
   if (fresh) {
     double s0[6];
