@@ -12,6 +12,8 @@
  *   b200mpc_rollout_batch      VectorXd globalKinematic(const VectorXd& state, const VectorXd& actuators, double dt)
  *                              global_kinematic_model/solution/main.cpp:18-19, 36-62
  *   b200mpc_closed_loop_batch  the feed-forward loop of mpc_to_line/solution/main.cpp:51-76
+ *   b200mpc_roadmap_reference_batch  nearest centre-line point + local-frame fit: the producer of (coeffs, cte, epsi)
+ *                              that mpc_to_line/src/custom_MPC.cpp:177-212 attempts (solution/main.cpp:25-37 for a line)
  *   b200mpc_params             the file-scope globals of MPC.cpp:14-31 (N, dt, Lf, ref_v), the unit cost weights of
  *                              :57-76, the actuator bounds of :194-203, and the Ipopt options tol / max_iter that
  *                              the option string at :232-235 leaves at their defaults
@@ -123,6 +125,18 @@ int b200mpc_rollout_batch(b200mpc_handle* h, int B, int H, const double* state4,
 /* Device buffers, field-major: d_state4[k*B+b], d_act[(s*2+j)*B+b], d_out[(s*4+k)*B+b]. */
 int b200mpc_rollout_batch_device(b200mpc_handle* h, int B, int H, const double* d_state4, const double* d_act,
                                  double dt, double Lf, double* d_out, void* stream);
+
+/* Roadmap front-end (the step in front of MPC::Solve): for B vehicle poses in the road's global frame,
+ * nearest centre-line point (what mpc_to_line/src/custom_MPC.cpp:177-185 computes), the 6 consecutive centre-line
+ * points from there, global -> vehicle frame, degree-3 polyfit, and the MPC inputs in the vehicle frame:
+ * state6 = (0, 0, 0, v, cte = p(0), epsi = -atan(p'(0))) as solution/main.cpp:34-37 defines cte / epsi.
+ *   pose4  B x 4 (x, y, psi, v);  centerline  n_wp x 2 (x, y), n_wp >= 6 (e.g. columns 4,5 of mpc_to_line/roadmap.csv)
+ *   state6_out  B x 6;  coeffs_out  B x 4 -- ready for b200mpc_solve_batch(..., ncoef = 4, ...) */
+int b200mpc_roadmap_reference_batch(b200mpc_handle* h, int B, const double* pose4, const double* centerline, int n_wp,
+                                    double* state6_out, double* coeffs_out);
+/* Device buffers: d_pose4[k*B+b] (field-major), d_centerline[i*2+j] (row-major), d_state6_out[k*B+b], d_coeffs_out[i*B+b]. */
+int b200mpc_roadmap_reference_batch_device(b200mpc_handle* h, int B, const double* d_pose4, const double* d_centerline,
+                                           int n_wp, double* d_state6_out, double* d_coeffs_out, void* stream);
 
 /* Execution mode of the solver (tuning; results do not depend on it).
  *   mode 0 (default)  per-pass kernels: init, then `rounds` rounds of (factor, forward, step) launched back to

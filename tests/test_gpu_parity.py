@@ -272,3 +272,43 @@ def test_config3_4096_line_problems_vs_reference(mpc):
     assert (np.abs(r["cost"] - g["obj"]) <= TOL_OBJ * np.abs(g["obj"])).all()
     np.testing.assert_allclose(r["out8"], g["out8"], rtol=0, atol=1e-8)
     assert (r["iters"] == g["iters"]).mean() >= 0.995
+
+
+def roadmap_reference_oracle(pose, cl):
+    """numpy restatement of the roadmap front-end (nearest centre-line point, 6-point window, global -> vehicle frame)
+    with the oracle's polyfit.  The reference only sketches this step (custom_MPC.cpp:177-212, not runnable), so the
+    selection/transform part is pinned by this restatement only; the fit is the pinned polyfit oracle."""
+    x, y, psi, v = pose
+    i = int(np.argmin((x - cl[:, 0]) ** 2 + (y - cl[:, 1]) ** 2))
+    i = min(i, len(cl) - 6)
+    dx, dy = cl[i:i + 6, 0] - x, cl[i:i + 6, 1] - y
+    c, s = np.cos(psi), np.sin(psi)
+    lx, ly = c * dx + s * dy, c * dy - s * dx
+    cf = ob.port_polyfit(lx, ly, 3)
+    return np.array([0, 0, 0, v, cf[0], -np.arctan(cf[1])]), cf
+
+
+def test_roadmap_front_end_and_pipeline(mpc):
+    cl = synth.roadmap_centerline()
+    rng = np.random.default_rng(11)
+    B = 512
+    k = rng.integers(0, len(cl) - 7, size=B)
+    seg = cl[k + 1] - cl[k]
+    heading = np.arctan2(seg[:, 1], seg[:, 0])
+    t = rng.random(B)
+    pos = cl[k] + t[:, None] * seg + rng.normal(scale=1.0, size=(B, 2))
+    poses = np.column_stack([pos, heading + rng.normal(scale=0.1, size=B), 5 + 30 * rng.random(B)])
+    st, cf = mp.roadmap_reference_batch(poses, cl, mpc=mpc)
+    for b in range(0, B, 7):
+        so, co = roadmap_reference_oracle(poses[b], cl)
+        np.testing.assert_allclose(cf[b], co, rtol=0, atol=1e-9 * max(1.0, np.abs(co).max()))
+        np.testing.assert_allclose(st[b], so, rtol=0, atol=1e-9)
+    # the whole pipeline on the device: pose -> reference polynomial -> MPC solve
+    r = mpc.solve_batch(st, cf, want_traj=True)
+    assert (r["status"] == 0).mean() > 0.99
+    for b in range(0, B, 64):
+        o = ob.port_solve(st[b], cf[b])
+        assert o["status"] == r["status"][b]
+        np.testing.assert_allclose(r["traj"][b], o["x"], rtol=0, atol=1e-8)
+    with pytest.raises(mp.B200MPCError):
+        mp.roadmap_reference_batch(poses, cl[:4], mpc=mpc)

@@ -43,6 +43,8 @@ SYMBOLS = {
     "b200mpc_rollout_batch": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _dp, _dp, ctypes.c_double, ctypes.c_double, _dp]),
     "b200mpc_rollout_batch_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_double,
                                                     ctypes.c_double, _vp, _vp]),
+    "b200mpc_roadmap_reference_batch": (ctypes.c_int, [_vp, ctypes.c_int, _dp, _dp, ctypes.c_int, _dp, _dp]),
+    "b200mpc_roadmap_reference_batch_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp, _vp]),
     "b200mpc_set_solver_mode": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "b200mpc_kernel_time_ms": (ctypes.c_int, [_vp, _dp, _ip, ctypes.c_int]),
     "b200mpc_measure_fp64_peak": (ctypes.c_int, [_vp, _dp]),
@@ -314,6 +316,19 @@ def rollout_batch(states, actuators, dt, Lf=2.0, mpc=None):
     out = np.empty((B, H, 4))
     _check(m_._lib.b200mpc_rollout_batch(m_.handle, B, H, _ptr(states), _ptr(actuators), float(dt), float(Lf), _ptr(out)))
     return out
+
+
+def roadmap_reference_batch(poses, centerline, mpc=None):
+    """Roadmap front-end: poses (B,4) = (x, y, psi, v) in the road's global frame, centerline (n_wp,2) ->
+    (state6 (B,6), coeffs (B,4)) in the vehicle frame, ready for MPC.solve_batch."""
+    m_ = mpc or _default_mpc()
+    poses = _f64(poses); centerline = _f64(centerline)
+    if poses.ndim != 2 or poses.shape[1] != 4 or centerline.ndim != 2 or centerline.shape[1] != 2:
+        raise ValueError("poses must be (B,4) and centerline (n_wp,2)")
+    B = poses.shape[0]
+    st = np.empty((B, 6)); cf = np.empty((B, 4))
+    _check(m_._lib.b200mpc_roadmap_reference_batch(m_.handle, B, _ptr(poses), _ptr(centerline), centerline.shape[0], _ptr(st), _ptr(cf)))
+    return st, cf
 
 
 def global_kinematic(state, actuators, dt, Lf=2.0, mpc=None):

@@ -438,6 +438,48 @@ int b200mpc_rollout_batch(b200mpc_handle* h, int B, int H, const double* state4,
   return 0;
 }
 
+int b200mpc_roadmap_reference_batch_device(b200mpc_handle* h, int B, const double* d_pose4, const double* d_centerline,
+                                           int n_wp, double* d_state6_out, double* d_coeffs_out, void* stream) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  if (B < 0 || n_wp < 6 || n_wp > 12000) return fail(B200MPC_ERR_ARG, "roadmap: need B >= 0 and 6 <= n_wp <= 12000");
+  if (B == 0) return 0;
+  if (!d_pose4 || !d_centerline || !d_state6_out || !d_coeffs_out) return fail(B200MPC_ERR_ARG, "null pointer");
+  CU(cudaSetDevice(h->device));
+  CU(launch_roadmap_reference(d_pose4, B, d_centerline, n_wp, d_state6_out, d_coeffs_out, stream ? (cudaStream_t)stream : h->stream));
+  h->launches += 1;
+  return 0;
+}
+
+int b200mpc_roadmap_reference_batch(b200mpc_handle* h, int B, const double* pose4, const double* centerline, int n_wp,
+                                    double* state6_out, double* coeffs_out) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  if (B < 0 || n_wp < 6 || n_wp > 12000) return fail(B200MPC_ERR_ARG, "roadmap: need B >= 0 and 6 <= n_wp <= 12000");
+  if (B == 0) return 0;
+  if (!pose4 || !centerline || !state6_out || !coeffs_out) return fail(B200MPC_ERR_ARG, "null pointer");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const size_t nb = (size_t)B;
+  CU(h->misc0.ensure((nb * 4 + (size_t)2 * n_wp) * sizeof(double)));   // AoS pose | centre line
+  CU(h->misc1.ensure(nb * 4 * sizeof(double)));                         // SoA pose
+  CU(h->misc2.ensure(nb * 10 * sizeof(double)));                        // SoA state6 | coeffs
+  CU(h->misc3.ensure(nb * 10 * sizeof(double)));                        // AoS state6 | coeffs
+  double* a = h->misc0.as<double>();
+  double* wp = a + nb * 4;
+  double* so = h->misc2.as<double>();
+  double* ao = h->misc3.as<double>();
+  CU(cudaMemcpyAsync(a, pose4, nb * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(wp, centerline, (size_t)2 * n_wp * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(launch_aos_to_soa(a, h->misc1.as<double>(), B, 4, s));
+  CU(launch_roadmap_reference(h->misc1.as<double>(), B, wp, n_wp, so, so + nb * 6, s));
+  CU(launch_soa_to_aos(so, ao, B, 6, s));
+  CU(launch_soa_to_aos(so + nb * 6, ao + nb * 6, B, 4, s));
+  h->launches += 4;
+  CU(cudaMemcpyAsync(state6_out, ao, nb * 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(coeffs_out, ao + nb * 6, nb * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 int b200mpc_kernel_time_ms(b200mpc_handle* h, double* total_ms, int* launches, int reset) {
   if (!h) return fail(B200MPC_ERR_ARG, "null handle");

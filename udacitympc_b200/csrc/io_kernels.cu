@@ -258,6 +258,58 @@ cudaError_t launch_polyeval(const double* coeffs, int ncoef, const double* x, do
 }
 
 // ---------------------------------------------------------------------------------------------
+// Roadmap front-end: the producer of (coeffs, cte, epsi) in front of MPC::Solve.  For every vehicle
+// pose (x, y, psi, v) in the road's global frame: nearest centre-line point (the argmin over squared distances that
+// mpc_to_line/src/custom_MPC.cpp:177-185 attempts inside the CppAD tape), the window of kWin consecutive points
+// starting there, global -> vehicle frame (translate by the position, rotate by -psi), degree-3 polyfit (K4), and the
+// MPC state in the vehicle frame: (0, 0, 0, v, cte = p(0), epsi = -atan(p'(0))) as solution/main.cpp:34-37 defines them.
+// The centre line is staged in shared memory once per block.
+constexpr int kWin = 6;
+__global__ void __launch_bounds__(128) roadmap_reference_kernel(const double* __restrict__ pose4, int B, const double* __restrict__ wp_xy,
+                                                                int n_wp, double* __restrict__ state6, double* __restrict__ coeffs) {
+  extern __shared__ double wp[];   // [2][n_wp]
+  for (int i = threadIdx.x; i < n_wp; i += blockDim.x) { wp[i] = wp_xy[2 * i]; wp[n_wp + i] = wp_xy[2 * i + 1]; }
+  __syncthreads();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double x = pose4[b], y = pose4[(size_t)B + b], psi = pose4[(size_t)2 * B + b], v = pose4[(size_t)3 * B + b];
+  int best = 0;
+  double bd = 1e300;
+  for (int i = 0; i < n_wp; ++i) {
+    const double dx = x - wp[i], dy = y - wp[n_wp + i];
+    const double d = dx * dx + dy * dy;
+    if (d < bd) { bd = d; best = i; }   // first minimum, like index_sort's ind[0]
+  }
+  if (best > n_wp - kWin) best = n_wp - kWin;
+  double sp, cp;
+  sincos(psi, &sp, &cp);
+  double lx[kWin], ly[kWin], c[4];
+#pragma unroll
+  for (int j = 0; j < kWin; ++j) {
+    const double dx = wp[best + j] - x, dy = wp[n_wp + best + j] - y;
+    lx[j] = cp * dx + sp * dy;
+    ly[j] = cp * dy - sp * dx;
+  }
+  polyfit_regs<kWin, 4>(lx, ly, c);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) coeffs[(size_t)i * B + b] = c[i];
+  state6[b] = 0.0; state6[(size_t)B + b] = 0.0; state6[(size_t)2 * B + b] = 0.0; state6[(size_t)3 * B + b] = v;
+  state6[(size_t)4 * B + b] = c[0];          // polyeval(coeffs, 0) - 0
+  state6[(size_t)5 * B + b] = -atan(c[1]);   // 0 - atan(p'(0))
+}
+cudaError_t launch_roadmap_reference(const double* pose4, int B, const double* wp_xy, int n_wp, double* state6, double* coeffs,
+                                     cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  const size_t smem = (size_t)2 * n_wp * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(roadmap_reference_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  roadmap_reference_kernel<<<(B + 127) / 128, 128, smem, stream>>>(pose4, B, wp_xy, n_wp, state6, coeffs);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // K5: H Euler steps of the bicycle model per vehicle, global_kinematic_model/solution/main.cpp:56-59
 // (note the evaluation order v / Lf * delta * dt there).
 __global__ void __launch_bounds__(256) rollout_kernel(const double* __restrict__ state4, const double* __restrict__ act, int B, int H,

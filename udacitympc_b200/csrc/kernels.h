@@ -34,6 +34,10 @@ cudaError_t launch_polyeval(const double* coeffs, int ncoef, const double* x, do
 cudaError_t launch_rollout(const double* state4, const double* act, int B, int H, double dt, double Lf, double* out,
                            cudaStream_t stream);
 
+// roadmap front-end: pose4 [4][B] (x,y,psi,v global), wp_xy [n_wp][2] -> state6 [6][B], coeffs [4][B] (vehicle frame)
+cudaError_t launch_roadmap_reference(const double* pose4, int B, const double* wp_xy, int n_wp, double* state6, double* coeffs,
+                                     cudaStream_t stream);
+
 // DFMA throughput microbenchmark: returns FLOP executed per launch; time it outside.
 cudaError_t launch_fp64_peak(double* sink, int blocks, int threads, int iters, cudaStream_t stream, double* flop);
 
