@@ -45,6 +45,8 @@ int hostsim_solve_mode(const hostsim_params* hp, const double* state6, const dou
   };
   if (mode == 0) {
     Solver<1> S(P, ws.data());
+    double carry[kCarry];
+    S.cr = carry; S.cs = 1;
     S.init(state6, coeffs, ncoef);
     while (S.phase != PH_DONE && trips < 100000) { S.trip(); ++trips; log_row(S); }
     S.finish(R, x_out, 1);
@@ -55,6 +57,8 @@ int hostsim_solve_mode(const hostsim_params* hp, const double* state6, const dou
     while (phase != PH_DONE && trips < 400000) {
       for (int k = 0; k < 3; ++k) {   // the three kernels of one round
         Solver<1> S(P, ws.data());
+        double carry[kCarry];
+        S.cr = carry; S.cs = 1;
         if (S.load_phase() != k) continue;
         S.set_coeffs(coeffs, ncoef);
         if (k == PH_FACTOR) S.kernel_factor();

@@ -93,6 +93,7 @@ enum Status {
 
 constexpr int kMaxCoef = 4;   // reference polynomial degree <= 3
 constexpr int kMaxFilter = 8;
+constexpr int kCarry = 24;    // stage-to-stage values of the STEP sweep
 
 // ---- workspace of one problem, in doubles -----------------------------------------------------------------
 // Element i of the problem owned by lane l of a 32-problem group lives at group_base[i*LANES + l] (LANES = 32 on
@@ -282,8 +283,12 @@ struct Solver {
   // transient (within a pass)
   double fw_alpha_pr, fw_alpha_du, fw_gbd;
   bool fw_tiny;
+  // carry buffer of the STEP sweep (kCarry doubles, element i at cr[i*cs]): shared memory in the per-pass kernel,
+  // a thread-local array elsewhere.  Must be set before step_sweep() runs.
+  double* cr;
+  int cs;
 
-  MPC_HD Solver(const Params& p, double* base, int lane = 0) : P(p), w{base, lane}, N(p.N), M(p.N - 1) {}
+  MPC_HD Solver(const Params& p, double* base, int lane = 0) : P(p), w{base, lane}, N(p.N), M(p.N - 1), cr(nullptr), cs(1) {}
 
   MPC_HD bool fl(int f) const { return (flags & f) != 0; }
   MPC_HD void setfl(int f, bool v) { flags = v ? (flags | f) : (flags & ~f); }
@@ -809,8 +814,10 @@ struct Solver {
     const double qv = 2.0 * P.w_v * df + dw, qe = 2.0 * P.w_epsi * df + dw, qc = 2.0 * P.w_cte * df + dw, q0 = dw;
     const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df, gc2 = 2.0 * P.w_cte * df;
     const int bO = kX * cur, bN = kX * (cur ^ 1);
-    double lp[6], lo[6], ln[6];   // lambda^+_{t+1}, lambda_old_{t+1}, lambda_new_{t+1}
-    double snn[6];                // s_new at t+1
+    // Values carried from stage t+1 to stage t live in the carry buffer (shared memory in the per-pass kernel) and are
+    // loaded where they are used, which keeps them out of the register file across the heavy parts of the stage body:
+    // CR(0..5) lambda^+_{t+1}, CR(6..11) lambda_old_{t+1}, CR(12..17) lambda_new_{t+1}, CR(18..23) s_new_{t+1}
+#define CR(i) cr[(i) * cs]
     double dinf = 0.0, l1 = 0.0, zz1 = 0.0, szmx = 0.0, szmn = 1e300, xm = 0.0, dlm = 0.0;
     double f = 0.0, th = 0.0, cm = 0.0, slog = 0.0;
     {
@@ -818,13 +825,13 @@ struct Solver {
       double s[6], ds[6], lam[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) { s[k] = w(r + bO + xS + k); ds[k] = w(r + oDS + k); lam[k] = w(r + bO + xLAM + k); }
+      double lp[6], ln[6], snn[6];
       lp[0] = -q0 * ds[0]; lp[1] = -q0 * ds[1]; lp[2] = -q0 * ds[2];
       lp[3] = -qv * ds[3] - gv2 * (s[3] - P.ref_v);
       lp[4] = -qc * ds[4] - gc2 * s[4];
       lp[5] = -qe * ds[5] - ge2 * s[5];
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
-        lo[k] = lam[k];
         dlm = dmax(dlm, fabs(lp[k] - lam[k]));
         ln[k] = lam[k] + a * (lp[k] - lam[k]);
         snn[k] = s[k] + a * ds[k];
@@ -832,6 +839,7 @@ struct Solver {
         w(r + bN + xS + k) = snn[k];
         l1 += fabs(ln[k]);
         xm = dmax(xm, fabs(snn[k]));
+        CR(k) = lp[k]; CR(6 + k) = lam[k]; CR(12 + k) = ln[k]; CR(18 + k) = snn[k];
       }
       f += state_cost(snn);
       dinf = dmax(dinf, dmax(fabs(ln[0]), dmax(fabs(ln[1]), fabs(ln[2]))));
@@ -853,7 +861,11 @@ struct Solver {
       if (t > 0) { um0 = w(r - kRec + bO + xU); um1 = w(r - kRec + bO + xU + 1); dum0 = w(r - kRec + oDU); dum1 = w(r - kRec + oDU + 1); }
       double zl0 = w(r + bO + xZL), zl1 = w(r + bO + xZL + 1), zu0 = w(r + bO + xZU), zu1 = w(r + bO + xZU + 1);
       // ---- current point: lambda^+_t from the stationarity rows
+      double lpn[6];   // lambda^+_t
       {
+        double lp[6], lo[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { lp[k] = CR(k); lo[k] = CR(6 + k); }
         double spo, cpo, seo, ceo;
         trig_of(r + bO, s, spo, cpo, seo, ceo);
         double p0, p1, p2, p3;
@@ -870,14 +882,14 @@ struct Solver {
         nl[4] = -qc * ds[4] - gc2 * s[4];
         nl[5] = at[5] - ((qe + H.ee) * ds[5] + H.ev * ds[3]) - ge2 * s[5];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { lp[k] = nl[k]; lo[k] = lam[k]; dlm = dmax(dlm, fabs(nl[k] - lam[k])); }
+        for (int k = 0; k < 6; ++k) { lpn[k] = nl[k]; CR(k) = nl[k]; CR(6 + k) = lam[k]; dlm = dmax(dlm, fabs(nl[k] - lam[k])); }
       }
       // ---- trial point
       double sn[6], lnew[6], un[2];
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         sn[k] = s[k] + a * ds[k];
-        lnew[k] = lam[k] + a * (lp[k] - lam[k]);
+        lnew[k] = lam[k] + a * (lpn[k] - lam[k]);
         w(r + bN + xLAM + k) = lnew[k];
         w(r + bN + xS + k) = sn[k];
         l1 += fabs(lnew[k]);
@@ -921,6 +933,9 @@ struct Solver {
         sincos(sn[2], &spn, &cpn);
         sincos(sn[5], &sen, &cen);
         poly_eval(cf, sn[0], p0, p1, p2, p3);
+        double snn[6], ln[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { snn[k] = CR(18 + k); ln[k] = CR(12 + k); }
         residual(sn, un, snn, spn, cpn, sen, p0, atan(p1), c);
 #if MPC_STORE_TRIG
         w(r + bN + xTR) = spn; w(r + bN + xTR + 1) = cpn; w(r + bN + xTR + 2) = sen; w(r + bN + xTR + 3) = cen;
@@ -946,12 +961,13 @@ struct Solver {
         dinf = dmax(dinf, dmax(fabs(g0), fabs(g1)));
       }
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { ln[k] = lnew[k]; snn[k] = sn[k]; }
+      for (int k = 0; k < 6; ++k) { CR(12 + k) = lnew[k]; CR(18 + k) = sn[k]; }
       unn0 = un[0]; unn1 = un[1];
       uc0 = um0; uc1 = um1; duc0 = dum0; duc1 = dum1;
     }
     dualinf = dinf; lam1 = l1; z1 = zz1; sz_max = szmx; sz_min = szmn; xmaxabs = xm; dlam_max = dlm;
     tr_f = df * f; tr_theta = th; tr_priminf = cm; tr_sumlog = slog;
+#undef CR
   }
 
   // ------------------------------------------------------------------------------------------

@@ -23,7 +23,7 @@ constexpr int kBlock = MPC_BLOCK;
 #define MPC_FWD_BLOCKS 8
 #endif
 #ifndef MPC_STEP_BLOCKS
-#define MPC_STEP_BLOCKS 4
+#define MPC_STEP_BLOCKS 6
 #endif
 constexpr int kFwdBlocks = MPC_FWD_BLOCKS, kStepBlocks = MPC_STEP_BLOCKS;
 
@@ -103,6 +103,8 @@ __global__ void __launch_bounds__(kBlock, kStepBlocks) mpc_step_kernel(const __g
   if (b >= A.B) return;
   Solver<32> S(P, problem_base(P, A, b), b & 31);
   if (S.load_phase() != PH_STEP) return;
+  __shared__ double carry[kCarry * kBlock];   // stage-to-stage values of the sweep, [value][thread]
+  S.cr = carry + threadIdx.x; S.cs = kBlock;
   load_coeffs(A, b, S.cf);
   S.kernel_step();
   if (S.phase == PH_DONE) write_result(P, A, b, S);
@@ -113,6 +115,8 @@ __global__ void __launch_bounds__(kBlock) mpc_fused_kernel(const __grid_constant
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= A.B) return;
   Solver<32> S(P, problem_base(P, A, b), b & 31);
+  double carry[kCarry];
+  S.cr = carry; S.cs = 1;
   load_coeffs(A, b, S.cf);
   if (fresh) {
     double s0[6];
