@@ -5,7 +5,19 @@
 #include <cstdlib>
 #include <vector>
 
+#define MPC_BOUNDS_CHECK 1
 #include "../../udacitympc_b200/csrc/mpc_core.cuh"
+
+// every workspace access of the solver core is range-checked in this build
+static thread_local int g_ws_limit = 0;
+namespace b200mpc {
+void mpc_bounds_check(int i) {
+  if (i < 0 || i >= g_ws_limit) {
+    std::fprintf(stderr, "hostsim: workspace index %d out of range [0, %d)\n", i, g_ws_limit);
+    std::abort();
+  }
+}
+}  // namespace b200mpc
 
 using namespace b200mpc;
 
@@ -31,6 +43,7 @@ int hostsim_solve_mode(const hostsim_params* hp, const double* state6, const dou
   P.max_iter = hp->max_iter;
   P.finalize();
   std::vector<double> ws((size_t)workspace_doubles_per_problem(P.N), 0.0);
+  g_ws_limit = (int)ws.size();
   int rows = 0, trips = 0, last_iter = -1;
   Result R;
   double df = 1.0;

@@ -136,11 +136,19 @@ MPC_HD int workspace_doubles_per_problem(int N) { return kRec * (N + 1); }
 #ifndef MPC_PREFETCH
 #define MPC_PREFETCH 1
 #endif
+#ifdef MPC_BOUNDS_CHECK
+void mpc_bounds_check(int i);
+#endif
 template <int LANES>
 struct Ws {
   double* b;   // base of this problem: group base + lane
   int lane;    // lane of this problem inside its group (0 on the host)
-  MPC_HD double& operator()(int i) const { return b[(size_t)i * LANES]; }
+  MPC_HD double& operator()(int i) const {
+#ifdef MPC_BOUNDS_CHECK   // host test build only (tests/hostsim): every workspace index is range-checked
+    mpc_bounds_check(i);
+#endif
+    return b[(size_t)i * LANES];
+  }
   // hint: rows [i, i+n) (n <= LANES) of this problem group will be read soon.  Each row of a warp is one 256-byte
   // pair of 128-byte lines; lane l touches both lines of row i+l, so two instructions cover up to 32 rows.
   MPC_HD void prefetch(int i, int n) const {
