@@ -7,6 +7,7 @@
 
 #define MPC_BOUNDS_CHECK 1
 #include "../../udacitympc_b200/csrc/mpc_core.cuh"
+#include "../../udacitympc_b200/csrc/mpc_coop.cuh"
 
 // every workspace access of the solver core is range-checked in this build
 static thread_local int g_ws_limit = 0;
@@ -20,6 +21,15 @@ void mpc_bounds_check(int i) {
 }  // namespace b200mpc
 
 using namespace b200mpc;
+
+struct HostExec {   // the cooperative solver's primitives on one CPU thread: lanes run one after the other
+  bool lane0() const { return true; }
+  void sync() const {}
+  template <class F>
+  void for_stages(int n, F f) const {
+    for (int t = 0; t < n; ++t) f(t);
+  }
+};
 
 extern "C" {
 
@@ -56,7 +66,30 @@ int hostsim_solve_mode(const hostsim_params* hp, const double* state6, const dou
       last_iter = S.iter;
     }
   };
-  if (mode == 0) {
+  if (mode >= 2) {
+    // cooperative (warp-per-problem) solver.  mode 2: from the start.  mode 3+: the thread version runs the first
+    // (mode - 3) trips / passes, then the cooperative solver takes the problem over wherever it is.
+    Solver<1> S(P, ws.data());
+    double carry[kCarry];
+    S.cr = carry; S.cs = 1;
+    S.init(state6, coeffs, ncoef);
+    if (mode >= 3) {
+      int passes = mode - 3;
+      while (S.phase != PH_DONE && passes > 0) {   // one pass at a time so the hand-over can happen in any phase
+        if (S.phase == PH_FACTOR) S.do_factor();
+        else if (S.phase == PH_FORWARD) S.do_forward();
+        else S.do_step();
+        --passes;
+      }
+    }
+    std::vector<CoopStage> st((size_t)P.N);
+    CoopPub pub;
+    CoopSolver<1, HostExec> C(S, st.data(), &pub, HostExec{});
+    C.run();
+    S.finish(R, x_out, 1);
+    df = S.df; cur = S.cur;
+    trips = S.iter;
+  } else if (mode == 0) {
     Solver<1> S(P, ws.data());
     double carry[kCarry];
     S.cr = carry; S.cs = 1;

@@ -65,10 +65,19 @@ def test_config1_closed_loop_on_device(mpc):
 
 
 @pytest.mark.parametrize("name", ["line_256.npz", "roadmap_256.npz"])
-def test_random_problems_vs_reference(mpc, name):
+@pytest.mark.parametrize("path", ["coop", "perpass", "fused"])
+def test_random_problems_vs_reference(name, path):
+    """Every execution path of the solver: cooperative warp-per-problem kernel (default for small batches), per-pass
+    thread-per-problem kernels (default for large batches; forced here with fused_below = 0) and the fused
+    thread-per-problem kernel."""
     g = golden(name)
     cf = g["coeffs"] if "coeffs" in g.files else g["fit"]
-    r = mpc.solve_batch(g["states"], cf, want_traj=True)
+    with mp.MPC(device=0) as m:
+        if path == "perpass":
+            m.set_solver_mode(0, 12, 0)    # 12 rounds only: about half of the problems finish in the cooperative finisher
+        elif path == "fused":
+            m.set_solver_mode(1, 0, -1)
+        r = m.solve_batch(g["states"], cf, want_traj=True)
     compare(r, g)
 
 

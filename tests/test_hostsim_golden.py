@@ -147,3 +147,22 @@ def test_config3_sample(hostsim):
         assert r["status"] == g["status"][b] and r["iters"] == g["iters"][b]
         np.testing.assert_allclose(r["out8"], g["out8"][b], rtol=0, atol=1e-8)
         assert abs(r["obj"] - g["obj"][b]) <= TOL_OBJ * abs(g["obj"][b])
+
+
+def test_cooperative_solver_matches_thread_version(hostsim):
+    """The warp-per-problem (latency path) solver, emulated lane by lane on the host: from the start (mode 2) and
+    taking a problem over from the thread version after k sweeps (mode 3+k), in whatever phase it is in."""
+    sets = [("line_256.npz", {}, range(0, 256, 8)), ("roadmap_256.npz", {}, range(0, 256, 8)), ("roadmap_N50_64.npz", dict(N=50), range(0, 64, 2))]
+    g = golden("line_params_64.npz")
+    N, dt, Lf, ref_v, dmax, amax = g["params"]
+    sets.append(("line_params_64.npz", dict(N=int(N), dt=dt, Lf=Lf, ref_v=ref_v, delta_max=dmax, a_max=amax), range(0, 64, 2)))
+    for name, kw, idx in sets:
+        g = golden(name)
+        cf = g["coeffs"] if "coeffs" in g.files else g["fit"]
+        for b in idx:
+            a = hostsim.solve(g["states"][b], cf[b], mode=0, **kw)
+            for mode in (2, 4, 5, 6, 3 + 3 * 7, 3 + 3 * 11 + 1, 3 + 3 * 30 + 2):
+                c = hostsim.solve(g["states"][b], cf[b], mode=mode, **kw)
+                assert a["status"] == c["status"] and a["iters"] == c["iters"], (name, b, mode)
+                np.testing.assert_allclose(a["x"], c["x"], rtol=0, atol=1e-10)
+                assert abs(a["obj"] - c["obj"]) <= 1e-12 * abs(a["obj"])

@@ -165,6 +165,7 @@ int b200mpc_create(const b200mpc_params* p, int device, b200mpc_handle** out) {
   h->P = to_core(*p);
   h->device = device;
   if (const char* e = getenv("B200MPC_NO_GRAPHS")) h->use_graphs = !(e[0] == '1');
+  if (const char* e = getenv("B200MPC_NO_COOP")) h->cfg.coop = !(e[0] == '1');
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
   *out = h;

@@ -17,7 +17,8 @@ enum SolveMode { kModePerPass = 0, kModeFused = 1 };
 struct SolveConfig {
   int mode = kModePerPass;
   int rounds = 24;        // per-pass mode: rounds of (factor, forward, step) before the fused finisher
-  int fused_below = 2048; // batches smaller than this use the fused kernel alone (launch latency dominates)
+  int fused_below = 2048; // batches smaller than this skip the per-pass rounds (one launch: latency path)
+  bool coop = true;       // latency path = cooperative warp-per-problem kernel (false: thread-per-problem fused kernel)
 };
 cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6, const double* coeffs, int ncoef,
                          double* ws, double* out8, double* traj, double* obj, int* status, int* iters,

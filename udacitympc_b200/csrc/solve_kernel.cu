@@ -11,6 +11,7 @@
 //   fused kernel      one launch loops the three passes per thread until its problem is done.  Used to finish
 //                     stragglers after the fixed number of rounds, and for tiny batches (latency).
 #include "kernels.h"
+#include "mpc_coop.cuh"
 
 namespace b200mpc {
 
@@ -131,6 +132,69 @@ __global__ void __launch_bounds__(kBlock) mpc_fused_kernel(const __grid_constant
   write_result(P, A, b, S);
 }
 
+// ---- cooperative kernel: one problem per warp (latency path: small batches, the tail of a batch, stragglers) -----
+struct DevExec {
+  int lane;
+  __device__ __forceinline__ bool lane0() const { return lane == 0; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  template <class F>
+  __device__ __forceinline__ void for_stages(int n, F f) const {
+    for (int t = lane; t < n; t += 32) f(t);
+  }
+};
+
+__global__ void __launch_bounds__(128) mpc_coop_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A, int fresh,
+                                                       int warps_per_block, int doubles_per_warp) {
+  extern __shared__ double coop_smem[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * warps_per_block + wib;   // one problem per warp
+  if (wib >= warps_per_block || b >= A.B) return;
+  double* mine = coop_smem + (size_t)wib * doubles_per_warp;
+  CoopStage* st = reinterpret_cast<CoopStage*>(mine);
+  CoopPub* pub = reinterpret_cast<CoopPub*>(mine + (size_t)P.N * kCoopStageDoubles);
+  Solver<32> S(P, problem_base(P, A, b), b & 31);
+  load_coeffs(A, b, S.cf);
+  if (fresh) {
+    if (lane == 0) {
+      double s0[6];
+      load_state6(A, b, s0);
+      S.init(s0, S.cf, kMaxCoef);
+    }
+  } else {
+    if (S.load_phase() == PH_DONE) return;   // whole warp
+    if (lane == 0) S.load_state();
+  }
+  __syncwarp();
+  CoopSolver<32, DevExec> C(S, st, pub, DevExec{lane});
+  C.run();
+  if (lane == 0) {
+    S.store_state();
+    write_result(P, A, b, S);
+  }
+}
+
+static size_t coop_doubles_per_warp(int N) { return (size_t)N * kCoopStageDoubles + (sizeof(CoopPub) + 7) / 8; }
+
+// launches the cooperative kernel if the horizon fits in shared memory; returns false otherwise
+static bool launch_coop(const Params& P, const SolveArgs& A, int fresh, cudaStream_t stream, cudaError_t* err) {
+  const size_t per_warp = coop_doubles_per_warp(P.N) * sizeof(double);
+  const size_t limit = 200 * 1024;
+  if (per_warp > limit) return false;
+  int wpb = (int)(limit / per_warp);
+  if (wpb > 4) wpb = 4;
+  const size_t smem = per_warp * wpb;
+  static bool attr_set = false;
+  if (!attr_set) {
+    *err = cudaFuncSetAttribute(mpc_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+    if (*err != cudaSuccess) return true;
+    attr_set = true;
+  }
+  const int grid = (A.B + wpb - 1) / wpb;
+  mpc_coop_kernel<<<grid, 128, smem, stream>>>(P, A, fresh, wpb, (int)coop_doubles_per_warp(P.N));
+  *err = cudaGetLastError();
+  return true;
+}
+
 cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6, const double* coeffs, int ncoef,
                          double* ws, double* out8, double* traj, double* obj, int* status, int* iters,
                          const SolveConfig& cfg, cudaStream_t stream, long long* n_launches) {
@@ -141,7 +205,9 @@ cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6
   for (int step = 0; step < steps; ++step) {
     A.step = step;
     if (cfg.mode == kModeFused || B < cfg.fused_below) {
-      mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 1);
+      cudaError_t ce = cudaSuccess;
+      if (!(cfg.coop && cfg.mode != kModeFused && launch_coop(P, A, 1, stream, &ce))) mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 1);
+      if (ce != cudaSuccess) return ce;
       ++n;
     } else {
       mpc_init_kernel<<<grid, kBlock, 0, stream>>>(P, A);
@@ -150,7 +216,9 @@ cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6
         mpc_forward_kernel<<<grid, kBlock, 0, stream>>>(P, A);
         mpc_step_kernel<<<grid, kBlock, 0, stream>>>(P, A);
       }
-      mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 0);
+      cudaError_t ce = cudaSuccess;
+      if (!(cfg.coop && launch_coop(P, A, 0, stream, &ce))) mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 0);
+      if (ce != cudaSuccess) return ce;
       n += 2 + 3LL * cfg.rounds;
     }
     cudaError_t e = cudaGetLastError();
