@@ -139,10 +139,13 @@ int b200mpc_roadmap_reference_batch_device(b200mpc_handle* h, int B, const doubl
                                            int n_wp, double* d_state6_out, double* d_coeffs_out, void* stream);
 
 /* Execution mode of the solver (tuning; results do not depend on it).
- *   mode 0 (default)  per-pass kernels: init, then `rounds` rounds of (factor, forward, step) launched back to
- *                     back on the stream, then one fused launch that finishes any problem still iterating
- *   mode 1            the fused kernel alone (one launch per solve; lowest latency for small batches)
- * rounds <= 0 / fused_below < 0 keep the current value.  Batches smaller than fused_below always use mode 1. */
+ *   mode 0 (default)  throughput path + latency path.  Batches of at least `fused_below` problems (default 3072) run
+ *                     `rounds` rounds (default 16) of the per-pass thread-per-problem kernels (factor, forward, step);
+ *                     whatever is still iterating then -- the thin tail of the batch and rare 30-50 iteration
+ *                     stragglers -- is finished by the cooperative warp-per-problem kernel.  Smaller batches (e.g. the
+ *                     reference's one-problem MPC::Solve call: 0.6 ms) use the cooperative kernel alone.
+ *   mode 1            the fused thread-per-problem kernel alone (one launch per solve; kept for comparison)
+ * rounds <= 0 / fused_below < 0 keep the current value.  The whole launch sequence of a solve is replayed as one CUDA graph. */
 int b200mpc_set_solver_mode(b200mpc_handle* h, int mode, int rounds, int fused_below);
 
 /* Measurement helpers (used by bench.py; not part of the reference interface). */

@@ -16,8 +16,8 @@ size_t solve_workspace_doubles(int N, int B);
 enum SolveMode { kModePerPass = 0, kModeFused = 1 };
 struct SolveConfig {
   int mode = kModePerPass;
-  int rounds = 24;        // per-pass mode: rounds of (factor, forward, step) before the fused finisher
-  int fused_below = 2048; // batches smaller than this skip the per-pass rounds (one launch: latency path)
+  int rounds = 16;        // per-pass mode: rounds of (factor, forward, step) before the finisher takes the thin tail
+  int fused_below = 3072; // batches smaller than this skip the per-pass rounds (one launch: latency path)
   bool coop = true;       // latency path = cooperative warp-per-problem kernel (false: thread-per-problem fused kernel)
 };
 cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6, const double* coeffs, int ncoef,
