@@ -44,7 +44,7 @@ def main():
             status = torch.empty(B, dtype=torch.int32, device=dev)
             iters = torch.empty(B, dtype=torch.int32, device=dev)
             with mp.MPC(device=0, N=N) as m:
-                m.set_solver_mode(0, max(24, N + 10), -1)
+                m.set_solver_mode(0, 20, -1)   # 20 per-pass rounds, then the cooperative finisher
 
                 def step():
                     m.solve_batch_device(B, st_d.data_ptr(), cf_d.data_ptr(), 4, out8.data_ptr(), 0, 0, status.data_ptr(),
