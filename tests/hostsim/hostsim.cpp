@@ -72,7 +72,11 @@ int hostsim_solve_mode(const hostsim_params* hp, const double* state6, const dou
     Solver<1> S(P, ws.data());
     double carry[kCarry];
     S.cr = carry; S.cs = 1;
-    S.init(state6, coeffs, ncoef);
+    std::vector<CoopStage> st((size_t)P.N);
+    CoopPub pub;
+    CoopSolver<1, HostExec> C(S, st.data(), &pub, HostExec{});
+    if (mode == 2) { S.set_coeffs(coeffs, ncoef); C.init(state6); }
+    else S.init(state6, coeffs, ncoef);
     if (mode >= 3) {
       int passes = mode - 3;
       while (S.phase != PH_DONE && passes > 0) {   // one pass at a time so the hand-over can happen in any phase
@@ -82,9 +86,6 @@ int hostsim_solve_mode(const hostsim_params* hp, const double* state6, const dou
         --passes;
       }
     }
-    std::vector<CoopStage> st((size_t)P.N);
-    CoopPub pub;
-    CoopSolver<1, HostExec> C(S, st.data(), &pub, HostExec{});
     C.run();
     S.finish(R, x_out, 1);
     df = S.df; cur = S.cur;

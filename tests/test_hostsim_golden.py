@@ -131,7 +131,7 @@ def test_least_square_multiplier_estimate_is_kept_when_small(hostsim):
     for b in range(6):
         st = g["states"][b].copy()
         st[3] = 5.0 + 0.2 * b
-        for mode in (0, 1):
+        for mode in (0, 1, 2, 4, 5, 6):
             r = hostsim.solve(st, g["coeffs"][b], mode=mode, ref_v=6.0)
             o = ob.port_solve(st, g["coeffs"][b], params=ob.default_params(ref_v=6.0))
             assert r["status"] == o["status"] and r["iters"] == o["iters"]

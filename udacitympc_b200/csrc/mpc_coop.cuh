@@ -29,7 +29,7 @@ struct CoopStage {
   double KF[13];           // K (2x4), Lambda^-1 (3), k (2)
   double ds[6], du[2];     // search direction of time t
   double sl[4], z[4];      // slacks (sl0,su0,sl1,su1) and multipliers (zl0,zu0,zl1,zu1) of u_t at the current iterate
-  double s[6], u[2], lam[6];   // current iterate of time t
+  double s[6], u[2], lam[6], tr[4];   // current iterate of time t and its trig values
   double sn[6], un[2], zn[4], trn[4];   // trial iterate of time t
   double bl[6], lp[6], ln[6];  // lambda^+ recurrence offset, lambda^+_t, lambda_trial_t
   double red[12];          // per-stage partial reductions
@@ -38,7 +38,7 @@ constexpr int kCoopStageDoubles = sizeof(CoopStage) / sizeof(double);
 
 struct CoopPub {   // scalars lane 0 publishes to the other lanes before a parallel phase
   double mu, tau, df, dw, alpha, alpha_du;
-  int cur, ls, use_csoc, phase;
+  int cur, ls, use_csoc, phase, lskeep;
 };
 
 template <int LANES, class Exec>
@@ -55,7 +55,7 @@ struct CoopSolver {
   MPC_HD void publish() {
     if (ex.lane0()) {
       pub->mu = S.mu; pub->tau = S.tau; pub->df = S.df; pub->dw = S.dw_curr; pub->alpha = S.alpha; pub->alpha_du = S.alpha_du;
-      pub->cur = S.cur; pub->ls = S.fl(F_LS) ? 1 : 0; pub->use_csoc = S.fl(F_INSOC) ? 1 : 0; pub->phase = S.phase;
+      pub->cur = S.cur; pub->ls = S.fl(F_LS) ? 1 : 0; pub->use_csoc = S.fl(F_INSOC) ? 1 : 0; pub->phase = S.phase; pub->lskeep = S.fl(F_LSKEEP) ? 1 : 0;
     }
     ex.sync();
   }
@@ -101,6 +101,7 @@ struct CoopSolver {
     const int r = S.rec(t) + kX * pub->cur;
     double sp, cp, se, ce, p0, p1, p2, p3;
     S.trig_of(r, c.s, sp, cp, se, ce);
+    c.tr[0] = sp; c.tr[1] = cp; c.tr[2] = se; c.tr[3] = ce;
     poly_eval(S.cf, c.s[0], p0, p1, p2, p3);
     const Lin A = make_lin(P, c.s[3], c.u[0], sp, cp, se, ce, p1, p2);
     c.A[0] = A.a1; c.A[1] = A.a2; c.A[2] = A.a3; c.A[3] = A.a4; c.A[4] = A.a5; c.A[5] = A.beta; c.A[6] = A.pp; c.A[7] = A.kap;
@@ -319,12 +320,15 @@ struct CoopSolver {
   // offset of the lambda^+ back-substitution of stage t.
   MPC_HD void step1(int t) {   // t < N
     CoopStage& c = st[t];
-    const double a = pub->alpha, a_du = pub->alpha_du, mu = pub->mu, df = pub->df, dw = pub->dw;
-    const double qv = 2.0 * P.w_v * df + dw, qe = 2.0 * P.w_epsi * df + dw, qc = 2.0 * P.w_cte * df + dw, q0 = dw;
+    // least-square multiplier pass (ls): H = I, the iterate does not move and nothing is written to the trial copy
+    const bool ls = pub->ls != 0;
+    const double a = ls ? 0.0 : pub->alpha, a_du = ls ? 0.0 : pub->alpha_du, mu = pub->mu, df = pub->df, dw = pub->dw;
+    const double qv = ls ? 1.0 : 2.0 * P.w_v * df + dw, qe = ls ? 1.0 : 2.0 * P.w_epsi * df + dw, qc = ls ? 1.0 : 2.0 * P.w_cte * df + dw,
+                 q0 = ls ? 1.0 : dw;
     const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df, gc2 = 2.0 * P.w_cte * df;
     const int rN = S.rec(t) + kX * (pub->cur ^ 1);
     double xm = 0.0, zz1 = 0.0, szmx = 0.0, szmn = 1e300, slog = 0.0;
-    for (int k = 0; k < 6; ++k) { c.sn[k] = c.s[k] + a * c.ds[k]; S.w(rN + xS + k) = c.sn[k]; xm = dmax(xm, fabs(c.sn[k])); }
+    for (int k = 0; k < 6; ++k) { c.sn[k] = c.s[k] + a * c.ds[k]; if (!ls) S.w(rN + xS + k) = c.sn[k]; xm = dmax(xm, fabs(c.sn[k])); }
     const double* ds = c.ds;
     if (t == M) {
       c.lp[0] = -q0 * ds[0]; c.lp[1] = -q0 * ds[1]; c.lp[2] = -q0 * ds[2];
@@ -334,38 +338,45 @@ struct CoopSolver {
     } else {
       const double du0 = c.du[0], du1 = c.du[1];
       c.un[0] = c.u[0] + a * du0; c.un[1] = c.u[1] + a * du1;
-      S.w(rN + xU) = c.un[0]; S.w(rN + xU + 1) = c.un[1];
+      if (!ls) { S.w(rN + xU) = c.un[0]; S.w(rN + xU + 1) = c.un[1]; }
       xm = dmax(xm, dmax(fabs(c.un[0]), fabs(c.un[1])));
       const double sl0 = c.sl[0], su0 = c.sl[1], sl1 = c.sl[2], su1 = c.sl[3];
       double zl0 = c.z[0], zu0 = c.z[1], zl1 = c.z[2], zu1 = c.z[3];
       const double b0 = safe_slack(c.un[0] - P.xl[0], mu, zl0, P.xl[0]) * safe_slack(P.xu[0] - c.un[0], mu, zu0, P.xu[0]);
       const double b1 = safe_slack(c.un[1] - P.xl[1], mu, zl1, P.xl[1]) * safe_slack(P.xu[1] - c.un[1], mu, zu1, P.xu[1]);
       slog = log(b0 * b1);
-      zl0 += a_du * ((mu - sl0 * zl0 - zl0 * du0) / sl0);
-      zu0 += a_du * ((mu - su0 * zu0 + zu0 * du0) / su0);
-      zl1 += a_du * ((mu - sl1 * zl1 - zl1 * du1) / sl1);
-      zu1 += a_du * ((mu - su1 * zu1 + zu1 * du1) / su1);
+      if (!ls) {
+        zl0 += a_du * ((mu - sl0 * zl0 - zl0 * du0) / sl0);
+        zu0 += a_du * ((mu - su0 * zu0 + zu0 * du0) / su0);
+        zl1 += a_du * ((mu - sl1 * zl1 - zl1 * du1) / sl1);
+        zu1 += a_du * ((mu - su1 * zu1 + zu1 * du1) / su1);
+      }
       const double nsl0 = safe_slack(c.un[0] - P.xl[0], mu, zl0, P.xl[0]), nsu0 = safe_slack(P.xu[0] - c.un[0], mu, zu0, P.xu[0]);
       const double nsl1 = safe_slack(c.un[1] - P.xl[1], mu, zl1, P.xl[1]), nsu1 = safe_slack(P.xu[1] - c.un[1], mu, zu1, P.xu[1]);
-      const double m0 = mu / nsl0, m1 = mu / nsu0, m2 = mu / nsl1, m3 = mu / nsu1;
-      zl0 = dclamp(zl0, 1e-10 * m0, 1e10 * m0);
-      zu0 = dclamp(zu0, 1e-10 * m1, 1e10 * m1);
-      zl1 = dclamp(zl1, 1e-10 * m2, 1e10 * m2);
-      zu1 = dclamp(zu1, 1e-10 * m3, 1e10 * m3);
-      S.w(rN + xZL) = zl0; S.w(rN + xZL + 1) = zl1; S.w(rN + xZU) = zu0; S.w(rN + xZU + 1) = zu1;
+      if (!ls) {
+        const double m0 = mu / nsl0, m1 = mu / nsu0, m2 = mu / nsl1, m3 = mu / nsu1;
+        zl0 = dclamp(zl0, 1e-10 * m0, 1e10 * m0);
+        zu0 = dclamp(zu0, 1e-10 * m1, 1e10 * m1);
+        zl1 = dclamp(zl1, 1e-10 * m2, 1e10 * m2);
+        zu1 = dclamp(zu1, 1e-10 * m3, 1e10 * m3);
+        S.w(rN + xZL) = zl0; S.w(rN + xZL + 1) = zl1; S.w(rN + xZU) = zu0; S.w(rN + xZU + 1) = zu1;
+      }
       c.zn[0] = zl0; c.zn[1] = zu0; c.zn[2] = zl1; c.zn[3] = zu1;
       zz1 = zl0 + zl1 + zu0 + zu1;
       const double c0 = nsl0 * zl0, c1 = nsl1 * zl1, c2 = nsu0 * zu0, c3 = nsu1 * zu1;
       szmx = dmax(dmax(c0, c1), dmax(c2, c3));
       szmn = dmin(dmin(c0, c1), dmin(c2, c3));
       // trig of the trial point
-      double spn, cpn, sen, cen;
-      sincos(c.sn[2], &spn, &cpn);
-      sincos(c.sn[5], &sen, &cen);
-      c.trn[0] = spn; c.trn[1] = cpn; c.trn[2] = sen; c.trn[3] = cen;
+      if (ls) { c.trn[0] = c.tr[0]; c.trn[1] = c.tr[1]; c.trn[2] = c.tr[2]; c.trn[3] = c.tr[3]; }
+      else {
+        double spn, cpn, sen, cen;
+        sincos(c.sn[2], &spn, &cpn);
+        sincos(c.sn[5], &sen, &cen);
+        c.trn[0] = spn; c.trn[1] = cpn; c.trn[2] = sen; c.trn[3] = cen;
 #if MPC_STORE_TRIG
-      S.w(rN + xTR) = spn; S.w(rN + xTR + 1) = cpn; S.w(rN + xTR + 2) = sen; S.w(rN + xTR + 3) = cen;
+        S.w(rN + xTR) = spn; S.w(rN + xTR + 1) = cpn; S.w(rN + xTR + 2) = sen; S.w(rN + xTR + 3) = cen;
 #endif
+      }
       // offset of lambda^+_t = A_t^T lambda^+_{t+1} + bl_t (current linearisation, staged by prep_factor)
       c.bl[0] = -(q0 + c.H[0]) * ds[0];
       c.bl[1] = -q0 * ds[1];
@@ -390,17 +401,19 @@ struct CoopSolver {
   // STEP, parallel part 2: trial multipliers, residuals and objective of stage t
   MPC_HD void step2(int t) {   // t < N
     CoopStage& c = st[t];
+    const bool ls = pub->ls != 0, keep = pub->lskeep != 0;
     const double a = pub->alpha;
-    const int rN = S.rec(t) + kX * (pub->cur ^ 1);
+    const int rN = S.rec(t) + kX * (ls ? pub->cur : (pub->cur ^ 1));
     double l1 = 0.0, dlm = 0.0, th = 0.0, cm = 0.0, f = 0.0;
     for (int k = 0; k < 6; ++k) {
-      c.ln[k] = c.lam[k] + a * (c.lp[k] - c.lam[k]);
-      S.w(rN + xLAM + k) = c.ln[k];
+      // ls: lam is 0; the first pass evaluates the norms for lambda = 0, the second (keep) stores the estimate
+      c.ln[k] = ls ? (keep ? c.lp[k] : 0.0) : c.lam[k] + a * (c.lp[k] - c.lam[k]);
+      if (!ls || keep) S.w(rN + xLAM + k) = c.ln[k];
       l1 += fabs(c.ln[k]);
       dlm = dmax(dlm, fabs(c.lp[k] - c.lam[k]));
     }
     f = S.state_cost(c.sn);
-    if (t < M) {
+    if (t < M && !ls) {
       double p0, p1, p2, p3, cres[6];
       poly_eval(S.cf, c.sn[0], p0, p1, p2, p3);
       S.residual(c.sn, c.un, st[t + 1].sn, c.trn[0], c.trn[1], c.trn[2], p0, atan(p1), cres);
@@ -488,9 +501,7 @@ struct CoopSolver {
       publish();
     }
     if (pub->phase == PH_STEP) {
-      if (pub->ls) {
-        if (ex.lane0()) { S.accept_ls(!S.fl(F_LSKEEP)); S.step_logic(); }
-      } else {
+      {
         ex.for_stages(N, [&](int t) { step1(t); });
         ex.sync();
         if (ex.lane0()) seq_step();
@@ -503,6 +514,22 @@ struct CoopSolver {
       }
       publish();
     }
+  }
+  // start point of a fresh problem, stage-parallel (Solver::init)
+  MPC_HD void init(const double* s0) {
+    if (ex.lane0()) S.init_scalars(s0, S.cf, kMaxCoef);
+    ex.for_stages(N, [&](int t) {
+      double f, th, cm, sl;
+      S.init_stage(t, s0, f, th, cm, sl);
+      st[t].red[0] = f; st[t].red[1] = th; st[t].red[2] = cm; st[t].red[3] = sl;
+    });
+    ex.sync();
+    if (ex.lane0()) {
+      double f = 0.0, th = 0.0, cm = 0.0, sl = 0.0;
+      for (int t = 0; t < N; ++t) { f += st[t].red[0]; th += st[t].red[1]; cm = dmax(cm, st[t].red[2]); sl += st[t].red[3]; }
+      S.init_finish(f, th, cm, sl);
+    }
+    ex.sync();
   }
   // A problem taken over in the middle of an iteration (phase FORWARD, or STEP during backtracking): re-stage what
   // the earlier sweeps of this iteration left in shared memory, without touching the control state.
@@ -520,7 +547,7 @@ struct CoopSolver {
   // runs the problem to completion; lane 0's Solver holds the final state
   MPC_HD void run() {
     publish();
-    if (pub->phase == PH_FORWARD || (pub->phase == PH_STEP && !pub->ls)) rebuild();
+    if (pub->phase == PH_FORWARD || pub->phase == PH_STEP) rebuild();
     while (pub->phase != PH_DONE) round();
   }
 };

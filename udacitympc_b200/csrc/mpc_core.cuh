@@ -394,7 +394,7 @@ struct Solver {
   // ------------------------------------------------------------------------------------------
   // start point, bounds, scaling, z, mu  (MPC.cpp:167-203; IpGradientScaling.cpp:99-116;
   // IpDefaultIterateInitializer.cpp:230-266, 469-649), residuals / objective / barrier at the start point
-  MPC_HD void init(const double* s0, const double* coef, int ncoef) {
+  MPC_HD void init_scalars(const double* s0, const double* coef, int ncoef) {
     set_coeffs(coef, ncoef);
     double gmax = dmax(fabs(2.0 * P.w_cte * s0[4]), fabs(2.0 * P.w_epsi * s0[5]));
     gmax = dmax(gmax, fabs(2.0 * P.w_v * (s0[3] - P.ref_v)));
@@ -419,13 +419,24 @@ struct Solver {
     n_steps = soc_count = 0;
     dualinf = lam1 = z1 = sz_max = sz_min = xmaxabs = 0.0;
     tr_f = tr_theta = tr_priminf = tr_sumlog = 0.0;
-    // states are zero except t = 0, controls at their (pushed) start value, z = 1, lambda = 0
+  }
+  MPC_HD void init(const double* s0, const double* coef, int ncoef) {
+    init_scalars(s0, coef, ncoef);
+    double f = 0.0, th = 0.0, cm = 0.0, sl = 0.0;
+    for (int t = 0; t < N; ++t) {
+      double ft, tht, cmt, slt;
+      init_stage(t, s0, ft, tht, cmt, slt);
+      f += ft; th += tht; cm = dmax(cm, cmt); sl += slt;
+    }
+    init_finish(f, th, cm, sl);
+  }
+  // stage t of the start point: states are zero except t = 0, controls at their (pushed) start value, z = 1,
+  // lambda = 0; partial objective / constraint violation / log-barrier of the stage
+  MPC_HD void init_stage(int t, const double* s0, double& f, double& th, double& cm, double& sl) {
     double s[6], sn[6], u[2];
     u[0] = P.u_init[0]; u[1] = P.u_init[1];
-    double f = 0.0, th = 0.0, cm = 0.0, sl = 0.0;
-    const double q = (u[0] - P.xl[0]) * (P.xu[0] - u[0]) * ((u[1] - P.xl[1]) * (P.xu[1] - u[1]));
-    const double lq = log(q);
-    for (int t = 0; t < N; ++t) {
+    f = 0.0; th = 0.0; cm = 0.0; sl = 0.0;
+    {
       const int r = rec(t);
 #pragma unroll
       for (int k = 0; k < 6; ++k) { s[k] = t == 0 ? s0[k] : 0.0; sn[k] = 0.0; w(r + xS + k) = s[k]; w(r + xLAM + k) = 0.0; }
@@ -449,9 +460,11 @@ struct Solver {
           th += fabs(c[k]); cm = dmax(cm, fabs(c[k]));
         }
         f += P.w_delta * (u[0] * u[0]) + P.w_a * (u[1] * u[1]);
-        sl += lq;
+        sl = log((u[0] - P.xl[0]) * (P.xu[0] - u[0]) * ((u[1] - P.xl[1]) * (P.xu[1] - u[1])));
       }
     }
+  }
+  MPC_HD void init_finish(double f, double th, double cm, double sl) {
     f_cur = df * f; theta_cur = th; priminf = cm; sumlog = sl;
     phase = PH_FACTOR;
   }

@@ -154,18 +154,16 @@ __global__ void __launch_bounds__(128) mpc_coop_kernel(const __grid_constant__ P
   CoopPub* pub = reinterpret_cast<CoopPub*>(mine + (size_t)P.N * kCoopStageDoubles);
   Solver<32> S(P, problem_base(P, A, b), b & 31);
   load_coeffs(A, b, S.cf);
+  CoopSolver<32, DevExec> C(S, st, pub, DevExec{lane});
   if (fresh) {
-    if (lane == 0) {
-      double s0[6];
-      load_state6(A, b, s0);
-      S.init(s0, S.cf, kMaxCoef);
-    }
+    double s0[6];
+    load_state6(A, b, s0);
+    C.init(s0);
   } else {
     if (S.load_phase() == PH_DONE) return;   // whole warp
     if (lane == 0) S.load_state();
+    __syncwarp();
   }
-  __syncwarp();
-  CoopSolver<32, DevExec> C(S, st, pub, DevExec{lane});
   C.run();
   if (lane == 0) {
     S.store_state();
