@@ -1,6 +1,6 @@
 """Latency of one host-buffer solve call vs batch size, for the cooperative-only path and the per-pass path."""
 import sys, time, numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import udacitympc_b200 as mp
 from udacitympc_b200 import synth
 st, cf = synth.line_problems(32768)

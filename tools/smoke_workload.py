@@ -1,5 +1,5 @@
 import numpy as np, sys
-sys.path.insert(0,'.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import udacitympc_b200 as mp
 from udacitympc_b200 import synth
 st, cf = synth.line_problems(97)
