@@ -105,12 +105,16 @@ __device__ __forceinline__ void polyfit_regs(const double* xs, const double* ys,
 #pragma unroll
       for (int i = 1; i < rr; ++i) A[k][k + i] = 0.0;
     } else {
-      beta = sqrt(c0 * c0 + tail);
-      if (c0 >= 0.0) beta = -beta;
-      const double inv = 1.0 / (c0 - beta);   // Eigen divides element-wise; one reciprocal differs by <= 1 ulp
+      // Eigen: beta = -sign(c0) sqrt(c0^2 + tail), tail /= (c0 - beta), tau = (beta - c0) / beta.  One rsqrt gives both
+      // |beta| and 1/|beta|, one reciprocal replaces the element-wise divisions (results differ by <= 2 ulp)
+      const double n2 = c0 * c0 + tail, rn = rsqrt(n2);
+      double ibeta = rn;
+      beta = n2 * rn;
+      if (c0 >= 0.0) { beta = -beta; ibeta = -ibeta; }
+      const double inv = 1.0 / (c0 - beta);
 #pragma unroll
       for (int i = 1; i < rr; ++i) A[k][k + i] = A[k][k + i] * inv;
-      tau = (beta - c0) / beta;
+      tau = (beta - c0) * ibeta;
     }
     h[k] = tau; A[k][k] = beta;
 #pragma unroll
