@@ -321,3 +321,24 @@ def test_roadmap_front_end_and_pipeline(mpc):
         np.testing.assert_allclose(r["traj"][b], o["x"], rtol=0, atol=1e-8)
     with pytest.raises(mp.B200MPCError):
         mp.roadmap_reference_batch(poses, cl[:4], mpc=mpc)
+
+
+def test_multi_device_sharding_in_one_process():
+    """b200mpc_solve_batch_multi with one handle per GPU (contiguous index ranges, one host thread per device)."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    g = golden("config3_line_4096.npz")
+    st, cf = synth.line_problems(4096)
+    ms = [mp.MPC(device=d) for d in range(min(n, 4))]
+    try:
+        for fb in (0, 1 << 30):   # per-pass + cooperative finisher, cooperative only
+            for m in ms:
+                m.set_solver_mode(0, 0, fb)
+            r = api.solve_batch_multi(ms, st, cf)
+            assert (r["status"] == 0).all()
+            np.testing.assert_allclose(r["out8"], g["out8"], rtol=0, atol=1e-8)
+    finally:
+        for m in ms:
+            m.close()

@@ -160,6 +160,7 @@ int b200mpc_create(const b200mpc_params* p, int device, b200mpc_handle** out) {
     return fail(B200MPC_ERR_CUDA, std::string("no CUDA device available (b200mpc has no CPU path): ") + cudaGetErrorString(e));
   if (device < 0 || device >= ndev) return fail(B200MPC_ERR_ARG, "device index out of range");
   CU(cudaSetDevice(device));
+  CU(solver_prepare_device());
   b200mpc_handle* h = new (std::nothrow) b200mpc_handle();
   if (!h) return fail(B200MPC_ERR_NOMEM, "out of host memory");
   h->P = to_core(*p);

@@ -13,6 +13,9 @@ size_t solve_workspace_doubles(int N, int B);
 // starting from the previous solve's predicted state).  All arrays field-major (SoA) over the batch.
 //   state6 [6][B], coeffs [ncoef][B], out8 [steps][8][B], traj [8N-2][B] (last step, optional),
 //   obj [steps][B] (optional), status [B] (last step, optional), iters [steps][B] (optional)
+// call once per device before the first solve on it
+cudaError_t solver_prepare_device();
+
 enum SolveMode { kModePerPass = 0, kModeFused = 1 };
 struct SolveConfig {
   int mode = kModePerPass;

@@ -171,6 +171,11 @@ __global__ void __launch_bounds__(128) mpc_coop_kernel(const __grid_constant__ P
   }
 }
 
+// per-device, once (b200mpc_create): the cooperative kernel uses up to 200 KB of dynamic shared memory per block
+cudaError_t solver_prepare_device() {
+  return cudaFuncSetAttribute(mpc_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
 static size_t coop_doubles_per_warp(int N) { return (size_t)N * kCoopStageDoubles + (sizeof(CoopPub) + 7) / 8; }
 
 // launches the cooperative kernel if the horizon fits in shared memory; returns false otherwise
@@ -181,12 +186,6 @@ static bool launch_coop(const Params& P, const SolveArgs& A, int fresh, cudaStre
   int wpb = (int)(limit / per_warp);
   if (wpb > 4) wpb = 4;
   const size_t smem = per_warp * wpb;
-  static bool attr_set = false;
-  if (!attr_set) {
-    *err = cudaFuncSetAttribute(mpc_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
-    if (*err != cudaSuccess) return true;
-    attr_set = true;
-  }
   const int grid = (A.B + wpb - 1) / wpb;
   mpc_coop_kernel<<<grid, 128, smem, stream>>>(P, A, fresh, wpb, (int)coop_doubles_per_warp(P.N));
   *err = cudaGetLastError();
