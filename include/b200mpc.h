@@ -105,6 +105,13 @@ int b200mpc_solve_batch_multi(b200mpc_handle* const* hs, int n_handles, int B, c
 int b200mpc_closed_loop_batch(b200mpc_handle* h, int B, int steps, const double* state6, const double* coeffs,
                               int ncoef, double* hist8, double* cost, int* iters);
 
+/* Warm start for b200mpc_closed_loop_batch (NOT reference behaviour: the reference cold-starts every call,
+ * MPC.cpp:167-177, and so does this library unless enabled here).  When enabled, every step after the first starts from
+ * the previous step's solution shifted by one stage, with the barrier parameter at mu_init (e.g. 1e-4).  The optimum
+ * reached is the same local optimum within the solver tolerance; the iterates, iteration counts and last digits of
+ * weakly active bounds differ from a cold start. */
+int b200mpc_set_warm_start(b200mpc_handle* h, int enable, double mu_init);
+
 /* B least-squares polynomial fits (unpivoted Householder QR of the Vandermonde matrix, as Eigen 3.3.3 does for
  * helpers.h:24-44).  xs, ys: B x m;  coeffs_out: B x (order+1).  Requires 1 <= order <= m-1 (helpers.h:26 assert). */
 int b200mpc_polyfit_batch(b200mpc_handle* h, int B, const double* xs, const double* ys, int m, int order,

@@ -129,6 +129,39 @@ int hostsim_solve_mode(const hostsim_params* hp, const double* state6, const dou
   return R.status;
 }
 
+// closed loop of solution/main.cpp:51-76 on one Solver object: `steps` solves, each fed the previous solve's predicted
+// state; warm != 0: steps after the first start from the shifted previous solution (Solver::init_warm)
+int hostsim_closed_loop(const hostsim_params* hp, const double* state6, const double* coeffs, int ncoef, int steps, int warm,
+                        double mu0, double* hist8, int* iters, int* status) {
+  Params P;
+  P.N = hp->N; P.dt = hp->dt; P.Lf = hp->Lf; P.ref_v = hp->ref_v;
+  P.w_cte = hp->w_cte; P.w_epsi = hp->w_epsi; P.w_v = hp->w_v; P.w_delta = hp->w_delta; P.w_a = hp->w_a;
+  P.w_ddelta = hp->w_ddelta; P.w_da = hp->w_da; P.delta_max = hp->delta_max; P.a_max = hp->a_max; P.tol = hp->tol;
+  P.max_iter = hp->max_iter;
+  P.finalize();
+  std::vector<double> ws((size_t)workspace_doubles_per_problem(P.N), 0.0);
+  g_ws_limit = (int)ws.size();
+  double s0[6];
+  for (int k = 0; k < 6; ++k) s0[k] = state6[k];
+  for (int step = 0; step < steps; ++step) {
+    Solver<1> S(P, ws.data());
+    double carry[kCarry];
+    S.cr = carry; S.cs = 1;
+    S.set_coeffs(coeffs, ncoef);
+    if (warm && step > 0) S.init_warm(s0, mu0);
+    else S.init(s0, coeffs, ncoef);
+    int trips = 0;
+    while (S.phase != PH_DONE && trips < 100000) { S.trip(); ++trips; }
+    S.store_state();
+    Result R;
+    S.finish(R, nullptr, 1);
+    for (int k = 0; k < 8; ++k) hist8[8 * step + k] = R.out8[k];
+    iters[step] = R.iters; status[step] = R.status;
+    for (int k = 0; k < 6; ++k) s0[k] = R.out8[k];
+  }
+  return 0;
+}
+
 int hostsim_solve(const hostsim_params* hp, const double* state6, const double* coeffs, int ncoef, double* x_out,
                   double* out8, double* obj, int* iters, double* lam_out, double* trace, int trace_cap, int* trace_rows) {
   return hostsim_solve_mode(hp, state6, coeffs, ncoef, x_out, out8, obj, iters, lam_out, trace, trace_cap, trace_rows, 0);

@@ -64,6 +64,23 @@ def test_config1_closed_loop_on_device(mpc):
     assert (r["iters"][:, 0] == g["iters"]).all()
 
 
+def test_warm_started_closed_loop(mpc):
+    """Optional warm start (off by default): same closed-loop trajectory as the cold-started reference loop within the
+    solver tolerance, with fewer iterations; on both execution paths."""
+    g = golden("config1_closed_loop.npz")
+    for fb in (1 << 30, 0):   # cooperative kernel / per-pass kernels + cooperative finisher
+        with mp.MPC(device=0) as m:
+            m.set_solver_mode(0, 0, fb)
+            cold = m.closed_loop(np.repeat(g["states"][:1], 3, axis=0), g["coeffs"], 50)
+            m.set_warm_start(True, 1e-4)
+            warm = m.closed_loop(np.repeat(g["states"][:1], 3, axis=0), g["coeffs"], 50)
+        np.testing.assert_allclose(cold["hist8"][:, 0, :], g["out8"], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(warm["hist8"][:, 0, :], g["out8"], rtol=0, atol=1e-6)
+        np.testing.assert_array_equal(warm["hist8"][:, 0, :], warm["hist8"][:, 2, :])
+        assert (cold["iters"][:, 0] == g["iters"]).all()
+        assert warm["iters"][:, 0].sum() < 0.5 * cold["iters"][:, 0].sum()
+
+
 @pytest.mark.parametrize("name", ["line_256.npz", "roadmap_256.npz"])
 @pytest.mark.parametrize("path", ["coop", "perpass", "fused"])
 def test_random_problems_vs_reference(name, path):

@@ -166,3 +166,27 @@ def test_cooperative_solver_matches_thread_version(hostsim):
                 assert a["status"] == c["status"] and a["iters"] == c["iters"], (name, b, mode)
                 np.testing.assert_allclose(a["x"], c["x"], rtol=0, atol=1e-10)
                 assert abs(a["obj"] - c["obj"]) <= 1e-12 * abs(a["obj"])
+
+
+def test_warm_started_closed_loop_reaches_the_same_trajectory(hostsim):
+    """Warm start (off by default; not reference behaviour): the 50-step closed loop of config 1 follows the cold-start
+    (= reference) trajectory within the solver tolerance with far fewer interior-point iterations."""
+    import ctypes
+    import oracle_bindings as ob
+    g = golden("config1_closed_loop.npz")
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+
+    def loop(warm, mu):
+        p = ob.default_params()
+        st = np.ascontiguousarray(g["states"][0]); c = np.ascontiguousarray(g["coeffs"])
+        h = np.zeros((50, 8)); it = np.zeros(50, dtype=np.int32); sts = np.zeros(50, dtype=np.int32)
+        hostsim.lib.hostsim_closed_loop(ctypes.byref(p), st.ctypes.data_as(dp), c.ctypes.data_as(dp), 2, 50, warm, ctypes.c_double(mu),
+                                        h.ctypes.data_as(dp), it.ctypes.data_as(ip), sts.ctypes.data_as(ip))
+        return h, it, sts
+    hc, ic, sc = loop(0, 0.0)
+    np.testing.assert_allclose(hc, g["out8"], rtol=0, atol=1e-9)
+    assert (ic == g["iters"]).all()
+    hw, iw, sw = loop(1, 1e-4)
+    assert (sw == 0).all()
+    np.testing.assert_allclose(hw, g["out8"], rtol=0, atol=1e-6)
+    assert iw[0] == ic[0] and iw.sum() < 0.5 * ic.sum()

@@ -51,7 +51,8 @@ struct b200mpc_handle {
   long long launches = 0;
   // CUDA graphs of whole solves (init + rounds x (factor, forward, step) + finisher), keyed by every launch argument
   struct GraphEntry {
-    int B, steps, ncoef, mode, rounds, fused_below;
+    int B, steps, ncoef, mode, rounds, fused_below, warm;
+    double warm_mu;
     const void *st, *cf, *ws, *out8, *traj, *obj, *status, *iters;
     cudaGraphExec_t exec;
     long long n_kernels;
@@ -94,11 +95,11 @@ int timed_solve(b200mpc_handle* h, int B, int steps, const double* st, const dou
   // ranks / streams per host otherwise become launch-bound).  The legacy default stream cannot be captured.
   bool done = false;
   if (h->use_graphs && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) {
-    b200mpc_handle::GraphEntry key{B, steps, ncoef, h->cfg.mode, h->cfg.rounds, h->cfg.fused_below, st, cf, h->ws.p, out8, traj, obj, status, iters, nullptr, 0};
+    b200mpc_handle::GraphEntry key{B, steps, ncoef, h->cfg.mode, h->cfg.rounds, h->cfg.fused_below, h->cfg.warm_start ? 1 : 0, h->cfg.warm_mu, st, cf, h->ws.p, out8, traj, obj, status, iters, nullptr, 0};
     b200mpc_handle::GraphEntry* hit = nullptr;
     for (auto& g : h->graphs)
       if (g.B == key.B && g.steps == key.steps && g.ncoef == key.ncoef && g.mode == key.mode && g.rounds == key.rounds &&
-          g.fused_below == key.fused_below && g.st == key.st && g.cf == key.cf && g.ws == key.ws && g.out8 == key.out8 &&
+          g.fused_below == key.fused_below && g.warm == key.warm && g.warm_mu == key.warm_mu && g.st == key.st && g.cf == key.cf && g.ws == key.ws && g.out8 == key.out8 &&
           g.traj == key.traj && g.obj == key.obj && g.status == key.status && g.iters == key.iters)
         hit = &g;
     if (!hit) {
@@ -193,6 +194,14 @@ int b200mpc_set_solver_mode(b200mpc_handle* h, int mode, int rounds, int fused_b
   h->cfg.mode = mode;
   if (rounds > 0) h->cfg.rounds = rounds;
   if (fused_below >= 0) h->cfg.fused_below = fused_below;
+  return 0;
+}
+
+int b200mpc_set_warm_start(b200mpc_handle* h, int enable, double mu_init) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  if (enable && !(mu_init > 0.0 && mu_init <= 0.1)) return fail(B200MPC_ERR_ARG, "warm start: mu_init must be in (0, 0.1]");
+  h->cfg.warm_start = enable != 0;
+  if (enable) h->cfg.warm_mu = mu_init;
   return 0;
 }
 

@@ -21,6 +21,8 @@ struct SolveConfig {
   int mode = kModePerPass;
   int rounds = 16;        // per-pass mode: rounds of (factor, forward, step) before the finisher takes the thin tail
   int fused_below = 3072; // batches smaller than this skip the per-pass rounds (one launch: latency path)
+  bool warm_start = false;   // closed loop only: steps after the first start from the shifted previous solution
+  double warm_mu = 1e-4;     // barrier parameter a warm-started solve begins with
   bool coop = true;       // latency path = cooperative warp-per-problem kernel (false: thread-per-problem fused kernel)
 };
 cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6, const double* coeffs, int ncoef,

@@ -470,6 +470,106 @@ struct Solver {
   }
 
   // ------------------------------------------------------------------------------------------
+  // Warm start of closed-loop step k+1 from the solution of step k (NOT reference behaviour -- the reference
+  // cold-starts every call, MPC.cpp:167-177 -- so it is off by default).  The previous solution, which sits in the current
+  // copy of the iterate, is shifted by one stage (the new initial state is its t=1 state, main.cpp:66), the last stage is
+  // rolled out with the last control, controls are pushed 1e-3 inside their bounds and multipliers kept >= 1e-3 (Ipopt's
+  // warm_start_bound_push / warm_start_mult_bound_push), mu starts at mu0.  The first pass over the shifted point is a
+  // zero-length STEP (alpha = 0, accepted unconditionally) that evaluates every norm top_of_loop() needs.
+  MPC_HD void init_warm(const double* s0, double mu0) {
+    const int b = kX * (int)w(iCUR);
+    const double df_old = w(dDF);
+    // shift in place (ascending t)
+    for (int t = 0; t < M; ++t) {
+      const int r = rec(t) + b, rn = rec(t + 1) + b;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { w(r + xS + k) = t == 0 ? s0[k] : w(rn + xS + k); w(r + xLAM + k) = w(rn + xLAM + k); }
+      if (t < M - 1) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { w(r + xU + j) = w(rn + xU + j); w(r + xZL + j) = w(rn + xZL + j); w(r + xZU + j) = w(rn + xZU + j); }
+      }
+    }
+    // objective scaling at the (new) start point, pushes, last stage, residuals / objective / barrier / trig
+    double gmax = 0.0, f = 0.0, th = 0.0, cm = 0.0, sl = 0.0;
+    double s[6], sn[6], u[2], up[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s[k] = w(rec(0) + b + xS + k);
+    for (int t = 0; t < M; ++t) {
+      const int r = rec(t) + b, rn = rec(t + 1) + b;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const double push = 1e-3 * dmax(1.0, fabs(P.xl[j]));
+        u[j] = dclamp(w(r + xU + j), P.xl[j] + push, P.xu[j] - push);
+        w(r + xU + j) = u[j];
+      }
+      double sp, cp, se, ce, p0, p1, p2, p3, c[6];
+      sincos(s[2], &sp, &cp);
+      sincos(s[5], &se, &ce);
+      poly_eval(cf, s[0], p0, p1, p2, p3);
+      const double psides = atan(p1);
+      if (t == M - 1) {   // last stage: roll the model out so the new rows start feasible
+        const double zero[6] = {0, 0, 0, 0, 0, 0};
+        residual(s, u, zero, sp, cp, se, p0, psides, c);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w(rn + xS + k) = -c[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) sn[k] = w(rn + xS + k);
+      residual(s, u, sn, sp, cp, se, p0, psides, c);
+#if MPC_STORE_TRIG
+      w(r + xTR) = sp; w(r + xTR + 1) = cp; w(r + xTR + 2) = se; w(r + xTR + 3) = ce;
+#endif
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+#if MPC_STORE_C
+        w(rn + xC + k) = c[k];
+#endif
+        th += fabs(c[k]); cm = dmax(cm, fabs(c[k]));
+      }
+      f += state_cost(s) + P.w_delta * (u[0] * u[0]) + P.w_a * (u[1] * u[1]);
+      if (t > 0) f += P.w_ddelta * ((u[0] - up[0]) * (u[0] - up[0])) + P.w_da * ((u[1] - up[1]) * (u[1] - up[1]));
+      sl += log((u[0] - P.xl[0]) * (P.xu[0] - u[0]) * ((u[1] - P.xl[1]) * (P.xu[1] - u[1])));
+      gmax = dmax(gmax, dmax(fabs(2.0 * P.w_cte * s[4]), dmax(fabs(2.0 * P.w_epsi * s[5]), fabs(2.0 * P.w_v * (s[3] - P.ref_v)))));
+      // control gradient entries are bounded by 2 (w + 2 w_d) |u|max; include them conservatively
+      gmax = dmax(gmax, 2.0 * (P.w_delta + 2.0 * P.w_ddelta) * fabs(u[0]));
+      gmax = dmax(gmax, 2.0 * (P.w_a + 2.0 * P.w_da) * fabs(u[1]));
+      up[0] = u[0]; up[1] = u[1];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { s[k] = sn[k]; w(rec(t) + oDS + k) = 0.0; }
+      w(rec(t) + oDU) = 0.0; w(rec(t) + oDU + 1) = 0.0;
+    }
+    f += state_cost(s);
+    gmax = dmax(gmax, dmax(fabs(2.0 * P.w_cte * s[4]), dmax(fabs(2.0 * P.w_epsi * s[5]), fabs(2.0 * P.w_v * (s[3] - P.ref_v)))));
+#pragma unroll
+    for (int k = 0; k < 6; ++k) w(rec(M) + oDS + k) = 0.0;
+    const int cur_keep = (int)w(iCUR);
+    init_scalars(s0, cf, kMaxCoef);
+    cur = cur_keep;
+    df = 1.0;
+    if (gmax > 100.0) df = 100.0 / gmax;
+    if (df < 1e-8) df = 1e-8;
+    mu_min = dmin(P.tol, 1e-4 * df) / (10.0 + 1.0);
+    mu = dmax(mu0, mu_min);
+    tau = dmax(0.99, 1.0 - mu);
+    // multipliers of the scaled problem follow the objective scaling; keep the bound multipliers away from zero
+    const double ratio = df / df_old;
+    for (int t = 0; t < N; ++t) {
+      const int r = rec(t) + b;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) w(r + xLAM + k) = ratio * w(r + xLAM + k);
+      if (t < M) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { w(r + xZL + j) = dmax(1e-3, ratio * w(r + xZL + j)); w(r + xZU + j) = dmax(1e-3, ratio * w(r + xZU + j)); }
+      }
+    }
+    f_cur = df * f; theta_cur = th; priminf = cm; sumlog = sl;
+    flags = F_TINYNOW;   // zero-length step, accepted without a filter test
+    alpha = 0.0; alpha_du = 0.0;
+    iter = -1;           // the zero-length step is not an interior-point iteration
+    phase = PH_STEP;
+  }
+
+  // ------------------------------------------------------------------------------------------
   // Backward Riccati sweep: factor + feed-forward for the right-hand side (grad L_mu, c).  use_csoc selects the
   // constraint right-hand side (second-order correction).  Returns false on wrong inertia.
   MPC_HD bool factor(double dw, bool use_csoc) {

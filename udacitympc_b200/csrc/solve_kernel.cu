@@ -35,6 +35,8 @@ size_t solve_workspace_doubles(int N, int B) {
 
 struct SolveArgs {
   int B, steps, step, ncoef;
+  int warm;               // closed loop: steps > 0 start from the shifted previous solution
+  double mu_warm;
   const double* state6;   // [6][B]
   const double* coeffs;   // [ncoef][B]
   double* ws;
@@ -77,7 +79,8 @@ __global__ void __launch_bounds__(kBlock) mpc_init_kernel(const __grid_constant_
   double s0[6], cf[kMaxCoef];
   load_state6(A, b, s0);
   load_coeffs(A, b, cf);
-  S.init(s0, cf, A.ncoef);
+  if (A.warm && A.step > 0) { S.set_coeffs(cf, A.ncoef); S.init_warm(s0, A.mu_warm); }
+  else S.init(s0, cf, A.ncoef);
   S.store_state();
 }
 
@@ -122,7 +125,8 @@ __global__ void __launch_bounds__(kBlock) mpc_fused_kernel(const __grid_constant
   if (fresh) {
     double s0[6];
     load_state6(A, b, s0);
-    S.init(s0, S.cf, kMaxCoef);
+    if (A.warm && A.step > 0) S.init_warm(s0, A.mu_warm);
+    else S.init(s0, S.cf, kMaxCoef);
   } else {
     if (S.load_phase() == PH_DONE) return;
     S.load_state();
@@ -158,7 +162,10 @@ __global__ void __launch_bounds__(128) mpc_coop_kernel(const __grid_constant__ P
   if (fresh) {
     double s0[6];
     load_state6(A, b, s0);
-    C.init(s0);
+    if (A.warm && A.step > 0) {
+      if (lane == 0) S.init_warm(s0, A.mu_warm);
+      __syncwarp();
+    } else C.init(s0);
   } else {
     if (S.load_phase() == PH_DONE) return;   // whole warp
     if (lane == 0) S.load_state();
@@ -197,7 +204,7 @@ cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6
                          const SolveConfig& cfg, cudaStream_t stream, long long* n_launches) {
   if (B <= 0) return cudaSuccess;
   const int grid = (B + kBlock - 1) / kBlock;
-  SolveArgs A{B, steps, 0, ncoef, state6, coeffs, ws, out8, traj, obj, status, iters};
+  SolveArgs A{B, steps, 0, ncoef, cfg.warm_start ? 1 : 0, cfg.warm_mu, state6, coeffs, ws, out8, traj, obj, status, iters};
   long long n = 0;
   for (int step = 0; step < steps; ++step) {
     A.step = step;
