@@ -5,6 +5,7 @@ with the tolerances BASELINE.json's north_star states:
   actuators delta/a 1e-5 absolute, objective 1e-6 relative, predicted trajectory 1e-5,
   global_kinematic_model rollouts 1e-12, polyfit coefficients 1e-10."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -192,6 +193,11 @@ def test_edge_batches(mpc):
     np.testing.assert_allclose(r["traj"][0], o["x"], rtol=0, atol=1e-8)
 
 
+def _ref_solve_one(a):
+    o = ob.ref_solve(a[0], a[1])
+    return o["x"], o["obj"], o["status"], o["iters"]
+
+
 def test_full_size_batch_properties(mpc):
     """BASELINE size (65 536 problems): size-independent properties + a sample against the oracle."""
     B = 65536
@@ -230,6 +236,19 @@ def test_full_size_batch_properties(mpc):
         assert o["status"] == r["status"][b]
         np.testing.assert_allclose(r["traj"][b], o["x"], rtol=0, atol=1e-8)
         assert abs(o["obj"] - r["cost"][b]) <= TOL_OBJ * abs(o["obj"])
+    # and a larger strided sample against the reference's own Ipopt + MUMPS binaries (oracle/_ref), all host cores
+    if ob.ref_available():
+        import multiprocessing as mpr
+        idx = list(range(7, B, B // 512))
+        with mpr.get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:
+            res = pool.map(_ref_solve_one, [(st[b], fit[b]) for b in idx])
+        for b, (x, obj, status, iters) in zip(idx, res):
+            assert status == r["status"][b] == 0
+            np.testing.assert_allclose(r["traj"][b, 6 * N:], x[6 * N:], rtol=0, atol=TOL_ACT)
+            np.testing.assert_allclose(r["traj"][b], x, rtol=0, atol=TOL_TRAJ)
+            assert abs(obj - r["cost"][b]) <= TOL_OBJ * abs(obj)
+            np.testing.assert_allclose(r["traj"][b], x, rtol=0, atol=1e-8)
+        assert np.mean([r["iters"][b] == it for b, (_, _, _, it) in zip(idx, res)]) >= 0.99
 
 
 def test_device_pointer_entry_and_multi_handle(mpc):
