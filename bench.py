@@ -125,7 +125,7 @@ def run_reference_arm(args):
         return
     states, coeffs = make_workload(args.workload, min(args.batch, 4096))
     cores = os.cpu_count() or 1
-    per_core = 24
+    per_core = 100   # solves per host core per step: ~0.6 s of CPU work per step, pool start-up amortised
     times = []
     rate = None
     for i in range(args.warmup + args.steps):
@@ -378,7 +378,7 @@ def run_ours(args):
             roofline=dict(bound="fp64", achieved=achieved, peak=fp64_peak, unit="TFLOP/s", frac=achieved / fp64_peak if fp64_peak else None,
                           traffic=profiled_traffic_bytes(), traffic_unit="bytes of DRAM read+write per step (ncu, profiles/r1_final_launches_time_dram.csv)",
                           hbm_achieved_gbs=(profiled_traffic_bytes() or 0.0) / (avg_kernel_ms * 1e-3) / 1e9 if profiled_traffic_bytes() else None,
-                          kernel=("mpc_{init,factor,forward,step,fused}_kernel: all solver kernels of one step (one CUDA graph), first to last"
+                          kernel=("mpc_{init,factor,forward,step,coop}_kernel: all solver kernels of one step (one CUDA graph), first to last"
                                   if args.mode == "perpass" else "mpc_fused_kernel"),
                           avg_kernel_ms=avg_kernel_ms, launches_timed=kern_n, solver_mode=args.mode, streams=S, e2e_host_threads=min(S, 3),
                           flop_per_launch=flop_per_launch, mean_ip_iters=mean_it,
