@@ -1,15 +1,17 @@
 // Interior-point solve kernels for sm_100a (K1 derivative evaluation, K2 Riccati KKT solve, K3 barrier / line
-// search / filter / convergence logic).  One problem per thread; every per-problem vector lives in a
-// warp-interleaved HBM workspace (each workspace access of a warp is one coalesced 256-byte row) and the 7x7
-// Riccati blocks live in registers.  Replaces CppAD::ipopt::solve at
+// search / filter / convergence logic).  Replaces CppAD::ipopt::solve at
 // /root/reference/mpc_to_line/solution/MPC.cpp:241-243.
 //
-// Two execution modes share the same pass code (mpc_core.cuh):
-//   per-pass kernels  init | factor | forward | step, launched round after round on one stream.  Each
-//                     kernel has its own register budget (the Riccati factorisation needs ~250 registers, the
-//                     other sweeps far fewer and run at 3-4x the occupancy) and a small instruction footprint.
-//   fused kernel      one launch loops the three passes per thread until its problem is done.  Used to finish
-//                     stragglers after the fixed number of rounds, and for tiny batches (latency).
+// Throughput path (mpc_core.cuh): one problem per thread; every per-problem vector lives in a warp-interleaved HBM
+// workspace (each workspace access of a warp is one coalesced 256-byte row) and the 7x7 Riccati blocks live in
+// registers.  One interior-point iteration = three sweeps over the horizon, each its own kernel
+//   init | factor | forward | step        launched round after round on one stream (replayed as one CUDA graph),
+// with its own register budget (the Riccati factorisation needs ~250 registers, the step sweep 168 with its
+// stage-to-stage values in shared memory, the forward sweep 128) and a small instruction footprint.
+// Latency path (mpc_coop.cuh): one problem per warp, lane <-> stage.  mpc_coop_kernel finishes whatever is still
+// iterating after the fixed number of rounds and solves small batches on its own.
+// mpc_fused_kernel loops the three thread-per-problem sweeps in one launch (comparison / fallback for horizons whose
+// per-stage scratch does not fit the cooperative kernel's shared memory).
 #include "kernels.h"
 #include "mpc_coop.cuh"
 
