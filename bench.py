@@ -217,9 +217,13 @@ def run_ours(args):
     B, K, W = args.batch, args.steps, args.warmup
 
     S = max(1, args.streams)
+    # concurrency comes either from the caller (S overlapped handles, no internal split) or from the library's
+    # internal batch split (one handle)
+    split = args.split if args.split > 0 else (1 if S > 1 else 4)
     mpcs = [mpcmod.MPC(device=local) for _ in range(S)]
     for m in mpcs:
         m.set_solver_mode({"perpass": 0, "fused": 1}[args.mode], args.rounds, -1)
+        m.set_batch_split(split)
     mpc = mpcs[0]
     # Four distinct 65 536-problem input sets, cycled step by step.  Every rank solves the SAME four sets (weak
     # scaling with identical per-GPU work by construction); about half of such sets contain a 30-50 iteration
@@ -382,7 +386,7 @@ def run_ours(args):
                                     if profiled_traffic_bytes() and peaks.get("hbm_gbs") else None),
                           kernel=("mpc_{init,factor,forward,step,coop}_kernel: all solver kernels of one step (one CUDA graph), first to last"
                                   if args.mode == "perpass" else "mpc_fused_kernel"),
-                          avg_kernel_ms=avg_kernel_ms, launches_timed=kern_n, solver_mode=args.mode, streams=S, e2e_host_threads=min(S, 3),
+                          avg_kernel_ms=avg_kernel_ms, launches_timed=kern_n, solver_mode=args.mode, streams=S, batch_split=split, e2e_host_threads=min(S, 3),
                           flop_per_launch=flop_per_launch, mean_ip_iters=mean_it,
                           peak_source="DFMA microbenchmark in this run (b200mpc_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                           hbm_peak_gbs=peaks.get("hbm_gbs"), algorithmic_io_bytes_per_solve=(6 + ncoef + 8 + 2) * 8,
@@ -414,6 +418,7 @@ def main():
     ap.add_argument("--cpu-per-core", type=int, default=150, help="cpu_baseline: solves per host core in the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--input-sets", type=int, default=4, help="distinct synthetic input batches cycled over the steps")
+    ap.add_argument("--split", type=int, default=0, help="internal batch split of one solve call (0 = 1 with several streams, 4 with one)")
     ap.add_argument("--streams", type=int, default=6, help="solver handles / CUDA streams consecutive steps alternate between")
     ap.add_argument("--mode", default="perpass", choices=["perpass", "fused"], help="solver execution mode (include/b200mpc.h)")
     ap.add_argument("--rounds", type=int, default=0, help="per-pass mode: rounds before the fused finisher (0 = library default)")

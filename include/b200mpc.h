@@ -112,6 +112,12 @@ int b200mpc_closed_loop_batch(b200mpc_handle* h, int B, int steps, const double*
  * weakly active bounds differ from a cold start. */
 int b200mpc_set_warm_start(b200mpc_handle* h, int enable, double mu_init);
 
+/* Internal concurrency of one large solve call: the batch is cut into `parts` (1..4) contiguous sub-batches whose
+ * kernels run concurrently on internal streams (joined before the call's stream continues, so the call keeps its
+ * stream-ordered semantics).  Results do not depend on it.  Default 4: best for a caller that issues one call at a
+ * time; a caller that already overlaps several calls on several handles / streams should set 1. */
+int b200mpc_set_batch_split(b200mpc_handle* h, int parts);
+
 /* B least-squares polynomial fits (unpivoted Householder QR of the Vandermonde matrix, as Eigen 3.3.3 does for
  * helpers.h:24-44).  xs, ys: B x m;  coeffs_out: B x (order+1).  Requires 1 <= order <= m-1 (helpers.h:26 assert). */
 int b200mpc_polyfit_batch(b200mpc_handle* h, int B, const double* xs, const double* ys, int m, int order,

@@ -390,6 +390,29 @@ def test_ragged_batch_on_the_throughput_path(mpc):
     np.testing.assert_allclose(r["out8"], g["out8"][:B], rtol=0, atol=1e-8)
 
 
+def test_internal_batch_split_does_not_change_results():
+    """b200mpc_set_batch_split: the sub-batches of one call run on internal streams; every split gives bit-identical
+    results (ragged batch, several closed-loop steps, trajectory output)."""
+    st, cf = synth.line_problems(4096)
+    B = 3999
+    ref = None
+    with mp.MPC(device=0) as m:
+        m.set_solver_mode(0, 12, 0)   # per-pass kernels + cooperative finisher also for the small parts
+        with pytest.raises(mp.B200MPCError):
+            m.set_batch_split(5)
+        for parts in (1, 2, 3, 4):
+            m.set_batch_split(parts)
+            r = m.solve_batch(st[:B], cf[:B], want_traj=True)
+            loop = m.closed_loop(st[:300], cf[0], 3)
+            if ref is None:
+                ref = (r, loop)
+                assert (r["status"] == 0).all()
+                continue
+            for k in ("out8", "traj", "obj", "status", "iters"):
+                np.testing.assert_array_equal(r[k], ref[0][k])
+            np.testing.assert_array_equal(loop["hist8"], ref[1]["hist8"])
+
+
 def test_long_horizon_falls_back_to_the_thread_finisher():
     """N = 200 does not fit the cooperative kernel's shared memory: the fused thread-per-problem kernel finishes the
     batch.  No oracle is fast enough at this size; check the size-independent properties instead."""

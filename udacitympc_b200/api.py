@@ -46,6 +46,7 @@ SYMBOLS = {
     "b200mpc_roadmap_reference_batch": (ctypes.c_int, [_vp, ctypes.c_int, _dp, _dp, ctypes.c_int, _dp, _dp]),
     "b200mpc_roadmap_reference_batch_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp, _vp]),
     "b200mpc_set_warm_start": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double]),
+    "b200mpc_set_batch_split": (ctypes.c_int, [_vp, ctypes.c_int]),
     "b200mpc_set_solver_mode": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "b200mpc_kernel_time_ms": (ctypes.c_int, [_vp, _dp, _ip, ctypes.c_int]),
     "b200mpc_measure_fp64_peak": (ctypes.c_int, [_vp, _dp]),
@@ -218,6 +219,11 @@ class MPC:
     def set_solver_mode(self, mode=0, rounds=0, fused_below=-1):
         """mode 0 = per-pass kernels (default), 1 = fused kernel; see include/b200mpc.h."""
         _check(self._lib.b200mpc_set_solver_mode(self._h, mode, rounds, fused_below))
+
+    def set_batch_split(self, parts):
+        """Cut large batches into `parts` (1..4) sub-batches that run concurrently inside one call (default 4; use 1
+        when the caller overlaps several calls itself)."""
+        _check(self._lib.b200mpc_set_batch_split(self._h, int(parts)))
 
     def set_warm_start(self, enable=True, mu_init=1e-4):
         """closed_loop() only: steps after the first start from the shifted previous solution (not reference behaviour)."""

@@ -44,6 +44,7 @@ struct DevBuf {
 struct b200mpc_handle {
   Params P;
   SolveConfig cfg;
+  SplitStreams ss;
   int device = 0;
   cudaStream_t stream = nullptr;
   DevBuf ws, in_aos, st_soa, cf_soa, out_soa, out_aos, traj_soa, traj_aos, obj, status, iters, misc0, misc1, misc2, misc3;
@@ -51,7 +52,7 @@ struct b200mpc_handle {
   long long launches = 0;
   // CUDA graphs of whole solves (init + rounds x (factor, forward, step) + finisher), keyed by every launch argument
   struct GraphEntry {
-    int B, steps, ncoef, mode, rounds, fused_below, warm;
+    int B, steps, ncoef, mode, rounds, fused_below, warm, split;
     double warm_mu;
     const void *st, *cf, *ws, *out8, *traj, *obj, *status, *iters;
     cudaGraphExec_t exec;
@@ -95,18 +96,18 @@ int timed_solve(b200mpc_handle* h, int B, int steps, const double* st, const dou
   // ranks / streams per host otherwise become launch-bound).  The legacy default stream cannot be captured.
   bool done = false;
   if (h->use_graphs && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) {
-    b200mpc_handle::GraphEntry key{B, steps, ncoef, h->cfg.mode, h->cfg.rounds, h->cfg.fused_below, h->cfg.warm_start ? 1 : 0, h->cfg.warm_mu, st, cf, h->ws.p, out8, traj, obj, status, iters, nullptr, 0};
+    b200mpc_handle::GraphEntry key{B, steps, ncoef, h->cfg.mode, h->cfg.rounds, h->cfg.fused_below, h->cfg.warm_start ? 1 : 0, h->cfg.split, h->cfg.warm_mu, st, cf, h->ws.p, out8, traj, obj, status, iters, nullptr, 0};
     b200mpc_handle::GraphEntry* hit = nullptr;
     for (auto& g : h->graphs)
       if (g.B == key.B && g.steps == key.steps && g.ncoef == key.ncoef && g.mode == key.mode && g.rounds == key.rounds &&
-          g.fused_below == key.fused_below && g.warm == key.warm && g.warm_mu == key.warm_mu && g.st == key.st && g.cf == key.cf && g.ws == key.ws && g.out8 == key.out8 &&
+          g.fused_below == key.fused_below && g.warm == key.warm && g.split == key.split && g.warm_mu == key.warm_mu && g.st == key.st && g.cf == key.cf && g.ws == key.ws && g.out8 == key.out8 &&
           g.traj == key.traj && g.obj == key.obj && g.status == key.status && g.iters == key.iters)
         hit = &g;
     if (!hit) {
       cudaGraph_t graph = nullptr;
       long long n = 0;
       if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
-        cudaError_t le = launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, &n);
+        cudaError_t le = launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, &h->ss, &n);
         cudaError_t ce = cudaStreamEndCapture(s, &graph);
         if (le == cudaSuccess && ce == cudaSuccess && graph) {
           cudaGraphExec_t exec = nullptr;
@@ -128,7 +129,7 @@ int timed_solve(b200mpc_handle* h, int B, int steps, const double* st, const dou
     }
   }
   if (!done)
-    CU(launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, &h->launches));
+    CU(launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, &h->ss, &h->launches));
   if (rec) {
     CU(cudaEventRecord(e1, s));
     h->timing.emplace_back(e0, e1);
@@ -170,6 +171,13 @@ int b200mpc_create(const b200mpc_params* p, int device, b200mpc_handle** out) {
   if (const char* e = getenv("B200MPC_NO_COOP")) h->cfg.coop = !(e[0] == '1');
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
+  for (int i = 0; i < 3; ++i) {   // auxiliary streams / events for the internal batch split
+    if (cudaStreamCreateWithFlags(&h->ss.aux[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ss.join[i], cudaEventDisableTiming) != cudaSuccess) break;
+    h->ss.n_aux = i + 1;
+  }
+  if (cudaEventCreateWithFlags(&h->ss.fork, cudaEventDisableTiming) != cudaSuccess) h->ss.n_aux = 0;
+  if (const char* sp = getenv("B200MPC_SPLIT")) { int v = atoi(sp); if (v >= 1 && v <= 4) h->cfg.split = v; }
   *out = h;
   return 0;
 }
@@ -180,6 +188,11 @@ void b200mpc_destroy(b200mpc_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& ev : h->timing) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+  for (int i = 0; i < 3; ++i) {
+    if (h->ss.aux[i]) { cudaStreamSynchronize(h->ss.aux[i]); cudaStreamDestroy(h->ss.aux[i]); }
+    if (h->ss.join[i]) cudaEventDestroy(h->ss.join[i]);
+  }
+  if (h->ss.fork) cudaEventDestroy(h->ss.fork);
   DevBuf* bufs[] = {&h->ws, &h->in_aos, &h->st_soa, &h->cf_soa, &h->out_soa, &h->out_aos, &h->traj_soa, &h->traj_aos,
                     &h->obj, &h->status, &h->iters, &h->misc0, &h->misc1, &h->misc2, &h->misc3};
   for (DevBuf* b : bufs) b->release();
@@ -202,6 +215,13 @@ int b200mpc_set_warm_start(b200mpc_handle* h, int enable, double mu_init) {
   if (enable && !(mu_init > 0.0 && mu_init <= 0.1)) return fail(B200MPC_ERR_ARG, "warm start: mu_init must be in (0, 0.1]");
   h->cfg.warm_start = enable != 0;
   if (enable) h->cfg.warm_mu = mu_init;
+  return 0;
+}
+
+int b200mpc_set_batch_split(b200mpc_handle* h, int parts) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  if (parts < 1 || parts > 4) return fail(B200MPC_ERR_ARG, "batch split: parts must be 1..4");
+  h->cfg.split = parts;
   return 0;
 }
 

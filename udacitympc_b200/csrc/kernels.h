@@ -23,11 +23,17 @@ struct SolveConfig {
   int fused_below = 3072; // batches smaller than this skip the per-pass rounds (one launch: latency path)
   bool warm_start = false;   // closed loop only: steps after the first start from the shifted previous solution
   double warm_mu = 1e-4;     // barrier parameter a warm-started solve begins with
+  int split = 4;             // large batches run as this many concurrent parts (see launch_solve)
   bool coop = true;       // latency path = cooperative warp-per-problem kernel (false: thread-per-problem fused kernel)
+};
+struct SplitStreams {   // auxiliary streams / events owned by the handle (n_aux <= 3)
+  int n_aux = 0;
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
 };
 cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6, const double* coeffs, int ncoef,
                          double* ws, double* out8, double* traj, double* obj, int* status, int* iters,
-                         const SolveConfig& cfg, cudaStream_t stream, long long* n_launches);
+                         const SolveConfig& cfg, cudaStream_t stream, const SplitStreams* ss, long long* n_launches);
 
 // K6 batch I/O: [B][K] <-> [K][B]
 cudaError_t launch_aos_to_soa(const double* in, double* out, int B, int K, cudaStream_t stream);

@@ -37,6 +37,7 @@ size_t solve_workspace_doubles(int N, int B) {
 
 struct SolveArgs {
   int B, steps, step, ncoef;
+  int b0, b1;             // this launch covers problems [b0, b1) of the B-problem batch (B stays the array stride)
   int warm;               // closed loop: steps > 0 start from the shifted previous solution
   double mu_warm;
   const double* state6;   // [6][B]
@@ -75,8 +76,8 @@ __device__ __forceinline__ void write_result(const Params& P, const SolveArgs& A
 
 // ---- per-pass kernels ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) mpc_init_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= A.B) return;
+  const int b = A.b0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.b1) return;
   Solver<32> S(P, problem_base(P, A, b), b & 31);
   double s0[6], cf[kMaxCoef];
   load_state6(A, b, s0);
@@ -87,8 +88,8 @@ __global__ void __launch_bounds__(kBlock) mpc_init_kernel(const __grid_constant_
 }
 
 __global__ void __launch_bounds__(kBlock) mpc_factor_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= A.B) return;
+  const int b = A.b0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.b1) return;
   Solver<32> S(P, problem_base(P, A, b), b & 31);
   if (S.load_phase() != PH_FACTOR) return;
   load_coeffs(A, b, S.cf);
@@ -96,8 +97,8 @@ __global__ void __launch_bounds__(kBlock) mpc_factor_kernel(const __grid_constan
 }
 
 __global__ void __launch_bounds__(kBlock, kFwdBlocks) mpc_forward_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= A.B) return;
+  const int b = A.b0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.b1) return;
   Solver<32> S(P, problem_base(P, A, b), b & 31);
   if (S.load_phase() != PH_FORWARD) return;
   load_coeffs(A, b, S.cf);
@@ -105,8 +106,8 @@ __global__ void __launch_bounds__(kBlock, kFwdBlocks) mpc_forward_kernel(const _
 }
 
 __global__ void __launch_bounds__(kBlock, kStepBlocks) mpc_step_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= A.B) return;
+  const int b = A.b0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.b1) return;
   Solver<32> S(P, problem_base(P, A, b), b & 31);
   if (S.load_phase() != PH_STEP) return;
   __shared__ double carry[kCarry * kBlock];   // stage-to-stage values of the sweep, [value][thread]
@@ -118,8 +119,8 @@ __global__ void __launch_bounds__(kBlock, kStepBlocks) mpc_step_kernel(const __g
 
 // ---- fused kernel: finishes whatever is still active (fresh == 1: starts from the inputs) ---------------------
 __global__ void __launch_bounds__(kBlock) mpc_fused_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A, int fresh) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= A.B) return;
+  const int b = A.b0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.b1) return;
   Solver<32> S(P, problem_base(P, A, b), b & 31);
   double carry[kCarry];
   S.cr = carry; S.cs = 1;
@@ -153,8 +154,8 @@ __global__ void __launch_bounds__(128) mpc_coop_kernel(const __grid_constant__ P
                                                        int warps_per_block, int doubles_per_warp) {
   extern __shared__ double coop_smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * warps_per_block + wib;   // one problem per warp
-  if (wib >= warps_per_block || b >= A.B) return;
+  const int b = A.b0 + blockIdx.x * warps_per_block + wib;   // one problem per warp
+  if (wib >= warps_per_block || b >= A.b1) return;
   double* mine = coop_smem + (size_t)wib * doubles_per_warp;
   CoopStage* st = reinterpret_cast<CoopStage*>(mine);
   CoopPub* pub = reinterpret_cast<CoopPub*>(mine + (size_t)P.N * kCoopStageDoubles);
@@ -195,26 +196,23 @@ static bool launch_coop(const Params& P, const SolveArgs& A, int fresh, cudaStre
   int wpb = (int)(limit / per_warp);
   if (wpb > 4) wpb = 4;
   const size_t smem = per_warp * wpb;
-  const int grid = (A.B + wpb - 1) / wpb;
+  const int grid = (A.b1 - A.b0 + wpb - 1) / wpb;
   mpc_coop_kernel<<<grid, 128, smem, stream>>>(P, A, fresh, wpb, (int)coop_doubles_per_warp(P.N));
   *err = cudaGetLastError();
   return true;
 }
 
-cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6, const double* coeffs, int ncoef,
-                         double* ws, double* out8, double* traj, double* obj, int* status, int* iters,
-                         const SolveConfig& cfg, cudaStream_t stream, long long* n_launches) {
-  if (B <= 0) return cudaSuccess;
-  const int grid = (B + kBlock - 1) / kBlock;
-  SolveArgs A{B, steps, 0, ncoef, cfg.warm_start ? 1 : 0, cfg.warm_mu, state6, coeffs, ws, out8, traj, obj, status, iters};
-  long long n = 0;
-  for (int step = 0; step < steps; ++step) {
+// launches every kernel of the solve of problems [b0, b1) on one stream
+static cudaError_t launch_part(const Params& P, SolveArgs A, const SolveConfig& cfg, cudaStream_t stream, long long* n) {
+  const int nb = A.b1 - A.b0;
+  const int grid = (nb + kBlock - 1) / kBlock;
+  for (int step = 0; step < A.steps; ++step) {
     A.step = step;
-    if (cfg.mode == kModeFused || B < cfg.fused_below) {
-      cudaError_t ce = cudaSuccess;
+    cudaError_t ce = cudaSuccess;
+    if (cfg.mode == kModeFused || A.B < cfg.fused_below) {
       if (!(cfg.coop && cfg.mode != kModeFused && launch_coop(P, A, 1, stream, &ce))) mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 1);
       if (ce != cudaSuccess) return ce;
-      ++n;
+      *n += 1;
     } else {
       mpc_init_kernel<<<grid, kBlock, 0, stream>>>(P, A);
       for (int r = 0; r < cfg.rounds; ++r) {
@@ -222,16 +220,51 @@ cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6
         mpc_forward_kernel<<<grid, kBlock, 0, stream>>>(P, A);
         mpc_step_kernel<<<grid, kBlock, 0, stream>>>(P, A);
       }
-      cudaError_t ce = cudaSuccess;
       if (!(cfg.coop && launch_coop(P, A, 0, stream, &ce))) mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 0);
       if (ce != cudaSuccess) return ce;
-      n += 2 + 3LL * cfg.rounds;
+      *n += 2 + 3LL * cfg.rounds;
     }
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) return ce;
+  }
+  return cudaSuccess;
+}
+
+// A large batch is cut into `split` contiguous parts that run concurrently on the caller's stream and on auxiliary
+// streams (fork / join with events; capturable into a CUDA graph): the kernels of different parts are in different
+// sweeps at any moment, which fills the partial waves of the 252-register factor kernel and hides the thin tail of
+// one part behind the bulk of another even when the caller uses a single stream.
+cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6, const double* coeffs, int ncoef,
+                         double* ws, double* out8, double* traj, double* obj, int* status, int* iters,
+                         const SolveConfig& cfg, cudaStream_t stream, const SplitStreams* ss, long long* n_launches) {
+  if (B <= 0) return cudaSuccess;
+  SolveArgs A{B, steps, 0, ncoef, 0, B, cfg.warm_start ? 1 : 0, cfg.warm_mu, state6, coeffs, ws, out8, traj, obj, status, iters};
+  long long n = 0;
+  int parts = 1;
+  if (ss && cfg.mode == kModePerPass && cfg.split > 1 && B >= cfg.split * cfg.fused_below) parts = cfg.split < ss->n_aux + 1 ? cfg.split : ss->n_aux + 1;
+  cudaError_t e = cudaSuccess;
+  if (parts == 1) {
+    e = launch_part(P, A, cfg, stream, &n);
+  } else {
+    const int per = (((B + parts - 1) / parts) + 63) / 64 * 64;
+    if ((e = cudaEventRecord(ss->fork, stream)) != cudaSuccess) return e;
+    for (int p = 1; p < parts; ++p)
+      if ((e = cudaStreamWaitEvent(ss->aux[p - 1], ss->fork, 0)) != cudaSuccess) return e;
+    for (int p = 0; p < parts && e == cudaSuccess; ++p) {
+      SolveArgs Ap = A;
+      Ap.b0 = p * per;
+      Ap.b1 = (p + 1) * per < B ? (p + 1) * per : B;
+      if (Ap.b0 >= Ap.b1) continue;
+      e = launch_part(P, Ap, cfg, p == 0 ? stream : ss->aux[p - 1], &n);
+    }
+    for (int p = 1; p < parts; ++p) {   // always join, also after an error, so a capture can end cleanly
+      cudaError_t e2 = cudaEventRecord(ss->join[p - 1], ss->aux[p - 1]);
+      if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(stream, ss->join[p - 1], 0);
+      if (e == cudaSuccess) e = e2;
+    }
   }
   if (n_launches) *n_launches += n;
-  return cudaSuccess;
+  return e;
 }
 
 // ---------------------------------------------------------------------------------------------
