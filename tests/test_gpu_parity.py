@@ -408,7 +408,7 @@ def test_internal_batch_split_does_not_change_results():
                 ref = (r, loop)
                 assert (r["status"] == 0).all()
                 continue
-            for k in ("out8", "traj", "obj", "status", "iters"):
+            for k in ("out8", "traj", "cost", "status", "iters"):
                 np.testing.assert_array_equal(r[k], ref[0][k])
             np.testing.assert_array_equal(loop["hist8"], ref[1]["hist8"])
 
