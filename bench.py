@@ -256,7 +256,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     fp64_peak = mpc.fp64_peak_tflops()
-    for i in range(max(W, S)):
+    # warm-up: at least W steps, and every (solver handle, input set) pair once -- each pair is its own CUDA graph,
+    # captured and instantiated at its first use
+    import math
+    for i in range(max(W, S * nsets // math.gcd(S, nsets))):
         dev_step(i)
     barrier()
     for m in mpcs:

@@ -118,6 +118,12 @@ int b200mpc_set_warm_start(b200mpc_handle* h, int enable, double mu_init);
  * time; a caller that already overlaps several calls on several handles / streams should set 1. */
 int b200mpc_set_batch_split(b200mpc_handle* h, int parts);
 
+/* Batch compaction of the throughput path: after every round from `from_round` on, when the problems that are still
+ * iterating fill at most `max_live_fraction` of the occupied workspace slots, they are moved to consecutive slots, so
+ * the following rounds run full warps on whole memory sectors instead of a few lanes per warp.  Results do not
+ * depend on it.  Default 0.7 from round 4; 0 switches it off. */
+int b200mpc_set_compaction(b200mpc_handle* h, double max_live_fraction, int from_round);
+
 /* B least-squares polynomial fits (unpivoted Householder QR of the Vandermonde matrix, as Eigen 3.3.3 does for
  * helpers.h:24-44).  xs, ys: B x m;  coeffs_out: B x (order+1).  Requires 1 <= order <= m-1 (helpers.h:26 assert). */
 int b200mpc_polyfit_batch(b200mpc_handle* h, int B, const double* xs, const double* ys, int m, int order,

@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY: compiles the solver core (udacitympc_b200/csrc/mpc_core.cuh) for the CPU so the
 // algorithm can be checked against the oracle in the GPU-less build container (pytest -m "not gpu").
 // It is NOT part of libb200mpc.so and is never used by the product path.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -99,7 +100,16 @@ int hostsim_solve_mode(const hostsim_params* hp, const double* state6, const dou
     S.finish(R, x_out, 1);
     df = S.df; cur = S.cur;
   } else {
+    // mode -1 / -2: as mode 1, and the problem is moved to another workspace (repack_problem, what the batch
+    // compaction does) after every round / after every pass; the destination is poisoned with NaN first, so anything
+    // the move leaves behind that a later pass reads shows up in the results.
     { Solver<1> S(P, ws.data()); S.init(state6, coeffs, ncoef); S.store_state(); }
+    std::vector<double> other(ws.size());
+    auto repack = [&]() {
+      for (auto& v : other) v = std::nan("");
+      repack_problem(P, Ws<1>{ws.data(), 0}, Ws<1>{other.data(), 0});
+      ws.swap(other);
+    };
     int phase = PH_FACTOR;
     while (phase != PH_DONE && trips < 400000) {
       for (int k = 0; k < 3; ++k) {   // the three kernels of one round
@@ -113,7 +123,9 @@ int hostsim_solve_mode(const hostsim_params* hp, const double* state6, const dou
         else S.kernel_step();
         phase = S.load_phase();
         if (k == PH_STEP) { S.load_state(); log_row(S); }
+        if (mode == -2 && phase != PH_DONE) repack();
       }
+      if (mode == -1 && phase != PH_DONE) repack();
       ++trips;
     }
     Solver<1> S(P, ws.data());

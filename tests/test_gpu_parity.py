@@ -413,6 +413,44 @@ def test_internal_batch_split_does_not_change_results():
             np.testing.assert_array_equal(loop["hist8"], ref[1]["hist8"])
 
 
+def test_batch_compaction_does_not_change_results():
+    """b200mpc_set_compaction: unfinished problems are moved to consecutive workspace slots between rounds (two
+    regions, ping-pong); any threshold gives bit-identical results (1.0 = move after every round, whatever state the
+    problems are in), also combined with the internal batch split, over several closed-loop steps, and when the
+    finisher is the thread-per-problem kernel."""
+    st, cf = synth.line_problems(4096)
+    B = 3999
+    with mp.MPC(device=0) as m:
+        m.set_solver_mode(0, 20, 0)
+        m.set_batch_split(1)
+        m.set_compaction(0.0)
+        ref = m.solve_batch(st[:B], cf[:B], want_traj=True)
+        ref_loop = m.closed_loop(st[:300], cf[0], 3)
+        assert (ref["status"] == 0).all()
+        with pytest.raises(mp.B200MPCError):
+            m.set_compaction(1.5)
+        for frac, first, parts in ((0.7, 4, 1), (1.0, 1, 1), (0.99, 2, 2), (0.5, 8, 3), (0.9, 12, 4), (0.3, 1, 1)):
+            m.set_compaction(frac, first)
+            m.set_batch_split(parts)
+            r = m.solve_batch(st[:B], cf[:B], want_traj=True)
+            for k in ("out8", "traj", "cost", "status", "iters"):
+                np.testing.assert_array_equal(r[k], ref[k], err_msg=f"{frac} {first} {parts} {k}")
+            loop = m.closed_loop(st[:300], cf[0], 3)
+            np.testing.assert_array_equal(loop["hist8"], ref_loop["hist8"])
+    os.environ["B200MPC_NO_COOP"] = "1"
+    try:
+        with mp.MPC(device=0) as m:
+            m.set_solver_mode(0, 14, 0)
+            m.set_compaction(0.0)
+            ref = m.solve_batch(st[:B], cf[:B], want_traj=True)
+            m.set_compaction(0.95, 3)
+            r = m.solve_batch(st[:B], cf[:B], want_traj=True)
+    finally:
+        del os.environ["B200MPC_NO_COOP"]
+    for k in ("out8", "traj", "cost", "status", "iters"):
+        np.testing.assert_array_equal(r[k], ref[k])
+
+
 def test_long_horizon_falls_back_to_the_thread_finisher():
     """N = 200 does not fit the cooperative kernel's shared memory: the fused thread-per-problem kernel finishes the
     batch.  No oracle is fast enough at this size; check the size-independent properties instead."""

@@ -123,6 +123,28 @@ def test_per_pass_state_persistence(hostsim):
             assert a["obj"] == c["obj"]
 
 
+def test_batch_compaction_moves_everything_a_problem_owns(hostsim):
+    """mode -1 / -2: as mode 1, with the problem moved to a NaN-poisoned workspace by repack_problem (the batch
+    compaction of the per-pass path) after every round / after every pass, i.e. in every state a problem can be in:
+    bit-identical results, including the rare paths (regularisation, backtracking, second-order correction) and the
+    kept least-square multiplier estimate."""
+    sets = [("line_256.npz", {}, range(0, 256, 8)), ("roadmap_256.npz", {}, range(0, 256, 8)), ("roadmap_N50_64.npz", dict(N=50), range(64))]
+    g = golden("line_params_64.npz")
+    N, dt, Lf, ref_v, dmax, amax = g["params"]
+    sets.append(("line_params_64.npz", dict(N=int(N), dt=dt, Lf=Lf, ref_v=ref_v, delta_max=dmax, a_max=amax), range(64)))
+    sets.append(("line_256.npz", dict(ref_v=6.0), range(0, 6)))
+    for name, kw, idx in sets:
+        g = golden(name)
+        cf = g["coeffs"] if "coeffs" in g.files else g["fit"]
+        for b in idx:
+            a = hostsim.solve(g["states"][b], cf[b], mode=0, **kw)
+            for mode in (-1, -2):
+                c = hostsim.solve(g["states"][b], cf[b], mode=mode, **kw)
+                assert a["status"] == c["status"] and a["iters"] == c["iters"], (name, b, mode)
+                np.testing.assert_array_equal(a["x"], c["x"])
+                assert a["obj"] == c["obj"]
+
+
 def test_least_square_multiplier_estimate_is_kept_when_small(hostsim):
     """With a small reference speed the least-square multiplier estimate stays below constr_mult_init_max = 1000 and
     Ipopt keeps it (IpDefaultIterateInitializer.cpp:651-718); with the reference's ref_v = 40 it is discarded."""

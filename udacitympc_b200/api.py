@@ -47,6 +47,7 @@ SYMBOLS = {
     "b200mpc_roadmap_reference_batch_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp, _vp]),
     "b200mpc_set_warm_start": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double]),
     "b200mpc_set_batch_split": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "b200mpc_set_compaction": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_int]),
     "b200mpc_set_solver_mode": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "b200mpc_kernel_time_ms": (ctypes.c_int, [_vp, _dp, _ip, ctypes.c_int]),
     "b200mpc_measure_fp64_peak": (ctypes.c_int, [_vp, _dp]),
@@ -224,6 +225,11 @@ class MPC:
         """Cut large batches into `parts` (1..4) sub-batches that run concurrently inside one call (default 4; use 1
         when the caller overlaps several calls itself)."""
         _check(self._lib.b200mpc_set_batch_split(self._h, int(parts)))
+
+    def set_compaction(self, max_live_fraction=0.7, from_round=4):
+        """Throughput path: after every round from `from_round` on, move the unfinished problems to consecutive
+        workspace slots when they fill at most this fraction of the occupied slots (0 = off)."""
+        _check(self._lib.b200mpc_set_compaction(self._h, float(max_live_fraction), int(from_round)))
 
     def set_warm_start(self, enable=True, mu_init=1e-4):
         """closed_loop() only: steps after the first start from the shifted previous solution (not reference behaviour)."""

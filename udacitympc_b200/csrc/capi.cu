@@ -52,7 +52,7 @@ struct b200mpc_handle {
   long long launches = 0;
   // CUDA graphs of whole solves (init + rounds x (factor, forward, step) + finisher), keyed by every launch argument
   struct GraphEntry {
-    int B, steps, ncoef, mode, rounds, fused_below, warm, split;
+    int B, steps, ncoef, mode, rounds, fused_below, warm, split, repack_gen;
     double warm_mu;
     const void *st, *cf, *ws, *out8, *traj, *obj, *status, *iters;
     cudaGraphExec_t exec;
@@ -60,6 +60,7 @@ struct b200mpc_handle {
   };
   std::vector<GraphEntry> graphs;
   bool use_graphs = true;
+  int repack_gen = 0;   // bumped when the compaction schedule changes (part of the graph key)
 };
 
 namespace {
@@ -96,11 +97,11 @@ int timed_solve(b200mpc_handle* h, int B, int steps, const double* st, const dou
   // ranks / streams per host otherwise become launch-bound).  The legacy default stream cannot be captured.
   bool done = false;
   if (h->use_graphs && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) {
-    b200mpc_handle::GraphEntry key{B, steps, ncoef, h->cfg.mode, h->cfg.rounds, h->cfg.fused_below, h->cfg.warm_start ? 1 : 0, h->cfg.split, h->cfg.warm_mu, st, cf, h->ws.p, out8, traj, obj, status, iters, nullptr, 0};
+    b200mpc_handle::GraphEntry key{B, steps, ncoef, h->cfg.mode, h->cfg.rounds, h->cfg.fused_below, h->cfg.warm_start ? 1 : 0, h->cfg.split, h->repack_gen, h->cfg.warm_mu, st, cf, h->ws.p, out8, traj, obj, status, iters, nullptr, 0};
     b200mpc_handle::GraphEntry* hit = nullptr;
     for (auto& g : h->graphs)
       if (g.B == key.B && g.steps == key.steps && g.ncoef == key.ncoef && g.mode == key.mode && g.rounds == key.rounds &&
-          g.fused_below == key.fused_below && g.warm == key.warm && g.split == key.split && g.warm_mu == key.warm_mu && g.st == key.st && g.cf == key.cf && g.ws == key.ws && g.out8 == key.out8 &&
+          g.fused_below == key.fused_below && g.warm == key.warm && g.split == key.split && g.repack_gen == key.repack_gen && g.warm_mu == key.warm_mu && g.st == key.st && g.cf == key.cf && g.ws == key.ws && g.out8 == key.out8 &&
           g.traj == key.traj && g.obj == key.obj && g.status == key.status && g.iters == key.iters)
         hit = &g;
     if (!hit) {
@@ -177,6 +178,11 @@ int b200mpc_create(const b200mpc_params* p, int device, b200mpc_handle** out) {
     h->ss.n_aux = i + 1;
   }
   if (cudaEventCreateWithFlags(&h->ss.fork, cudaEventDisableTiming) != cudaSuccess) h->ss.n_aux = 0;
+  if (const char* rp = getenv("B200MPC_COMPACT")) {   // tuning override: "<max live fraction>[,<first round>]"
+    h->cfg.compact_max_live = atof(rp);
+    if (const char* c = strchr(rp, ',')) h->cfg.compact_from = atoi(c + 1) > 0 ? atoi(c + 1) : 1;
+  }
+  if (const char* rr = getenv("B200MPC_ROUNDS")) { int v = atoi(rr); if (v > 0) h->cfg.rounds = v; }
   if (const char* sp = getenv("B200MPC_SPLIT")) { int v = atoi(sp); if (v >= 1 && v <= 4) h->cfg.split = v; }
   *out = h;
   return 0;
@@ -222,6 +228,16 @@ int b200mpc_set_batch_split(b200mpc_handle* h, int parts) {
   if (!h) return fail(B200MPC_ERR_ARG, "null handle");
   if (parts < 1 || parts > 4) return fail(B200MPC_ERR_ARG, "batch split: parts must be 1..4");
   h->cfg.split = parts;
+  return 0;
+}
+
+int b200mpc_set_compaction(b200mpc_handle* h, double max_live_fraction, int from_round) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  if (!(max_live_fraction >= 0.0 && max_live_fraction <= 1.0)) return fail(B200MPC_ERR_ARG, "compaction: max_live_fraction must be in [0, 1]");
+  if (from_round < 1) return fail(B200MPC_ERR_ARG, "compaction: from_round must be >= 1");
+  h->cfg.compact_max_live = max_live_fraction;
+  h->cfg.compact_from = from_round;
+  ++h->repack_gen;
   return 0;
 }
 

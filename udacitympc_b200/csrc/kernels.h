@@ -19,11 +19,16 @@ cudaError_t solver_prepare_device();
 enum SolveMode { kModePerPass = 0, kModeFused = 1 };
 struct SolveConfig {
   int mode = kModePerPass;
-  int rounds = 16;        // per-pass mode: rounds of (factor, forward, step) before the finisher takes the thin tail
+  int rounds = 18;        // per-pass mode: rounds of (factor, forward, step) before the finisher takes the thin tail
   int fused_below = 3072; // batches smaller than this skip the per-pass rounds (one launch: latency path)
   bool warm_start = false;   // closed loop only: steps after the first start from the shifted previous solution
   double warm_mu = 1e-4;     // barrier parameter a warm-started solve begins with
   int split = 4;             // large batches run as this many concurrent parts (see launch_solve)
+  // batch compaction: after every round from compact_from on, if the unfinished problems fill at most
+  // compact_max_live of the occupied workspace slots, they are moved to consecutive slots, so that later rounds run
+  // full warps on whole 32-byte sectors (0 = off)
+  double compact_max_live = 0.7;
+  int compact_from = 4;
   bool coop = true;       // latency path = cooperative warp-per-problem kernel (false: thread-per-problem fused kernel)
 };
 struct SplitStreams {   // auxiliary streams / events owned by the handle (n_aux <= 3)

@@ -271,6 +271,32 @@ struct Result {
 enum Phase { PH_FACTOR = 0, PH_FORWARD = 1, PH_STEP = 2, PH_DONE = 3 };
 enum Flags { F_INSOC = 1, F_SOCDONE = 2, F_LS = 4, F_LSKEEP = 8, F_TINYLAST = 16, F_TINYFLAG = 32, F_TINYNOW = 64 };
 
+// ---- batch compaction ----------------------------------------------------------------------------------------
+// Moves one unfinished problem from workspace slot `s` to slot `d` (another workspace region) between two passes.
+// A problem that waits for a new factorisation owns nothing but its scalar record and the current copy of the
+// iterate block (everything else is rewritten by the passes before it is read); in any other state the whole
+// workspace of the problem is moved.
+template <int LS_, int LD_>
+MPC_HD void repack_rows(const Ws<LS_>& s, const Ws<LD_>& d, int r, int n) {
+  int i = 0;
+  for (; i + 8 <= n; i += 8) {
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = s(r + i + k);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d(r + i + k) = v[k];
+  }
+  for (; i < n; ++i) d(r + i) = s(r + i);
+}
+template <int LS_, int LD_>
+MPC_HD void repack_problem(const Params& P, const Ws<LS_>& s, const Ws<LD_>& d) {
+  repack_rows(s, d, 0, (int)kNumScal);
+  const int phase = (int)s(iPHASE), flags = (int)s(iFLAGS), cur = (int)s(iCUR);
+  const bool lean = phase == PH_FACTOR && !(flags & F_INSOC);
+  const int lo = lean ? kX * cur : 0, n = lean ? (MPC_STORE_C ? (int)kX : (int)xC) : (int)kRec;
+  for (int t = 0; t < P.N; ++t) repack_rows(s, d, (t + 1) * kRec + lo, n);
+}
+
 // The per-problem solver.  All "passes" are loops over the horizon that touch the workspace once per stage.
 template <int LANES>
 struct Solver {

@@ -30,10 +30,17 @@ constexpr int kBlock = MPC_BLOCK;
 #endif
 constexpr int kFwdBlocks = MPC_FWD_BLOCKS, kStepBlocks = MPC_STEP_BLOCKS;
 
-size_t solve_workspace_doubles(int N, int B) {
+// One workspace region holds every problem of a batch; the buffer the handle allocates has two of them (the batch
+// compaction moves the unfinished problems back and forth), two slot -> problem maps and the counters.
+constexpr int kMaxParts = 4;
+// per-part compaction state in device memory (ints)
+enum Desc { kLevel = 0, kCount, kLive, kAlloc, kTicket, kDescInts = 8 };
+static size_t region_doubles(int N, int B) {
   size_t groups = ((size_t)B + 31) / 32;
   return groups * (size_t)workspace_doubles_per_problem(N) * 32;
 }
+static size_t aux_doubles(int B) { return ((size_t)B + 1) / 2 * 2 + kMaxParts * kDescInts; }   // 2 int maps + state
+size_t solve_workspace_doubles(int N, int B) { return 2 * region_doubles(N, B) + aux_doubles(B); }
 
 struct SolveArgs {
   int B, steps, step, ncoef;
@@ -42,7 +49,14 @@ struct SolveArgs {
   double mu_warm;
   const double* state6;   // [6][B]
   const double* coeffs;   // [ncoef][B]
-  double* ws;
+  double* ws;             // workspace region 0: slot == problem (level 0)
+  // batch compaction (desc == null: off).  Level k >= 1 lives in region k & 1 with the slot -> problem map (k - 1) & 1;
+  // desc = {level, occupied slots, live problems counted by the step kernel, slot allocator, block ticket}
+  double* ws1;
+  int* map0;
+  int* map1;
+  int* desc;
+  int count_live;         // step kernel: count the problems that are not finished (a compaction attempt follows)
   double* out8;           // [steps][8][B]
   double* traj;           // [8N-2][B] or null (last step)
   double* obj;            // [steps][B] or null
@@ -50,8 +64,22 @@ struct SolveArgs {
   int* iters;             // [steps][B] or null
 };
 
-__device__ __forceinline__ double* problem_base(const Params& P, const SolveArgs& A, int b) {
-  return A.ws + (size_t)(b >> 5) * (size_t)workspace_doubles_per_problem(P.N) * 32 + (b & 31);
+__device__ __forceinline__ double* slot_base(const Params& P, double* ws, int slot) {
+  return ws + (size_t)(slot >> 5) * (size_t)workspace_doubles_per_problem(P.N) * 32 + (slot & 31);
+}
+// thread (or warp) i of a launch -> workspace slot (+ its region) and problem index; false: nothing to do
+__device__ __forceinline__ bool locate(const SolveArgs& A, int i, int& slot, int& b, double*& ws) {
+  slot = A.b0 + i;
+  const int level = A.desc ? A.desc[kLevel] : 0;
+  if (level == 0) {
+    if (slot >= A.b1) return false;
+    b = slot; ws = A.ws;
+  } else {
+    if (i >= A.desc[kCount]) return false;
+    b = ((level & 1) ? A.map0 : A.map1)[slot];
+    ws = (level & 1) ? A.ws1 : A.ws;
+  }
+  return true;
 }
 __device__ __forceinline__ void load_coeffs(const SolveArgs& A, int b, double* cf) {
 #pragma unroll
@@ -74,11 +102,19 @@ __device__ __forceinline__ void write_result(const Params& P, const SolveArgs& A
   if (A.status && A.step == A.steps - 1) A.status[b] = R.status;
 }
 
+// one atomic per group of converged lanes
+__device__ __forceinline__ void count_live(int* counter) {
+  const unsigned m = __activemask();
+  if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(counter, __popc(m));
+}
+
 // ---- per-pass kernels ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) mpc_init_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
-  const int b = A.b0 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = A.b0 + blockIdx.x * blockDim.x + threadIdx.x;   // always launched on the uncompacted batch
   if (b >= A.b1) return;
-  Solver<32> S(P, problem_base(P, A, b), b & 31);
+  if (b == A.b0 && A.desc)
+    for (int k = 0; k < kDescInts; ++k) A.desc[k] = 0;
+  Solver<32> S(P, slot_base(P, A.ws, b), b & 31);
   double s0[6], cf[kMaxCoef];
   load_state6(A, b, s0);
   load_coeffs(A, b, cf);
@@ -88,40 +124,92 @@ __global__ void __launch_bounds__(kBlock) mpc_init_kernel(const __grid_constant_
 }
 
 __global__ void __launch_bounds__(kBlock) mpc_factor_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
-  const int b = A.b0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= A.b1) return;
-  Solver<32> S(P, problem_base(P, A, b), b & 31);
+  int slot, b;
+  double* ws;
+  if (!locate(A, blockIdx.x * blockDim.x + threadIdx.x, slot, b, ws)) return;
+  Solver<32> S(P, slot_base(P, ws, slot), slot & 31);
   if (S.load_phase() != PH_FACTOR) return;
   load_coeffs(A, b, S.cf);
   S.kernel_factor();
+  if (S.phase == PH_DONE) {   // inertia correction exhausted (IpPDPerturbationHandler.cpp:380-388)
+    S.load_state();
+    write_result(P, A, b, S);
+  }
 }
 
 __global__ void __launch_bounds__(kBlock, kFwdBlocks) mpc_forward_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
-  const int b = A.b0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= A.b1) return;
-  Solver<32> S(P, problem_base(P, A, b), b & 31);
+  int slot, b;
+  double* ws;
+  if (!locate(A, blockIdx.x * blockDim.x + threadIdx.x, slot, b, ws)) return;
+  Solver<32> S(P, slot_base(P, ws, slot), slot & 31);
   if (S.load_phase() != PH_FORWARD) return;
   load_coeffs(A, b, S.cf);
   S.kernel_forward();
 }
 
 __global__ void __launch_bounds__(kBlock, kStepBlocks) mpc_step_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
-  const int b = A.b0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= A.b1) return;
-  Solver<32> S(P, problem_base(P, A, b), b & 31);
-  if (S.load_phase() != PH_STEP) return;
+  int slot, b;
+  double* ws;
+  if (!locate(A, blockIdx.x * blockDim.x + threadIdx.x, slot, b, ws)) return;
+  Solver<32> S(P, slot_base(P, ws, slot), slot & 31);
+  const int ph = S.load_phase();
+  if (ph != PH_STEP) {
+    if (A.count_live && ph != PH_DONE) count_live(A.desc + kLive);
+    return;
+  }
   __shared__ double carry[kCarry * kBlock];   // stage-to-stage values of the sweep, [value][thread]
   S.cr = carry + threadIdx.x; S.cs = kBlock;
   load_coeffs(A, b, S.cf);
   S.kernel_step();
   if (S.phase == PH_DONE) write_result(P, A, b, S);
+  else if (A.count_live) count_live(A.desc + kLive);
+}
+
+// ---- batch compaction ------------------------------------------------------------------------------------------
+// Runs after a step kernel that counted the live (unfinished) problems.  If they fill at most `max_live` of the
+// occupied slots they move to consecutive slots of the other region (level + 1); the following launches find the new
+// level in desc.  The running lanes of a warp take consecutive destination slots, so the rows they write are
+// contiguous; the slot order among warps is first come, first served (results do not depend on the slot a problem
+// sits in).  The last block to finish commits the new level and clears the counters.
+__global__ void __launch_bounds__(256) mpc_repack_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A,
+                                                         double max_live) {
+  int* desc = A.desc;
+  const int level = desc[kLevel], live_n = desc[kLive];
+  const int occupied = level == 0 ? A.b1 - A.b0 : desc[kCount];
+  const bool go = live_n > 0 && (double)live_n <= max_live * (double)occupied;
+  if (go) {
+    int slot = 0, b = 0;
+    double* ws = A.ws;
+    const bool in = locate(A, blockIdx.x * blockDim.x + threadIdx.x, slot, b, ws);
+    const Ws<32> src{slot_base(P, ws, slot), slot & 31};
+    const bool live = in && (int)src(iPHASE) != PH_DONE;
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (m != 0 && lane == 0) base = atomicAdd(desc + kAlloc, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (live) {
+      const int ds = A.b0 + base + __popc(m & ((1u << lane) - 1u));
+      (((level + 1) & 1) ? A.map0 : A.map1)[ds] = b;
+      repack_problem(P, src, Ws<32>{slot_base(P, ((level + 1) & 1) ? A.ws1 : A.ws, ds), ds & 31});
+    }
+  }
+  __syncthreads();   // every thread of the block has read desc
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(desc + kTicket, 1) == (int)gridDim.x - 1) {
+      if (go) { desc[kCount] = desc[kAlloc]; desc[kLevel] = level + 1; }
+      desc[kLive] = 0; desc[kAlloc] = 0; desc[kTicket] = 0;
+    }
+  }
 }
 
 // ---- fused kernel: finishes whatever is still active (fresh == 1: starts from the inputs) ---------------------
 __global__ void __launch_bounds__(kBlock) mpc_fused_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A, int fresh) {
-  const int b = A.b0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= A.b1) return;
-  Solver<32> S(P, problem_base(P, A, b), b & 31);
+  int slot, b;
+  double* ws;
+  if (!locate(A, blockIdx.x * blockDim.x + threadIdx.x, slot, b, ws)) return;
+  Solver<32> S(P, slot_base(P, ws, slot), slot & 31);
   double carry[kCarry];
   S.cr = carry; S.cs = 1;
   load_coeffs(A, b, S.cf);
@@ -154,12 +242,13 @@ __global__ void __launch_bounds__(128) mpc_coop_kernel(const __grid_constant__ P
                                                        int warps_per_block, int doubles_per_warp) {
   extern __shared__ double coop_smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = A.b0 + blockIdx.x * warps_per_block + wib;   // one problem per warp
-  if (wib >= warps_per_block || b >= A.b1) return;
+  int slot, b;   // one problem per warp
+  double* ws;
+  if (wib >= warps_per_block || !locate(A, blockIdx.x * warps_per_block + wib, slot, b, ws)) return;
   double* mine = coop_smem + (size_t)wib * doubles_per_warp;
   CoopStage* st = reinterpret_cast<CoopStage*>(mine);
   CoopPub* pub = reinterpret_cast<CoopPub*>(mine + (size_t)P.N * kCoopStageDoubles);
-  Solver<32> S(P, problem_base(P, A, b), b & 31);
+  Solver<32> S(P, slot_base(P, ws, slot), slot & 31);
   load_coeffs(A, b, S.cf);
   CoopSolver<32, DevExec> C(S, st, pub, DevExec{lane});
   if (fresh) {
@@ -210,15 +299,24 @@ static cudaError_t launch_part(const Params& P, SolveArgs A, const SolveConfig& 
     A.step = step;
     cudaError_t ce = cudaSuccess;
     if (cfg.mode == kModeFused || A.B < cfg.fused_below) {
+      A.desc = nullptr;
       if (!(cfg.coop && cfg.mode != kModeFused && launch_coop(P, A, 1, stream, &ce))) mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 1);
       if (ce != cudaSuccess) return ce;
       *n += 1;
     } else {
       mpc_init_kernel<<<grid, kBlock, 0, stream>>>(P, A);
       for (int r = 0; r < cfg.rounds; ++r) {
+        // a compaction attempt follows every round from compact_from on (not the last: only the finisher is left)
+        const bool attempt = A.desc && r + 1 >= cfg.compact_from && r + 1 < cfg.rounds;
+        SolveArgs Ar = A;
+        Ar.count_live = attempt ? 1 : 0;
         mpc_factor_kernel<<<grid, kBlock, 0, stream>>>(P, A);
         mpc_forward_kernel<<<grid, kBlock, 0, stream>>>(P, A);
-        mpc_step_kernel<<<grid, kBlock, 0, stream>>>(P, A);
+        mpc_step_kernel<<<grid, kBlock, 0, stream>>>(P, Ar);
+        if (attempt) {
+          mpc_repack_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(P, A, cfg.compact_max_live);
+          *n += 1;
+        }
       }
       if (!(cfg.coop && launch_coop(P, A, 0, stream, &ce))) mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 0);
       if (ce != cudaSuccess) return ce;
@@ -238,7 +336,15 @@ cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6
                          double* ws, double* out8, double* traj, double* obj, int* status, int* iters,
                          const SolveConfig& cfg, cudaStream_t stream, const SplitStreams* ss, long long* n_launches) {
   if (B <= 0) return cudaSuccess;
-  SolveArgs A{B, steps, 0, ncoef, 0, B, cfg.warm_start ? 1 : 0, cfg.warm_mu, state6, coeffs, ws, out8, traj, obj, status, iters};
+  // buffer layout: region 0 | region 1 | map 0 | map 1 | compaction state of every part
+  const size_t reg = region_doubles(P.N, B);
+  int* ints = reinterpret_cast<int*>(ws + 2 * reg);
+  const size_t map_ints = ((size_t)B + 1) / 2 * 2;
+  int* desc = ints + 2 * map_ints;
+  // a warm-started step reads the previous solution at the problem's own slot: no compaction then
+  if (!(cfg.compact_max_live > 0.0) || cfg.warm_start) desc = nullptr;
+  SolveArgs A{B, steps, 0, ncoef, 0, B, cfg.warm_start ? 1 : 0, cfg.warm_mu, state6, coeffs, ws, ws + reg, ints, ints + map_ints, desc, 0,
+              out8, traj, obj, status, iters};
   long long n = 0;
   int parts = 1;
   if (ss && cfg.mode == kModePerPass && cfg.split > 1 && B >= cfg.split * cfg.fused_below) parts = cfg.split < ss->n_aux + 1 ? cfg.split : ss->n_aux + 1;
@@ -254,6 +360,7 @@ cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6
       SolveArgs Ap = A;
       Ap.b0 = p * per;
       Ap.b1 = (p + 1) * per < B ? (p + 1) * per : B;
+      if (desc) Ap.desc = desc + p * kDescInts;
       if (Ap.b0 >= Ap.b1) continue;
       e = launch_part(P, Ap, cfg, p == 0 ? stream : ss->aux[p - 1], &n);
     }
