@@ -39,9 +39,9 @@ def f_iter(N):
 
 def profiled_traffic_bytes():
     """DRAM bytes (read + write) of all solver kernels of ONE step, from the committed ncu launch list of this same
-    command (profiles/r1_final_launches_time_dram.csv: one init ... next init).  None if the file is missing."""
+    command (profiles/r1_compact_launches_time_dram.csv: one init ... next init).  None if the file is missing."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1_final_launches_time_dram.csv")
+    path = os.path.join(ROOT, "profiles", "r1_compact_launches_time_dram.csv")
     try:
         rows = [r for r in csv.reader(open(path)) if len(r) > 5]
         hdr = rows[0]
@@ -383,7 +383,7 @@ def run_ours(args):
             gpu_launches=int(launches),
             clocks=clocks, per_rank_ms_per_step=per_rank_ms, per_rank_sm_mhz=per_rank_mhz,
             roofline=dict(bound="fp64", achieved=achieved, peak=fp64_peak, unit="TFLOP/s", frac=achieved / fp64_peak if fp64_peak else None,
-                          traffic=profiled_traffic_bytes(), traffic_unit="bytes of DRAM read+write per step (ncu, profiles/r1_final_launches_time_dram.csv)",
+                          traffic=profiled_traffic_bytes(), traffic_unit="bytes of DRAM read+write per step (ncu, profiles/r1_compact_launches_time_dram.csv)",
                           hbm_achieved_gbs=(profiled_traffic_bytes() or 0.0) / (avg_kernel_ms * 1e-3) / 1e9 if profiled_traffic_bytes() else None,
                           hbm_frac=((profiled_traffic_bytes() or 0.0) / (avg_kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]
                                     if profiled_traffic_bytes() and peaks.get("hbm_gbs") else None),

@@ -279,12 +279,12 @@ enum Flags { F_INSOC = 1, F_SOCDONE = 2, F_LS = 4, F_LSKEEP = 8, F_TINYLAST = 16
 template <int LS_, int LD_>
 MPC_HD void repack_rows(const Ws<LS_>& s, const Ws<LD_>& d, int r, int n) {
   int i = 0;
-  for (; i + 8 <= n; i += 8) {
-    double v[8];
+  for (; i + 16 <= n; i += 16) {   // loads first, then stores: 16 rows in flight per lane
+    double v[16];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = s(r + i + k);
+    for (int k = 0; k < 16; ++k) v[k] = s(r + i + k);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) d(r + i + k) = v[k];
+    for (int k = 0; k < 16; ++k) d(r + i + k) = v[k];
   }
   for (; i < n; ++i) d(r + i) = s(r + i);
 }
@@ -292,9 +292,22 @@ template <int LS_, int LD_>
 MPC_HD void repack_problem(const Params& P, const Ws<LS_>& s, const Ws<LD_>& d) {
   repack_rows(s, d, 0, (int)kNumScal);
   const int phase = (int)s(iPHASE), flags = (int)s(iFLAGS), cur = (int)s(iCUR);
-  const bool lean = phase == PH_FACTOR && !(flags & F_INSOC);
-  const int lo = lean ? kX * cur : 0, n = lean ? (MPC_STORE_C ? (int)kX : (int)xC) : (int)kRec;
-  for (int t = 0; t < P.N; ++t) repack_rows(s, d, (t + 1) * kRec + lo, n);
+  if (phase == PH_FACTOR && !(flags & F_INSOC)) {
+    constexpr int n = MPC_STORE_C ? (int)kX : (int)xC;
+    const int lo = kX * cur;
+    int t = 0;
+    for (; t + 2 <= P.N; t += 2) {   // two stages (44 rows) in flight per lane
+      const int r0 = (t + 1) * kRec + lo, r1 = r0 + kRec;
+      double v[2 * n];
+#pragma unroll
+      for (int k = 0; k < n; ++k) { v[k] = s(r0 + k); v[n + k] = s(r1 + k); }
+#pragma unroll
+      for (int k = 0; k < n; ++k) { d(r0 + k) = v[k]; d(r1 + k) = v[n + k]; }
+    }
+    if (t < P.N) repack_rows(s, d, (t + 1) * kRec + lo, n);
+  } else {
+    for (int t = 0; t < P.N; ++t) repack_rows(s, d, (t + 1) * kRec, (int)kRec);
+  }
 }
 
 // The per-problem solver.  All "passes" are loops over the horizon that touch the workspace once per stage.
