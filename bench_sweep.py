@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--horizons", default="10,25,50,100")
     ap.add_argument("--batches", default="1024,16384,65536,262144,1048576")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--rounds", type=int, default=0, help="per-pass rounds before the cooperative finisher (0 = library default)")
     args = ap.parse_args()
     import torch
     import udacitympc_b200 as mp
@@ -44,7 +45,7 @@ def main():
             status = torch.empty(B, dtype=torch.int32, device=dev)
             iters = torch.empty(B, dtype=torch.int32, device=dev)
             with mp.MPC(device=0, N=N) as m:
-                m.set_solver_mode(0, 20, -1)   # 20 per-pass rounds, then the cooperative finisher
+                m.set_solver_mode(0, args.rounds, -1)
 
                 def step():
                     m.solve_batch_device(B, st_d.data_ptr(), cf_d.data_ptr(), 4, out8.data_ptr(), 0, 0, status.data_ptr(),
@@ -61,7 +62,7 @@ def main():
             sc = status.cpu().numpy()
             it = iters.cpu().numpy()
             hist = {int(k): int(v) for k, v in zip(*np.unique(sc, return_counts=True))}
-            rows.append(dict(N=N, batch=B, ms_per_batch=ms, solves_per_s=B / (ms * 1e-3), mean_iters=float(it.mean()),
+            rows.append(dict(N=N, batch=B, rounds=args.rounds, ms_per_batch=ms, solves_per_s=B / (ms * 1e-3), mean_iters=float(it.mean()),
                              max_iters=int(it.max()), status_hist=hist, solved_fraction=float((sc == 0).mean())))
             print(json.dumps(rows[-1]), file=sys.stderr)
             del st_d, cf_d, out8

@@ -23,7 +23,7 @@ namespace b200mpc {
 constexpr int kBlock = MPC_BLOCK;
 // resident blocks per SM the light sweeps are compiled for (register cap = 65536 / (64 * blocks))
 #ifndef MPC_FWD_BLOCKS
-#define MPC_FWD_BLOCKS 8
+#define MPC_FWD_BLOCKS 6
 #endif
 #ifndef MPC_STEP_BLOCKS
 #define MPC_STEP_BLOCKS 6
