@@ -141,7 +141,7 @@ def run_reference_arm(args):
                 data="synthetic", config=config_dict(args, args.batch),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=rate["cores"], kind=rate["kind"], sample=rate["sample"]),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
+    emit(line)
 
 
 def config_dict(args, batch):
@@ -340,11 +340,21 @@ def run_ours(args):
         list(ex.map(lambda k: worker(k, K), range(T)))
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
+    # unloaded latency of one host-buffer call at a time, on a handle with the library's default settings (a lone
+    # call is cut into concurrent sub-batches by the library itself)
     lat = []
-    for i in range(max(K, args.latency_reps)):   # unloaded latency of one call
-        a = time.perf_counter()
-        host_step(i, 0)
-        lat.append(time.perf_counter() - a)
+    with mpcmod.MPC(device=local) as lone:
+        lone.set_solver_mode({"perpass": 0, "fused": 1}[args.mode], args.rounds, -1)
+        mpcs.append(lone)
+        hout.append(hout[0])
+        for i in range(3):
+            host_step(i, len(mpcs) - 1)
+        for i in range(max(K, args.latency_reps)):
+            a = time.perf_counter()
+            host_step(i, len(mpcs) - 1)
+            lat.append(time.perf_counter() - a)
+        mpcs.pop()
+        hout.pop()
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     p99 = torch.tensor([float(np.percentile(lat, 99))], dtype=torch.float64, device=dev)
     if world > 1:
@@ -402,11 +412,32 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             st, cf = sets[0]
             line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate(st[:4096], cf[:4096], args.cpu_per_core).items()}
-        print(json.dumps(line))
+        emit(line)
     for m in mpcs:
         m.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Rank 0 must print exactly ONE line on stdout, but libraries write there too (NCCL's version banner comes from C
+    code).  Everything written to fd 1 from here on goes to stderr; emit() writes the JSON line to the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -427,6 +458,7 @@ def main():
     ap.add_argument("--rounds", type=int, default=0, help="per-pass mode: rounds before the fused finisher (0 = library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
