@@ -451,6 +451,47 @@ def test_batch_compaction_does_not_change_results():
         np.testing.assert_array_equal(r[k], ref[k])
 
 
+def test_overlapped_solves_are_deterministic():
+    """The same 65 536-problem batch (bench.py's input set 3, which contains a 60+ iteration straggler) solved 12 times
+    on three overlapped solver handles / streams: every result is bit-identical to the first one."""
+    import torch
+    B, S, reps = 65536, 3, 12
+    xs, ys = synth.roadmap_windows(B, synth.MT19937_64(synth.SEED + 3000))
+    dev = torch.device("cuda", 0)
+    mpcs = [mp.MPC(device=0) for _ in range(S)]
+    try:
+        for h in mpcs:
+            h.set_batch_split(1)
+        fit = mp.polyfit_batch(xs, ys, 3, mpc=mpcs[0])
+        st = synth.roadmap_problems(B, fit, synth.MT19937_64(synth.SEED + 3001))
+        st_d = torch.from_numpy(np.ascontiguousarray(st.T)).to(dev)
+        cf_d = torch.from_numpy(np.ascontiguousarray(fit.T)).to(dev)
+        streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
+        outs = [dict(out8=torch.empty((8, B), dtype=torch.float64, device=dev), status=torch.empty(B, dtype=torch.int32, device=dev),
+                     iters=torch.empty(B, dtype=torch.int32, device=dev)) for _ in range(reps)]
+        torch.cuda.synchronize()
+        for i, o in enumerate(outs):
+            mpcs[i % S].solve_batch_device(B, st_d.data_ptr(), cf_d.data_ptr(), 4, o["out8"].data_ptr(), 0, 0, o["status"].data_ptr(),
+                                           o["iters"].data_ptr(), streams[i % S].cuda_stream)
+        torch.cuda.synchronize()
+        assert int((outs[0]["status"] != 0).sum()) == 0
+        assert int(outs[0]["iters"].max()) >= 40   # the straggler is in the set
+        for o in outs[1:]:
+            assert torch.equal(o["out8"], outs[0]["out8"]) and torch.equal(o["iters"], outs[0]["iters"])
+            assert torch.equal(o["status"], outs[0]["status"])
+        # the straggler against the reference binaries
+        j = int(outs[0]["iters"].argmax())
+        r = ob.ref_solve(st[j], fit[j])
+        got = outs[0]["out8"][:, j].cpu().numpy()
+        print("straggler", j, "iters", int(outs[0]["iters"][j]), "reference iters", r["iters"], "status", r["status"])
+        assert r["status"] == 0
+        np.testing.assert_allclose(got[6:], [r["x"][6 * 25], r["x"][7 * 25 - 1]], rtol=0, atol=TOL_ACT)
+        np.testing.assert_allclose(got[:6], [r["x"][k * 25 + 1] for k in range(6)], rtol=0, atol=TOL_TRAJ)
+    finally:
+        for h in mpcs:
+            h.close()
+
+
 def test_long_horizon_falls_back_to_the_thread_finisher():
     """N = 200 does not fit the cooperative kernel's shared memory: the fused thread-per-problem kernel finishes the
     batch.  No oracle is fast enough at this size; check the size-independent properties instead."""
