@@ -7,7 +7,9 @@
 // registers.  One interior-point iteration = three sweeps over the horizon, each its own kernel
 //   init | factor | forward | step        launched round after round on one stream (replayed as one CUDA graph),
 // with its own register budget (the Riccati factorisation needs ~250 registers, the step sweep 168 with its
-// stage-to-stage values in shared memory, the forward sweep 128) and a small instruction footprint.
+// stage-to-stage values in shared memory, the forward sweep 168) and a small instruction footprint.
+// Between rounds mpc_repack_kernel compacts the problems that are still iterating into consecutive workspace slots
+// (second workspace region, slot -> problem map, level state in device memory), so late rounds run full warps.
 // Latency path (mpc_coop.cuh): one problem per warp, lane <-> stage.  mpc_coop_kernel finishes whatever is still
 // iterating after the fixed number of rounds and solves small batches on its own.
 // mpc_fused_kernel loops the three thread-per-problem sweeps in one launch (comparison / fallback for horizons whose
