@@ -326,14 +326,17 @@ def run_ours(args):
         if rc:
             raise RuntimeError(lib.b200mpc_last_error().decode())
 
-    T = min(S, 3)   # host threads of the end-to-end leg (one solver handle each)
+    # host threads of the end-to-end leg (one solver handle each): up to 6, but not more than the rank's share of the
+    # host cores (never fewer than 3)
+    T = args.e2e_threads if args.e2e_threads > 0 else min(6, max(3, (os.cpu_count() or 6) // world))
+    T = max(1, min(S, T))
 
     def worker(k, n):
         for i in range(k, n, T):
             host_step(i, k)
 
-    for i in range(max(3, W)):
-        host_step(i)
+    for i in range(max(3, W, T)):   # every handle of the leg allocates its buffers and captures its graph here
+        host_step(i, i % T)
     barrier()
     with ThreadPoolExecutor(T) as ex:
         t0 = time.perf_counter()
@@ -399,7 +402,7 @@ def run_ours(args):
                                     if profiled_traffic_bytes() and peaks.get("hbm_gbs") else None),
                           kernel=("mpc_{init,factor,forward,step,coop}_kernel: all solver kernels of one step (one CUDA graph), first to last"
                                   if args.mode == "perpass" else "mpc_fused_kernel"),
-                          avg_kernel_ms=avg_kernel_ms, launches_timed=kern_n, solver_mode=args.mode, streams=S, batch_split=split, e2e_host_threads=min(S, 3),
+                          avg_kernel_ms=avg_kernel_ms, launches_timed=kern_n, solver_mode=args.mode, streams=S, batch_split=split, e2e_host_threads=T,
                           flop_per_launch=flop_per_launch, mean_ip_iters=mean_it,
                           peak_source="DFMA microbenchmark in this run (b200mpc_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                           hbm_peak_gbs=peaks.get("hbm_gbs"), algorithmic_io_bytes_per_solve=(6 + ncoef + 8 + 2) * 8,
@@ -452,6 +455,7 @@ def main():
     ap.add_argument("--cpu-per-core", type=int, default=150, help="cpu_baseline: solves per host core in the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--input-sets", type=int, default=4, help="distinct synthetic input batches cycled over the steps")
+    ap.add_argument("--e2e-threads", type=int, default=0, help="host threads (one solver handle each) of the end-to-end leg (0 = auto)")
     ap.add_argument("--split", type=int, default=0, help="internal batch split of one solve call (0 = 1 with several streams, 4 with one)")
     ap.add_argument("--streams", type=int, default=6, help="solver handles / CUDA streams consecutive steps alternate between")
     ap.add_argument("--mode", default="perpass", choices=["perpass", "fused"], help="solver execution mode (include/b200mpc.h)")
