@@ -99,10 +99,15 @@ def test_random_problems_vs_reference(name, path):
     compare(r, g)
 
 
+@pytest.mark.parametrize("path", ["default", "perpass"])
 @pytest.mark.parametrize("N", [10, 50])
-def test_other_horizons(N):
+def test_other_horizons(N, path):
     g = golden(f"roadmap_N{N}_64.npz")
     with mp.MPC(N=N) as m:
+        if path == "perpass":   # per-pass kernels with batch compaction, 2 sub-batches, then the cooperative finisher
+            m.set_solver_mode(0, 14, 0)
+            m.set_compaction(0.9, 2)
+            m.set_batch_split(2)
         r = m.solve_batch(g["states"], g["coeffs"], want_traj=True)
     sel = np.where((g["status"] == 0) & (g["used_restoration"] == 0))[0]
     assert len(sel) >= 56
