@@ -114,7 +114,7 @@ def main():
     print("golden fixtures written to", HERE)
 
 
-if __name__ == "__main__" and "--config3" not in sys.argv:
+if __name__ == "__main__" and "--config3" not in sys.argv and "--n100" not in sys.argv:
     main()
 
 
@@ -139,3 +139,16 @@ def _solve_one(a):
 
 if __name__ == "__main__" and "--config3" in sys.argv:
     config3()
+
+
+def n100():
+    """BASELINE configs[4] at its longest horizon: the first 64 roadmap problems with N=100 (same inputs as
+    roadmap_N{10,50}_64.npz)."""
+    g = np.load(os.path.join(HERE, "roadmap_256.npz"))
+    st3, fit = g["states"], g["fit"]
+    np.savez_compressed(os.path.join(HERE, "roadmap_N100_64.npz"), states=st3[:64], coeffs=fit[:64],
+                        **solve_set(st3[:64], fit[:64], N=100))
+
+
+if __name__ == "__main__" and "--n100" in sys.argv:
+    n100()

@@ -100,7 +100,7 @@ def test_random_problems_vs_reference(name, path):
 
 
 @pytest.mark.parametrize("path", ["default", "perpass"])
-@pytest.mark.parametrize("N", [10, 50])
+@pytest.mark.parametrize("N", [10, 50, 100])
 def test_other_horizons(N, path):
     g = golden(f"roadmap_N{N}_64.npz")
     with mp.MPC(N=N) as m:

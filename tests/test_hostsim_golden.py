@@ -46,7 +46,7 @@ def test_random_problems(hostsim, name):
     assert same >= 254   # identical interior-point iteration counts (a knife-edge termination test may flip one)
 
 
-@pytest.mark.parametrize("N", [10, 50])
+@pytest.mark.parametrize("N", [10, 50, 100])
 def test_other_horizons(hostsim, N):
     g = golden(f"roadmap_N{N}_64.npz")
     n_cmp = 0
