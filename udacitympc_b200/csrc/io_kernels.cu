@@ -88,7 +88,7 @@ __device__ __forceinline__ void polyfit_regs(const double* xs, const double* ys,
   for (int i = 0; i < NN - 1; ++i)
 #pragma unroll
     for (int j = 0; j < MM; ++j) A[i + 1][j] = A[i][j] * xs[j];   // helpers.h:34-38
-  double c[MM], h[NN];
+  double c[MM], h[NN], ib[NN];   // ib[k] = 1 / R(k,k) for the back substitution
 #pragma unroll
   for (int j = 0; j < MM; ++j) c[j] = ys[j];
   constexpr int size = MM < NN ? MM : NN;
@@ -102,6 +102,7 @@ __device__ __forceinline__ void polyfit_regs(const double* xs, const double* ys,
     double beta, tau;
     if (tail <= DBL_MIN) {   // Householder.h:79-84
       tau = 0.0; beta = c0;
+      ib[k] = 1.0 / c0;
 #pragma unroll
       for (int i = 1; i < rr; ++i) A[k][k + i] = 0.0;
     } else {
@@ -115,6 +116,7 @@ __device__ __forceinline__ void polyfit_regs(const double* xs, const double* ys,
 #pragma unroll
       for (int i = 1; i < rr; ++i) A[k][k + i] = A[k][k + i] * inv;
       tau = (beta - c0) * ibeta;
+      ib[k] = ibeta;
     }
     h[k] = tau; A[k][k] = beta;
 #pragma unroll
@@ -149,7 +151,7 @@ __device__ __forceinline__ void polyfit_regs(const double* xs, const double* ys,
     double s = c[i];
 #pragma unroll
     for (int j = i + 1; j < size; ++j) s -= A[j][i] * out[j];
-    out[i] = s / A[i][i];
+    out[i] = s * ib[i];   // the reciprocal of the diagonal is already there from the reflector (<= 1 ulp from s / R(i,i))
   }
 }
 
