@@ -31,7 +31,7 @@
  *     (Ipopt-3.12.7/Ipopt/src/Interfaces/IpReturnCodes_inc.h:16-39): 0 Solve_Succeeded, 1 Solved_To_Acceptable_Level,
  *     3 Search_Direction_Becomes_Too_Small, 4 Diverging_Iterates, -1 Maximum_Iterations_Exceeded,
  *     -2 Restoration_Failed (the line search failed; the restoration phase is not implemented),
- *     -3 Error_In_Step_Computation.  Like MPC::Solve (MPC.cpp:248-249) the solution is returned regardless.
+ *     -3 Error_In_Step_Computation, -13 Invalid_Number_Detected (NaN / Inf in the inputs).  Like MPC::Solve (MPC.cpp:248-249) the solution is returned regardless.
  */
 #ifndef B200MPC_H
 #define B200MPC_H

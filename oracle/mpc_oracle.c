@@ -711,6 +711,9 @@ int oracle_mpc_solve(const oracle_params* p, const double* state6, const double*
 
   /* least-square multipliers: [[I, J^T],[J, 0]] (sol_x, y) = (zL - zU - grad f, 0)  (IpLeastSquareMults.cpp:51-83) */
   eval_point(s, s->x, &s->f, s->c);
+  /* NaN / Inf in the inputs: Ipopt stops at the starting point with Invalid_Number_Detected (-13), no iteration */
+  int invalid_start = !(fabs(s->f) <= DBL_MAX);
+  for (int i = 0; i < m; ++i) if (!(fabs(s->c[i]) <= DBL_MAX)) invalid_start = 1;
   eval_derivs(s);
   {
     int r = kkt_factor(s, 1, 0.0, 0.0);
@@ -731,6 +734,7 @@ int oracle_mpc_solve(const oracle_params* p, const double* state6, const double*
   const double mu_min = (p->tol < 1e-4 * s->df ? p->tol : 1e-4 * s->df) / (10.0 + 1.0);
 
   for (;;) {
+    if (invalid_start) { status = -13; break; }
     /* ---- quantities at the current iterate ---- */
     eval_point(s, s->x, &s->f, s->c);
     eval_derivs(s);

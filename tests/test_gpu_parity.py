@@ -497,6 +497,24 @@ def test_overlapped_solves_are_deterministic():
             h.close()
 
 
+def test_invalid_numbers_are_reported_per_problem():
+    """NaN / Inf inputs: status -13 (Ipopt's Invalid_Number_Detected) for those problems only, on both paths."""
+    g = golden("line_256.npz")
+    st, cf = g["states"][:64].copy(), g["coeffs"][:64].copy()
+    st[3, 1] = np.nan
+    st[17, 3] = np.inf
+    cf[40, 0] = np.nan
+    bad = np.array([3, 17, 40])
+    good = np.setdiff1d(np.arange(64), bad)
+    for fb in (1 << 30, 0):   # cooperative kernel / per-pass kernels
+        with mp.MPC(device=0) as m:
+            m.set_solver_mode(0, 0, fb)
+            r = m.solve_batch(st, cf, want_traj=True)
+        assert (r["status"][bad] == -13).all() and (r["iters"][bad] == 0).all()
+        assert (r["status"][good] == g["status"][good]).all()
+        np.testing.assert_allclose(r["traj"][good], g["x"][good], rtol=0, atol=1e-8)
+
+
 def test_long_horizon_falls_back_to_the_thread_finisher():
     """N = 200 does not fit the cooperative kernel's shared memory: the fused thread-per-problem kernel finishes the
     batch.  No oracle is fast enough at this size; check the size-independent properties instead."""

@@ -212,3 +212,22 @@ def test_warm_started_closed_loop_reaches_the_same_trajectory(hostsim):
     assert (sw == 0).all()
     np.testing.assert_allclose(hw, g["out8"], rtol=0, atol=1e-6)
     assert iw[0] == ic[0] and iw.sum() < 0.5 * ic.sum()
+
+
+def test_invalid_numbers_stop_at_the_starting_point(hostsim):
+    """NaN / Inf in the state or the coefficients: the reference's Ipopt returns Invalid_Number_Detected (-13) without an
+    iteration; so do both execution shapes of the solver core."""
+    import oracle_bindings as ob
+    g = golden("line_256.npz")
+    cases = []
+    st = g["states"][0].copy(); st[1] = np.nan; cases.append((st, g["coeffs"][0]))
+    st = g["states"][0].copy(); st[3] = np.inf; cases.append((st, g["coeffs"][0]))
+    cf = g["coeffs"][0].copy(); cf[0] = np.nan; cases.append((g["states"][0], cf))
+    for st, cf in cases:
+        o = ob.ref_solve(st, cf)
+        assert o["status"] == -13 and o["iters"] == 0
+        o = ob.port_solve(st, cf)
+        assert o["status"] == -13 and o["iters"] == 0
+        for mode in (0, 1, 2):
+            r = hostsim.solve(st, cf, mode=mode)
+            assert r["status"] == -13 and r["iters"] == 0, mode

@@ -88,7 +88,8 @@ enum Status {
   kDivergingIterates = 4,
   kMaxIterExceeded = -1,
   kRestorationFailed = -2,      // line search failed; the restoration phase is not implemented
-  kErrorInStepComputation = -3  // inertia correction exhausted
+  kErrorInStepComputation = -3, // inertia correction exhausted
+  kInvalidNumberDetected = -13  // NaN / Inf at the starting point
 };
 
 constexpr int kMaxCoef = 4;   // reference polynomial degree <= 3
@@ -506,6 +507,9 @@ struct Solver {
   MPC_HD void init_finish(double f, double th, double cm, double sl) {
     f_cur = df * f; theta_cur = th; priminf = cm; sumlog = sl;
     phase = PH_FACTOR;
+    // NaN / Inf in the inputs: Ipopt stops at the starting point with Invalid_Number_Detected (IpIpoptAlg.cpp:397-470
+    // maps the evaluation error; no iteration is counted)
+    if (!(fabs(f_cur) <= DBL_MAX) || !(th <= DBL_MAX)) { status = kInvalidNumberDetected; phase = PH_DONE; }
   }
 
   // ------------------------------------------------------------------------------------------

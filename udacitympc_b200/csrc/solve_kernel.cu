@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(kBlock) mpc_init_kernel(const __grid_constant_
   if (A.warm && A.step > 0) { S.set_coeffs(cf, A.ncoef); S.init_warm(s0, A.mu_warm); }
   else S.init(s0, cf, A.ncoef);
   S.store_state();
+  if (S.phase == PH_DONE) write_result(P, A, b, S);   // invalid number at the starting point
 }
 
 __global__ void __launch_bounds__(kBlock) mpc_factor_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
