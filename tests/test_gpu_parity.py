@@ -65,6 +65,24 @@ def test_config1_closed_loop_on_device(mpc):
     assert (r["iters"][:, 0] == g["iters"]).all()
 
 
+def test_closed_loop_of_several_vehicles_vs_reference_loop(mpc):
+    """solution/main.cpp:51-76 for 12 vehicles with their own degree-3 references, 8 steps, on the device
+    (b200mpc_closed_loop_batch) against the same loop run with the reference binaries, one MPC::Solve at a time."""
+    g = golden("roadmap_256.npz")
+    sel = np.arange(0, 240, 20)
+    st, cf = g["states"][sel], g["fit"][sel]
+    r = mpc.closed_loop(st, cf, 8)
+    for j in range(len(sel)):
+        s = st[j].copy()
+        for k in range(8):
+            o = ob.ref_solve(s, cf[j])
+            assert o["status"] == 0
+            np.testing.assert_allclose(r["hist8"][k, j], o["out8"], rtol=0, atol=1e-7)
+            assert abs(r["cost"][k, j] - o["obj"]) <= TOL_OBJ * abs(o["obj"])
+            assert r["iters"][k, j] == o["iters"]
+            s = o["out8"][:6].copy()
+
+
 def test_warm_started_closed_loop(mpc):
     """Optional warm start (off by default): same closed-loop trajectory as the cold-started reference loop within the
     solver tolerance, with fewer iterations; on both execution paths."""
