@@ -159,7 +159,8 @@ int b200mpc_roadmap_reference_batch_device(b200mpc_handle* h, int B, const doubl
 
 /* Execution mode of the solver (tuning; results do not depend on it).
  *   mode 0 (default)  throughput path + latency path.  Batches of at least `fused_below` problems (default 3072) run
- *                     `rounds` rounds (default 16) of the per-pass thread-per-problem kernels (factor, forward, step);
+ *                     `rounds` rounds (default: 18, or 16 when the call is cut into concurrent sub-batches, see
+ *                     b200mpc_set_batch_split) of the per-pass thread-per-problem kernels (factor, forward, step);
  *                     whatever is still iterating then -- the thin tail of the batch and rare 30-50 iteration
  *                     stragglers -- is finished by the cooperative warp-per-problem kernel.  Smaller batches (e.g. the
  *                     reference's one-problem MPC::Solve call: 0.6 ms) use the cooperative kernel alone.

@@ -19,7 +19,10 @@ cudaError_t solver_prepare_device();
 enum SolveMode { kModePerPass = 0, kModeFused = 1 };
 struct SolveConfig {
   int mode = kModePerPass;
-  int rounds = 18;        // per-pass mode: rounds of (factor, forward, step) before the finisher takes the thin tail
+  // per-pass mode: rounds of (factor, forward, step) before the finisher takes the thin tail.  0 = automatic: 18, or 16
+  // when the call is cut into concurrent sub-batches (a lone call: its compacted late rounds are latency bound and
+  // nothing else hides them, so the cooperative finisher takes over two rounds earlier)
+  int rounds = 0;
   int fused_below = 3072; // batches smaller than this skip the per-pass rounds (one launch: latency path)
   bool warm_start = false;   // closed loop only: steps after the first start from the shifted previous solution
   double warm_mu = 1e-4;     // barrier parameter a warm-started solve begins with

@@ -295,7 +295,7 @@ static bool launch_coop(const Params& P, const SolveArgs& A, int fresh, cudaStre
 }
 
 // launches every kernel of the solve of problems [b0, b1) on one stream
-static cudaError_t launch_part(const Params& P, SolveArgs A, const SolveConfig& cfg, cudaStream_t stream, long long* n) {
+static cudaError_t launch_part(const Params& P, SolveArgs A, const SolveConfig& cfg, int rounds, cudaStream_t stream, long long* n) {
   const int nb = A.b1 - A.b0;
   const int grid = (nb + kBlock - 1) / kBlock;
   for (int step = 0; step < A.steps; ++step) {
@@ -308,9 +308,9 @@ static cudaError_t launch_part(const Params& P, SolveArgs A, const SolveConfig& 
       *n += 1;
     } else {
       mpc_init_kernel<<<grid, kBlock, 0, stream>>>(P, A);
-      for (int r = 0; r < cfg.rounds; ++r) {
+      for (int r = 0; r < rounds; ++r) {
         // a compaction attempt follows every round from compact_from on (not the last: only the finisher is left)
-        const bool attempt = A.desc && r + 1 >= cfg.compact_from && r + 1 < cfg.rounds;
+        const bool attempt = A.desc && r + 1 >= cfg.compact_from && r + 1 < rounds;
         SolveArgs Ar = A;
         Ar.count_live = attempt ? 1 : 0;
         mpc_factor_kernel<<<grid, kBlock, 0, stream>>>(P, A);
@@ -323,7 +323,7 @@ static cudaError_t launch_part(const Params& P, SolveArgs A, const SolveConfig& 
       }
       if (!(cfg.coop && launch_coop(P, A, 0, stream, &ce))) mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 0);
       if (ce != cudaSuccess) return ce;
-      *n += 2 + 3LL * cfg.rounds;
+      *n += 2 + 3LL * rounds;
     }
     ce = cudaGetLastError();
     if (ce != cudaSuccess) return ce;
@@ -351,9 +351,10 @@ cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6
   long long n = 0;
   int parts = 1;
   if (ss && cfg.mode == kModePerPass && cfg.split > 1 && B >= cfg.split * cfg.fused_below) parts = cfg.split < ss->n_aux + 1 ? cfg.split : ss->n_aux + 1;
+  const int rounds = cfg.rounds > 0 ? cfg.rounds : (parts > 1 ? 16 : 18);
   cudaError_t e = cudaSuccess;
   if (parts == 1) {
-    e = launch_part(P, A, cfg, stream, &n);
+    e = launch_part(P, A, cfg, rounds, stream, &n);
   } else {
     const int per = (((B + parts - 1) / parts) + 63) / 64 * 64;
     if ((e = cudaEventRecord(ss->fork, stream)) != cudaSuccess) return e;
@@ -365,7 +366,7 @@ cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6
       Ap.b1 = (p + 1) * per < B ? (p + 1) * per : B;
       if (desc) Ap.desc = desc + p * kDescInts;
       if (Ap.b0 >= Ap.b1) continue;
-      e = launch_part(P, Ap, cfg, p == 0 ? stream : ss->aux[p - 1], &n);
+      e = launch_part(P, Ap, cfg, rounds, p == 0 ? stream : ss->aux[p - 1], &n);
     }
     for (int p = 1; p < parts; ++p) {   // always join, also after an error, so a capture can end cleanly
       cudaError_t e2 = cudaEventRecord(ss->join[p - 1], ss->aux[p - 1]);
