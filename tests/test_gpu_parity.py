@@ -533,6 +533,30 @@ def test_invalid_numbers_are_reported_per_problem():
         np.testing.assert_allclose(r["traj"][good], g["x"][good], rtol=0, atol=1e-8)
 
 
+def test_plain_launches_and_changing_batch_sizes():
+    """B200MPC_NO_GRAPHS=1 (plain launches instead of CUDA-graph replay, including the fork / join of a split call) gives
+    the same results; one handle serves changing batch sizes (its workspace grows, graphs are re-captured)."""
+    st, cf = synth.line_problems(8192)
+    with mp.MPC(device=0) as m:
+        a = m.solve_batch(st[:4096], cf[:4096])
+        b = m.solve_batch(st, cf)                      # larger batch: the workspace is reallocated
+        c = m.solve_batch(st[:4096], cf[:4096])        # back to the first size
+        d = m.solve_batch(st[:100], cf[:100])          # latency path on the same handle
+    for k in ("out8", "cost", "status", "iters"):
+        np.testing.assert_array_equal(a[k], c[k])
+        np.testing.assert_array_equal(a[k][:100], d[k]) if k in ("status", "iters") else None
+    np.testing.assert_allclose(b["out8"][:4096], a["out8"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(d["out8"], a["out8"][:100], rtol=0, atol=1e-9)
+    os.environ["B200MPC_NO_GRAPHS"] = "1"
+    try:
+        with mp.MPC(device=0) as m:
+            e = m.solve_batch(st, cf)
+    finally:
+        del os.environ["B200MPC_NO_GRAPHS"]
+    for k in ("out8", "cost", "status", "iters"):
+        np.testing.assert_array_equal(e[k], b[k])
+
+
 def test_long_horizon_falls_back_to_the_thread_finisher():
     """N = 200 does not fit the cooperative kernel's shared memory: the fused thread-per-problem kernel finishes the
     batch.  No oracle is fast enough at this size; check the size-independent properties instead."""
