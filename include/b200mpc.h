@@ -161,8 +161,10 @@ int b200mpc_roadmap_reference_batch_device(b200mpc_handle* h, int B, const doubl
 
 /* Execution mode of the solver (tuning; results do not depend on it).
  *   mode 0 (default)  throughput path + latency path.  Batches of at least `fused_below` problems (default 3072) run
- *                     `rounds` rounds (default: 18, or 16 when the call is cut into concurrent sub-batches, see
- *                     b200mpc_set_batch_split) of the per-pass thread-per-problem kernels (factor, forward, step);
+ *                     rounds of the per-pass thread-per-problem kernels (factor, forward, step).  By default the
+ *                     number of rounds adapts to the batch: after every round from the 14th on (at most 20) the
+ *                     cooperative kernel takes the rest over as soon as the compacted batch fits one of its waves
+ *                     (1184 problems); a positive `rounds` fixes the hand-over point instead;
  *                     whatever is still iterating then -- the thin tail of the batch and rare 30-50 iteration
  *                     stragglers -- is finished by the cooperative warp-per-problem kernel.  Smaller batches (e.g. the
  *                     reference's one-problem MPC::Solve call: 0.6 ms) use the cooperative kernel alone.

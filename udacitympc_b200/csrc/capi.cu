@@ -182,6 +182,10 @@ int b200mpc_create(const b200mpc_params* p, int device, b200mpc_handle** out) {
     h->cfg.compact_max_live = atof(rp);
     if (const char* c = strchr(rp, ',')) h->cfg.compact_from = atoi(c + 1) > 0 ? atoi(c + 1) : 1;
   }
+  if (const char* hb = getenv("B200MPC_HANDOVER")) {   // tuning override: "<occupied slots>[,<max rounds>]" (0 = static rounds)
+    h->cfg.handover_below = atoi(hb);
+    if (const char* c = strchr(hb, ',')) { int v = atoi(c + 1); if (v > 0) h->cfg.handover_max_rounds = v; }
+  }
   if (const char* rr = getenv("B200MPC_ROUNDS")) { int v = atoi(rr); if (v > 0) h->cfg.rounds = v; }
   if (const char* sp = getenv("B200MPC_SPLIT")) { int v = atoi(sp); if (v >= 1 && v <= 4) h->cfg.split = v; }
   *out = h;

@@ -19,9 +19,8 @@ cudaError_t solver_prepare_device();
 enum SolveMode { kModePerPass = 0, kModeFused = 1 };
 struct SolveConfig {
   int mode = kModePerPass;
-  // per-pass mode: rounds of (factor, forward, step) before the finisher takes the thin tail.  0 = automatic: 18, or 16
-  // when the call is cut into concurrent sub-batches (a lone call: its compacted late rounds are latency bound and
-  // nothing else hides them, so the cooperative finisher takes over two rounds earlier)
+  // per-pass mode: rounds of (factor, forward, step) before the finisher takes the thin tail.  0 = automatic: adaptive
+  // hand-over (below); without batch compaction 18, or 16 when the call is cut into concurrent sub-batches
   int rounds = 0;
   int fused_below = 3072; // batches smaller than this skip the per-pass rounds (one launch: latency path)
   bool warm_start = false;   // closed loop only: steps after the first start from the shifted previous solution
@@ -30,6 +29,10 @@ struct SolveConfig {
   // batch compaction: after every round from compact_from on, if the unfinished problems fill at most
   // compact_max_live of the occupied workspace slots, they are moved to consecutive slots, so that later rounds run
   // full warps on whole 32-byte sectors (0 = off)
+  // adaptive hand-over (automatic rounds only): occupied slots (whole call) at which the cooperative kernel takes over
+  int handover_below = 1184;      // one wave of 8 warps on 148 SMs
+  int handover_from = 14;         // first round after which it may happen
+  int handover_max_rounds = 20;
   double compact_max_live = 0.7;
   int compact_from = 4;
   bool coop = true;       // latency path = cooperative warp-per-problem kernel (false: thread-per-problem fused kernel)

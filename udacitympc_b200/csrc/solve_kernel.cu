@@ -36,7 +36,7 @@ constexpr int kFwdBlocks = MPC_FWD_BLOCKS, kStepBlocks = MPC_STEP_BLOCKS;
 // compaction moves the unfinished problems back and forth), two slot -> problem maps and the counters.
 constexpr int kMaxParts = 4;
 // per-part compaction state in device memory (ints)
-enum Desc { kLevel = 0, kCount, kLive, kAlloc, kTicket, kDescInts = 8 };
+enum Desc { kLevel = 0, kCount, kLive, kAlloc, kTicket, kHanded, kDescInts = 8 };
 static size_t region_doubles(int N, int B) {
   size_t groups = ((size_t)B + 31) / 32;
   return groups * (size_t)workspace_doubles_per_problem(N) * 32;
@@ -70,9 +70,10 @@ __device__ __forceinline__ double* slot_base(const Params& P, double* ws, int sl
   return ws + (size_t)(slot >> 5) * (size_t)workspace_doubles_per_problem(P.N) * 32 + (slot & 31);
 }
 // thread (or warp) i of a launch -> workspace slot (+ its region) and problem index; false: nothing to do
-__device__ __forceinline__ bool locate(const SolveArgs& A, int i, int& slot, int& b, double*& ws) {
+__device__ __forceinline__ bool locate(const SolveArgs& A, int i, int& slot, int& b, double*& ws, bool sweeps = true) {
   slot = A.b0 + i;
   const int level = A.desc ? A.desc[kLevel] : 0;
+  if (sweeps && level > 0 && A.desc[kHanded]) return false;   // the cooperative kernel has taken the rest over
   if (level == 0) {
     if (slot >= A.b1) return false;
     b = slot; ws = A.ws;
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(256) mpc_repack_kernel(const __grid_constant__
 __global__ void __launch_bounds__(kBlock) mpc_fused_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A, int fresh) {
   int slot, b;
   double* ws;
-  if (!locate(A, blockIdx.x * blockDim.x + threadIdx.x, slot, b, ws)) return;
+  if (!locate(A, blockIdx.x * blockDim.x + threadIdx.x, slot, b, ws, false)) return;
   Solver<32> S(P, slot_base(P, ws, slot), slot & 31);
   double carry[kCarry];
   S.cr = carry; S.cs = 1;
@@ -241,13 +242,20 @@ struct DevExec {
   }
 };
 
+// take_below > 0: conditional hand-over after a round -- the kernel acts only once the batch has been compacted to at
+// most take_below occupied slots (two waves of the cooperative kernel); from then on the sweeps of later rounds find
+// nothing to do
 __global__ void __launch_bounds__(128) mpc_coop_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A, int fresh,
-                                                       int warps_per_block, int doubles_per_warp) {
+                                                       int warps_per_block, int doubles_per_warp, int take_below) {
   extern __shared__ double coop_smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (take_below > 0) {
+    if (!A.desc || A.desc[kLevel] == 0 || A.desc[kCount] > take_below) return;
+    if (threadIdx.x == 0) A.desc[kHanded] = 1;   // only the sweeps read it
+  }
   int slot, b;   // one problem per warp
   double* ws;
-  if (wib >= warps_per_block || !locate(A, blockIdx.x * warps_per_block + wib, slot, b, ws)) return;
+  if (wib >= warps_per_block || !locate(A, blockIdx.x * warps_per_block + wib, slot, b, ws, false)) return;
   double* mine = coop_smem + (size_t)wib * doubles_per_warp;
   CoopStage* st = reinterpret_cast<CoopStage*>(mine);
   CoopPub* pub = reinterpret_cast<CoopPub*>(mine + (size_t)P.N * kCoopStageDoubles);
@@ -281,21 +289,22 @@ cudaError_t solver_prepare_device() {
 static size_t coop_doubles_per_warp(int N) { return (size_t)N * kCoopStageDoubles + (sizeof(CoopPub) + 7) / 8; }
 
 // launches the cooperative kernel if the horizon fits in shared memory; returns false otherwise
-static bool launch_coop(const Params& P, const SolveArgs& A, int fresh, cudaStream_t stream, cudaError_t* err) {
+static bool launch_coop(const Params& P, const SolveArgs& A, int fresh, cudaStream_t stream, cudaError_t* err, int take_below = 0) {
   const size_t per_warp = coop_doubles_per_warp(P.N) * sizeof(double);
   const size_t limit = 200 * 1024;
   if (per_warp > limit) return false;
   int wpb = (int)(limit / per_warp);
   if (wpb > 4) wpb = 4;
   const size_t smem = per_warp * wpb;
-  const int grid = (A.b1 - A.b0 + wpb - 1) / wpb;
-  mpc_coop_kernel<<<grid, 128, smem, stream>>>(P, A, fresh, wpb, (int)coop_doubles_per_warp(P.N));
+  const int n = take_below > 0 && take_below < A.b1 - A.b0 ? take_below : A.b1 - A.b0;
+  const int grid = (n + wpb - 1) / wpb;
+  mpc_coop_kernel<<<grid, 128, smem, stream>>>(P, A, fresh, wpb, (int)coop_doubles_per_warp(P.N), take_below);
   *err = cudaGetLastError();
   return true;
 }
 
 // launches every kernel of the solve of problems [b0, b1) on one stream
-static cudaError_t launch_part(const Params& P, SolveArgs A, const SolveConfig& cfg, int rounds, cudaStream_t stream, long long* n) {
+static cudaError_t launch_part(const Params& P, SolveArgs A, const SolveConfig& cfg, int rounds, int take_below, cudaStream_t stream, long long* n) {
   const int nb = A.b1 - A.b0;
   const int grid = (nb + kBlock - 1) / kBlock;
   for (int step = 0; step < A.steps; ++step) {
@@ -319,6 +328,10 @@ static cudaError_t launch_part(const Params& P, SolveArgs A, const SolveConfig& 
         if (attempt) {
           mpc_repack_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(P, A, cfg.compact_max_live);
           *n += 1;
+          if (take_below > 0 && r + 1 >= cfg.handover_from && cfg.coop && launch_coop(P, A, 0, stream, &ce, take_below)) {
+            if (ce != cudaSuccess) return ce;
+            *n += 1;
+          }
         }
       }
       if (!(cfg.coop && launch_coop(P, A, 0, stream, &ce))) mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 0);
@@ -351,10 +364,15 @@ cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6
   long long n = 0;
   int parts = 1;
   if (ss && cfg.mode == kModePerPass && cfg.split > 1 && B >= cfg.split * cfg.fused_below) parts = cfg.split < ss->n_aux + 1 ? cfg.split : ss->n_aux + 1;
-  const int rounds = cfg.rounds > 0 ? cfg.rounds : (parts > 1 ? 16 : 18);
+  // automatic setting: up to handover_max_rounds rounds, and after every late round the cooperative kernel takes the
+  // rest over as soon as the compacted batch fits its two waves (the launches after that find nothing to do); a fixed
+  // number of rounds (b200mpc_set_solver_mode) hands over exactly there
+  const bool adaptive = cfg.rounds <= 0 && desc != nullptr && cfg.coop && cfg.handover_below > 0;
+  const int rounds = cfg.rounds > 0 ? cfg.rounds : (adaptive ? cfg.handover_max_rounds : (parts > 1 ? 16 : 18));
+  const int take_below = adaptive ? (cfg.handover_below / parts > 64 ? cfg.handover_below / parts : 64) : 0;
   cudaError_t e = cudaSuccess;
   if (parts == 1) {
-    e = launch_part(P, A, cfg, rounds, stream, &n);
+    e = launch_part(P, A, cfg, rounds, take_below, stream, &n);
   } else {
     const int per = (((B + parts - 1) / parts) + 63) / 64 * 64;
     if ((e = cudaEventRecord(ss->fork, stream)) != cudaSuccess) return e;
@@ -366,7 +384,7 @@ cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6
       Ap.b1 = (p + 1) * per < B ? (p + 1) * per : B;
       if (desc) Ap.desc = desc + p * kDescInts;
       if (Ap.b0 >= Ap.b1) continue;
-      e = launch_part(P, Ap, cfg, rounds, p == 0 ? stream : ss->aux[p - 1], &n);
+      e = launch_part(P, Ap, cfg, rounds, take_below, p == 0 ? stream : ss->aux[p - 1], &n);
     }
     for (int p = 1; p < parts; ++p) {   // always join, also after an error, so a capture can end cleanly
       cudaError_t e2 = cudaEventRecord(ss->join[p - 1], ss->aux[p - 1]);
