@@ -252,7 +252,15 @@ def test_full_size_batch_properties(mpc):
     np.testing.assert_array_equal(r2["out8"], r["out8"])
     h = B // 2
     ra, rb = mpc.solve_batch(st[:h], fit[:h]), mpc.solve_batch(st[h:], fit[h:])
-    np.testing.assert_array_equal(np.concatenate([ra["out8"], rb["out8"]]), r["out8"])
+    # (the hand-over to the cooperative kernel adapts to the batch, and the two kernels sum in different orders: the few
+    # problems that finish on the other side of it may differ in the last bit)
+    np.testing.assert_allclose(np.concatenate([ra["out8"], rb["out8"]]), r["out8"], rtol=0, atol=1e-13)
+    np.testing.assert_array_equal(np.concatenate([ra["iters"], rb["iters"]]), r["iters"])
+    with mp.MPC(device=0) as m:   # with a fixed hand-over point the halves reproduce the whole bit for bit
+        m.set_solver_mode(0, 18, -1)
+        whole = m.solve_batch(st, fit)
+        ra, rb = m.solve_batch(st[:h], fit[:h]), m.solve_batch(st[h:], fit[h:])
+    np.testing.assert_array_equal(np.concatenate([ra["out8"], rb["out8"]]), whole["out8"])
     # a strided sample against the CPU oracle (the C port; 40 ms per solve)
     for b in range(0, B, B // 24):
         o = ob.port_solve(st[b], fit[b])
