@@ -115,8 +115,8 @@ int b200mpc_set_warm_start(b200mpc_handle* h, int enable, double mu_init);
 /* Internal concurrency of one large solve call: the batch is cut into `parts` (1..4) contiguous sub-batches whose
  * kernels run concurrently on internal streams (joined before the call's stream continues, so the call keeps its
  * stream-ordered semantics).  Results do not depend on it for a fixed number of rounds (with the automatic setting of
- * b200mpc_set_solver_mode a split call hands over to the cooperative kernel two rounds earlier, which can change the
- * last bits of the few problems that finish there).  Default 4: best for a caller that issues one call at a
+ * b200mpc_set_solver_mode the hand-over to the cooperative kernel adapts to the sub-batch, which can change the last
+ * bit of the few problems that finish on the other side of it).  Default 4: best for a caller that issues one call at a
  * time; a caller that already overlaps several calls on several handles / streams should set 1. */
 int b200mpc_set_batch_split(b200mpc_handle* h, int parts);
 

@@ -11,7 +11,7 @@
 // Between rounds mpc_repack_kernel compacts the problems that are still iterating into consecutive workspace slots
 // (second workspace region, slot -> problem map, level state in device memory), so late rounds run full warps.
 // Latency path (mpc_coop.cuh): one problem per warp, lane <-> stage.  mpc_coop_kernel finishes whatever is still
-// iterating after the fixed number of rounds and solves small batches on its own.
+// iterating once the compacted batch fits one of its waves (or after the last round) and solves small batches on its own.
 // mpc_fused_kernel loops the three thread-per-problem sweeps in one launch (comparison / fallback for horizons whose
 // per-stage scratch does not fit the cooperative kernel's shared memory).
 #include "kernels.h"
