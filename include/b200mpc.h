@@ -126,6 +126,15 @@ int b200mpc_set_batch_split(b200mpc_handle* h, int parts);
  * depend on it.  Default 0.7 from round 4; 0 switches it off. */
 int b200mpc_set_compaction(b200mpc_handle* h, double max_live_fraction, int from_round);
 
+/* Restoration after a failed line search (Ipopt: IpBacktrackingLineSearch.cpp:531-585 -> IpRestoMinC_1Nrm.cpp).  Never
+ * needed at the reference's N = 25; a few per cent of the problems at N = 100 get there.  Enabled (default): the
+ * problem continues from the model roll-out of its current controls (a feasible point) with
+ * lambda = 0, as Ipopt continues from the point its restoration phase returns.  This is NOT a restatement of Ipopt's
+ * nested restoration solve: on these problems the iteration count differs from Ipopt's, the solution is the same
+ * whenever both end in the same local minimum.  Disabled: such a problem returns status -2 (Restoration_Failed) at the
+ * iteration where Ipopt would switch to its restoration phase. */
+int b200mpc_set_restoration(b200mpc_handle* h, int enable);
+
 /* B least-squares polynomial fits (unpivoted Householder QR of the Vandermonde matrix, as Eigen 3.3.3 does for
  * helpers.h:24-44).  xs, ys: B x m;  coeffs_out: B x (order+1).  Requires 1 <= order <= m-1 (helpers.h:26 assert). */
 int b200mpc_polyfit_batch(b200mpc_handle* h, int B, const double* xs, const double* ys, int m, int order,

@@ -39,6 +39,8 @@ struct hostsim_params {
   double dt, Lf, ref_v, w_cte, w_epsi, w_v, w_delta, w_a, w_ddelta, w_da, delta_max, a_max, tol;
   int max_iter;
 };
+static int g_resto = 1;   // Params::resto of the following solves
+void hostsim_set_restoration(int enable) { g_resto = enable != 0; }
 
 // trace rows of 8: iter, mu, alpha_pr, alpha_du, dw, f, theta, phase-trips
 // mode 0: one Solver object loops trip() (what the single fused kernel does)
@@ -52,6 +54,7 @@ int hostsim_solve_mode(const hostsim_params* hp, const double* state6, const dou
   P.w_cte = hp->w_cte; P.w_epsi = hp->w_epsi; P.w_v = hp->w_v; P.w_delta = hp->w_delta; P.w_a = hp->w_a;
   P.w_ddelta = hp->w_ddelta; P.w_da = hp->w_da; P.delta_max = hp->delta_max; P.a_max = hp->a_max; P.tol = hp->tol;
   P.max_iter = hp->max_iter;
+  P.resto = g_resto;
   P.finalize();
   std::vector<double> ws((size_t)workspace_doubles_per_problem(P.N), 0.0);
   g_ws_limit = (int)ws.size();
@@ -125,6 +128,14 @@ int hostsim_solve_mode(const hostsim_params* hp, const double* state6, const dou
         if (k == PH_STEP) { S.load_state(); log_row(S); }
         if (mode == -2 && phase != PH_DONE) repack();
       }
+      if (phase == PH_RESTO) {   // the per-pass kernels leave it to the finisher: a fresh Solver does the restoration step
+        Solver<1> S(P, ws.data());
+        S.set_coeffs(coeffs, ncoef);
+        S.load_state();
+        S.do_resto();
+        S.store_state();
+        phase = S.load_phase();
+      }
       if (mode == -1 && phase != PH_DONE) repack();
       ++trips;
     }
@@ -150,6 +161,7 @@ int hostsim_closed_loop(const hostsim_params* hp, const double* state6, const do
   P.w_cte = hp->w_cte; P.w_epsi = hp->w_epsi; P.w_v = hp->w_v; P.w_delta = hp->w_delta; P.w_a = hp->w_a;
   P.w_ddelta = hp->w_ddelta; P.w_da = hp->w_da; P.delta_max = hp->delta_max; P.a_max = hp->a_max; P.tol = hp->tol;
   P.max_iter = hp->max_iter;
+  P.resto = g_resto;
   P.finalize();
   std::vector<double> ws((size_t)workspace_doubles_per_problem(P.N), 0.0);
   g_ws_limit = (int)ws.size();

@@ -1,0 +1,78 @@
+"""TEST INFRASTRUCTURE: how often does the restoration step (Solver::do_resto) end in the local minimum the reference's
+Ipopt reaches through its own restoration phase?  Solver core compiled for the host (tests/hostsim) against THE
+REFERENCE ITSELF (oracle/_ref binaries) on n random roadmap problems at horizon N.
+
+    python tools/resto_campaign.py N n [mode]      (reference answers are cached in /tmp)
+"""
+import multiprocessing as mp
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
+import oracle_bindings as ob  # noqa: E402
+from conftest import _HostSim  # noqa: E402
+from udacitympc_b200 import synth  # noqa: E402
+
+hs = None
+
+
+def ref_work(a):
+    st, cf, N = a
+    r = ob.ref_solve(st, cf, N=N, trace=True)
+    return np.concatenate([[r["status"], r["iters"], r["obj"], int((r["trace"][:, 9] >= 100).any())], r["out8"]])
+
+
+def host_work(a):
+    global hs
+    if hs is None:
+        hs = _HostSim()
+    st, cf, N, mode = a
+    h = hs.solve(st, cf, mode=mode, N=N)
+    return np.concatenate([[h["status"], h["iters"], h["obj"]], h["out8"]])
+
+
+def problems(n, seed=0):
+    xs, ys = synth.roadmap_windows(n, synth.MT19937_64(878 + seed))
+    V = np.stack([xs ** i for i in range(4)], axis=2)
+    fit = np.stack([np.linalg.lstsq(V[b], ys[b], rcond=None)[0] for b in range(n)])
+    return synth.roadmap_problems(n, fit, synth.MT19937_64(879 + seed)), fit
+
+
+if __name__ == "__main__":
+    N = int(sys.argv[1]); n = int(sys.argv[2]); mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    S, C = problems(n)
+    cache = f"/tmp/resto_ref_N{N}_{n}.npy"
+    ctx = mp.get_context("fork")
+    if os.path.exists(cache):
+        ref = np.load(cache)
+    else:
+        t = time.time()
+        with ctx.Pool(os.cpu_count()) as pool:
+            ref = np.array(pool.map(ref_work, [(S[b], C[b], N) for b in range(n)], chunksize=4))
+        np.save(cache, ref)
+        print(f"reference: {time.time() - t:.0f} s")
+    t = time.time()
+    with ctx.Pool(os.cpu_count()) as pool:
+        got = np.array(pool.map(host_work, [(S[b], C[b], N, mode) for b in range(n)], chunksize=4))
+    used = ref[:, 3] == 1
+    ok_ref = ref[:, 0] == 0
+    relobj = np.abs(got[:, 2] - ref[:, 2]) / np.abs(ref[:, 2])
+    dact = np.abs(got[:, 9:11] - ref[:, 10:12]).max(axis=1)
+    same = (got[:, 0] == 0) & ok_ref & (relobj < 1e-6) & (dact < 1e-5)
+    ours_resto = (got[:, 0] == 0) & ok_ref & ~used & (got[:, 1] != ref[:, 1])
+    print(f"N {N} n {n} mode {mode}: reference ok {int(ok_ref.sum())}, reference used restoration {int(used.sum())}; "
+          f"ours status!=0 {int((got[:, 0] != 0).sum())} {np.unique(got[:, 0], return_counts=True)}")
+    print(f"  no-restoration problems: same solution {int((same & ~used).sum())} / {int((~used & ok_ref).sum())}, "
+          f"iteration-count mismatches {int(ours_resto.sum())}")
+    print(f"  restoration problems: same solution {int((same & used).sum())} / {int((used & ok_ref).sum())}; "
+          f"ours better {int(((got[:, 0] == 0) & used & ~same & (got[:, 2] < ref[:, 2])).sum())}, "
+          f"ours worse {int(((got[:, 0] == 0) & used & ~same & (got[:, 2] > ref[:, 2])).sum())}; "
+          f"mean iters ours {got[used, 1].mean():.1f} ref {ref[used, 1].mean():.1f}; {time.time() - t:.0f} s")
+    bad = np.nonzero(used & ~same)[0]
+    for b in bad[:12]:
+        print(f"    #{b}: ours status {int(got[b, 0])} iters {int(got[b, 1])} obj {got[b, 2]:.6f} | ref iters {int(ref[b, 1])} obj {ref[b, 2]:.6f}")

@@ -48,6 +48,7 @@ SYMBOLS = {
     "b200mpc_set_warm_start": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double]),
     "b200mpc_set_batch_split": (ctypes.c_int, [_vp, ctypes.c_int]),
     "b200mpc_set_compaction": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_int]),
+    "b200mpc_set_restoration": (ctypes.c_int, [_vp, ctypes.c_int]),
     "b200mpc_set_solver_mode": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "b200mpc_kernel_time_ms": (ctypes.c_int, [_vp, _dp, _ip, ctypes.c_int]),
     "b200mpc_measure_fp64_peak": (ctypes.c_int, [_vp, _dp]),
@@ -225,6 +226,11 @@ class MPC:
         """Cut large batches into `parts` (1..4) sub-batches that run concurrently inside one call (default 4; use 1
         when the caller overlaps several calls itself)."""
         _check(self._lib.b200mpc_set_batch_split(self._h, int(parts)))
+
+    def set_restoration(self, enable=True):
+        """Restoration step after a failed line search (on by default; off: such a problem returns status -2 at the
+        iteration where the reference's Ipopt enters its restoration phase).  See b200mpc_set_restoration."""
+        _check(self._lib.b200mpc_set_restoration(self._h, 1 if enable else 0))
 
     def set_compaction(self, max_live_fraction=0.7, from_round=4):
         """Throughput path: after every round from `from_round` on, move the unfinished problems to consecutive

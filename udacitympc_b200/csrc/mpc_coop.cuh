@@ -476,6 +476,20 @@ struct CoopSolver {
   // One round: the three phases a problem may be in, each followed by the thread version's control logic on lane 0.
   MPC_HD void round() {
     publish();
+    if (pub->phase == PH_RESTO) {
+      // restoration step (Solver::do_resto, sequential over the horizon): lane 0 rewrites the current iterate in the
+      // workspace, then every lane re-stages its stage with a zero search direction for the zero-length STEP that follows
+      if (ex.lane0()) S.do_resto();
+      publish();
+      ex.for_stages(N, [&](int t) {
+        load_iterate(t);
+        for (int k = 0; k < 6; ++k) st[t].ds[k] = 0.0;
+        st[t].du[0] = st[t].du[1] = 0.0;
+      });
+      ex.sync();
+      ex.for_stages(M, [&](int t) { prep_factor(t); });
+      ex.sync();
+    }
     if (pub->phase == PH_FACTOR) {
       ex.for_stages(N, [&](int t) { load_iterate(t); });
       ex.sync();

@@ -57,6 +57,7 @@ struct Params {
   double delta_max, a_max;
   double tol;
   int max_iter;
+  int resto;            // 1: a failed line search hands the problem to the restoration step (Solver::do_resto)
   // derived
   double dtLf;          // dt / Lf
   double xl[2], xu[2];  // relaxed bounds of (delta, a): +-(b + 1e-8 max(1,|b|)), IpOrigIpoptNLP.cpp:369-372
@@ -87,7 +88,7 @@ enum Status {
   kSearchDirectionTooSmall = 3,
   kDivergingIterates = 4,
   kMaxIterExceeded = -1,
-  kRestorationFailed = -2,      // line search failed; the restoration phase is not implemented
+  kRestorationFailed = -2,      // line search failed at an almost feasible point (or with the restoration switched off)
   kErrorInStepComputation = -3, // inertia correction exhausted
   kInvalidNumberDetected = -13  // NaN / Inf at the starting point
 };
@@ -95,6 +96,10 @@ enum Status {
 constexpr int kMaxCoef = 4;   // reference polynomial degree <= 3
 constexpr int kMaxFilter = 8;
 constexpr int kCarry = 24;    // stage-to-stage values of the STEP sweep
+#ifndef MPC_RESTO_BETA
+#define MPC_RESTO_BETA 0.05
+#endif
+constexpr double kRestoBeta = MPC_RESTO_BETA;   // fraction of the constraint defects the restoration step removes
 
 // ---- workspace of one problem, in doubles -----------------------------------------------------------------
 // Element i of the problem owned by lane l of a 32-problem group lives at group_base[i*LANES + l] (LANES = 32 on
@@ -269,8 +274,10 @@ struct Result {
   double out8[8];
 };
 
-enum Phase { PH_FACTOR = 0, PH_FORWARD = 1, PH_STEP = 2, PH_DONE = 3 };
-enum Flags { F_INSOC = 1, F_SOCDONE = 2, F_LS = 4, F_LSKEEP = 8, F_TINYLAST = 16, F_TINYFLAG = 32, F_TINYNOW = 64 };
+// PH_RESTO: the line search failed; the problem waits for Solver::do_resto (run by the finisher kernels, never by the
+// per-pass sweeps, which skip any phase that is not theirs)
+enum Phase { PH_FACTOR = 0, PH_FORWARD = 1, PH_STEP = 2, PH_DONE = 3, PH_RESTO = 4 };
+enum Flags { F_INSOC = 1, F_SOCDONE = 2, F_LS = 4, F_LSKEEP = 8, F_TINYLAST = 16, F_TINYFLAG = 32, F_TINYNOW = 64, F_RESTO = 128 };
 
 // ---- batch compaction ----------------------------------------------------------------------------------------
 // Moves one unfinished problem from workspace slot `s` to slot `d` (another workspace region) between two passes.
@@ -1291,8 +1298,8 @@ struct Solver {
           } else {   // give up: restore the Newton direction, continue backtracking
             setfl(F_INSOC, false); setfl(F_SOCDONE, true);
             alpha = 0.5 * alpha_max; n_steps = 1;
-            phase = alpha > alpha_min ? PH_FACTOR : PH_DONE;
-            if (phase == PH_DONE) status = kRestorationFailed;
+            if (alpha > alpha_min) phase = PH_FACTOR;
+            else line_search_failed();
           }
         } else if (!fl(F_SOCDONE) && alpha == alpha_max && ref_theta <= tr_theta) {   // start SOC (IpFilterLSAcceptor.cpp:473-587)
           setfl(F_INSOC, true); soc_count = 0;
@@ -1303,7 +1310,7 @@ struct Solver {
           phase = PH_FACTOR;
         } else {
           alpha *= 0.5; ++n_steps;
-          if (!(alpha > alpha_min)) { status = kRestorationFailed; phase = PH_DONE; }
+          if (!(alpha > alpha_min)) line_search_failed();
         }
         return;
       }
@@ -1312,8 +1319,8 @@ struct Solver {
       // ---- accept: the trial copy becomes the current iterate
       cur ^= 1;
       f_cur = tr_f; theta_cur = tr_theta; priminf = tr_priminf; sumlog = tr_sumlog;
-      setfl(F_TINYLAST, tiny_now ? dlam_max < 1e-2 : false);
-      setfl(F_INSOC, false); setfl(F_SOCDONE, false);
+      setfl(F_TINYLAST, tiny_now && !fl(F_RESTO) ? dlam_max < 1e-2 : false);
+      setfl(F_INSOC, false); setfl(F_SOCDONE, false); setfl(F_RESTO, false);
       ++iter;
     }
     phase = top_of_loop() ? PH_FACTOR : PH_DONE;
@@ -1321,6 +1328,95 @@ struct Solver {
       if (dw_curr > 0.0) dw_last = dw_curr;
       dw_curr = 0.0;
     }
+  }
+  // ------------------------------------------------------------------------------------------
+  // Failed line search (alpha <= alpha_min).  Ipopt switches to its restoration phase here
+  // (IpBacktrackingLineSearch.cpp:531-585); at an almost feasible point it gives up instead (:548-563).
+  MPC_HD void line_search_failed() {
+    if (P.resto && ref_theta > 1e-2 * P.tol) phase = PH_RESTO;
+    else { status = kRestorationFailed; phase = PH_DONE; }
+  }
+  // Restoration step.  Ipopt's restoration phase (IpRestoMinC_1Nrm.cpp:150-330) runs a nested interior-point solve of
+  // min rho ||c(x)||_1 + eta/2 ||D_R (x - x_R)||^2 until a point is acceptable to the filter with theta <= 0.9 theta_R.
+  // This solver is NOT a restatement of that nested solve: the constraints here are a discrete-time recursion
+  // s_{t+1} = F(s_t, u_t), so a point with ANY prescribed fraction of the current defects is available in closed form by
+  // one forward sweep -- keep the controls (and with them the slacks and the barrier term), and set
+  //     s_{t+1} := F(s_t, u_t) + (1 - beta) c_{t+1}(x_R),          theta(x) = (1 - beta) theta(x_R) exactly,
+  // which for beta = 1 is the roll-out of the model with the current controls (theta = 0: acceptable to every filter
+  // entry).  What follows mirrors what Ipopt does when its restoration phase returns (IpRestoMinC_1Nrm.cpp:262-330,
+  // IpBacktrackingLineSearch.cpp:537): the point x_R enters the filter before it is left, lambda is reset to zero
+  // (constr_mult_reset_threshold = 0), z takes the step towards mu / slack limited by the fraction-to-the-boundary rule
+  // and is reset to 1 if it exceeds bound_mult_reset_threshold = 1000, mu and the filter are kept, and the restoration
+  // counts as one iteration.  The new point is evaluated by a zero-length STEP pass (as in init_warm), which provides
+  // every norm top_of_loop() needs.  Iteration counts therefore differ from Ipopt's on the problems that get here
+  // (none at N = 25); the solutions agree whenever both end in the same local minimum (tests/test_restoration.py).
+  MPC_HD void do_resto() {
+    filter_add(ref_barr - 1e-8 * ref_theta, (1.0 - 1e-5) * ref_theta);   // FilterLSAcceptor::PrepareRestoPhaseStart
+    const int b = kX * cur;
+    const double keep = 1.0 - kRestoBeta;
+    // dual step length of z := z + a (mu / slack - z), fraction-to-the-boundary (IpRestoMinC_1Nrm.cpp:283-301)
+    double a_du = 1.0;
+    for (int t = 0; t < M; ++t) {
+      const int r = rec(t) + b;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const double u = w(r + xU + j), zl = w(r + xZL + j), zu = w(r + xZU + j);
+        const double dl = mu / safe_slack(u - P.xl[j], mu, zl, P.xl[j]) - zl, du = mu / safe_slack(P.xu[j] - u, mu, zu, P.xu[j]) - zu;
+        if (dl < 0.0) a_du = dmin(a_du, -tau / dl * zl);
+        if (du < 0.0) a_du = dmin(a_du, -tau / du * zu);
+      }
+    }
+    double so[6], sn[6], zmax = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { so[k] = sn[k] = w(rec(0) + b + xS + k); }
+    for (int t = 0; t < M; ++t) {
+      const int r = rec(t) + b, rn = r + kRec;
+      double u[2], son[6], co[6], cn[6], sp, cp, se, ce, p0, p1, p2, p3;
+      u[0] = w(r + xU); u[1] = w(r + xU + 1);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) son[k] = w(rn + xS + k);
+      // defect of the rows of time t+1 at x_R
+      trig_of(r, so, sp, cp, se, ce);
+      poly_eval(cf, so[0], p0, p1, p2, p3);
+      residual(so, u, son, sp, cp, se, p0, atan(p1), co);
+      // model step from the new s_t
+      const double zero[6] = {0, 0, 0, 0, 0, 0};
+      sincos(sn[2], &sp, &cp);
+      sincos(sn[5], &se, &ce);
+      poly_eval(cf, sn[0], p0, p1, p2, p3);
+      residual(sn, u, zero, sp, cp, se, p0, atan(p1), cn);
+#if MPC_STORE_TRIG
+      w(r + xTR) = sp; w(r + xTR + 1) = cp; w(r + xTR + 2) = se; w(r + xTR + 3) = ce;
+#endif
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        so[k] = son[k];
+        sn[k] = keep * co[k] - cn[k];
+        w(rn + xS + k) = sn[k];
+        w(r + xLAM + k) = 0.0;
+        w(rec(t) + oDS + k) = 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double zl = w(r + xZL + j), zu = w(r + xZU + j);
+        zl += a_du * (mu / safe_slack(u[j] - P.xl[j], mu, zl, P.xl[j]) - zl);
+        zu += a_du * (mu / safe_slack(P.xu[j] - u[j], mu, zu, P.xu[j]) - zu);
+        w(r + xZL + j) = zl; w(r + xZU + j) = zu;
+        zmax = dmax(zmax, dmax(zl, zu));
+        w(rec(t) + oDU + j) = 0.0;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { w(rec(M) + b + xLAM + k) = 0.0; w(rec(M) + oDS + k) = 0.0; }
+    if (zmax > 1000.0)
+      for (int t = 0; t < M; ++t) {
+        const int r = rec(t) + b;
+        w(r + xZL) = 1.0; w(r + xZL + 1) = 1.0; w(r + xZU) = 1.0; w(r + xZU + 1) = 1.0;
+      }
+    setfl(F_INSOC, false); setfl(F_SOCDONE, false);
+    setfl(F_TINYNOW, true); setfl(F_RESTO, true);   // zero-length step, accepted without a filter test
+    alpha = 0.0; alpha_du = 0.0;
+    phase = PH_STEP;
   }
   MPC_HD void init_csoc() {
     for (int t = 0; t < M; ++t) {
@@ -1388,6 +1484,7 @@ struct Solver {
 #undef STI
 
   MPC_HD void trip() {
+    if (phase == PH_RESTO) do_resto();
     if (phase == PH_FACTOR) do_factor();
     if (phase == PH_FORWARD) do_forward();
     if (phase == PH_STEP) do_step();
