@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """bench_sweep.py -- BASELINE.json configs[4]: horizon / batch sweep (N in 10..100, batch 1K..1M), degree-3 reference
 from roadmap windows, one B200.  Device-resident inputs, CUDA events.  For every point: solves/s, mean / max
-interior-point iterations and the status histogram (status -2 = the line search failed and Ipopt would have entered
-its restoration phase, which is not implemented; such problems are reported, never hidden).
+interior-point iterations and the status histogram (a failed line search, where Ipopt enters its restoration phase, is
+followed by the library's restoration step -- b200mpc_set_restoration, on by default; status -2 only with it off).
 `python bench_sweep.py > profiles/r1_sweep.json`"""
 import argparse
 import json

@@ -19,7 +19,9 @@
  *   MUMPS's sparse LDL^T (generic; not restated) -> dense Bunch-Kaufman LDL^T with inertia below.
  *   polyfit / polyeval              mpc_to_line/src/helpers.h:13-19, 24-44 (+ Eigen 3.3.3 HouseholderQR)
  *   globalKinematic                 global_kinematic_model/solution/main.cpp:36-62
- * Not restated (documented gaps): restoration phase (IpRestoMinC_1Nrm.cpp), watchdog, constraint-row
+ * Not restated (documented gaps): restoration phase (IpRestoMinC_1Nrm.cpp; the port returns -2 where Ipopt enters it --
+ * the product's own restoration step is checked against the reference binaries' answers instead,
+ * tests/golden/resto_N*.npz), watchdog, constraint-row
  * scaling (never triggered for |Jacobian entries| <= 100).  A solve that would need them returns -2.
  */
 #include "mpc_oracle.h"

@@ -114,7 +114,7 @@ def main():
     print("golden fixtures written to", HERE)
 
 
-if __name__ == "__main__" and "--config3" not in sys.argv and "--n100" not in sys.argv:
+if __name__ == "__main__" and not {"--config3", "--n100", "--resto"} & set(sys.argv):
     main()
 
 
@@ -152,3 +152,34 @@ def n100():
 
 if __name__ == "__main__" and "--n100" in sys.argv:
     n100()
+
+
+def _solve_resto(a):
+    r = ob.ref_solve(a[0], a[1], N=a[2], trace=True)
+    return r["out8"], r["obj"], r["status"], r["iters"], int((r["trace"][:, 9] >= 100).any()), r["x"]
+
+
+def resto():
+    """Problems on which the reference's Ipopt entered its restoration phase: the first 48 such problems among 8192
+    random roadmap problems at N=100 and all 14 among 65 536 at N=50 (inputs: synth.roadmap_windows / roadmap_problems
+    with the seeds below; the fit is numpy's least-squares fit of the window).  Takes ~4 min on 8 cores."""
+    import multiprocessing as mp
+    from udacitympc_b200 import synth
+    for N, n, keep in ((100, 8192, 48), (50, 65536, 14)):
+        xs, ys = synth.roadmap_windows(n, synth.MT19937_64(878))
+        V = np.stack([xs ** i for i in range(4)], axis=2)
+        fit = np.stack([np.linalg.lstsq(V[b], ys[b], rcond=None)[0] for b in range(n)])
+        st = synth.roadmap_problems(n, fit, synth.MT19937_64(879))
+        with mp.get_context("fork").Pool(os.cpu_count()) as pool:
+            res = pool.map(_solve_resto, [(st[b], fit[b], N) for b in range(n)], chunksize=8)
+        sel = [b for b in range(n) if res[b][4] and res[b][2] == 0][:keep]
+        np.savez_compressed(os.path.join(HERE, f"resto_N{N}_{len(sel)}.npz"), index=np.array(sel, dtype=np.int32),
+                            states=st[sel], coeffs=fit[sel], out8=np.array([res[b][0] for b in sel]),
+                            obj=np.array([res[b][1] for b in sel]), iters=np.array([res[b][3] for b in sel], dtype=np.int32),
+                            x=np.array([res[b][5] for b in sel]).astype(np.float64), n_problems=n,
+                            n_used_restoration=int(sum(r[4] for r in res)))
+        print(f"N={N}: {int(sum(r[4] for r in res))} of {n} problems used the restoration phase; kept {len(sel)}")
+
+
+if __name__ == "__main__" and "--resto" in sys.argv:
+    resto()
