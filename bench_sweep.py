@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--horizons", default="10,25,50,100")
     ap.add_argument("--batches", default="1024,16384,65536,262144,1048576")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--streams", type=int, default=1, help="solver handles / streams whose batches overlap (as bench.py does); "
+                    "1 = one batch at a time, where the slowest problem of a batch sets its time")
     ap.add_argument("--rounds", type=int, default=0, help="per-pass rounds before the cooperative finisher (0 = library default)")
     args = ap.parse_args()
     import torch
@@ -41,28 +43,46 @@ def main():
             t = (B + nb - 1) // nb
             st_d = torch.from_numpy(np.ascontiguousarray(np.tile(st, (t, 1))[:B].T)).to(dev)
             cf_d = torch.from_numpy(np.ascontiguousarray(np.tile(fit, (t, 1))[:B].T)).to(dev)
-            out8 = torch.empty((8, B), dtype=torch.float64, device=dev)
-            status = torch.empty(B, dtype=torch.int32, device=dev)
-            iters = torch.empty(B, dtype=torch.int32, device=dev)
-            with mp.MPC(device=0, N=N) as m:
-                m.set_solver_mode(0, args.rounds, -1)
+            S = max(1, min(args.streams, int(150e9 // (2 * B * 83 * (N + 1) * 8))))
+            streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(S - 1)]
+            out8 = [torch.empty((8, B), dtype=torch.float64, device=dev) for _ in range(S)]
+            status = torch.empty((S, B), dtype=torch.int32, device=dev)
+            iters = torch.empty((S, B), dtype=torch.int32, device=dev)
+            handles = [mp.MPC(device=0, N=N) for _ in range(S)]
+            try:
+                for m in handles:
+                    m.set_solver_mode(0, args.rounds, -1)
+                    if S > 1:
+                        m.set_batch_split(1)   # the caller overlaps the batches itself
 
-                def step():
-                    m.solve_batch_device(B, st_d.data_ptr(), cf_d.data_ptr(), 4, out8.data_ptr(), 0, 0, status.data_ptr(),
-                                         iters.data_ptr(), stream.cuda_stream)
-                step()
+                def step(k):
+                    handles[k].solve_batch_device(B, st_d.data_ptr(), cf_d.data_ptr(), 4, out8[k].data_ptr(), 0, 0,
+                                                  status[k].data_ptr(), iters[k].data_ptr(), streams[k].cuda_stream)
+                for k in range(S):
+                    step(k)
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
+                for s_ in streams[1:]:
+                    s_.wait_event(e0)
                 for _ in range(args.reps):
-                    step()
+                    for k in range(S):
+                        step(k)
+                for s_ in streams[1:]:
+                    ev = torch.cuda.Event()
+                    ev.record(s_)
+                    stream.wait_event(ev)
                 e1.record(stream)
                 torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1) / args.reps
+                ms = e0.elapsed_time(e1) / (args.reps * S)
+            finally:
+                for m in handles:
+                    m.close()
+            status, iters = status[0], iters[0]
             sc = status.cpu().numpy()
             it = iters.cpu().numpy()
             hist = {int(k): int(v) for k, v in zip(*np.unique(sc, return_counts=True))}
-            rows.append(dict(N=N, batch=B, rounds=args.rounds, ms_per_batch=ms, solves_per_s=B / (ms * 1e-3), mean_iters=float(it.mean()),
+            rows.append(dict(N=N, batch=B, rounds=args.rounds, streams=S, ms_per_batch=ms, solves_per_s=B / (ms * 1e-3), mean_iters=float(it.mean()),
                              max_iters=int(it.max()), status_hist=hist, solved_fraction=float((sc == 0).mean())))
             print(json.dumps(rows[-1]), file=sys.stderr)
             del st_d, cf_d, out8

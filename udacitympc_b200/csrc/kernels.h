@@ -32,7 +32,7 @@ struct SolveConfig {
   // adaptive hand-over (automatic rounds only): occupied slots (whole call) at which the cooperative kernel takes over
   int handover_below = 1184;      // one wave of 8 warps on 148 SMs
   int handover_from = 14;         // first round after which it may happen
-  int handover_max_rounds = 20;
+  int handover_max_rounds = 0;    // 0 = by horizon: 20 up to N = 50, 2 N - 80 above (120 at N = 100); see launch_solve
   double compact_max_live = 0.7;
   int compact_from = 4;
   bool coop = true;       // latency path = cooperative warp-per-problem kernel (false: thread-per-problem fused kernel)

@@ -368,7 +368,12 @@ cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6
   // rest over as soon as the compacted batch fits its two waves (the launches after that find nothing to do); a fixed
   // number of rounds (b200mpc_set_solver_mode) hands over exactly there
   const bool adaptive = cfg.rounds <= 0 && desc != nullptr && cfg.coop && cfg.handover_below > 0;
-  const int rounds = cfg.rounds > 0 ? cfg.rounds : (adaptive ? cfg.handover_max_rounds : (parts > 1 ? 16 : 18));
+  // Longer horizons have a longer tail of iteration counts (N = 100: 3.6 % of the problems need more than 20, 1.8 % more
+  // than 100) and a slower cooperative kernel (0.34 ms per problem and iteration at N = 100, 2 warps per SM), so the sweeps
+  // keep the tail longer there: measured with 4 overlapped batches of 65 536 problems at N = 100, 20 rounds 267 ms per
+  // batch, 120 rounds 225 ms; N <= 50 does not gain (profiles/r1_handover_sweep_long_horizons.log).
+  const int max_rounds = cfg.handover_max_rounds > 0 ? cfg.handover_max_rounds : (P.N <= 50 ? 20 : 2 * P.N - 80);
+  const int rounds = cfg.rounds > 0 ? cfg.rounds : (adaptive ? max_rounds : (parts > 1 ? 16 : 18));
   const int take_below = adaptive ? (cfg.handover_below / parts > 64 ? cfg.handover_below / parts : 64) : 0;
   cudaError_t e = cudaSuccess;
   if (parts == 1) {
