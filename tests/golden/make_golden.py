@@ -161,24 +161,33 @@ def _solve_resto(a):
 
 def resto():
     """Problems on which the reference's Ipopt entered its restoration phase: the first 48 such problems among 8192
-    random roadmap problems at N=100 and all 14 among 65 536 at N=50 (inputs: synth.roadmap_windows / roadmap_problems
-    with the seeds below; the fit is numpy's least-squares fit of the window).  Takes ~4 min on 8 cores."""
+    random roadmap problems at N=100, all 14 among 65 536 at N=50, and the first 32 among 32 768 at the reference's own
+    N=25 with initial states far outside the benchmark distribution (lateral offset +-20 m, heading error +-1.5 rad,
+    speed 1..60 m/s; 346 of them use it).  Inputs: synth.roadmap_windows / roadmap_problems with the seeds below; the
+    fit is numpy's least-squares fit of the window.  Takes ~5 min on 8 cores."""
     import multiprocessing as mp
     from udacitympc_b200 import synth
-    for N, n, keep in ((100, 8192, 48), (50, 65536, 14)):
+    for N, n, keep, wild in ((100, 8192, 48, False), (50, 65536, 14, False), (25, 32768, 32, True)):
         xs, ys = synth.roadmap_windows(n, synth.MT19937_64(878))
         V = np.stack([xs ** i for i in range(4)], axis=2)
         fit = np.stack([np.linalg.lstsq(V[b], ys[b], rcond=None)[0] for b in range(n)])
         st = synth.roadmap_problems(n, fit, synth.MT19937_64(879))
+        if wild:
+            u = synth.MT19937_64(880).uniform(3 * n).reshape(n, 3)
+            y = -20.0 + 40.0 * u[:, 0]
+            psi = np.arctan(fit[:, 1]) - 1.5 + 3.0 * u[:, 1]
+            v = 1.0 + 59.0 * u[:, 2]
+            st = np.ascontiguousarray(np.stack([np.zeros(n), y, psi, v, fit[:, 0] - y, psi - np.arctan(fit[:, 1])], axis=1))
         with mp.get_context("fork").Pool(os.cpu_count()) as pool:
             res = pool.map(_solve_resto, [(st[b], fit[b], N) for b in range(n)], chunksize=8)
         sel = [b for b in range(n) if res[b][4] and res[b][2] == 0][:keep]
-        np.savez_compressed(os.path.join(HERE, f"resto_N{N}_{len(sel)}.npz"), index=np.array(sel, dtype=np.int32),
+        name = f"resto_N{N}_{'wild_' if wild else ''}{len(sel)}.npz"
+        np.savez_compressed(os.path.join(HERE, name), index=np.array(sel, dtype=np.int32),
                             states=st[sel], coeffs=fit[sel], out8=np.array([res[b][0] for b in sel]),
                             obj=np.array([res[b][1] for b in sel]), iters=np.array([res[b][3] for b in sel], dtype=np.int32),
                             x=np.array([res[b][5] for b in sel]).astype(np.float64), n_problems=n,
                             n_used_restoration=int(sum(r[4] for r in res)))
-        print(f"N={N}: {int(sum(r[4] for r in res))} of {n} problems used the restoration phase; kept {len(sel)}")
+        print(f"N={N}{' wild' if wild else ''}: {int(sum(r[4] for r in res))} of {n} problems used the restoration phase; kept {len(sel)}")
 
 
 if __name__ == "__main__" and "--resto" in sys.argv:

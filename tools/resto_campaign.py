@@ -2,7 +2,8 @@
 Ipopt reaches through its own restoration phase?  Solver core compiled for the host (tests/hostsim) against THE
 REFERENCE ITSELF (oracle/_ref binaries) on n random roadmap problems at horizon N.
 
-    python tools/resto_campaign.py N n [mode]      (reference answers are cached in /tmp)
+    python tools/resto_campaign.py N n [mode] [--wild]      (reference answers are cached in /tmp; --wild: initial
+                                                             states far outside the benchmark distribution)
 """
 import multiprocessing as mp
 import os
@@ -36,17 +37,26 @@ def host_work(a):
     return np.concatenate([[h["status"], h["iters"], h["obj"]], h["out8"]])
 
 
-def problems(n, seed=0):
+def problems(n, seed=0, wild=False):
     xs, ys = synth.roadmap_windows(n, synth.MT19937_64(878 + seed))
     V = np.stack([xs ** i for i in range(4)], axis=2)
     fit = np.stack([np.linalg.lstsq(V[b], ys[b], rcond=None)[0] for b in range(n)])
-    return synth.roadmap_problems(n, fit, synth.MT19937_64(879 + seed)), fit
+    st = synth.roadmap_problems(n, fit, synth.MT19937_64(879 + seed))
+    if wild:   # far outside SURVEY 8d config 4: lateral offset +-20 m, heading error +-1.5 rad, speed 1..60 m/s
+        u = synth.MT19937_64(880 + seed).uniform(3 * n).reshape(n, 3)
+        c0, c1 = fit[:, 0], fit[:, 1]
+        y = -20.0 + 40.0 * u[:, 0]
+        psi = np.arctan(c1) - 1.5 + 3.0 * u[:, 1]
+        v = 1.0 + 59.0 * u[:, 2]
+        st = np.ascontiguousarray(np.stack([np.zeros(n), y, psi, v, c0 - y, psi - np.arctan(c1)], axis=1))
+    return st, fit
 
 
 if __name__ == "__main__":
     N = int(sys.argv[1]); n = int(sys.argv[2]); mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-    S, C = problems(n)
-    cache = f"/tmp/resto_ref_N{N}_{n}.npy"
+    wild = "--wild" in sys.argv
+    S, C = problems(n, wild=wild)
+    cache = f"/tmp/resto_ref_N{N}_{n}{'_wild' if wild else ''}.npy"
     ctx = mp.get_context("fork")
     if os.path.exists(cache):
         ref = np.load(cache)
