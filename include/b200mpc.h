@@ -126,14 +126,19 @@ int b200mpc_set_batch_split(b200mpc_handle* h, int parts);
  * depend on it.  Default 0.7 from round 4; 0 switches it off. */
 int b200mpc_set_compaction(b200mpc_handle* h, double max_live_fraction, int from_round);
 
-/* Restoration after a failed line search (Ipopt: IpBacktrackingLineSearch.cpp:531-585 -> IpRestoMinC_1Nrm.cpp).  Never
- * needed at the reference's N = 25; a few per cent of the problems at N = 100 get there.  Enabled (default): the
- * problem continues from the model roll-out of its current controls (a feasible point) with
- * lambda = 0, as Ipopt continues from the point its restoration phase returns.  This is NOT a restatement of Ipopt's
- * nested restoration solve: on these problems the iteration count differs from Ipopt's, the solution is the same
- * whenever both end in the same local minimum.  Disabled: such a problem returns status -2 (Restoration_Failed) at the
- * iteration where Ipopt would switch to its restoration phase. */
-int b200mpc_set_restoration(b200mpc_handle* h, int enable);
+/* What follows a failed line search (Ipopt: IpBacktrackingLineSearch.cpp:498-585 -> soft restoration phase, then
+ * IpRestoMinC_1Nrm.cpp).  Never reached on the benchmark workloads at the reference's N = 25; 1 % of problems with
+ * initial states far off the road and 2 % of the problems at N = 100 get there.
+ *   mode 0: such a problem returns status -2 (Restoration_Failed) at the iteration where Ipopt would switch.
+ *   mode 1 (default): the restoration step -- a forward sweep removes 5 % of every constraint defect with the controls
+ *           kept, the point left enters the filter, lambda is reset to 0, z moves towards mu / slack -- i.e. what Ipopt
+ *           does around its restoration phase, with a closed-form point instead of Ipopt's nested restoration solve.
+ *           NOT a restatement of that solve: the iteration count of such a problem differs from Ipopt's; the solution
+ *           is the reference's on 346 / 346 (N = 25), 14 / 14 (N = 50), 170 / 179 (N = 100) such problems.
+ *   mode 2: as 1, preceded by Ipopt's soft restoration phase (damped full primal-dual steps accepted on the primal-dual
+ *           system error, IpBacktrackingLineSearch.cpp:1043-1140), restated exactly: the few problems on which Ipopt
+ *           takes such steps then keep its iterates and iteration count. */
+int b200mpc_set_restoration(b200mpc_handle* h, int mode);
 
 /* B least-squares polynomial fits (unpivoted Householder QR of the Vandermonde matrix, as Eigen 3.3.3 does for
  * helpers.h:24-44).  xs, ys: B x m;  coeffs_out: B x (order+1).  Requires 1 <= order <= m-1 (helpers.h:26 assert). */

@@ -114,7 +114,7 @@ def main():
     print("golden fixtures written to", HERE)
 
 
-if __name__ == "__main__" and not {"--config3", "--n100", "--resto"} & set(sys.argv):
+if __name__ == "__main__" and not {"--config3", "--n100", "--resto", "--soft"} & set(sys.argv):
     main()
 
 
@@ -192,3 +192,29 @@ def resto():
 
 if __name__ == "__main__" and "--resto" in sys.argv:
     resto()
+
+
+def soft():
+    """Problems on which the reference's Ipopt takes soft-restoration steps ('s' / 'S' in its iteration log) and never
+    enters the restoration phase proper: #1606, #7262, #14731 of the 16 384 wild N=50 problems (same generator and seeds
+    as resto(); found with tools/resto_campaign.py 50 16384 --wild as the iteration-count mismatches of mode 1 that
+    vanish in mode 2)."""
+    from udacitympc_b200 import synth
+    n, N, sel = 16384, 50, [1606, 7262, 14731]
+    xs, ys = synth.roadmap_windows(n, synth.MT19937_64(878))
+    V = np.stack([xs ** i for i in range(4)], axis=2)
+    fit = np.stack([np.linalg.lstsq(V[b], ys[b], rcond=None)[0] for b in range(n)])
+    u = synth.MT19937_64(880).uniform(3 * n).reshape(n, 3)
+    y = -20.0 + 40.0 * u[:, 0]
+    psi = np.arctan(fit[:, 1]) - 1.5 + 3.0 * u[:, 1]
+    v = 1.0 + 59.0 * u[:, 2]
+    st = np.ascontiguousarray(np.stack([np.zeros(n), y, psi, v, fit[:, 0] - y, psi - np.arctan(fit[:, 1])], axis=1))
+    res = [_solve_resto((st[b], fit[b], N)) for b in sel]
+    assert all(r[2] == 0 and r[4] == 0 for r in res)
+    np.savez_compressed(os.path.join(HERE, "soft_N50_3.npz"), index=np.array(sel, dtype=np.int32), states=st[sel], coeffs=fit[sel],
+                        out8=np.array([r[0] for r in res]), obj=np.array([r[1] for r in res]),
+                        iters=np.array([r[3] for r in res], dtype=np.int32), x=np.array([r[5] for r in res]))
+
+
+if __name__ == "__main__" and "--soft" in sys.argv:
+    soft()

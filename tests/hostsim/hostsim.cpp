@@ -39,8 +39,8 @@ struct hostsim_params {
   double dt, Lf, ref_v, w_cte, w_epsi, w_v, w_delta, w_a, w_ddelta, w_da, delta_max, a_max, tol;
   int max_iter;
 };
-static int g_resto = 1;   // Params::resto of the following solves
-void hostsim_set_restoration(int enable) { g_resto = enable != 0; }
+static int g_resto = 2;   // Params::resto of the following solves (0 off, 1 restoration step, 2 soft restoration phase first)
+void hostsim_set_restoration(int mode) { g_resto = mode; }
 
 // trace rows of 8: iter, mu, alpha_pr, alpha_du, dw, f, theta, phase-trips
 // mode 0: one Solver object loops trip() (what the single fused kernel does)
@@ -128,11 +128,13 @@ int hostsim_solve_mode(const hostsim_params* hp, const double* state6, const dou
         if (k == PH_STEP) { S.load_state(); log_row(S); }
         if (mode == -2 && phase != PH_DONE) repack();
       }
-      if (phase == PH_RESTO) {   // the per-pass kernels leave it to the finisher: a fresh Solver does the restoration step
+      if (phase == PH_RESTO) {   // the per-pass kernels leave it to the finisher, which runs the problem to completion
         Solver<1> S(P, ws.data());
+        double carry[kCarry];
+        S.cr = carry; S.cs = 1;
         S.set_coeffs(coeffs, ncoef);
         S.load_state();
-        S.do_resto();
+        while (S.phase != PH_DONE && trips < 400000) { S.trip(); ++trips; log_row(S); }
         S.store_state();
         phase = S.load_phase();
       }

@@ -47,7 +47,7 @@ def test_hostsim_restoration_off_reports_minus_2(hostsim):
     try:
         st = [hostsim.solve(g["states"][b], g["coeffs"][b], N=50)["status"] for b in range(len(g["obj"]))]
     finally:
-        hostsim.lib.hostsim_set_restoration(1)
+        hostsim.lib.hostsim_set_restoration(2)
     assert st.count(-2) >= 12 and set(st) <= {0, -2}
 
 
@@ -79,12 +79,50 @@ def test_hostsim_restoration_never_runs_at_the_reference_horizon(hostsim):
         try:
             o = hostsim.solve(g["states"][b], g["fit"][b])
         finally:
-            hostsim.lib.hostsim_set_restoration(1)
+            hostsim.lib.hostsim_set_restoration(2)
         assert a["status"] == o["status"] == 0 and a["iters"] == o["iters"]
         np.testing.assert_array_equal(a["x"], o["x"])
 
 
+def test_hostsim_soft_restoration_phase_tracks_ipopt(hostsim):
+    """Problems on which the reference's Ipopt takes soft-restoration steps (IpBacktrackingLineSearch.cpp:426-530,
+    1043-1140) and never enters the restoration phase proper: with the soft phase restated (mode 2, the default) the
+    iterates are Ipopt's again -- same iteration count (one knife-edge termination apart) and the same solution to
+    1e-8; with the restoration step alone (mode 1) the first problem ends in another local minimum."""
+    g = golden("soft_N50_3.npz")
+    for mode in (0, 1, -2, 2):
+        for b in range(3):
+            r = hostsim.solve(g["states"][b], g["coeffs"][b], mode=mode, N=50)
+            assert r["status"] == 0 and abs(r["iters"] - g["iters"][b]) <= 1
+            np.testing.assert_allclose(r["x"], g["x"][b], rtol=0, atol=1e-8)
+            assert abs(r["obj"] - g["obj"][b]) <= 1e-9 * abs(g["obj"][b])
+    hostsim.lib.hostsim_set_restoration(1)
+    try:
+        r = hostsim.solve(g["states"][0], g["coeffs"][0], N=50)
+    finally:
+        hostsim.lib.hostsim_set_restoration(2)
+    assert r["status"] == 0 and abs(r["obj"] - g["obj"][0]) > 1e-3 * abs(g["obj"][0])
+
+
 # ---------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_gpu_soft_restoration_phase_tracks_ipopt():
+    import udacitympc_b200 as mp
+    g = golden("soft_N50_3.npz")
+    for reps in (1, 100):   # cooperative kernel alone / per-pass kernels, then the finisher
+        st, cf = np.tile(g["states"], (reps, 1)), np.tile(g["coeffs"], (reps, 1))
+        with mp.MPC(N=50) as m:
+            if reps > 1:
+                m.set_solver_mode(0, 14, 0)
+            r = m.solve_batch(st, cf, want_traj=True)
+        assert (r["status"] == 0).all()
+        for k in range(reps):
+            assert (np.abs(r["iters"][3 * k:3 * k + 3] - g["iters"]) <= 1).all()
+            np.testing.assert_allclose(r["traj"][3 * k:3 * k + 3], g["x"], rtol=0, atol=1e-6)
+            assert (np.abs(r["cost"][3 * k:3 * k + 3] - g["obj"]) <= 1e-8 * np.abs(g["obj"])).all()
+
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", ["default", "perpass"])
 @pytest.mark.parametrize("name,N,min_same", [("resto_N100_48.npz", 100, 43), ("resto_N50_14.npz", 50, 14),

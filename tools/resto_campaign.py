@@ -2,8 +2,9 @@
 Ipopt reaches through its own restoration phase?  Solver core compiled for the host (tests/hostsim) against THE
 REFERENCE ITSELF (oracle/_ref binaries) on n random roadmap problems at horizon N.
 
-    python tools/resto_campaign.py N n [mode] [--wild]      (reference answers are cached in /tmp; --wild: initial
-                                                             states far outside the benchmark distribution)
+    python tools/resto_campaign.py N n [mode] [--wild] [--soft]   (reference answers are cached in /tmp; --wild: initial
+                                        states far outside the benchmark distribution; --soft: with Ipopt's soft
+                                        restoration phase restated before the restoration step, Params::resto = 2)
 """
 import multiprocessing as mp
 import os
@@ -32,6 +33,7 @@ def host_work(a):
     global hs
     if hs is None:
         hs = _HostSim()
+        hs.lib.hostsim_set_restoration(2 if "--soft" in sys.argv else 1)
     st, cf, N, mode = a
     h = hs.solve(st, cf, mode=mode, N=N)
     return np.concatenate([[h["status"], h["iters"], h["obj"]], h["out8"]])

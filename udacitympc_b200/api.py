@@ -227,10 +227,11 @@ class MPC:
         when the caller overlaps several calls itself)."""
         _check(self._lib.b200mpc_set_batch_split(self._h, int(parts)))
 
-    def set_restoration(self, enable=True):
-        """Restoration step after a failed line search (on by default; off: such a problem returns status -2 at the
-        iteration where the reference's Ipopt enters its restoration phase).  See b200mpc_set_restoration."""
-        _check(self._lib.b200mpc_set_restoration(self._h, 1 if enable else 0))
+    def set_restoration(self, mode=True):
+        """What follows a failed line search: 0 / False = status -2 at the iteration where the reference's Ipopt enters
+        its restoration phase, 1 / True = the restoration step, 2 = Ipopt's soft restoration phase first, then the
+        restoration step.  See b200mpc_set_restoration."""
+        _check(self._lib.b200mpc_set_restoration(self._h, int(mode)))
 
     def set_compaction(self, max_live_fraction=0.7, from_round=4):
         """Throughput path: after every round from `from_round` on, move the unfinished problems to consecutive

@@ -71,7 +71,7 @@ Params to_core(const b200mpc_params& p) {
   P.w_cte = p.w_cte; P.w_epsi = p.w_epsi; P.w_v = p.w_v; P.w_delta = p.w_delta; P.w_a = p.w_a;
   P.w_ddelta = p.w_ddelta; P.w_da = p.w_da; P.delta_max = p.delta_max; P.a_max = p.a_max;
   P.tol = p.tol; P.max_iter = p.max_iter;
-  P.resto = 1;
+  P.resto = 2;
   P.finalize();
   return P;
 }
@@ -171,7 +171,7 @@ int b200mpc_create(const b200mpc_params* p, int device, b200mpc_handle** out) {
   h->device = device;
   if (const char* e = getenv("B200MPC_NO_GRAPHS")) h->use_graphs = !(e[0] == '1');
   if (const char* e = getenv("B200MPC_NO_COOP")) h->cfg.coop = !(e[0] == '1');
-  if (const char* e = getenv("B200MPC_NO_RESTORATION")) h->P.resto = e[0] == '1' ? 0 : 1;
+  if (const char* e = getenv("B200MPC_RESTORATION")) { int v = atoi(e); if (v >= 0 && v <= 2) h->P.resto = v; }
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
   for (int i = 0; i < 3; ++i) {   // auxiliary streams / events for the internal batch split
@@ -247,9 +247,10 @@ int b200mpc_set_compaction(b200mpc_handle* h, double max_live_fraction, int from
   return 0;
 }
 
-int b200mpc_set_restoration(b200mpc_handle* h, int enable) {
+int b200mpc_set_restoration(b200mpc_handle* h, int mode) {
   if (!h) return fail(B200MPC_ERR_ARG, "null handle");
-  h->P.resto = enable != 0;
+  if (mode < 0 || mode > 2) return fail(B200MPC_ERR_ARG, "restoration: mode must be 0, 1 or 2");
+  h->P.resto = mode;
   ++h->repack_gen;   // the parameters are baked into captured graphs
   return 0;
 }

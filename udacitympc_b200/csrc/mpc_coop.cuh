@@ -37,8 +37,8 @@ struct CoopStage {
 constexpr int kCoopStageDoubles = sizeof(CoopStage) / sizeof(double);
 
 struct CoopPub {   // scalars lane 0 publishes to the other lanes before a parallel phase
-  double mu, tau, df, dw, alpha, alpha_du;
-  int cur, ls, use_csoc, phase, lskeep;
+  double mu, tau, df, dw, alpha, alpha_du, alpha_lam;
+  int cur, ls, use_csoc, phase, lskeep, resto_step;
 };
 
 template <int LANES, class Exec>
@@ -54,8 +54,8 @@ struct CoopSolver {
 
   MPC_HD void publish() {
     if (ex.lane0()) {
-      pub->mu = S.mu; pub->tau = S.tau; pub->df = S.df; pub->dw = S.dw_curr; pub->alpha = S.alpha; pub->alpha_du = S.alpha_du;
-      pub->cur = S.cur; pub->ls = S.fl(F_LS) ? 1 : 0; pub->use_csoc = S.fl(F_INSOC) ? 1 : 0; pub->phase = S.phase; pub->lskeep = S.fl(F_LSKEEP) ? 1 : 0;
+      pub->mu = S.mu; pub->tau = S.tau; pub->df = S.df; pub->dw = S.dw_curr; pub->alpha = S.alpha; pub->alpha_du = S.alpha_du; pub->alpha_lam = S.fl(F_SOFTFIX) ? S.soft_alpha : S.alpha;
+      pub->cur = S.cur; pub->ls = S.fl(F_LS) ? 1 : 0; pub->use_csoc = S.fl(F_INSOC) ? 1 : 0; pub->phase = S.phase; pub->lskeep = S.fl(F_LSKEEP) ? 1 : 0; pub->resto_step = S.fl(F_RESTO) ? 1 : 0;
     }
     ex.sync();
   }
@@ -402,7 +402,7 @@ struct CoopSolver {
   MPC_HD void step2(int t) {   // t < N
     CoopStage& c = st[t];
     const bool ls = pub->ls != 0, keep = pub->lskeep != 0;
-    const double a = pub->alpha;
+    const double a = pub->alpha_lam;
     const int rN = S.rec(t) + kX * (ls ? pub->cur : (pub->cur ^ 1));
     double l1 = 0.0, dlm = 0.0, th = 0.0, cm = 0.0, f = 0.0;
     for (int k = 0; k < 6; ++k) {
@@ -477,18 +477,21 @@ struct CoopSolver {
   MPC_HD void round() {
     publish();
     if (pub->phase == PH_RESTO) {
-      // restoration step (Solver::do_resto, sequential over the horizon): lane 0 rewrites the current iterate in the
-      // workspace, then every lane re-stages its stage with a zero search direction for the zero-length STEP that follows
-      if (ex.lane0()) S.do_resto();
+      // failed line search (Solver::resto_entry).  Restoration step (Solver::do_resto, sequential over the horizon): lane 0
+      // rewrites the current iterate in the workspace, then every lane re-stages its stage with a zero search direction
+      // for the zero-length STEP that follows
+      if (ex.lane0()) S.resto_entry();
       publish();
-      ex.for_stages(N, [&](int t) {
-        load_iterate(t);
-        for (int k = 0; k < 6; ++k) st[t].ds[k] = 0.0;
-        st[t].du[0] = st[t].du[1] = 0.0;
-      });
-      ex.sync();
-      ex.for_stages(M, [&](int t) { prep_factor(t); });
-      ex.sync();
+      if (pub->resto_step) {   // not a soft restoration step, which reuses the staged Newton direction
+        ex.for_stages(N, [&](int t) {
+          load_iterate(t);
+          for (int k = 0; k < 6; ++k) st[t].ds[k] = 0.0;
+          st[t].du[0] = st[t].du[1] = 0.0;
+        });
+        ex.sync();
+        ex.for_stages(M, [&](int t) { prep_factor(t); });
+        ex.sync();
+      }
     }
     if (pub->phase == PH_FACTOR) {
       ex.for_stages(N, [&](int t) { load_iterate(t); });
@@ -554,14 +557,14 @@ struct CoopSolver {
     ex.sync();
     if (ex.lane0()) {
       seq_factor();
-      if (pub->phase == PH_STEP) seq_forward();
+      if (pub->phase == PH_STEP || pub->phase == PH_RESTO) seq_forward();
     }
     ex.sync();
   }
   // runs the problem to completion; lane 0's Solver holds the final state
   MPC_HD void run() {
     publish();
-    if (pub->phase == PH_FORWARD || pub->phase == PH_STEP) rebuild();
+    if (pub->phase == PH_FORWARD || pub->phase == PH_STEP || pub->phase == PH_RESTO) rebuild();
     while (pub->phase != PH_DONE) round();
   }
 };

@@ -57,7 +57,8 @@ struct Params {
   double delta_max, a_max;
   double tol;
   int max_iter;
-  int resto;            // 1: a failed line search hands the problem to the restoration step (Solver::do_resto)
+  int resto;            // after a failed line search: 0 = status -2, 1 = restoration step (Solver::do_resto),
+                        // 2 = Ipopt's soft restoration phase first, then the restoration step (Solver::resto_entry)
   // derived
   double dtLf;          // dt / Lf
   double xl[2], xu[2];  // relaxed bounds of (delta, a): +-(b + 1e-8 max(1,|b|)), IpOrigIpoptNLP.cpp:369-372
@@ -122,9 +123,9 @@ enum StageOff {
 enum ScalarD {
   dDF, dMU, dTAU, dMUMIN, dDWC, dDWL, dTHMAX, dTHMIN, dF, dTH, dPINF, dDINF, dLAM1, dZ1, dSZMAX, dSZMIN, dSLOG, dXMAX,
   dDLMAX, dRTH, dRBARR, dRGBD, dALPHA, dAMAX, dAMIN, dADU, dATEST, dTRF, dTRTH, dTRPINF, dTRSLOG, dTHSOC, dASOC, dCOBJ,
-  dLOBJ, dFILT /* 2*kMaxFilter */, kNumD = dFILT + 2 * kMaxFilter
+  dLOBJ, dSOFTA, dFILT /* 2*kMaxFilter */, kNumD = dFILT + 2 * kMaxFilter
 };
-enum ScalarI { iPHASE = kNumD, iFLAGS, iCUR, iITER, iSTATUS, iNSTEPS, iSOCCNT, iACCCNT, iNF, kNumScal };
+enum ScalarI { iPHASE = kNumD, iFLAGS, iCUR, iITER, iSTATUS, iNSTEPS, iSOCCNT, iACCCNT, iNF, iSOFTCNT, kNumScal };
 static_assert(kNumScal <= kRec, "scalar record must fit one stage record");
 
 MPC_HD int workspace_doubles_per_problem(int N) { return kRec * (N + 1); }
@@ -277,7 +278,9 @@ struct Result {
 // PH_RESTO: the line search failed; the problem waits for Solver::do_resto (run by the finisher kernels, never by the
 // per-pass sweeps, which skip any phase that is not theirs)
 enum Phase { PH_FACTOR = 0, PH_FORWARD = 1, PH_STEP = 2, PH_DONE = 3, PH_RESTO = 4 };
-enum Flags { F_INSOC = 1, F_SOCDONE = 2, F_LS = 4, F_LSKEEP = 8, F_TINYLAST = 16, F_TINYFLAG = 32, F_TINYNOW = 64, F_RESTO = 128 };
+// F_SOFT / F_SOFTTRY / F_HARD: soft restoration phase (Params::resto == 2), see Solver::resto_entry
+enum Flags { F_INSOC = 1, F_SOCDONE = 2, F_LS = 4, F_LSKEEP = 8, F_TINYLAST = 16, F_TINYFLAG = 32, F_TINYNOW = 64, F_RESTO = 128,
+             F_SOFT = 256, F_SOFTTRY = 512, F_HARD = 1024, F_FILTDONE = 2048, F_SOFTFIX = 4096 };
 
 // ---- batch compaction ----------------------------------------------------------------------------------------
 // Moves one unfinished problem from workspace slot `s` to slot `d` (another workspace region) between two passes.
@@ -333,8 +336,8 @@ struct Solver {
   double ref_theta, ref_barr, ref_gbd, alpha, alpha_max, alpha_min, alpha_du, alpha_test;
   double tr_f, tr_theta, tr_priminf, tr_sumlog;   // at the last evaluated trial point
   double theta_soc_old, alpha_soc;
-  double curr_obj, last_obj;
-  int phase, flags, cur, iter, status, n_steps, soc_count, acceptable_counter, nf;
+  double curr_obj, last_obj, soft_alpha;
+  int phase, flags, cur, iter, status, n_steps, soc_count, acceptable_counter, nf, soft_count;
   // transient (within a pass)
   double fw_alpha_pr, fw_alpha_du, fw_gbd;
   bool fw_tiny;
@@ -363,10 +366,10 @@ struct Solver {
   X(dSZMAX, sz_max) X(dSZMIN, sz_min) X(dSLOG, sumlog) X(dXMAX, xmaxabs) X(dDLMAX, dlam_max) X(dRTH, ref_theta)          \
   X(dRBARR, ref_barr) X(dRGBD, ref_gbd) X(dALPHA, alpha) X(dAMAX, alpha_max) X(dAMIN, alpha_min) X(dADU, alpha_du)       \
   X(dATEST, alpha_test) X(dTRF, tr_f) X(dTRTH, tr_theta) X(dTRPINF, tr_priminf) X(dTRSLOG, tr_sumlog)                   \
-  X(dTHSOC, theta_soc_old) X(dASOC, alpha_soc) X(dCOBJ, curr_obj) X(dLOBJ, last_obj)
+  X(dTHSOC, theta_soc_old) X(dASOC, alpha_soc) X(dCOBJ, curr_obj) X(dLOBJ, last_obj) X(dSOFTA, soft_alpha)
 #define MPC_SCALARS_I(X)                                                                                                \
   X(iPHASE, phase) X(iFLAGS, flags) X(iCUR, cur) X(iITER, iter) X(iSTATUS, status) X(iNSTEPS, n_steps)                   \
-  X(iSOCCNT, soc_count) X(iACCCNT, acceptable_counter) X(iNF, nf)
+  X(iSOCCNT, soc_count) X(iACCCNT, acceptable_counter) X(iNF, nf) X(iSOFTCNT, soft_count)
   MPC_HD void load_state() {
 #define X(idx, name) name = w(idx);
     MPC_SCALARS(X)
@@ -464,6 +467,7 @@ struct Solver {
     ref_theta = ref_barr = ref_gbd = 0.0;
     theta_soc_old = alpha_soc = 0.0;
     n_steps = soc_count = 0;
+    soft_count = 0; soft_alpha = 0.0;
     dualinf = lam1 = z1 = sz_max = sz_min = xmaxabs = 0.0;
     tr_f = tr_theta = tr_priminf = tr_sumlog = 0.0;
   }
@@ -981,7 +985,7 @@ struct Solver {
   // (IpIpoptAlg.cpp:880-951), and every norm the convergence test / mu update need at the trial iterate
   // (IpIpoptCalculatedQuantities.cpp:2672-2832, 3279-3306).  Everything is written to the OTHER copy of the iterate
   // block; the caller flips `cur` if the trial point is accepted.
-  MPC_HD void step_sweep(double a, double a_du, double dw) {
+  MPC_HD void step_sweep(double a, double a_lam, double a_du, double dw) {
     const double qv = 2.0 * P.w_v * df + dw, qe = 2.0 * P.w_epsi * df + dw, qc = 2.0 * P.w_cte * df + dw, q0 = dw;
     const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df, gc2 = 2.0 * P.w_cte * df;
     const int bO = kX * cur, bN = kX * (cur ^ 1);
@@ -1004,7 +1008,7 @@ struct Solver {
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         dlm = dmax(dlm, fabs(lp[k] - lam[k]));
-        ln[k] = lam[k] + a * (lp[k] - lam[k]);
+        ln[k] = lam[k] + a_lam * (lp[k] - lam[k]);
         snn[k] = s[k] + a * ds[k];
         w(r + bN + xLAM + k) = ln[k];
         w(r + bN + xS + k) = snn[k];
@@ -1060,7 +1064,7 @@ struct Solver {
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         sn[k] = s[k] + a * ds[k];
-        lnew[k] = lam[k] + a * (lpn[k] - lam[k]);
+        lnew[k] = lam[k] + a_lam * (lpn[k] - lam[k]);
         w(r + bN + xLAM + k) = lnew[k];
         w(r + bN + xS + k) = sn[k];
         l1 += fabs(lnew[k]);
@@ -1253,6 +1257,12 @@ struct Solver {
       alpha_max = fw_alpha_pr;
       alpha = alpha_max;
       n_steps = 0;
+      if (fl(F_SOFT) && !fw_tiny) {
+        // in the soft restoration phase only the damped full step is tried (IpBacktrackingLineSearch.cpp:426-448)
+        if (++soft_count > 10) { setfl(F_HARD, true); phase = PH_RESTO; }   // max_soft_resto_iters
+        else { soft_alpha = 0.0; alpha_soc = fw_alpha_du; alpha = alpha_du = dmin(alpha_max, fw_alpha_du); setfl(F_SOFTTRY, true); }
+        return;
+      }
       if (fw_tiny) {
         if (fl(F_TINYLAST)) setfl(F_TINYFLAG, true);
       } else {
@@ -1269,10 +1279,14 @@ struct Solver {
     step_pass();
     step_logic();
   }
+  // FIN = false: the per-pass sweep kernels, which never see a problem in the soft restoration phase (a failed line
+  // search parks the problem for the finisher); the soft branches are compiled out of them.
+  template <bool FIN = true>
   MPC_HD void step_pass() {
     if (fl(F_LS)) accept_ls(!fl(F_LSKEEP));
-    else step_sweep(alpha, alpha_du, dw_curr);
+    else step_sweep(alpha, FIN && fl(F_SOFTFIX) ? soft_alpha : alpha, alpha_du, dw_curr);
   }
+  template <bool FIN = true>
   MPC_HD void step_logic() {
     if (fl(F_LS)) {
       if (!fl(F_LSKEEP) && dlam_max <= 1000.0) { setfl(F_LSKEEP, true); return; }   // estimate within constr_mult_init_max: store it
@@ -1281,8 +1295,35 @@ struct Solver {
       // ---- line search decision on the trial point (IpBacktrackingLineSearch.cpp:637-797)
       const double tbarr = tr_f - mu * tr_sumlog;
       const bool tiny_now = fl(F_TINYNOW), in_soc = fl(F_INSOC);
-      bool acc;
-      if (tiny_now) acc = true;
+      bool acc, soft_step = false;
+      if (FIN && fl(F_SOFTFIX)) {   // second pass of an 'S' step: multipliers recomputed, accepted as it is
+        setfl(F_SOFTFIX, false);
+        acc = soft_step = true;
+      } else if (FIN && fl(F_SOFTTRY)) {
+        // TrySoftRestoStep (IpBacktrackingLineSearch.cpp:1043-1140): the damped full step (same step size for x,
+        // lambda and z) is taken if the original acceptance test passes with alpha_test = 0 ('S': back to the regular
+        // algorithm) or if it reduces the primal-dual system error by the factor 1 - 1e-4 ('s': stay in the soft
+        // phase); the filter is not augmented.  Otherwise the restoration step follows.
+        setfl(F_SOFTTRY, false);
+        const bool orig = check_accept(0.0, tr_theta, tbarr);
+        if (!orig && !(pd_error(cur ^ 1) <= (1.0 - 1e-4) * pd_error(cur))) {
+          setfl(F_HARD, true);
+          phase = PH_RESTO;
+          return;
+        }
+        setfl(F_SOFT, !orig); setfl(F_FILTDONE, false);
+        if (orig) {
+          // 'S': back to the regular algorithm.  Ipopt then repeats the dual step with the primal step size its line
+          // search variable holds (the last failed one on the first attempt, 0 inside the soft phase) for lambda and
+          // the full fraction-to-the-boundary step for z (IpBacktrackingLineSearch.cpp:595-603): one more STEP pass.
+          soft_count = 0;
+          setfl(F_SOFTFIX, true);
+          alpha_du = alpha_soc;
+          phase = PH_STEP;
+          return;
+        }
+        acc = soft_step = true;
+      } else if (tiny_now) acc = true;
       else {
         if (!in_soc) alpha_test = alpha;
         acc = check_accept(alpha_test, tr_theta, tbarr);
@@ -1299,7 +1340,7 @@ struct Solver {
             setfl(F_INSOC, false); setfl(F_SOCDONE, true);
             alpha = 0.5 * alpha_max; n_steps = 1;
             if (alpha > alpha_min) phase = PH_FACTOR;
-            else line_search_failed();
+            else { setfl(F_HARD, true); line_search_failed(); }   // DS / DU hold the corrected direction: no soft step
           }
         } else if (!fl(F_SOCDONE) && alpha == alpha_max && ref_theta <= tr_theta) {   // start SOC (IpFilterLSAcceptor.cpp:473-587)
           setfl(F_INSOC, true); soc_count = 0;
@@ -1314,7 +1355,7 @@ struct Solver {
         }
         return;
       }
-      if (!tiny_now && (!is_ftype(alpha_test) || !armijo(alpha_test, tbarr)))
+      if (!tiny_now && !soft_step && (!is_ftype(alpha_test) || !armijo(alpha_test, tbarr)))
         filter_add(ref_barr - 1e-8 * ref_theta, (1.0 - 1e-5) * ref_theta);
       // ---- accept: the trial copy becomes the current iterate
       cur ^= 1;
@@ -1333,25 +1374,76 @@ struct Solver {
   // Failed line search (alpha <= alpha_min).  Ipopt switches to its restoration phase here
   // (IpBacktrackingLineSearch.cpp:531-585); at an almost feasible point it gives up instead (:548-563).
   MPC_HD void line_search_failed() {
-    if (P.resto && ref_theta > 1e-2 * P.tol) phase = PH_RESTO;
+    if (P.resto) phase = PH_RESTO;
     else { status = kRestorationFailed; phase = PH_DONE; }
   }
-  // Restoration step.  Ipopt's restoration phase (IpRestoMinC_1Nrm.cpp:150-330) runs a nested interior-point solve of
-  // min rho ||c(x)||_1 + eta/2 ||D_R (x - x_R)||^2 until a point is acceptable to the filter with theta <= 0.9 theta_R.
-  // This solver is NOT a restatement of that nested solve: the constraints here are a discrete-time recursion
-  // s_{t+1} = F(s_t, u_t), so a point with ANY prescribed fraction of the current defects is available in closed form by
-  // one forward sweep -- keep the controls (and with them the slacks and the barrier term), and set
-  //     s_{t+1} := F(s_t, u_t) + (1 - beta) c_{t+1}(x_R),          theta(x) = (1 - beta) theta(x_R) exactly,
-  // which for beta = 1 is the roll-out of the model with the current controls (theta = 0: acceptable to every filter
-  // entry).  What follows mirrors what Ipopt does when its restoration phase returns (IpRestoMinC_1Nrm.cpp:262-330,
-  // IpBacktrackingLineSearch.cpp:537): the point x_R enters the filter before it is left, lambda is reset to zero
-  // (constr_mult_reset_threshold = 0), z takes the step towards mu / slack limited by the fraction-to-the-boundary rule
-  // and is reset to 1 if it exceeds bound_mult_reset_threshold = 1000, mu and the filter are kept, and the restoration
-  // counts as one iteration.  The new point is evaluated by a zero-length STEP pass (as in init_warm), which provides
-  // every norm top_of_loop() needs.  Iteration counts therefore differ from Ipopt's on the problems that get here
-  // (none at N = 25); the solutions agree whenever both end in the same local minimum (tests/test_restoration.py).
+  // Primal-dual system error of the iterate copy `buf` for the barrier parameter mu
+  // (IpIpoptCalculatedQuantities.cpp:2835-2884): 1-norms of grad_x L, c and the relaxed complementarity, each divided
+  // by its number of entries.  Rare path: its own sweep over the workspace.
+  MPC_HD double pd_error(int buf) const {
+    const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df, gc2 = 2.0 * P.w_cte * df;
+    const int b = kX * buf;
+    double dual = 0.0, prim = 0.0, cmpl = 0.0;
+    double sn[6], ln[6], un0 = 0.0, un1 = 0.0;
+    {
+      const int r = rec(M) + b;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { sn[k] = w(r + xS + k); ln[k] = w(r + xLAM + k); }
+      dual += fabs(ln[0]) + fabs(ln[1]) + fabs(ln[2]) + fabs(gv2 * (sn[3] - P.ref_v) + ln[3]) + fabs(gc2 * sn[4] + ln[4]) +
+              fabs(ge2 * sn[5] + ln[5]);
+    }
+    for (int t = M - 1; t >= 0; --t) {
+      const int r = rec(t) + b;
+      double s[6], lam[6], u[2], um0 = 0.0, um1 = 0.0, sp, cp, se, ce, p0, p1, p2, p3, c[6], at[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { s[k] = w(r + xS + k); lam[k] = w(r + xLAM + k); }
+      u[0] = w(r + xU); u[1] = w(r + xU + 1);
+      if (t > 0) { um0 = w(r - kRec + xU); um1 = w(r - kRec + xU + 1); }
+      const double zl0 = w(r + xZL), zl1 = w(r + xZL + 1), zu0 = w(r + xZU), zu1 = w(r + xZU + 1);
+      trig_of(r, s, sp, cp, se, ce);
+      poly_eval(cf, s[0], p0, p1, p2, p3);
+      residual(s, u, sn, sp, cp, se, p0, atan(p1), c);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) prim += fabs(c[k]);
+      const Lin A = make_lin(P, s[3], u[0], sp, cp, se, ce, p1, p2);
+      applyAT6(A, ln, at);
+      dual += fabs(lam[0] - at[0]) + fabs(lam[1] - at[1]) + fabs(lam[2] - at[2]) + fabs(gv2 * (s[3] - P.ref_v) + lam[3] - at[3]) +
+              fabs(gc2 * s[4] + lam[4]) + fabs(ge2 * s[5] + lam[5] - at[5]);
+      dual += fabs(grad_u(0, t, u[0], um0, un0) - A.beta * (ln[2] + ln[5]) - zl0 + zu0) +
+              fabs(grad_u(1, t, u[1], um1, un1) - P.dt * ln[3] - zl1 + zu1);
+      cmpl += fabs(safe_slack(u[0] - P.xl[0], mu, zl0, P.xl[0]) * zl0 - mu) + fabs(safe_slack(P.xu[0] - u[0], mu, zu0, P.xu[0]) * zu0 - mu) +
+              fabs(safe_slack(u[1] - P.xl[1], mu, zl1, P.xl[1]) * zl1 - mu) + fabs(safe_slack(P.xu[1] - u[1], mu, zu1, P.xu[1]) * zu1 - mu);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { sn[k] = s[k]; ln[k] = lam[k]; }
+      un0 = u[0]; un1 = u[1];
+    }
+    return dual / (8.0 * N - 2.0) + prim / (6.0 * N) + cmpl / (4.0 * M);
+  }
+  // What the finisher does with a problem whose line search failed (phase PH_RESTO).
+  //   Params::resto == 2: Ipopt's soft restoration phase first (IpBacktrackingLineSearch.cpp:498-530): the current point
+  //   enters the filter and the damped full Newton step is tried (a STEP pass with the flag F_SOFTTRY, decided in
+  //   step_logic); while such steps are accepted on the primal-dual error alone the problem stays in the soft phase
+  //   (F_SOFT, at most 10 iterations in a row, forward_logic).  A rejected soft step comes back here with F_HARD.
+  //   Otherwise, and always for Params::resto == 1: the restoration step do_resto().
+  MPC_HD void resto_entry() {
+    const bool first = !fl(F_HARD);   // straight from a failed backtracking line search with the Newton direction
+    if (!fl(F_FILTDONE) && !fl(F_SOFT))
+      filter_add(ref_barr - 1e-8 * ref_theta, (1.0 - 1e-5) * ref_theta);   // FilterLSAcceptor::PrepareRestoPhaseStart
+    if (P.resto >= 2 && first && !fl(F_SOFT)) {
+      setfl(F_FILTDONE, true);
+      setfl(F_SOFTTRY, true);
+      setfl(F_SOCDONE, false);
+      soft_alpha = alpha; alpha_soc = alpha_du;   // step sizes of the failed line search, for an 'S' step
+      alpha = alpha_du = dmin(alpha_max, alpha_du);
+      phase = PH_STEP;
+      return;
+    }
+    setfl(F_HARD, false); setfl(F_FILTDONE, false); setfl(F_SOFT, false);
+    soft_count = 0;
+    if (!(ref_theta > 1e-2 * P.tol)) { status = kRestorationFailed; phase = PH_DONE; return; }   // :548-563
+    do_resto();
+  }
   MPC_HD void do_resto() {
-    filter_add(ref_barr - 1e-8 * ref_theta, (1.0 - 1e-5) * ref_theta);   // FilterLSAcceptor::PrepareRestoPhaseStart
     const int b = kX * cur;
     const double keep = 1.0 - kRestoBeta;
     // dual step length of z := z + a (mu / slack - z), fraction-to-the-boundary (IpRestoMinC_1Nrm.cpp:283-301)
@@ -1464,14 +1556,14 @@ struct Solver {
   MPC_HD void kernel_step() {
     LDI(iFLAGS, flags); LDI(iCUR, cur); LDD(dDF, df); LDD(dMU, mu); LDD(dALPHA, alpha); LDD(dADU, alpha_du); LDD(dDWC, dw_curr);
     phase = PH_STEP;
-    step_pass();
+    step_pass<false>();
     LDD(dRTH, ref_theta); LDD(dRBARR, ref_barr); LDD(dRGBD, ref_gbd); LDD(dTHMAX, theta_max); LDD(dTHMIN, theta_min);
     LDD(dATEST, alpha_test); LDD(dAMAX, alpha_max); LDD(dAMIN, alpha_min); LDD(dTHSOC, theta_soc_old); LDD(dASOC, alpha_soc);
     LDD(dTAU, tau); LDD(dMUMIN, mu_min); LDD(dCOBJ, curr_obj); LDD(dLOBJ, last_obj); LDD(dDWL, dw_last);
     LDD(dF, f_cur); LDD(dTH, theta_cur); LDD(dPINF, priminf); LDD(dSLOG, sumlog);
     LDI(iSOCCNT, soc_count); LDI(iNSTEPS, n_steps); LDI(iNF, nf); LDI(iSTATUS, status); LDI(iACCCNT, acceptable_counter);
     LDI(iITER, iter);
-    step_logic();
+    step_logic<false>();
     STD_(dTHMAX, theta_max); STD_(dTHMIN, theta_min); STD_(dATEST, alpha_test); STD_(dALPHA, alpha); STD_(dTHSOC, theta_soc_old);
     STD_(dASOC, alpha_soc); STD_(dF, f_cur); STD_(dTH, theta_cur); STD_(dPINF, priminf); STD_(dSLOG, sumlog); STD_(dMU, mu);
     STD_(dTAU, tau); STD_(dCOBJ, curr_obj); STD_(dLOBJ, last_obj); STD_(dDWC, dw_curr); STD_(dDWL, dw_last);
@@ -1484,7 +1576,7 @@ struct Solver {
 #undef STI
 
   MPC_HD void trip() {
-    if (phase == PH_RESTO) do_resto();
+    if (phase == PH_RESTO) resto_entry();
     if (phase == PH_FACTOR) do_factor();
     if (phase == PH_FORWARD) do_forward();
     if (phase == PH_STEP) do_step();
