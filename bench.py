@@ -149,7 +149,7 @@ def config_dict(args, batch):
                           if args.workload == "roadmap" else "BASELINE configs[2]: batched mpc_to_line, degree-1 reference y=-1"),
                 horizon_N=HORIZON, dt=0.05, batch_per_gpu=batch, problems_per_step=batch * args.gpus,
                 sharding="contiguous index ranges per GPU, no collective",
-                l2="per-step working set (solver workspace region, 17.4 KB/problem = 1.14 GB at 65 536) >> 126 MB L2; "
+                l2="per-step working set (solver workspace region, 17.9 KB/problem = 1.18 GB at 65 536) >> 126 MB L2; "
                    "inputs cycle over 4 distinct batches, the same on every rank")
 
 

@@ -38,12 +38,12 @@ def main():
     rows = []
     for N in [int(n) for n in args.horizons.split(",")]:
         for B in [int(b) for b in args.batches.split(",")]:
-            if B * 83 * (N + 1) * 8 > 60e9:
+            if B * 83 * (N + 2) * 8 > 60e9:
                 continue
             t = (B + nb - 1) // nb
             st_d = torch.from_numpy(np.ascontiguousarray(np.tile(st, (t, 1))[:B].T)).to(dev)
             cf_d = torch.from_numpy(np.ascontiguousarray(np.tile(fit, (t, 1))[:B].T)).to(dev)
-            S = max(1, min(args.streams, int(150e9 // (2 * B * 83 * (N + 1) * 8))))
+            S = max(1, min(args.streams, int(150e9 // (2 * B * 83 * (N + 2) * 8))))
             streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(S - 1)]
             out8 = [torch.empty((8, B), dtype=torch.float64, device=dev) for _ in range(S)]
             status = torch.empty((S, B), dtype=torch.int32, device=dev)

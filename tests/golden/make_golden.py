@@ -114,7 +114,7 @@ def main():
     print("golden fixtures written to", HERE)
 
 
-if __name__ == "__main__" and not {"--config3", "--n100", "--resto", "--soft"} & set(sys.argv):
+if __name__ == "__main__" and not {"--config3", "--n100", "--resto", "--soft", "--long-filter"} & set(sys.argv):
     main()
 
 
@@ -218,3 +218,28 @@ def soft():
 
 if __name__ == "__main__" and "--soft" in sys.argv:
     soft()
+
+
+def long_filter():
+    """Long solves from extreme initial states (lateral offset up to +-80 m, heading error +-3 rad, 0.1..80 m/s: the
+    |cte| > 50 objective-scaling branch) whose filter grows beyond 8 entries: 12 of the 32 768 "wilder" N=25 problems of
+    tools/resto_campaign.py that the reference solves without its restoration phase."""
+    from udacitympc_b200 import synth
+    n, N, sel = 32768, 25, [82, 505, 1535, 1543, 1606, 1612, 1870, 2957, 3534, 3666, 4014, 4418]
+    xs, ys = synth.roadmap_windows(n, synth.MT19937_64(878))
+    V = np.stack([xs ** i for i in range(4)], axis=2)
+    fit = np.stack([np.linalg.lstsq(V[b], ys[b], rcond=None)[0] for b in range(n)])
+    u = synth.MT19937_64(880).uniform(3 * n).reshape(n, 3)
+    y = -80.0 + 160.0 * u[:, 0]
+    psi = np.arctan(fit[:, 1]) - 3.0 + 6.0 * u[:, 1]
+    v = 0.1 + 79.9 * u[:, 2]
+    st = np.ascontiguousarray(np.stack([np.zeros(n), y, psi, v, fit[:, 0] - y, psi - np.arctan(fit[:, 1])], axis=1))
+    res = [_solve_resto((st[b], fit[b], N)) for b in sel]
+    assert all(r[2] == 0 and r[4] == 0 for r in res)
+    np.savez_compressed(os.path.join(HERE, "long_filter_N25_12.npz"), index=np.array(sel, dtype=np.int32), states=st[sel],
+                        coeffs=fit[sel], out8=np.array([r[0] for r in res]), obj=np.array([r[1] for r in res]),
+                        iters=np.array([r[3] for r in res], dtype=np.int32), x=np.array([r[5] for r in res]))
+
+
+if __name__ == "__main__" and "--long-filter" in sys.argv:
+    long_filter()

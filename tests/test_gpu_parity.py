@@ -585,3 +585,21 @@ def test_long_horizon_falls_back_to_the_thread_finisher():
         roll = mp.rollout_batch(st[ok][:, :4], np.stack([DEL, ACC], axis=2), 0.05, 2.67, mpc=m0)
     err = np.abs(np.stack([T[:, 1:N], T[:, N + 1:2 * N], T[:, 2 * N + 1:3 * N], T[:, 3 * N + 1:4 * N]], axis=2) - roll).max()
     assert err < 1e-4
+
+
+def test_long_solves_keep_every_filter_entry():
+    """Extreme initial states (|cte| up to 80 m, 40-130 iterations): the filter grows beyond 8 entries; it lives in its own
+    workspace record (41 entries) and moves with the problem in the batch compaction.  Same solutions as the reference
+    binaries (these solves are sensitive: the iteration count is required to agree on two thirds only)."""
+    g = golden("long_filter_N25_12.npz")
+    for reps in (1, 300):   # cooperative kernel alone / per-pass kernels with compaction, then the finisher
+        st, cf = np.tile(g["states"], (reps, 1)), np.tile(g["coeffs"], (reps, 1))
+        with mp.MPC() as m:
+            if reps > 1:
+                m.set_solver_mode(0, 30, 0)
+                m.set_compaction(0.9, 2)
+            r = m.solve_batch(st, cf, want_traj=True)
+        assert (r["status"] == 0).all()
+        same = (np.abs(r["traj"][:12] - g["x"]).max(axis=1) <= TOL_TRAJ) & (np.abs(r["cost"][:12] - g["obj"]) <= TOL_OBJ * np.abs(g["obj"]))
+        assert same.sum() >= 10, same
+        assert (r["iters"][:12] == g["iters"]).sum() >= 8

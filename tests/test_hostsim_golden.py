@@ -231,3 +231,20 @@ def test_invalid_numbers_stop_at_the_starting_point(hostsim):
         for mode in (0, 1, 2):
             r = hostsim.solve(st, cf, mode=mode)
             assert r["status"] == -13 and r["iters"] == 0, mode
+
+
+def test_long_solves_keep_every_filter_entry(hostsim):
+    """Extreme initial states (|cte| up to 80 m: objective scaling active, 40-130 iterations at mu = 0.1) grow the filter
+    beyond 8 entries; with the filter in its own workspace record (41 entries) the iterates stay Ipopt's: same iteration
+    counts and solutions on the thread path, through the per-pass kernels with compaction (the filter entries move with
+    the problem) and on the cooperative path."""
+    g = golden("long_filter_N25_12.npz")
+    for mode in (0, -2, 2):
+        same = 0
+        for b in range(12):
+            r = hostsim.solve(g["states"][b], g["coeffs"][b], mode=mode)
+            assert r["status"] == 0
+            np.testing.assert_allclose(r["x"], g["x"][b], rtol=0, atol=1e-7)
+            assert abs(r["obj"] - g["obj"][b]) <= TOL_OBJ * abs(g["obj"][b])
+            same += int(r["iters"] == g["iters"][b])
+        assert same >= 11, (mode, same)

@@ -47,18 +47,23 @@ def problems(n, seed=0, wild=False):
     if wild:   # far outside SURVEY 8d config 4: lateral offset +-20 m, heading error +-1.5 rad, speed 1..60 m/s
         u = synth.MT19937_64(880 + seed).uniform(3 * n).reshape(n, 3)
         c0, c1 = fit[:, 0], fit[:, 1]
-        y = -20.0 + 40.0 * u[:, 0]
-        psi = np.arctan(c1) - 1.5 + 3.0 * u[:, 1]
-        v = 1.0 + 59.0 * u[:, 2]
+        if wild == 2:   # --wilder: +-80 m, +-3 rad, 0.1..80 m/s (objective scaling branch, |cte| > 50)
+            y = -80.0 + 160.0 * u[:, 0]
+            psi = np.arctan(c1) - 3.0 + 6.0 * u[:, 1]
+            v = 0.1 + 79.9 * u[:, 2]
+        else:
+            y = -20.0 + 40.0 * u[:, 0]
+            psi = np.arctan(c1) - 1.5 + 3.0 * u[:, 1]
+            v = 1.0 + 59.0 * u[:, 2]
         st = np.ascontiguousarray(np.stack([np.zeros(n), y, psi, v, c0 - y, psi - np.arctan(c1)], axis=1))
     return st, fit
 
 
 if __name__ == "__main__":
     N = int(sys.argv[1]); n = int(sys.argv[2]); mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-    wild = "--wild" in sys.argv
+    wild = 2 if "--wilder" in sys.argv else int("--wild" in sys.argv)
     S, C = problems(n, wild=wild)
-    cache = f"/tmp/resto_ref_N{N}_{n}{'_wild' if wild else ''}.npy"
+    cache = f"/tmp/resto_ref_N{N}_{n}{['', '_wild', '_wilder'][wild]}.npy"
     ctx = mp.get_context("fork")
     if os.path.exists(cache):
         ref = np.load(cache)
@@ -77,6 +82,7 @@ if __name__ == "__main__":
     dact = np.abs(got[:, 9:11] - ref[:, 10:12]).max(axis=1)
     same = (got[:, 0] == 0) & ok_ref & (relobj < 1e-6) & (dact < 1e-5)
     ours_resto = (got[:, 0] == 0) & ok_ref & ~used & (got[:, 1] != ref[:, 1])
+    print(f"  reference status histogram {np.unique(ref[:, 0], return_counts=True)}; status differs on {int((got[:, 0] != ref[:, 0]).sum())}")
     print(f"N {N} n {n} mode {mode}: reference ok {int(ok_ref.sum())}, reference used restoration {int(used.sum())}; "
           f"ours status!=0 {int((got[:, 0] != 0).sum())} {np.unique(got[:, 0], return_counts=True)}")
     print(f"  no-restoration problems: same solution {int((same & ~used).sum())} / {int((~used & ok_ref).sum())}, "

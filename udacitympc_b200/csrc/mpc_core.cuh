@@ -95,7 +95,7 @@ enum Status {
 };
 
 constexpr int kMaxCoef = 4;   // reference polynomial degree <= 3
-constexpr int kMaxFilter = 8;
+constexpr int kMaxFilter = 41;   // filter entries (phi, theta); they fill one workspace record of their own (record N+1)
 constexpr int kCarry = 24;    // stage-to-stage values of the STEP sweep
 #ifndef MPC_RESTO_BETA
 #define MPC_RESTO_BETA 0.05
@@ -104,7 +104,8 @@ constexpr double kRestoBeta = MPC_RESTO_BETA;   // fraction of the constraint de
 
 // ---- workspace of one problem, in doubles -----------------------------------------------------------------
 // Element i of the problem owned by lane l of a 32-problem group lives at group_base[i*LANES + l] (LANES = 32 on
-// the device: every access of a warp is one coalesced 256-byte row).  Record 0 holds the scalar state, records
+// the device: every access of a warp is one coalesced 256-byte row).  Record 0 holds the scalar state, record N+1 the
+// filter entries, records
 // 1..N the per-stage data of time t = 0..N-1 at fixed offsets.
 // The iterate block X = {S, U, LAM, ZL, ZU, TR, C} exists twice (current / trial); buffer b starts at 28*b.
 enum StageOff {
@@ -123,12 +124,13 @@ enum StageOff {
 enum ScalarD {
   dDF, dMU, dTAU, dMUMIN, dDWC, dDWL, dTHMAX, dTHMIN, dF, dTH, dPINF, dDINF, dLAM1, dZ1, dSZMAX, dSZMIN, dSLOG, dXMAX,
   dDLMAX, dRTH, dRBARR, dRGBD, dALPHA, dAMAX, dAMIN, dADU, dATEST, dTRF, dTRTH, dTRPINF, dTRSLOG, dTHSOC, dASOC, dCOBJ,
-  dLOBJ, dSOFTA, dFILT /* 2*kMaxFilter */, kNumD = dFILT + 2 * kMaxFilter
+  dLOBJ, dSOFTA, kNumD
 };
 enum ScalarI { iPHASE = kNumD, iFLAGS, iCUR, iITER, iSTATUS, iNSTEPS, iSOCCNT, iACCCNT, iNF, iSOFTCNT, kNumScal };
 static_assert(kNumScal <= kRec, "scalar record must fit one stage record");
 
-MPC_HD int workspace_doubles_per_problem(int N) { return kRec * (N + 1); }
+static_assert(2 * kMaxFilter <= kRec, "the filter must fit one record");
+MPC_HD int workspace_doubles_per_problem(int N) { return kRec * (N + 2); }
 
 // HBM traffic vs recomputation (the solver kernels are HBM-bound with FP64 issue slots to spare):
 //   MPC_STORE_TRIG 0: sin/cos(psi_t), sin/cos(epsi_t) are recomputed by every sweep instead of stored (16 doubles/stage/iter)
@@ -302,6 +304,7 @@ MPC_HD void repack_rows(const Ws<LS_>& s, const Ws<LD_>& d, int r, int n) {
 template <int LS_, int LD_>
 MPC_HD void repack_problem(const Params& P, const Ws<LS_>& s, const Ws<LD_>& d) {
   repack_rows(s, d, 0, (int)kNumScal);
+  repack_rows(s, d, (P.N + 1) * kRec, 2 * (int)s(iNF));   // the filter entries in use
   const int phase = (int)s(iPHASE), flags = (int)s(iFLAGS), cur = (int)s(iCUR);
   if (phase == PH_FACTOR && !(flags & F_INSOC)) {
     constexpr int n = MPC_STORE_C ? (int)kX : (int)xC;
@@ -352,7 +355,7 @@ struct Solver {
   MPC_HD void setfl(int f, bool v) { flags = v ? (flags | f) : (flags & ~f); }
   // record of time t starts at (t+1)*kRec
   MPC_HD int rec(int t) const { return (t + 1) * kRec; }
-  MPC_HD double& filt(int i) const { return w(dFILT + i); }
+  MPC_HD double& filt(int i) const { return w(rec(N) + i); }   // record N+1, after the stage records
 
   MPC_HD void set_coeffs(const double* coef, int ncoef) {
 #pragma unroll
