@@ -188,6 +188,99 @@ int hostsim_closed_loop(const hostsim_params* hp, const double* state6, const do
   return 0;
 }
 
+// The DEVICE memory layout on the host: B problems in warp-interleaved groups of 32 (Solver<32>, element i of slot s at
+// region[((s >> 5) * doubles_per_problem + i) * 32 + (s & 31)], the arithmetic of slot_base() / region_doubles() in
+// solve_kernel.cu), two regions, per-pass execution with the scalar state reloaded for every pass, and after every
+// round (compact != 0) the batch compaction: the live problems move to consecutive slots of the other region, which is
+// poisoned with NaN first.  Guard words behind both regions catch any write outside a region.  Returns 0, or -1 if a
+// guard word changed.
+int hostsim_batch_interleaved(const hostsim_params* hp, int B, const double* states, const double* coeffs, int ncoef,
+                              int compact, double* out8, double* obj, int* iters, int* status) {
+  Params P;
+  P.N = hp->N; P.dt = hp->dt; P.Lf = hp->Lf; P.ref_v = hp->ref_v;
+  P.w_cte = hp->w_cte; P.w_epsi = hp->w_epsi; P.w_v = hp->w_v; P.w_delta = hp->w_delta; P.w_a = hp->w_a;
+  P.w_ddelta = hp->w_ddelta; P.w_da = hp->w_da; P.delta_max = hp->delta_max; P.a_max = hp->a_max; P.tol = hp->tol;
+  P.max_iter = hp->max_iter;
+  P.resto = g_resto;
+  P.finalize();
+  const size_t wdpp = (size_t)workspace_doubles_per_problem(P.N), groups = ((size_t)B + 31) / 32, region = groups * wdpp * 32;
+  const size_t guard = 4096;
+  const double kGuard = -7.25e77;
+  std::vector<double> mem[2];
+  for (auto& m : mem) { m.assign(region + guard, std::nan("")); for (size_t i = region; i < region + guard; ++i) m[i] = kGuard; }
+  g_ws_limit = (int)wdpp;
+  auto base = [&](int r, int slot) { return mem[r].data() + (size_t)(slot >> 5) * wdpp * 32 + (slot & 31); };
+  std::vector<int> prob(B), where(B);   // slot -> problem of the current region, problem -> slot
+  for (int b = 0; b < B; ++b) { prob[b] = b; where[b] = b; }
+  int cur = 0, occupied = B;
+  for (int b = 0; b < B; ++b) {
+    Solver<32> S(P, base(0, b), b & 31);
+    S.init(states + 6 * b, coeffs + (size_t)ncoef * b, ncoef);
+    S.store_state();
+  }
+  std::vector<char> done(B, 0);
+  auto finish = [&](int slot) {
+    const int b = prob[slot];
+    Solver<32> S(P, base(cur, slot), slot & 31);
+    S.set_coeffs(coeffs + (size_t)ncoef * b, ncoef);
+    S.load_state();
+    Result R;
+    S.finish(R, nullptr, 1);
+    for (int k = 0; k < 8; ++k) out8[8 * b + k] = R.out8[k];
+    obj[b] = R.obj; iters[b] = R.iters; status[b] = R.status;
+    done[b] = 1;
+  };
+  for (int round = 0; round < 100000; ++round) {
+    int live = 0;
+    for (int slot = 0; slot < occupied; ++slot) {
+      const int b = prob[slot];
+      if (done[b]) continue;
+      for (int k = 0; k < 3; ++k) {
+        Solver<32> S(P, base(cur, slot), slot & 31);
+        double carry[kCarry];
+        S.cr = carry; S.cs = 1;
+        if (S.load_phase() != k) continue;
+        S.set_coeffs(coeffs + (size_t)ncoef * b, ncoef);
+        if (k == PH_FACTOR) S.kernel_factor();
+        else if (k == PH_FORWARD) S.kernel_forward();
+        else S.kernel_step();
+      }
+      Solver<32> S(P, base(cur, slot), slot & 31);
+      if (S.load_phase() == PH_RESTO) {   // finisher
+        double carry[kCarry];
+        S.cr = carry; S.cs = 1;
+        S.set_coeffs(coeffs + (size_t)ncoef * b, ncoef);
+        S.load_state();
+        int guard_trips = 0;
+        while (S.phase != PH_DONE && guard_trips++ < 400000) S.trip();
+        S.store_state();
+      }
+      if (S.load_phase() == PH_DONE) finish(slot);
+      else ++live;
+    }
+    if (live == 0) break;
+    if (compact) {   // live problems to consecutive slots of the other region, in reverse order for good measure
+      const int other = cur ^ 1;
+      for (size_t i = 0; i < region; ++i) mem[other][i] = std::nan("");
+      std::vector<int> np_;
+      for (int slot = occupied - 1; slot >= 0; --slot) {
+        const int b = prob[slot];
+        if (done[b]) continue;
+        const int ds = (int)np_.size();
+        repack_problem(P, Ws<32>{base(cur, slot), slot & 31}, Ws<32>{base(other, ds), ds & 31});
+        np_.push_back(b);
+      }
+      for (size_t i = 0; i < np_.size(); ++i) { prob[i] = np_[i]; where[np_[i]] = (int)i; }
+      occupied = (int)np_.size();
+      cur = other;
+    }
+  }
+  for (auto& m : mem)
+    for (size_t i = region; i < region + guard; ++i)
+      if (m[i] != kGuard) return -1;
+  return 0;
+}
+
 int hostsim_solve(const hostsim_params* hp, const double* state6, const double* coeffs, int ncoef, double* x_out,
                   double* out8, double* obj, int* iters, double* lam_out, double* trace, int trace_cap, int* trace_rows) {
   return hostsim_solve_mode(hp, state6, coeffs, ncoef, x_out, out8, obj, iters, lam_out, trace, trace_cap, trace_rows, 0);

@@ -248,3 +248,35 @@ def test_long_solves_keep_every_filter_entry(hostsim):
             assert abs(r["obj"] - g["obj"][b]) <= TOL_OBJ * abs(g["obj"][b])
             same += int(r["iters"] == g["iters"][b])
         assert same >= 11, (mode, same)
+
+
+@pytest.mark.parametrize("compact", [False, True])
+def test_device_memory_layout_on_the_host(hostsim, compact):
+    """The device layout (warp-interleaved groups of 32 problems, two regions, slot arithmetic of slot_base() /
+    region_doubles(), filter record, per-pass execution, batch compaction into a NaN-poisoned region, guard words behind
+    the regions) gives bit-identical results to the one-problem-at-a-time build on a mixed batch of 70 problems (a
+    partial last group) that includes long solves, restoration and soft-restoration cases."""
+    a, b, c = golden("long_filter_N25_12.npz"), golden("resto_N25_wild_32.npz"), golden("roadmap_256.npz")
+    st = np.concatenate([a["states"], b["states"], c["states"][:26]])
+    cf = np.concatenate([a["coeffs"], b["coeffs"], c["fit"][:26]])
+    r = hostsim.batch_interleaved(st, cf, compact=compact)
+    assert r["rc"] == 0, "a write landed outside a workspace region"
+    for k in range(len(st)):
+        one = hostsim.solve(st[k], cf[k])
+        assert r["status"][k] == one["status"] == 0 and r["iters"][k] == one["iters"]
+        np.testing.assert_array_equal(r["out8"][k], one["out8"])
+        assert r["obj"][k] == one["obj"]
+
+
+def test_device_memory_layout_on_the_host_long_horizon(hostsim):
+    """Same at N = 50, with the problems that take Ipopt's soft restoration steps and its restoration phase."""
+    a, b = golden("soft_N50_3.npz"), golden("resto_N50_14.npz")
+    st = np.tile(np.concatenate([a["states"], b["states"]]), (3, 1))   # 51 problems: one full group and a partial one
+    cf = np.tile(np.concatenate([a["coeffs"], b["coeffs"]]), (3, 1))
+    r = hostsim.batch_interleaved(st, cf, compact=True, N=50)
+    assert r["rc"] == 0
+    for k in range(17):
+        one = hostsim.solve(st[k], cf[k], N=50)
+        for rep in range(3):
+            assert r["status"][k + 17 * rep] == 0 and r["iters"][k + 17 * rep] == one["iters"]
+            np.testing.assert_array_equal(r["out8"][k + 17 * rep], one["out8"])
