@@ -58,7 +58,7 @@ class _HostSim:
                                          lam.ctypes.data_as(dp), tr.ctypes.data_as(dp), 400, ctypes.byref(nr), mode)
         return dict(status=rc, x=x, out8=o8, obj=obj.value, iters=it.value, lam=lam, trace=tr[:nr.value])
 
-    def batch_interleaved(self, states, coeffs, compact=True, **params):
+    def batch_interleaved(self, states, coeffs, compact=True, max_rounds=0, coop=False, **params):
         """B problems in the device memory layout (Solver<32>, two regions, per-pass execution, batch compaction)."""
         ob, dp = self.ob, self.dp
         p = ob.default_params(**params)
@@ -68,7 +68,8 @@ class _HostSim:
         out8 = np.zeros((B, 8)); obj = np.zeros(B); it = np.zeros(B, dtype=np.int32); status = np.zeros(B, dtype=np.int32)
         ip = ctypes.POINTER(ctypes.c_int)
         rc = self.lib.hostsim_batch_interleaved(ctypes.byref(p), B, st.ctypes.data_as(dp), c.ctypes.data_as(dp), c.shape[1],
-                                                1 if compact else 0, out8.ctypes.data_as(dp), obj.ctypes.data_as(dp),
+                                                1 if compact else 0, int(max_rounds), 1 if coop else 0, out8.ctypes.data_as(dp),
+                                                obj.ctypes.data_as(dp),
                                                 it.ctypes.data_as(ip), status.ctypes.data_as(ip))
         return dict(rc=rc, out8=out8, obj=obj, iters=it, status=status)
 

@@ -194,8 +194,10 @@ int hostsim_closed_loop(const hostsim_params* hp, const double* state6, const do
 // round (compact != 0) the batch compaction: the live problems move to consecutive slots of the other region, which is
 // poisoned with NaN first.  Guard words behind both regions catch any write outside a region.  Returns 0, or -1 if a
 // guard word changed.
+// max_rounds > 0: after that many rounds the finisher takes every live problem over (coop != 0: the cooperative solver,
+// else the thread-per-problem loop), as launch_solve does on the device.
 int hostsim_batch_interleaved(const hostsim_params* hp, int B, const double* states, const double* coeffs, int ncoef,
-                              int compact, double* out8, double* obj, int* iters, int* status) {
+                              int compact, int max_rounds, int coop, double* out8, double* obj, int* iters, int* status) {
   Params P;
   P.N = hp->N; P.dt = hp->dt; P.Lf = hp->Lf; P.ref_v = hp->ref_v;
   P.w_cte = hp->w_cte; P.w_epsi = hp->w_epsi; P.w_v = hp->w_v; P.w_delta = hp->w_delta; P.w_a = hp->w_a;
@@ -246,13 +248,20 @@ int hostsim_batch_interleaved(const hostsim_params* hp, int B, const double* sta
         else S.kernel_step();
       }
       Solver<32> S(P, base(cur, slot), slot & 31);
-      if (S.load_phase() == PH_RESTO) {   // finisher
+      if (S.load_phase() == PH_RESTO || (max_rounds > 0 && round + 1 >= max_rounds && S.load_phase() != PH_DONE)) {   // finisher
         double carry[kCarry];
         S.cr = carry; S.cs = 1;
         S.set_coeffs(coeffs + (size_t)ncoef * b, ncoef);
         S.load_state();
-        int guard_trips = 0;
-        while (S.phase != PH_DONE && guard_trips++ < 400000) S.trip();
+        if (coop) {
+          std::vector<CoopStage> stg((size_t)P.N);
+          CoopPub pub;
+          CoopSolver<32, HostExec> C(S, stg.data(), &pub, HostExec{});
+          C.run();
+        } else {
+          int guard_trips = 0;
+          while (S.phase != PH_DONE && guard_trips++ < 400000) S.trip();
+        }
         S.store_state();
       }
       if (S.load_phase() == PH_DONE) finish(slot);

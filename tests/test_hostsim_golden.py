@@ -280,3 +280,14 @@ def test_device_memory_layout_on_the_host_long_horizon(hostsim):
         for rep in range(3):
             assert r["status"][k + 17 * rep] == 0 and r["iters"][k + 17 * rep] == one["iters"]
             np.testing.assert_array_equal(r["out8"][k + 17 * rep], one["out8"])
+
+
+def test_device_memory_layout_with_the_cooperative_finisher(hostsim):
+    """As on the device: 14 per-pass rounds with compaction, then the cooperative solver takes every live problem over
+    (a failed line search hands a problem to it earlier).  Same solutions as the one-problem cooperative run."""
+    a, b = golden("long_filter_N25_12.npz"), golden("resto_N25_wild_32.npz")
+    st, cf = np.concatenate([a["states"], b["states"]]), np.concatenate([a["coeffs"], b["coeffs"]])
+    ref_x = np.concatenate([a["out8"], b["out8"]])
+    r = hostsim.batch_interleaved(st, cf, compact=True, max_rounds=14, coop=True)
+    assert r["rc"] == 0 and (r["status"] == 0).all()
+    np.testing.assert_allclose(r["out8"], ref_x, rtol=0, atol=1e-6)
