@@ -12,6 +12,10 @@
 //                                         IpFilterLSAcceptor.cpp:227-587,800-813, IpIpoptAlg.cpp:559-727,880-951,
 //                                         IpOptErrorConvCheck.cpp:204-329, IpGradientScaling.cpp:69-119,
 //                                         IpOrigIpoptNLP.cpp:361-372,466-482,875-883
+//                                         soft restoration phase: IpBacktrackingLineSearch.cpp:426-448,498-530,595-603,
+//                                         1043-1140, IpIpoptCalculatedQuantities.cpp:2835-2884 (Solver::resto_entry);
+//                                         Ipopt's restoration phase proper (IpRestoMinC_1Nrm.cpp) is NOT restated: a
+//                                         closed-form restoration step stands in for its nested solve (Solver::do_resto)
 //   Ipopt .../LinearSolvers + MUMPS       generic sparse LDL^T of the 348x348 augmented system -> the stage-wise
 //                                         Riccati recursion below (inertia test = all 2x2 control blocks positive definite)
 //
