@@ -19,7 +19,8 @@
  *   MUMPS's sparse LDL^T (generic; not restated) -> dense Bunch-Kaufman LDL^T with inertia below.
  *   polyfit / polyeval              mpc_to_line/src/helpers.h:13-19, 24-44 (+ Eigen 3.3.3 HouseholderQR)
  *   globalKinematic                 global_kinematic_model/solution/main.cpp:36-62
- * Not restated (documented gaps): restoration phase (IpRestoMinC_1Nrm.cpp; the port returns -2 where Ipopt enters it --
+ * The soft restoration phase (IpBacktrackingLineSearch.cpp:426-448, 498-530, 595-603, 1043-1140) is restated.
+ * Not restated (documented gaps): restoration phase proper (IpRestoMinC_1Nrm.cpp; the port returns -2 where Ipopt enters it --
  * the product's own restoration step is checked against the reference binaries' answers instead,
  * tests/golden/resto_N*.npz), watchdog, constraint-row
  * scaling (never triggered for |Jacobian entries| <= 100).  A solve that would need them returns -2.
@@ -658,6 +659,32 @@ static int check_accept(ip_t* s, const ls_ref* r, double alpha_test, double tria
   return filter_ok(s, trial_barr, trial_theta);
 }
 
+/* Primal-dual system error for the barrier parameter mu at (x, lam, zL, zU): 1-norms of grad_x L, c and the relaxed
+ * complementarity, each divided by its number of entries (IpIpoptCalculatedQuantities.cpp:2835-2884).  Used by the soft
+ * restoration phase only; evaluates the NLP into scratch memory. */
+static double pd_system_error(const ip_t* s, const double* x, const double* lam, const double* zL, const double* zU) {
+  const int n = s->n, m = s->m, nb = s->nb;
+  double* g = (double*)calloc((size_t)n + (size_t)m + (size_t)m * n, sizeof(double));
+  double *c = g + n, *J = c + m;
+  nlp_grad(&s->q, x, g);
+  for (int j = 0; j < n; ++j) g[j] *= s->df;
+  nlp_g(&s->q, x, c);
+  nlp_jac(&s->q, x, J);
+  for (int i = 0; i < m; ++i) {
+    c[i] -= s->rhs_c[i];
+    const double l = lam[i];
+    if (l == 0.0) continue;
+    const double* Ji = J + (size_t)i * n;
+    for (int j = 0; j < n; ++j) g[j] += Ji[j] * l;
+  }
+  for (int k = 0; k < nb; ++k) g[s->b0 + k] += -zL[k] + zU[k];
+  double cm = 0.0;
+  for (int k = 0; k < nb; ++k) cm += fabs(slackL(s, x, k) * zL[k] - s->mu) + fabs(slackU(s, x, k) * zU[k] - s->mu);
+  const double r = vasum(g, n) / n + vasum(c, m) / m + cm / (2.0 * nb);
+  free(g);
+  return r;
+}
+
 int oracle_mpc_solve(const oracle_params* p, const double* state6, const double* coeffs, int ncoef, double* x_out,
                      double* out8, double* obj_out, int* iters_out, double* lambda_out, double* trace, int trace_cap,
                      int* trace_rows) {
@@ -732,6 +759,7 @@ int oracle_mpc_solve(const oracle_params* p, const double* state6, const double*
 
   int acceptable_counter = 0; double curr_obj_val = -1e50, last_obj_val = -1e50;
   int tiny_step_last = 0, tiny_step_flag = 0, mu_initialized = 0;
+  int in_soft_resto = 0, soft_resto_counter = 0; /* IpBacktrackingLineSearch.cpp: in_soft_resto_phase_, soft_resto_counter_ */
   double info_alpha_pr = 0.0, info_alpha_du = 0.0, info_dnorm = 0.0; int info_ls = 0; double info_regu = 0.0;
   const double mu_min = (p->tol < 1e-4 * s->df ? p->tol : 1e-4 * s->df) / (10.0 + 1.0);
 
@@ -810,6 +838,7 @@ int oracle_mpc_solve(const oracle_params* p, const double* state6, const double*
     }
     double *adl = s->dlam, *adzL = s->dzL, *adzU = s->dzU; /* actual_delta */
     double alpha = 0.0; int n_steps = 0, accept = 0;
+    int soft_step = 0; double soft_a_lam = 0.0, soft_a_z = 0.0; /* a soft restoration step was taken: step sizes of lambda, z */
     /* tiny step (:1145-1200, :377-423) */
     int tiny = 1;
     for (int j = 0; j < n && tiny; ++j) if (fabs(s->dx[j]) / (fabs(s->x[j]) + 1.0) > 10.0 * DBL_EPSILON) tiny = 0;
@@ -831,8 +860,40 @@ int oracle_mpc_solve(const oracle_params* p, const double* state6, const double*
         }
         alpha_min = 0.05 * am;
       }
+      /* TrySoftRestoStep (:1043-1140): the damped full step, the same step size for x, lambda and z.  1: acceptable to the
+       * original test with alpha_test = 0, 2: reduces the primal-dual system error by 1 - 1e-4, 0: rejected. */
+#define TRY_SOFT(result)                                                                                               \
+  do {                                                                                                                \
+    double a_du_max = frac_to_bound_dual(s, s->dzL, s->dzU, s->tau);                                                  \
+    double a_s = alpha_max < a_du_max ? alpha_max : a_du_max;                                                         \
+    for (int j = 0; j < n; ++j) s->xt[j] = s->x[j] + a_s * s->dx[j];                                                  \
+    eval_point(s, s->xt, &s->ft, s->ct);                                                                              \
+    (result) = 0;                                                                                                     \
+    if (check_accept(s, &R, 0.0, vasum(s->ct, m), barrier_obj(s, s->xt, s->ft))) (result) = 1;                        \
+    else {                                                                                                            \
+      for (int i = 0; i < m; ++i) sdl[i] = s->lam[i] + a_s * s->dlam[i];                                              \
+      for (int k = 0; k < nb; ++k) { sdzL[k] = s->zL[k] + a_s * s->dzL[k]; sdzU[k] = s->zU[k] + a_s * s->dzU[k]; }    \
+      if (pd_system_error(s, s->xt, sdl, sdzL, sdzU) <= (1.0 - 1e-4) * pd_system_error(s, s->x, s->lam, s->zL, s->zU)) \
+        (result) = 2;                                                                                                 \
+    }                                                                                                                 \
+    if (result) {                                                                                                     \
+      soft_step = 1;                                                                                                  \
+      /* 'S': Ipopt repeats the dual step with the primal step size its line-search variable holds (the last failed   \
+         trial, or 0 inside the soft phase) for lambda and the full step for z (:595-603); 's': the soft step size */ \
+      soft_a_lam = (result) == 1 ? alpha : a_s; soft_a_z = (result) == 1 ? a_du_max : a_s;                            \
+      alpha = a_s; adl = s->dlam; adzL = s->dzL; adzU = s->dzU;                                                       \
+    }                                                                                                                 \
+  } while (0)
       alpha = alpha_max;
       double alpha_test = alpha;
+      if (in_soft_resto) { /* :426-448: only soft steps while in the soft restoration phase, at most 10 in a row */
+        alpha = 0.0;
+        if (++soft_resto_counter <= 10) {
+          int r; TRY_SOFT(r);
+          accept = r != 0;
+          if (r == 1) { in_soft_resto = 0; soft_resto_counter = 0; }
+        }
+      } else
       while (alpha > alpha_min || n_steps == 0) {
         for (int j = 0; j < n; ++j) s->xt[j] = s->x[j] + alpha * s->dx[j];
         eval_point(s, s->xt, &s->ft, s->ct);
@@ -860,22 +921,30 @@ int oracle_mpc_solve(const oracle_params* p, const double* state6, const double*
         }
         alpha *= 0.5; ++n_steps;
       }
-      if (accept) { /* UpdateForNextIteration :800-813 */
+      if (accept && !soft_step) { /* UpdateForNextIteration :800-813 */
         double tbarr = barrier_obj(s, s->xt, s->ft);
         if (!is_ftype(&R, alpha_test) || !armijo(&R, alpha_test, tbarr))
           filter_add(s, R.ref_barr - 1e-8 * R.ref_theta, (1.0 - 1e-5) * R.ref_theta);
       }
+      if (!accept && !in_soft_resto) { /* :498-530: start the soft restoration phase; the current point enters the filter */
+        filter_add(s, R.ref_barr - 1e-8 * R.ref_theta, (1.0 - 1e-5) * R.ref_theta);
+        int r; TRY_SOFT(r);
+        accept = r != 0;
+        if (r == 2) in_soft_resto = 1;
+      }
+#undef TRY_SOFT
       info_ls = n_steps + 1;
     }
-    if (!accept) { status = -2; break; } /* would enter the restoration phase */
+    if (!accept) { status = -2; break; } /* would enter the restoration phase proper (not restated) */
 
     /* ---- dual step (PerformDualStep :852-941) ---- */
-    double alpha_du = frac_to_bound_dual(s, adzL, adzU, s->tau);
+    double alpha_du = soft_step ? soft_a_z : frac_to_bound_dual(s, adzL, adzU, s->tau);
+    const double alpha_lam = soft_step ? soft_a_lam : alpha;
     for (int k = 0; k < nb; ++k) { s->zL[k] += alpha_du * adzL[k]; s->zU[k] += alpha_du * adzU[k]; }
-    for (int i = 0; i < m; ++i) s->lam[i] += alpha * adl[i];
+    for (int i = 0; i < m; ++i) s->lam[i] += alpha_lam * adl[i];
     info_alpha_pr = alpha; info_alpha_du = alpha_du;
     /* ---- accept; kappa_sigma safeguard (IpIpoptAlg.cpp:623-681, 880-951) ---- */
-    memcpy(s->x, s->xt, sizeof(double) * (size_t)n);
+    for (int j = 0; j < n; ++j) s->x[j] = s->xt[j];
     for (int k = 0; k < nb; ++k) {
       double sl = slackL(s, s->x, k), su = slackU(s, s->x, k), hi, lo;
       hi = 1e10 * s->mu / sl; lo = s->mu / (1e10 * sl);

@@ -107,3 +107,15 @@ def test_port_derivatives_match_reference_tnlp():
     b = ob.ref_eval(x, lam, c, sigma=0.7)
     for u, v in zip(a, b):
         np.testing.assert_allclose(u, v, rtol=0, atol=1e-12)
+
+
+def test_port_soft_restoration_phase_matches_reference():
+    """Problems on which the reference's Ipopt takes soft-restoration steps (tests/golden/soft_N50_3.npz): the port
+    restates that phase (IpBacktrackingLineSearch.cpp:426-448, 498-530, 595-603, 1043-1140) and reproduces the
+    reference's iteration counts and solutions."""
+    g = golden("soft_N50_3.npz")
+    for b in range(3):
+        o = ob.port_solve(g["states"][b], g["coeffs"][b], params=ob.default_params(N=50))
+        assert o["status"] == 0 and o["iters"] == g["iters"][b]
+        np.testing.assert_allclose(o["x"], g["x"][b], rtol=0, atol=1e-10)
+        assert abs(o["obj"] - g["obj"][b]) <= 1e-12 * abs(g["obj"][b])
