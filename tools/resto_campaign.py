@@ -39,6 +39,18 @@ def host_work(a):
     return np.concatenate([[h["status"], h["iters"], h["obj"]], h["out8"]])
 
 
+def line_problems_wild(n, seed=0):
+    """Degree-1 reference y = -1 (the reference's own mpc_to_line setting) from far-off states: x +-50 m, lateral offset
+    +-40 m, heading +-2 rad, speed 0.5..70 m/s."""
+    u = synth.MT19937_64(881 + seed).uniform(4 * n).reshape(n, 4)
+    x = -50.0 + 100.0 * u[:, 0]
+    y = -1.0 - 40.0 + 80.0 * u[:, 1]
+    psi = -2.0 + 4.0 * u[:, 2]
+    v = 0.5 + 69.5 * u[:, 3]
+    st = np.ascontiguousarray(np.stack([x, y, psi, v, -1.0 - y, psi], axis=1))
+    return st, np.tile(np.array([-1.0, 0.0]), (n, 1))
+
+
 def problems(n, seed=0, wild=False):
     xs, ys = synth.roadmap_windows(n, synth.MT19937_64(878 + seed))
     V = np.stack([xs ** i for i in range(4)], axis=2)
@@ -64,6 +76,9 @@ if __name__ == "__main__":
     wild = 2 if "--wilder" in sys.argv else int("--wild" in sys.argv)
     S, C = problems(n, wild=wild)
     cache = f"/tmp/resto_ref_N{N}_{n}{['', '_wild', '_wilder'][wild]}.npy"
+    if "--line" in sys.argv:
+        S, C = line_problems_wild(n)
+        cache = f"/tmp/resto_ref_N{N}_{n}_line.npy"
     ctx = mp.get_context("fork")
     if os.path.exists(cache):
         ref = np.load(cache)
