@@ -131,7 +131,7 @@ enum ScalarD {
   dLOBJ, dSOFTA, kNumD
 };
 enum ScalarI { iPHASE = kNumD, iFLAGS, iCUR, iITER, iSTATUS, iNSTEPS, iSOCCNT, iACCCNT, iNF, iSOFTCNT, kNumScal };
-static_assert(kNumScal <= kRec, "scalar record must fit one stage record");
+static_assert((int)kNumScal <= (int)kRec, "scalar record must fit one stage record");
 
 static_assert(2 * kMaxFilter <= kRec, "the filter must fit one record");
 MPC_HD int workspace_doubles_per_problem(int N) { return kRec * (N + 2); }
