@@ -384,6 +384,7 @@ typedef struct {
   double dx_curr, dx_last, dc_curr;
   /* filter */
   double fphi[MAXF], fth[MAXF]; int nf;
+  int last_rej_filter, count_rej_filter; /* filter reset heuristic (IpFilterLSAcceptor.cpp:357-379) */
   double theta_max, theta_min;
   int regu_tries;
 } ip_t;
@@ -655,8 +656,15 @@ static int check_accept(ip_t* s, const ls_ref* r, double alpha_test, double tria
       accept = cmp_le(trial_theta, (1.0 - 1e-5) * r->ref_theta, r->ref_theta) ||
                cmp_le(trial_barr - r->ref_barr, -1e-8 * r->ref_theta, r->ref_barr);
   }
-  if (!accept) return 0;
-  return filter_ok(s, trial_barr, trial_theta);
+  if (!accept) { s->last_rej_filter = 0; return 0; }
+  if (!filter_ok(s, trial_barr, trial_theta)) { s->last_rej_filter = 1; return 0; }
+  /* filter reset heuristic :357-379 (filter_reset_trigger = 5; Ipopt 3.12.7 never counts the resets, so
+   * max_filter_resets = 5 is not reached) */
+  if (s->last_rej_filter) {
+    if (++s->count_rej_filter >= 5) { s->nf = 0; s->count_rej_filter = 0; }
+  } else s->count_rej_filter = 0;
+  s->last_rej_filter = 0;
+  return 1;
 }
 
 /* Primal-dual system error for the barrier parameter mu at (x, lam, zL, zU): 1-norms of grad_x L, c and the relaxed
@@ -811,7 +819,7 @@ int oracle_mpc_solve(const oracle_params* p, const double* state6, const double*
           cm = compl_err(s, s->mu) / sc; if (cm > Emu) Emu = cm;
           done = Emu > 10.0 * s->mu;
         }
-        if (done && changed) s->nf = 0; /* linesearch_->Reset(): filter cleared */
+        if (done && changed) { s->nf = 0; s->last_rej_filter = 0; s->count_rej_filter = 0; } /* linesearch_->Reset(): filter cleared */
         tiny = 0;
       }
       (void)mu_initialized; mu_initialized = 1;

@@ -114,7 +114,7 @@ def main():
     print("golden fixtures written to", HERE)
 
 
-if __name__ == "__main__" and not {"--config3", "--n100", "--resto", "--soft", "--long-filter"} & set(sys.argv):
+if __name__ == "__main__" and not {"--config3", "--n100", "--resto", "--soft", "--long-filter", "--rare-paths"} & set(sys.argv):
     main()
 
 
@@ -226,6 +226,10 @@ def long_filter():
     tools/resto_campaign.py that the reference solves without its restoration phase."""
     from udacitympc_b200 import synth
     n, N, sel = 32768, 25, [82, 505, 1535, 1543, 1606, 1612, 1870, 2957, 3534, 3666, 4014, 4418]
+    if "--rare-paths" in sys.argv:
+        # filter reset heuristic (IpFilterLSAcceptor.cpp:357-379) active: the first ten; a soft restoration step right
+        # after a failed second-order correction: #15085
+        sel = [5000, 8393, 11169, 14810, 17473, 19085, 22428, 31634, 31855, 32637, 15085]
     xs, ys = synth.roadmap_windows(n, synth.MT19937_64(878))
     V = np.stack([xs ** i for i in range(4)], axis=2)
     fit = np.stack([np.linalg.lstsq(V[b], ys[b], rcond=None)[0] for b in range(n)])
@@ -236,10 +240,11 @@ def long_filter():
     st = np.ascontiguousarray(np.stack([np.zeros(n), y, psi, v, fit[:, 0] - y, psi - np.arctan(fit[:, 1])], axis=1))
     res = [_solve_resto((st[b], fit[b], N)) for b in sel]
     assert all(r[2] == 0 and r[4] == 0 for r in res)
-    np.savez_compressed(os.path.join(HERE, "long_filter_N25_12.npz"), index=np.array(sel, dtype=np.int32), states=st[sel],
+    np.savez_compressed(os.path.join(HERE, "rare_paths_N25_11.npz" if "--rare-paths" in sys.argv else "long_filter_N25_12.npz"),
+                        index=np.array(sel, dtype=np.int32), states=st[sel],
                         coeffs=fit[sel], out8=np.array([r[0] for r in res]), obj=np.array([r[1] for r in res]),
                         iters=np.array([r[3] for r in res], dtype=np.int32), x=np.array([r[5] for r in res]))
 
 
-if __name__ == "__main__" and "--long-filter" in sys.argv:
+if __name__ == "__main__" and ("--long-filter" in sys.argv or "--rare-paths" in sys.argv):
     long_filter()

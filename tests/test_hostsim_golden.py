@@ -291,3 +291,20 @@ def test_device_memory_layout_with_the_cooperative_finisher(hostsim):
     r = hostsim.batch_interleaved(st, cf, compact=True, max_rounds=14, coop=True)
     assert r["rc"] == 0 and (r["status"] == 0).all()
     np.testing.assert_allclose(r["out8"], ref_x, rtol=0, atol=1e-6)
+
+
+def test_filter_reset_heuristic_and_soft_step_after_a_failed_soc(hostsim):
+    """Ipopt resets the filter when in 5 successive iterations the last rejected trial point was rejected by the filter
+    (IpFilterLSAcceptor.cpp:357-379); ten extreme-state problems where that happens, and one where the line search fails
+    right after a failed second-order correction and a soft restoration step follows (the Newton direction is restored
+    first).  Same iteration counts and solutions as the reference binaries, on the thread and cooperative paths and in
+    the C port (which restates both as well)."""
+    import oracle_bindings as ob
+    g = golden("rare_paths_N25_11.npz")
+    for b in range(11):
+        for mode in (0, -2, 2):
+            r = hostsim.solve(g["states"][b], g["coeffs"][b], mode=mode)
+            assert r["status"] == 0 and r["iters"] == g["iters"][b], (b, mode, r["iters"], g["iters"][b])
+            np.testing.assert_allclose(r["x"], g["x"][b], rtol=0, atol=1e-7)
+        o = ob.port_solve(g["states"][b], g["coeffs"][b])
+        assert o["status"] == 0 and o["iters"] == g["iters"][b]

@@ -130,7 +130,7 @@ enum ScalarD {
   dDLMAX, dRTH, dRBARR, dRGBD, dALPHA, dAMAX, dAMIN, dADU, dATEST, dTRF, dTRTH, dTRPINF, dTRSLOG, dTHSOC, dASOC, dCOBJ,
   dLOBJ, dSOFTA, kNumD
 };
-enum ScalarI { iPHASE = kNumD, iFLAGS, iCUR, iITER, iSTATUS, iNSTEPS, iSOCCNT, iACCCNT, iNF, iSOFTCNT, kNumScal };
+enum ScalarI { iPHASE = kNumD, iFLAGS, iCUR, iITER, iSTATUS, iNSTEPS, iSOCCNT, iACCCNT, iNF, iSOFTCNT, iFRCNT, kNumScal };
 static_assert((int)kNumScal <= (int)kRec, "scalar record must fit one stage record");
 
 static_assert(2 * kMaxFilter <= kRec, "the filter must fit one record");
@@ -286,7 +286,8 @@ struct Result {
 enum Phase { PH_FACTOR = 0, PH_FORWARD = 1, PH_STEP = 2, PH_DONE = 3, PH_RESTO = 4 };
 // F_SOFT / F_SOFTTRY / F_HARD: soft restoration phase (Params::resto == 2), see Solver::resto_entry
 enum Flags { F_INSOC = 1, F_SOCDONE = 2, F_LS = 4, F_LSKEEP = 8, F_TINYLAST = 16, F_TINYFLAG = 32, F_TINYNOW = 64, F_RESTO = 128,
-             F_SOFT = 256, F_SOFTTRY = 512, F_HARD = 1024, F_FILTDONE = 2048, F_SOFTFIX = 4096 };
+             F_SOFT = 256, F_SOFTTRY = 512, F_HARD = 1024, F_FILTDONE = 2048, F_SOFTFIX = 4096,
+             F_LASTREJF = 8192 /* the last rejected trial point was rejected by the filter */ };
 
 // ---- batch compaction ----------------------------------------------------------------------------------------
 // Moves one unfinished problem from workspace slot `s` to slot `d` (another workspace region) between two passes.
@@ -344,7 +345,7 @@ struct Solver {
   double tr_f, tr_theta, tr_priminf, tr_sumlog;   // at the last evaluated trial point
   double theta_soc_old, alpha_soc;
   double curr_obj, last_obj, soft_alpha;
-  int phase, flags, cur, iter, status, n_steps, soc_count, acceptable_counter, nf, soft_count;
+  int phase, flags, cur, iter, status, n_steps, soc_count, acceptable_counter, nf, soft_count, filt_rej_count;
   // transient (within a pass)
   double fw_alpha_pr, fw_alpha_du, fw_gbd;
   bool fw_tiny;
@@ -376,7 +377,7 @@ struct Solver {
   X(dTHSOC, theta_soc_old) X(dASOC, alpha_soc) X(dCOBJ, curr_obj) X(dLOBJ, last_obj) X(dSOFTA, soft_alpha)
 #define MPC_SCALARS_I(X)                                                                                                \
   X(iPHASE, phase) X(iFLAGS, flags) X(iCUR, cur) X(iITER, iter) X(iSTATUS, status) X(iNSTEPS, n_steps)                   \
-  X(iSOCCNT, soc_count) X(iACCCNT, acceptable_counter) X(iNF, nf) X(iSOFTCNT, soft_count)
+  X(iSOCCNT, soc_count) X(iACCCNT, acceptable_counter) X(iNF, nf) X(iSOFTCNT, soft_count) X(iFRCNT, filt_rej_count)
   MPC_HD void load_state() {
 #define X(idx, name) name = w(idx);
     MPC_SCALARS(X)
@@ -474,7 +475,7 @@ struct Solver {
     ref_theta = ref_barr = ref_gbd = 0.0;
     theta_soc_old = alpha_soc = 0.0;
     n_steps = soc_count = 0;
-    soft_count = 0; soft_alpha = 0.0;
+    soft_count = 0; soft_alpha = 0.0; filt_rej_count = 0;
     dualinf = lam1 = z1 = sz_max = sz_min = xmaxabs = 0.0;
     tr_f = tr_theta = tr_priminf = tr_sumlog = 0.0;
   }
@@ -1188,8 +1189,15 @@ struct Solver {
       if (acc)
         acc = cmp_le(trial_theta, (1.0 - 1e-5) * ref_theta, ref_theta) || cmp_le(trial_barr - ref_barr, -1e-8 * ref_theta, ref_barr);
     }
-    if (!acc) return false;
-    return filter_ok(trial_barr, trial_theta);
+    if (!acc) { setfl(F_LASTREJF, false); return false; }
+    if (!filter_ok(trial_barr, trial_theta)) { setfl(F_LASTREJF, true); return false; }
+    // filter reset heuristic (IpFilterLSAcceptor.cpp:357-379; max_filter_resets = 5 is never reached: Ipopt 3.12.7 does
+    // not count the resets): 5 successive iterations whose last rejected trial point was rejected by the filter
+    if (fl(F_LASTREJF)) {
+      if (++filt_rej_count >= 5) { nf = 0; filt_rej_count = 0; }
+    } else filt_rej_count = 0;
+    setfl(F_LASTREJF, false);
+    return true;
   }
 
   // ------------------------------------------------------------------------------------------
@@ -1224,7 +1232,7 @@ struct Solver {
         Emu = dmax(dualinf / sd, dmax(priminf, dmax(sz_max - mu, mu - sz_min) / sc));
         done = Emu > 10.0 * mu;
       }
-      if (done && changed) nf = 0;
+      if (done && changed) { nf = 0; filt_rej_count = 0; setfl(F_LASTREJF, false); }   // FilterLSAcceptor::Reset
       tiny = false;
     }
     return true;
@@ -1256,6 +1264,7 @@ struct Solver {
       alpha = fw_alpha_pr;   // alpha_primal_soc
     } else if (fl(F_SOCDONE)) {
       // direction restored after a failed SOC: resume backtracking with the alpha set in step_logic
+      if (!(alpha > alpha_min)) phase = PH_RESTO;   // line search failed (only reached with Params::resto != 0)
     } else {
       ref_theta = theta_cur;
       ref_barr = f_cur - mu * sumlog;
@@ -1346,8 +1355,10 @@ struct Solver {
           } else {   // give up: restore the Newton direction, continue backtracking
             setfl(F_INSOC, false); setfl(F_SOCDONE, true);
             alpha = 0.5 * alpha_max; n_steps = 1;
-            if (alpha > alpha_min) phase = PH_FACTOR;
-            else { setfl(F_HARD, true); line_search_failed(); }   // DS / DU hold the corrected direction: no soft step
+            // DS / DU hold the corrected direction: the Newton direction is recomputed first, also when the halved step
+            // is already below alpha_min (the soft restoration step that follows the failure needs it; forward_logic)
+            if (alpha > alpha_min || P.resto) phase = PH_FACTOR;
+            else line_search_failed();
           }
         } else if (!fl(F_SOCDONE) && alpha == alpha_max && ref_theta <= tr_theta) {   // start SOC (IpFilterLSAcceptor.cpp:473-587)
           setfl(F_INSOC, true); soc_count = 0;
@@ -1568,13 +1579,13 @@ struct Solver {
     LDD(dATEST, alpha_test); LDD(dAMAX, alpha_max); LDD(dAMIN, alpha_min); LDD(dTHSOC, theta_soc_old); LDD(dASOC, alpha_soc);
     LDD(dTAU, tau); LDD(dMUMIN, mu_min); LDD(dCOBJ, curr_obj); LDD(dLOBJ, last_obj); LDD(dDWL, dw_last);
     LDD(dF, f_cur); LDD(dTH, theta_cur); LDD(dPINF, priminf); LDD(dSLOG, sumlog);
-    LDI(iSOCCNT, soc_count); LDI(iNSTEPS, n_steps); LDI(iNF, nf); LDI(iSTATUS, status); LDI(iACCCNT, acceptable_counter);
+    LDI(iSOCCNT, soc_count); LDI(iNSTEPS, n_steps); LDI(iNF, nf); LDI(iFRCNT, filt_rej_count); LDI(iSTATUS, status); LDI(iACCCNT, acceptable_counter);
     LDI(iITER, iter);
     step_logic<false>();
     STD_(dTHMAX, theta_max); STD_(dTHMIN, theta_min); STD_(dATEST, alpha_test); STD_(dALPHA, alpha); STD_(dTHSOC, theta_soc_old);
     STD_(dASOC, alpha_soc); STD_(dF, f_cur); STD_(dTH, theta_cur); STD_(dPINF, priminf); STD_(dSLOG, sumlog); STD_(dMU, mu);
     STD_(dTAU, tau); STD_(dCOBJ, curr_obj); STD_(dLOBJ, last_obj); STD_(dDWC, dw_curr); STD_(dDWL, dw_last);
-    STI(iSOCCNT, soc_count); STI(iNSTEPS, n_steps); STI(iNF, nf); STI(iACCCNT, acceptable_counter); STI(iITER, iter);
+    STI(iSOCCNT, soc_count); STI(iNSTEPS, n_steps); STI(iNF, nf); STI(iFRCNT, filt_rej_count); STI(iACCCNT, acceptable_counter); STI(iITER, iter);
     STI(iCUR, cur); STI(iFLAGS, flags); STI(iSTATUS, status); STI(iPHASE, phase);
   }
 #undef LDD
