@@ -3,15 +3,21 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--workload roadmap|line]
 
-A "step" is one pass of the hot path over one batch of synthetic input: B independent MPC::Solve problems
-(N=25 horizon) solved by one launch of the fused interior-point kernel.  Default workload = BASELINE.json
-configs[3]: 65 536 problems with a degree-3 reference fitted (on the GPU, K4) to roadmap.csv segments.
-Under torchrun (N>1) every rank drives its own GPU with its own 65 536 problems (weak scaling, no data-path
-collective); torch.distributed (NCCL) is used only for the barrier and the max-over-ranks of the device time.
+A "step" is one pass of the hot path over one batch of synthetic input: B = 65 536 independent MPC::Solve problems
+(N=25 horizon).  Default workload = BASELINE.json configs[3]: a degree-3 reference fitted (on the GPU, K4) to
+roadmap.csv segments, ONE batch per step sharded by problem index over the GPUs ("scaling": "strong"; rank r of N
+solves problems [r*B/N, (r+1)*B/N), udacitympc_b200/sharding.py).  There is no data-path collective;
+torch.distributed (NCCL) is used only for the barrier and the max-over-ranks of the device time.  --scaling weak
+gives every GPU its own B problems per step instead.
 
-value    whole-job solves/s with inputs already resident in HBM (device-pointer C-ABI call, CUDA events)
-e2e      the same through the host-buffer C-ABI call the reference's MPC::Solve would bind: pinned host buffers,
-         H2D + D2H inside the timed region
+value        whole-job solves/s with inputs already resident in HBM (device-pointer C-ABI call, CUDA events; the timed
+             region repeats the K-step sequence until it lasts --min-seconds)
+e2e          the same through the host-buffer C-ABI call the reference's MPC::Solve would bind: pinned host buffers,
+             H2D + D2H inside the timed region
+lone_caller  one handle, one stream, one call at a time (the figures above overlap consecutive steps on several handles)
+one_process_multi_gpu (N > 1)  b200mpc_solve_batch_multi on the whole batch from rank 0: one host thread per GPU, host
+             gather, per-call latency percentiles
+weak_scaling (N > 1)  the weak-scaling figure next to the strong one
 """
 import argparse
 import json
@@ -60,6 +66,22 @@ def profiled_traffic_bytes():
         return float(sum(b for k, b in seq[starts[0]:starts[1]] if "mpc_" in k))
     except Exception:
         return None
+
+
+def profiled_counters():
+    """Per-step counters that come from committed ncu captures of this same command (one GPU, 65 536 problems per step):
+    profiles/r2_counters.json (written by tools/ncu_counters.py from the launch list) when present, else the round-1
+    launch list (DRAM bytes only)."""
+    path = os.path.join(ROOT, "profiles", "r2_counters.json")
+    try:
+        d = json.load(open(path))
+        if d.get("dram_bytes_per_step"):
+            return d
+    except Exception:
+        pass
+    t = profiled_traffic_bytes()
+    return dict(dram_bytes_per_step=t,
+                traffic_unit="bytes of DRAM read+write of all solver kernels of one 65 536-problem step (ncu, profiles/r1_compact_launches_time_dram.csv)")
 
 
 def make_workload(kind, B, seed_shift=0, mpc=None):
@@ -112,51 +134,61 @@ def cpu_reference_rate(states, coeffs, per_core, cores=None):
     solved = sum(len(c[1]) for c in chunks)
     busy = max(r[0] for r in res)
     iters = sum(r[1] for r in res)
-    return dict(value=solved / busy, unit=UNIT, cores=len(chunks), kind=kind,
-                sample=f"first {solved} problems of the workload, {per} per process, one process per host core "
+    return dict(value=solved / busy, unit=UNIT, cores=len(chunks), kind=kind, solved=solved,
+                sample=f"first {solved} problems of the workload, {per} per process ({busy:.2f} s of CPU work on the slowest), one process per host core "
                        f"(Ipopt 3.12.7 + MUMPS 4.10.0 reference binaries, hand-derived derivatives standing in for CppAD)"
                 if kind == "reference" else f"first {solved} problems, C port of the reference algorithm",
                 wall_s=wall, mean_iters=iters / max(1, solved))
 
 
 def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref = its Ipopt 3.12.7 + MUMPS
+    binaries; the C port when they are absent) on every host core, on a bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    states, coeffs = make_workload(args.workload, min(args.batch, 4096))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_bindings as ob
+    ob.ref_available() and ob.ref()   # dlopen oracle/_ref/libmpc_ref.so in THIS process too (the solves run in forked workers)
+    states, coeffs = make_workload(args.workload, min(args.batch, 8192))
     cores = os.cpu_count() or 1
-    per_core = 100   # solves per host core per step: ~0.6 s of CPU work per step, pool start-up amortised
+    per_core = args.ref_per_core   # solves per host core per step: >= 1 s of CPU work per core and step
     times = []
     rate = None
     for i in range(args.warmup + args.steps):
         r = cpu_reference_rate(states, coeffs, per_core, cores)
         if i >= args.warmup:
-            times.append(per_core * r["cores"] / r["value"])
+            times.append(r["solved"] / r["value"])
             rate = r
-    solved_per_step = per_core * rate["cores"]
+    solved_per_step = rate["solved"]
     ms = 1e3 * float(np.mean(times))
     value = solved_per_step / (ms * 1e-3)
     line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                data="synthetic", config=config_dict(args, args.batch),
+                warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f64",
+                data="synthetic", config=config_dict(args),
+                solved_per_step=solved_per_step,
+                note=f"each step of this arm solves a bounded sample of the workload ({solved_per_step} problems = {per_core} per host "
+                     f"core), not all {args.batch}; value = solved problems per second of wall time of the slowest worker",
                 cpu_baseline=dict(value=value, unit=UNIT, cores=rate["cores"], kind=rate["kind"], sample=rate["sample"]),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     emit(line)
 
 
-def config_dict(args, batch):
-    return dict(workload=("BASELINE configs[3]: batched MPC, degree-3 reference fitted to roadmap.csv segments"
-                          if args.workload == "roadmap" else "BASELINE configs[2]: batched mpc_to_line, degree-1 reference y=-1"),
-                horizon_N=HORIZON, dt=0.05, batch_per_gpu=batch, problems_per_step=batch * args.gpus,
-                sharding="contiguous index ranges per GPU, no collective",
-                l2="per-step working set (solver workspace region, 17.9 KB/problem = 1.18 GB at 65 536) >> 126 MB L2; "
-                   "inputs cycle over 4 distinct batches, the same on every rank")
+def config_dict(args):
+    """The workload both arms are measured on (identical in the two JSON lines)."""
+    return dict(workload=("BASELINE configs[3]: batched MPC, 65 536 problems per step, degree-3 reference fitted to roadmap.csv segments, "
+                          "one batch sharded by index over the GPUs" if args.workload == "roadmap" else
+                          "BASELINE configs[2]: batched mpc_to_line, degree-1 reference y=-1"),
+                horizon_N=HORIZON, dt=0.05, problems_per_step=args.batch,
+                sharding="contiguous index ranges per GPU (rank r solves [r*B/N, (r+1)*B/N)), no collective, results gathered by the host",
+                l2="per-step working set (solver workspace, 17.9 KB per problem in flight) >> 126 MB L2; the inputs cycle over "
+                   "4 distinct 65 536-problem batches")
 
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, index):
         self.rows = []
@@ -188,20 +220,35 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                busy = float(r[7]) > 50.0 if len(r) > 7 else True
+                if busy:   # median under load: idle samples (workload generation, CPU legs) would only dilute it
+                    sm.append(float(r[0]))
+                mx.append(float(r[1]))
                 for nme, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nme)
             except Exception:
                 pass
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=float(max(mx)) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(self.rows), samples_under_load=len(sm))
+
+
+def auto_streams(per_gpu_batch):
+    """Solver handles / streams whose consecutive steps overlap: 6 at 65 536 problems per GPU and step, more for the
+    smaller per-GPU shards of a strong-scaled batch (about 6 x 65 536 problems in flight per GPU), at most 16."""
+    return int(min(16, max(6, round(6 * 65536 / max(1, per_gpu_batch)))))
 
 
 def run_ours(args):
+    import ctypes
+    import math
+    from concurrent.futures import ThreadPoolExecutor
+
     import torch
     import torch.distributed as dist
     import udacitympc_b200 as mpcmod
+    from udacitympc_b200 import api as mpcapi
+    from udacitympc_b200.sharding import max_over_ranks, shard_range, throughput
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
@@ -215,8 +262,14 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B, K, W = args.batch, args.steps, args.warmup
+    strong = args.scaling == "strong"
+    # strong (default, BASELINE configs[3]): ONE B-problem batch per step, rank r solves its index range of it;
+    # weak: every rank solves all B problems of its own copy
+    lo, hi = shard_range(B, world, rank) if strong else (0, B)
+    Bl = hi - lo
+    total_per_step = B if strong else B * world
 
-    S = max(1, args.streams)
+    S = args.streams if args.streams > 0 else auto_streams(Bl)
     # concurrency comes either from the caller (S overlapped handles, no internal split) or from the library's
     # internal batch split (one handle)
     split = args.split if args.split > 0 else (1 if S > 1 else 4)
@@ -225,29 +278,29 @@ def run_ours(args):
         m.set_solver_mode({"perpass": 0, "fused": 1}[args.mode], args.rounds, -1)
         m.set_batch_split(split)
     mpc = mpcs[0]
-    # Four distinct 65 536-problem input sets, cycled step by step.  Every rank solves the SAME four sets (weak
-    # scaling with identical per-GPU work by construction); about half of such sets contain a 30-50 iteration
-    # straggler, so cycling several makes the single-GPU figure representative of the workload.
+    # Four distinct B-problem input sets, cycled step by step (every rank generates the same sets and keeps its index
+    # range); about half of such sets contain a 30-50 iteration straggler, so cycling several makes the
+    # figure representative of the workload.
     nsets = args.input_sets
     sets = [make_workload(args.workload, B, seed_shift=s, mpc=mpc) for s in range(nsets)]
     ncoef = sets[0][1].shape[1]
-    # device-resident, field-major inputs and outputs (one output set per stream)
-    d_in = [(torch.from_numpy(np.ascontiguousarray(st.T)).to(dev), torch.from_numpy(np.ascontiguousarray(cf.T)).to(dev))
-            for st, cf in sets]
-    d_out = [dict(out8=torch.empty((8, B), dtype=torch.float64, device=dev), obj=torch.empty(B, dtype=torch.float64, device=dev),
-                  status=torch.empty(B, dtype=torch.int32, device=dev), iters=torch.empty(B, dtype=torch.int32, device=dev))
-             for _ in range(S)]
+
+    def device_inputs(a, b):   # field-major device copies of problems [a, b) of every set
+        return [(torch.from_numpy(np.ascontiguousarray(st[a:b].T)).to(dev), torch.from_numpy(np.ascontiguousarray(cf[a:b].T)).to(dev))
+                for st, cf in sets]
+
+    def device_outputs(n, count):
+        return [dict(out8=torch.empty((8, n), dtype=torch.float64, device=dev), obj=torch.empty(n, dtype=torch.float64, device=dev),
+                     status=torch.empty(n, dtype=torch.int32, device=dev), iters=torch.empty(n, dtype=torch.int32, device=dev))
+                for _ in range(count)]
+
+    d_in = device_inputs(lo, hi)
+    d_out = device_outputs(Bl, S)
     # real (non-default) streams: kernels and timing events share them.  With S > 1 consecutive steps alternate
     # between S solver handles / streams so that the thin tail of one batch (few problems still iterating)
     # overlaps the bulk of the next.
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     torch.cuda.synchronize()
-
-    def dev_step(i):
-        st, cf = d_in[i % nsets]
-        o = d_out[i % S]
-        mpcs[i % S].solve_batch_device(B, st.data_ptr(), cf.data_ptr(), ncoef, o["out8"].data_ptr(), 0, o["obj"].data_ptr(),
-                                       o["status"].data_ptr(), o["iters"].data_ptr(), streams[i % S].cuda_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -255,167 +308,250 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_device_region(handles, strs, n, ins, outs, steps):
+        """`steps` solves of n problems, step i on handle / stream i % len(handles); device time in ms (CUDA events on
+        the launching streams: e0 before the first launch, e1 after every stream has drained into stream 0)."""
+        ns = len(handles)
+
+        def one(i):
+            st, cf = ins[i % nsets]
+            o = outs[i % ns]
+            handles[i % ns].solve_batch_device(n, st.data_ptr(), cf.data_ptr(), ncoef, o["out8"].data_ptr(), 0, o["obj"].data_ptr(),
+                                               o["status"].data_ptr(), o["iters"].data_ptr(), strs[i % ns].cuda_stream)
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(strs[0])
+        for s_ in strs[1:]:
+            s_.wait_event(e0)
+        for i in range(steps):
+            one(i)
+        for s_ in strs[1:]:
+            ev = torch.cuda.Event()
+            ev.record(s_)
+            strs[0].wait_event(ev)
+        e1.record(strs[0])
+        return e0, e1
+
+    def agreed(ms):   # the same number on every rank (max), so that every rank runs the same number of steps
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        return max_over_ranks(dist, t, world)
+
     fp64_peak = mpc.fp64_peak_tflops()
     # warm-up: at least W steps, and every (solver handle, input set) pair once -- each pair is its own CUDA graph,
     # captured and instantiated at its first use
-    import math
-    for i in range(max(W, S * nsets // math.gcd(S, nsets))):
-        dev_step(i)
+    wsteps = max(W, S * nsets // math.gcd(S, nsets))
+    e0, e1 = timed_device_region(mpcs, streams, Bl, d_in, d_out, wsteps)
     barrier()
-    for m in mpcs:
-        m.kernel_time_ms(reset=True)
+    # the timed region is R repetitions of the K-step sequence, R chosen so that it lasts >= --min-seconds
+    e0, e1 = timed_device_region(mpcs, streams, Bl, d_in, d_out, K)
+    barrier()
+    est_ms, _ = agreed(e0.elapsed_time(e1))
+    R = max(1, int(math.ceil(args.min_seconds * 1e3 / max(est_ms, 1e-3))))
     launches0 = sum(m.launch_count() for m in mpcs)
     sampler = ClockSampler(local)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(streams[0])
-    for s_ in streams[1:]:
-        s_.wait_event(e0)
-    for i in range(K):
-        dev_step(i)
-    for s_ in streams[1:]:
-        ev = torch.cuda.Event()
-        ev.record(s_)
-        streams[0].wait_event(ev)
-    e1.record(streams[0])
     barrier()
-    ms_total = e0.elapsed_time(e1)
-    kern = [m.kernel_time_ms(reset=True) for m in mpcs]
-    kern_ms, kern_n = sum(k[0] for k in kern), sum(k[1] for k in kern)
+    e0, e1 = timed_device_region(mpcs, streams, Bl, d_in, d_out, K * R)
+    barrier()
+    ms_total, per_rank_total = agreed(e0.elapsed_time(e1))
     launches = sum(m.launch_count() for m in mpcs) - launches0
-    # mean iterations of the two input sets (for the algorithmic FLOP count)
-    iters_mean = []
-    ok_frac = []
+    per_rank_ms = [x / (K * R) for x in per_rank_total]
+    value = throughput(total_per_step, K * R, ms_total)
+
+    # ---- one caller, one call at a time: 1 handle (library defaults: the call is cut into 4 concurrent sub-batches
+    # inside), 1 stream; every solve bracketed by CUDA events inside the C ABI (b200mpc_set_timing)
+    lone = mpcmod.MPC(device=local)
+    lone.set_solver_mode({"perpass": 0, "fused": 1}[args.mode], args.rounds, -1)
+    lone.set_timing(True)
+    lone_out = device_outputs(Bl, 1)
+    n_lone = max(K, 2 * nsets)
+    timed_device_region([lone], streams[:1], Bl, d_in, lone_out, nsets)   # graphs
+    barrier()
+    lone.kernel_time_ms(reset=True)
+    e0, e1 = timed_device_region([lone], streams[:1], Bl, d_in, lone_out, n_lone)
+    barrier()
+    lone_ms, _ = agreed(e0.elapsed_time(e1))
+    lone_kern_ms, lone_kern_n = lone.kernel_time_ms(reset=True)
+    lone_value = throughput(total_per_step, n_lone, lone_ms)
+    # mean iterations / solved fraction of this rank's share of every input set
+    iters_sum, ok_sum = 0.0, 0.0
     for s in range(nsets):
-        st, cf = d_in[s]
-        o = d_out[0]
-        mpc.solve_batch_device(B, st.data_ptr(), cf.data_ptr(), ncoef, o["out8"].data_ptr(), 0, o["obj"].data_ptr(),
-                               o["status"].data_ptr(), o["iters"].data_ptr(), streams[0].cuda_stream)
+        timed_device_region([lone], streams[:1], Bl, d_in[s:] + d_in[:s], lone_out, 1)
         torch.cuda.synchronize()
-        iters_mean.append(float(o["iters"].double().mean().item()))
-        ok_frac.append(float((o["status"] == 0).double().mean().item()))
-    mpc.kernel_time_ms(reset=True)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    per_rank_ms = [ms_total / K]
+        iters_sum += float(lone_out[0]["iters"].double().sum().item())
+        ok_sum += float((lone_out[0]["status"] == 0).double().sum().item())
+    tt = torch.tensor([iters_sum, ok_sum, float(Bl * nsets)], dtype=torch.float64, device=dev)
     if world > 1:
-        allt = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(allt, t)
-        per_rank_ms = [float(x.item()) / K for x in allt]
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = world * B * K / (ms_total * 1e-3)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+    mean_it, solved_fraction = float(tt[0] / tt[2]), float(tt[1] / tt[2])
+    lone.set_timing(False)
 
     # ---- e2e: host buffers (pinned), H2D + D2H inside the timed region, through the host-buffer C-ABI call;
-    # S host threads, one per solver handle (the call blocks until its results are in the caller's buffers)
-    import ctypes
-    from concurrent.futures import ThreadPoolExecutor
-    pin = [(torch.from_numpy(st).pin_memory(), torch.from_numpy(cf).pin_memory()) for st, cf in sets]
-    hout = [dict(out8=torch.empty((B, 8), dtype=torch.float64).pin_memory(), obj=torch.empty(B, dtype=torch.float64).pin_memory(),
-                 status=torch.empty(B, dtype=torch.int32).pin_memory(), iters=torch.empty(B, dtype=torch.int32).pin_memory())
-            for _ in range(S)]
+    # T host threads, one solver handle each (the call blocks until its results are in the caller's buffers)
+    pin = [(torch.from_numpy(np.ascontiguousarray(st[lo:hi])).pin_memory(), torch.from_numpy(np.ascontiguousarray(cf[lo:hi])).pin_memory())
+           for st, cf in sets]
     lib = mpcmod.load_library()
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
 
-    def host_step(i, k=None):
-        k = i % S if k is None else k
+    def host_outputs(n):
+        return dict(out8=torch.empty((n, 8), dtype=torch.float64).pin_memory(), obj=torch.empty(n, dtype=torch.float64).pin_memory(),
+                    status=torch.empty(n, dtype=torch.int32).pin_memory(), iters=torch.empty(n, dtype=torch.int32).pin_memory())
+
+    hout = [host_outputs(Bl) for _ in range(S)]
+
+    def host_step(i, k, handle=None, out=None):
         st, cf = pin[i % nsets]
-        o = hout[k]
-        rc = lib.b200mpc_solve_batch(mpcs[k].handle, B, ctypes.cast(st.data_ptr(), dp), ctypes.cast(cf.data_ptr(), dp), ncoef,
+        o = out or hout[k]
+        rc = lib.b200mpc_solve_batch((handle or mpcs[k]).handle, Bl, ctypes.cast(st.data_ptr(), dp), ctypes.cast(cf.data_ptr(), dp), ncoef,
                                      ctypes.cast(o["out8"].data_ptr(), dp), None, ctypes.cast(o["obj"].data_ptr(), dp),
                                      ctypes.cast(o["status"].data_ptr(), ip), ctypes.cast(o["iters"].data_ptr(), ip))
         if rc:
             raise RuntimeError(lib.b200mpc_last_error().decode())
 
-    # host threads of the end-to-end leg (one solver handle each): up to 6, but not more than the rank's share of the
-    # host cores (never fewer than 3)
-    T = args.e2e_threads if args.e2e_threads > 0 else min(6, max(3, (os.cpu_count() or 6) // world))
+    # host threads of the end-to-end leg (one solver handle each): one per handle, but not more than the rank's share
+    # of the host cores (never fewer than 3)
+    T = args.e2e_threads if args.e2e_threads > 0 else min(S, max(3, (os.cpu_count() or 6) // world))
     T = max(1, min(S, T))
 
     def worker(k, n):
         for i in range(k, n, T):
             host_step(i, k)
 
-    for i in range(max(3, W, T)):   # every handle of the leg allocates its buffers and captures its graph here
+    for i in range(max(3, T)):   # every handle of the leg allocates its staging buffers and captures its graph here
         host_step(i, i % T)
     barrier()
+    n_e2e = K * R
     with ThreadPoolExecutor(T) as ex:
         t0 = time.perf_counter()
-        list(ex.map(lambda k: worker(k, K), range(T)))
+        list(ex.map(lambda k: worker(k, n_e2e), range(T)))
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
-    # unloaded latency of one host-buffer call at a time, on a handle with the library's default settings (a lone
-    # call is cut into concurrent sub-batches by the library itself)
+    e2e_max_s, _ = agreed(e2e_s)
+    e2e_value = total_per_step * n_e2e / e2e_max_s
+    # unloaded latency of one host-buffer call at a time (the lone handle: library defaults)
     lat = []
-    with mpcmod.MPC(device=local) as lone:
-        lone.set_solver_mode({"perpass": 0, "fused": 1}[args.mode], args.rounds, -1)
-        mpcs.append(lone)
-        hout.append(hout[0])
-        for i in range(3):
-            host_step(i, len(mpcs) - 1)
-        for i in range(max(K, args.latency_reps)):
-            a = time.perf_counter()
-            host_step(i, len(mpcs) - 1)
-            lat.append(time.perf_counter() - a)
-        mpcs.pop()
-        hout.pop()
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    p99 = torch.tensor([float(np.percentile(lat, 99))], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(p99, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * K / float(t.item())
-    for m in mpcs:
-        m.kernel_time_ms(reset=True)
+    for i in range(3):
+        host_step(i, 0, lone, hout[0])
+    for i in range(args.latency_reps):
+        a = time.perf_counter()
+        host_step(i, 0, lone, hout[0])
+        lat.append(time.perf_counter() - a)
+    p99, _ = agreed(float(np.percentile(lat, 99)))
+    p50, _ = agreed(float(np.percentile(lat, 50)))
     clocks = sampler.stop()
-    per_rank_mhz = [clocks.get("sm_mhz") or 0.0]
-    if world > 1:
-        c = torch.tensor([clocks.get("sm_mhz") or 0.0], dtype=torch.float64, device=dev)
-        allc = [torch.zeros_like(c) for _ in range(world)]
-        dist.all_gather(allc, c)
-        per_rank_mhz = [float(x.item()) for x in allc]
+    cmhz, per_rank_mhz = agreed(clocks.get("sm_mhz") or 0.0)
+
+    # ---- one process, one host thread per GPU, host gather: b200mpc_solve_batch_multi on the WHOLE batch (rank 0
+    # only, the other ranks wait; SURVEY 8e "results gathered by the host")
+    multi = None
+    barrier()
+    if world > 1 and rank == 0 and strong and torch.cuda.device_count() >= world and not args.no_multi_leg:
+        hs = [mpcmod.MPC(device=d) for d in range(world)]
+        try:
+            full = [(torch.from_numpy(st).pin_memory(), torch.from_numpy(cf).pin_memory()) for st, cf in sets]
+            fo = host_outputs(B)
+            harr = (ctypes.c_void_p * world)(*[h.handle for h in hs])
+
+            def multi_step(i):
+                st, cf = full[i % nsets]
+                rc = lib.b200mpc_solve_batch_multi(harr, world, B, ctypes.cast(st.data_ptr(), dp), ctypes.cast(cf.data_ptr(), dp), ncoef,
+                                                   ctypes.cast(fo["out8"].data_ptr(), dp), None, ctypes.cast(fo["obj"].data_ptr(), dp),
+                                                   ctypes.cast(fo["status"].data_ptr(), ip), ctypes.cast(fo["iters"].data_ptr(), ip))
+                if rc:
+                    raise RuntimeError(lib.b200mpc_last_error().decode())
+
+            for i in range(nsets + 1):
+                multi_step(i)
+            ml = []
+            for i in range(args.latency_reps):
+                a = time.perf_counter()
+                multi_step(i)
+                ml.append(time.perf_counter() - a)
+            multi = dict(entry="b200mpc_solve_batch_multi", handles=world, problems_per_call=B, calls=len(ml), host_buffers="pinned",
+                         value=B / float(np.mean(ml)), unit=UNIT, p50_batch_latency_ms=1e3 * float(np.percentile(ml, 50)),
+                         p99_batch_latency_ms=1e3 * float(np.percentile(ml, 99)), solved_fraction=float((fo["status"] == 0).double().mean()))
+        finally:
+            for h in hs:
+                h.close()
+    barrier()
+
+    # ---- weak-scaling figure next to the strong one (N > 1): every rank solves a whole B-problem batch per step
+    weak = None
+    if world > 1 and strong and not args.no_weak_leg:
+        Sw = min(S, 6)
+        w_in = device_inputs(0, B)
+        w_out = device_outputs(B, Sw)
+        timed_device_region(mpcs[:Sw], streams[:Sw], B, w_in, w_out, max(3, Sw * nsets // math.gcd(Sw, nsets)))
+        barrier()
+        e0, e1 = timed_device_region(mpcs[:Sw], streams[:Sw], B, w_in, w_out, max(K, 20))
+        barrier()
+        wms, _ = agreed(e0.elapsed_time(e1))
+        weak = dict(value=throughput(B * world, max(K, 20), wms), unit=UNIT, problems_per_gpu_per_step=B, steps=max(K, 20), streams=Sw)
 
     if rank == 0:
-        mean_it = float(np.mean(iters_mean))
-        flop_per_launch = f_iter(HORIZON) * mean_it * B
-        # device time of the solver kernels per step: with one stream, the first-to-last-kernel interval of each
-        # step (CUDA events inside the C ABI); with overlapped streams the intervals overlap, so the per-step share of
-        # the timed region is used instead
-        avg_kernel_ms = kern_ms / max(1, kern_n) if S == 1 else ms_total / K
-        achieved = flop_per_launch / (avg_kernel_ms * 1e-3) / 1e12
+        flop_per_step = f_iter(HORIZON) * mean_it * total_per_step
+        # device time of the solver kernels per step, read both ways: (a) with S overlapped streams the per-step share of
+        # the timed region (the intervals of consecutive steps overlap); (b) one stream, one call at a time: the
+        # first-to-last-kernel interval of each solve (CUDA events inside the C ABI)
+        avg_kernel_ms = ms_total / (K * R)
+        lone_kernel_ms = lone_kern_ms / max(1, lone_kern_n)
+        achieved = flop_per_step / (avg_kernel_ms * 1e-3) / 1e12 / world      # per GPU
+        lone_achieved = f_iter(HORIZON) * mean_it * Bl / (lone_kernel_ms * 1e-3) / 1e12
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        prof = profiled_counters()
+        traffic = prof.get("dram_bytes_per_step")
         line = dict(
-            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K,
-            higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-            config=config_dict(args, B),
-            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=B * (6 + ncoef) * 8, d2h_bytes_per_step=B * (8 + 1) * 8 + 2 * B * 4,
-                     p99_batch_latency_ms=1e3 * float(p99.item()), latency_reps=len(lat)),
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / (K * R),
+            higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f64", data="synthetic",
+            config=config_dict(args),
+            timed=dict(passes=K * R, repeats_of_the_k_step_sequence=R, seconds=ms_total * 1e-3, min_seconds=args.min_seconds,
+                       problems_per_gpu_per_step=Bl, streams=S, batch_split=split,
+                       note="value = problems_per_step x passes / seconds (max over ranks of the CUDA-event time)"),
+            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=total_per_step * (6 + ncoef) * 8,
+                     d2h_bytes_per_step=total_per_step * (8 + 1) * 8 + 2 * total_per_step * 4, passes=n_e2e, seconds=e2e_max_s,
+                     host_threads_per_gpu=T, p50_batch_latency_ms=1e3 * p50, p99_batch_latency_ms=1e3 * p99, latency_reps=len(lat),
+                     latency_note="one host-buffer call at a time on one handle with library defaults, this rank's share of the batch"),
+            lone_caller=dict(value=lone_value, unit=UNIT, handles=1, streams=1, batch_split=4, passes=n_lone,
+                             avg_kernel_ms=lone_kernel_ms, launches_timed=lone_kern_n,
+                             note="device-resident inputs, one solve call at a time on one handle (library defaults)"),
             gpu_launches=int(launches),
-            clocks=clocks, per_rank_ms_per_step=per_rank_ms, per_rank_sm_mhz=per_rank_mhz,
+            clocks=dict(clocks, sm_mhz=cmhz if world > 1 else clocks.get("sm_mhz")), per_rank_ms_per_step=per_rank_ms, per_rank_sm_mhz=per_rank_mhz,
             roofline=dict(bound="fp64", achieved=achieved, peak=fp64_peak, unit="TFLOP/s", frac=achieved / fp64_peak if fp64_peak else None,
-                          traffic=profiled_traffic_bytes(), traffic_unit="bytes of DRAM read+write per step (ncu, profiles/r1_compact_launches_time_dram.csv)",
-                          hbm_achieved_gbs=(profiled_traffic_bytes() or 0.0) / (avg_kernel_ms * 1e-3) / 1e9 if profiled_traffic_bytes() else None,
-                          hbm_frac=((profiled_traffic_bytes() or 0.0) / (avg_kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]
-                                    if profiled_traffic_bytes() and peaks.get("hbm_gbs") else None),
-                          kernel=("mpc_{init,factor,forward,step,coop}_kernel: all solver kernels of one step (one CUDA graph), first to last"
+                          traffic=traffic, traffic_unit=prof.get("traffic_unit"),
+                          hbm_achieved_gbs=traffic / (avg_kernel_ms * 1e-3) / 1e9 * (Bl / 65536.0) if traffic else None,
+                          hbm_frac=(traffic / (avg_kernel_ms * 1e-3) / 1e9 * (Bl / 65536.0) / peaks["hbm_gbs"] if traffic and peaks.get("hbm_gbs") else None),
+                          kernel=("mpc_{init,factor,forward,step,repack,coop}_kernel: all solver kernels of one step (one CUDA graph), first to last"
                                   if args.mode == "perpass" else "mpc_fused_kernel"),
-                          avg_kernel_ms=avg_kernel_ms, launches_timed=kern_n, solver_mode=args.mode, streams=S, batch_split=split, e2e_host_threads=T,
-                          flop_per_launch=flop_per_launch, mean_ip_iters=mean_it,
+                          avg_kernel_ms=avg_kernel_ms, avg_kernel_ms_one_stream=lone_kernel_ms,
+                          frac_one_stream=lone_achieved / fp64_peak if fp64_peak else None,
+                          executed_flop_per_step=prof.get("executed_flop_per_step"),
+                          frac_executed=(prof["executed_flop_per_step"] * (Bl / 65536.0) / (avg_kernel_ms * 1e-3) / 1e12 / fp64_peak
+                                         if prof.get("executed_flop_per_step") and fp64_peak else None),
+                          executed_flop_source=prof.get("executed_flop_source"),
+                          solver_mode=args.mode, streams=S, batch_split=split,
+                          flop_per_step=flop_per_step, mean_ip_iters=mean_it,
                           peak_source="DFMA microbenchmark in this run (b200mpc_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                           hbm_peak_gbs=peaks.get("hbm_gbs"), algorithmic_io_bytes_per_solve=(6 + ncoef + 8 + 2) * 8,
-                          note="SURVEY 8d classifies the solver as FP64 bound (intensity >> ridge, no tensor cores): achieved = F_iter(25)=62204 FLOP x mean "
-                               "iterations x B / step device time over the measured DFMA peak.  The kernels exploit the sparsity of the dynamics "
-                               "(~4x fewer executed FLOP) and in practice sit between the issue and the HBM roof: hbm_frac = measured DRAM "
-                               "traffic of one step (ncu) / step time / measured copy bandwidth"),
-            solved_fraction=float(np.mean(ok_frac)),
+                          note="SURVEY 8d classifies the solver as FP64 bound (intensity >> ridge, no tensor cores): achieved = F_iter(25)=62204 FLOP "
+                               "(dense Riccati count) x mean iterations x problems / step device time, per GPU, over the measured DFMA peak.  The "
+                               "kernels exploit the sparsity of the dynamics (frac_executed = FP64 FLOP actually executed, ncu) and in practice "
+                               "sit between the issue and the HBM roof: hbm_frac = measured DRAM traffic of one step (ncu) / step time / measured "
+                               "copy bandwidth"),
+            solved_fraction=solved_fraction,
         )
+        if multi:
+            line["one_process_multi_gpu"] = multi
+        if weak:
+            line["weak_scaling"] = weak
         if world == 1 and not args.no_cpu_baseline:
             st, cf = sets[0]
-            line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate(st[:4096], cf[:4096], args.cpu_per_core).items()}
+            line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate(st[:8192], cf[:8192], args.cpu_per_core).items()}
         emit(line)
+    lone.close()
     for m in mpcs:
         m.close()
     if world > 1:
@@ -449,15 +585,22 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=65536, help="problems per GPU per step")
+    ap.add_argument("--batch", type=int, default=65536, help="problems per step (the whole batch; sharded over the GPUs when --scaling strong)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default, BASELINE configs[3]): one --batch-problem batch per step sharded by index over the GPUs; "
+                         "weak: every GPU solves its own --batch problems per step")
+    ap.add_argument("--min-seconds", type=float, default=2.0, help="the timed regions repeat the K-step sequence until they last this long")
+    ap.add_argument("--ref-per-core", type=int, default=200, help="--impl reference: solves per host core per step")
+    ap.add_argument("--no-multi-leg", action="store_true", help="N > 1: skip the one-process b200mpc_solve_batch_multi leg")
+    ap.add_argument("--no-weak-leg", action="store_true", help="N > 1: skip the weak-scaling figure")
     ap.add_argument("--workload", default="roadmap", choices=["roadmap", "line"])
     ap.add_argument("--latency-reps", type=int, default=100)
-    ap.add_argument("--cpu-per-core", type=int, default=150, help="cpu_baseline: solves per host core in the sample")
+    ap.add_argument("--cpu-per-core", type=int, default=400, help="cpu_baseline: solves per host core in the sample (>= 2 s per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--input-sets", type=int, default=4, help="distinct synthetic input batches cycled over the steps")
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads (one solver handle each) of the end-to-end leg (0 = auto)")
     ap.add_argument("--split", type=int, default=0, help="internal batch split of one solve call (0 = 1 with several streams, 4 with one)")
-    ap.add_argument("--streams", type=int, default=6, help="solver handles / CUDA streams consecutive steps alternate between")
+    ap.add_argument("--streams", type=int, default=0, help="solver handles / CUDA streams consecutive steps alternate between (0 = auto: 6 at 65 536 problems per GPU, up to 16 for smaller shards)")
     ap.add_argument("--mode", default="perpass", choices=["perpass", "fused"], help="solver execution mode (include/b200mpc.h)")
     ap.add_argument("--rounds", type=int, default=0, help="per-pass mode: rounds before the fused finisher (0 = library default)")
     args = ap.parse_args()

@@ -25,12 +25,14 @@
  *     host<->device copies themselves; *_batch_device functions take DEVICE buffers in the structure-of-arrays
  *     layout the kernels consume (field-major: element k of problem b at ptr[k*B + b]) and are asynchronous on
  *     the given cudaStream_t (passed as void*; NULL = the handle's own stream).
- *   - a handle is bound to one CUDA device and is the unit of thread safety (one handle per host thread).
+ *   - a handle is bound to one CUDA device and is the unit of thread safety: one handle per host thread AND one solve
+ *     in flight per handle (every call on a handle uses the handle's one workspace and its auxiliary streams; a second
+ *     *_device call on the same handle, on whatever stream, first waits on the device for the previous one).
  *   - there is no CPU fallback: without a CUDA device b200mpc_create fails with B200MPC_ERR_CUDA.
  *   - per-problem status values are Ipopt's ApplicationReturnStatus numbers
  *     (Ipopt-3.12.7/Ipopt/src/Interfaces/IpReturnCodes_inc.h:16-39): 0 Solve_Succeeded, 1 Solved_To_Acceptable_Level,
  *     3 Search_Direction_Becomes_Too_Small, 4 Diverging_Iterates, -1 Maximum_Iterations_Exceeded,
- *     -2 Restoration_Failed (the line search failed; the restoration phase is not implemented),
+ *     -2 Restoration_Failed (the line search failed at an almost feasible point, or b200mpc_set_restoration mode 0),
  *     -3 Error_In_Step_Computation, -13 Invalid_Number_Detected (NaN / Inf in the inputs).  Like MPC::Solve (MPC.cpp:248-249) the solution is returned regardless.
  */
 #ifndef B200MPC_H
@@ -92,8 +94,12 @@ int b200mpc_solve_batch_device(b200mpc_handle* h, int B, const double* d_state6,
                                double* d_out8, double* d_traj, double* d_obj, int* d_status, int* d_iters,
                                void* stream);
 
-/* The same batch sharded by contiguous index ranges over several handles (one per device), one host thread per
- * device, no inter-device communication.  Host buffers as b200mpc_solve_batch. */
+/* The same batch sharded by contiguous index ranges over several handles (normally one per device; several handles on
+ * one device are allowed), one host thread per handle, no inter-device communication: handle g solves
+ * problems [g * (B / n), (g + 1) * (B / n)), the last one also the remainder.  Host buffers as b200mpc_solve_batch.
+ * Every handle must have been created with the same b200mpc_params and the same restoration mode, and no handle may
+ * appear twice (B200MPC_ERR_ARG otherwise: the result rows of the shards would not line up, or two threads would share
+ * one workspace). */
 int b200mpc_solve_batch_multi(b200mpc_handle* const* hs, int n_handles, int B, const double* state6,
                               const double* coeffs, int ncoef, double* out8, double* traj, double* obj, int* status,
                               int* iters);
@@ -130,12 +136,12 @@ int b200mpc_set_compaction(b200mpc_handle* h, double max_live_fraction, int from
  * IpRestoMinC_1Nrm.cpp).  Never reached on the benchmark workloads at the reference's N = 25; 1 % of problems with
  * initial states far off the road and 2 % of the problems at N = 100 get there.
  *   mode 0: such a problem returns status -2 (Restoration_Failed) at the iteration where Ipopt would switch.
- *   mode 1 (default): the restoration step -- a forward sweep removes 5 % of every constraint defect with the controls
+ *   mode 1: the restoration step -- a forward sweep removes 5 % of every constraint defect with the controls
  *           kept, the point left enters the filter, lambda is reset to 0, z moves towards mu / slack -- i.e. what Ipopt
  *           does around its restoration phase, with a closed-form point instead of Ipopt's nested restoration solve.
  *           NOT a restatement of that solve: the iteration count of such a problem differs from Ipopt's; the solution
  *           is the reference's on 346 / 346 (N = 25), 14 / 14 (N = 50), 170 / 179 (N = 100) such problems.
- *   mode 2: as 1, preceded by Ipopt's soft restoration phase (damped full primal-dual steps accepted on the primal-dual
+ *   mode 2 (default): as 1, preceded by Ipopt's soft restoration phase (damped full primal-dual steps accepted on the primal-dual
  *           system error, IpBacktrackingLineSearch.cpp:1043-1140), restated exactly: the few problems on which Ipopt
  *           takes such steps then keep its iterates and iteration count. */
 int b200mpc_set_restoration(b200mpc_handle* h, int mode);
@@ -187,8 +193,11 @@ int b200mpc_roadmap_reference_batch_device(b200mpc_handle* h, int B, const doubl
 int b200mpc_set_solver_mode(b200mpc_handle* h, int mode, int rounds, int fused_below);
 
 /* Measurement helpers (used by bench.py; not part of the reference interface). */
+/* Off by default.  When enabled, every solve is bracketed by a pair of CUDA events on its stream (kept until
+ * b200mpc_kernel_time_ms reads / resets them; at most 8192 pairs). */
+int b200mpc_set_timing(b200mpc_handle* h, int enable);
 /* Total device time in ms of the solver's kernels (one interval per batch: first to last kernel of a solve) since the
- * last reset, measured with CUDA events on the launching stream, and the number of intervals. */
+ * last reset, measured with CUDA events on the launching stream, and the number of intervals (0 with timing off). */
 int b200mpc_kernel_time_ms(b200mpc_handle* h, double* total_ms, int* launches, int reset);
 /* Sustained FP64 FMA throughput of the device in TFLOP/s (dependent-chain DFMA microbenchmark, 2 FLOP per FMA). */
 int b200mpc_measure_fp64_peak(b200mpc_handle* h, double* tflops);

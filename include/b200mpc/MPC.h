@@ -92,10 +92,20 @@ class MPC {
   // {x1, y1, psi1, v1, cte1, epsi1, delta0, a0}  (MPC.cpp:253-256).  Like the reference (MPC.cpp:248-249) the solver
   // status is not checked here; last_status() exposes it.  The reference prints "Cost <obj>" on every call
   // (MPC.cpp:251-252); set print_cost(false) to silence it.
+  //
+  // Reference polynomial: FG_eval reads coeffs[0] and coeffs[1] only (MPC.cpp:117-118: f0 = coeffs[0] + coeffs[1] * x0,
+  // psides0 = atan(coeffs[1])) whatever the length of the vector, and so does this call by default.  The degree-2/3
+  // reference of BASELINE configs[3] (f = polyeval(coeffs, x), psides = atan(f'(x))) is an EXTENSION of the reference
+  // behaviour: switch it on with use_full_polynomial(true) (at most 4 coefficients), or use SolveBatch / the C ABI,
+  // where ncoef is explicit.
   template <class V1, class V2>
   std::vector<double> Solve(const V1& x0, const V2& coeffs) {
-    const std::vector<double> s = b200mpc::detail::to_std(x0), c = b200mpc::detail::to_std(coeffs);
+    const std::vector<double> s = b200mpc::detail::to_std(x0);
+    std::vector<double> c = b200mpc::detail::to_std(coeffs);
     if (s.size() != 6) throw std::invalid_argument("MPC::Solve: state must have 6 entries");
+    if (c.size() < 2) throw std::invalid_argument("MPC::Solve: coeffs must have at least 2 entries (MPC.cpp:117-118)");
+    if (!full_polynomial_) c.resize(2);
+    else if (c.size() > B200MPC_MAX_COEFFS) throw std::invalid_argument("MPC::Solve: the full-polynomial extension takes at most 4 coefficients");
     std::vector<double> out(8);
     b200mpc::detail::check(b200mpc_solve_batch(h_, 1, s.data(), c.data(), (int)c.size(), out.data(), nullptr, &cost_, &status_, &iters_));
     if (print_cost_) std::cout << "Cost " << cost_ << std::endl;
@@ -117,6 +127,7 @@ class MPC {
   int last_iterations() const { return iters_; }
   double last_cost() const { return cost_; }
   void print_cost(bool on) { print_cost_ = on; }
+  void use_full_polynomial(bool on) { full_polynomial_ = on; }
   b200mpc_handle* handle() const { return h_; }
 
  private:
@@ -125,6 +136,7 @@ class MPC {
   int status_ = 0, iters_ = 0;
   double cost_ = 0.0;
   bool print_cost_ = true;
+  bool full_polynomial_ = false;
 };
 
 // helpers.h:13-19

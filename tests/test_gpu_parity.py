@@ -130,8 +130,13 @@ def test_other_horizons(N, path):
     sel = np.where((g["status"] == 0) & (g["used_restoration"] == 0))[0]
     assert len(sel) >= 56
     compare(r, g, sel)
+    # the problems where the reference used its restoration phase: the library's default (soft restoration phase, then its
+    # own restoration step, b200mpc_set_restoration mode 2) solves every one of them; all but at most one (N = 100) end in
+    # the reference's local minimum
     rest = np.setdiff1d(np.arange(64), sel)
-    assert np.isin(r["status"][rest], [0, -2]).all()   # restoration phase not implemented: reported, never hidden
+    assert (r["status"][rest] == 0).all()
+    same = np.abs(r["cost"][rest] - g["obj"][rest]) <= 1e-6 * np.abs(g["obj"][rest])
+    assert same.sum() >= len(rest) - 1
 
 
 def test_other_parameters():
@@ -302,7 +307,14 @@ def test_device_pointer_entry_and_multi_handle(mpc):
     np.testing.assert_allclose(out8.T.cpu().numpy(), g["out8"], rtol=0, atol=1e-8)
     assert (status.cpu().numpy() == 0).all()
     ms, n = mpc.kernel_time_ms(reset=True)
-    assert n >= 1 and ms > 0
+    assert n == 0   # timing events are opt-in (b200mpc_set_timing)
+    mpc.set_timing(True)
+    mpc.solve_batch_device(B, st.data_ptr(), cf.data_ptr(), 2, out8.data_ptr(), traj.data_ptr(), obj.data_ptr(),
+                           status.data_ptr(), iters.data_ptr(), s.cuda_stream)
+    torch.cuda.synchronize()
+    ms, n = mpc.kernel_time_ms(reset=True)
+    mpc.set_timing(False)
+    assert n == 1 and ms > 0
     # sharded over two handles (here both on device 0; on a multi-GPU box one per device)
     with mp.MPC(device=0) as m2:
         r = api.solve_batch_multi([mpc, m2], g["states"], g["coeffs"], want_traj=True)
@@ -388,6 +400,69 @@ def test_roadmap_front_end_and_pipeline(mpc):
         np.testing.assert_allclose(r["traj"][b], o["x"], rtol=0, atol=1e-8)
     with pytest.raises(mp.B200MPCError):
         mp.roadmap_reference_batch(poses, cl[:4], mpc=mpc)
+
+
+def test_reference_shaped_solve_reads_two_coefficients_like_fg_eval():
+    """MPC.cpp:117-118 uses coeffs[0] and coeffs[1] whatever the vector's length; the full polynomial is an option."""
+    state = np.array([0.0, 0.0, 0.0, 12.0, -0.7, 0.05])
+    c4 = np.array([-0.7, -0.05, 0.004, 0.0002])
+    with mp.MPC() as m, mp.MPC(full_polynomial=True) as mf:
+        a = m.Solve(state, c4)
+        b = m.Solve(state, c4[:2])
+        assert a == b
+        c = mf.Solve(state, c4)
+        assert np.abs(np.array(c) - np.array(a)).max() > 1e-6
+        np.testing.assert_allclose(c, m.solve_batch(state[None], c4[None])["out8"][0], rtol=0, atol=1e-12)
+
+
+def test_multi_entry_point_rejects_mismatched_or_repeated_handles(mpc):
+    """b200mpc_solve_batch_multi: shards write rows of one result array, so every handle must share the horizon /
+    parameters, and a handle may not appear twice (two host threads on one workspace)."""
+    st, cf = synth.line_problems(256)
+    with mp.MPC(device=0, N=10) as other_n, mp.MPC(device=0, ref_v=30.0) as other_p, mp.MPC(device=0) as same:
+        for bad in ([mpc, other_n], [mpc, other_p], [mpc, mpc], [mpc, same, mpc]):
+            with pytest.raises(mp.B200MPCError) as e:
+                api.solve_batch_multi(bad, st, cf)
+            assert "handle" in str(e.value)
+        same.set_restoration(1)
+        with pytest.raises(mp.B200MPCError):
+            api.solve_batch_multi([mpc, same], st, cf)
+        same.set_restoration(2)
+        # ragged split over three handles on one device (85 + 85 + 86 problems), and more handles than problems
+        with mp.MPC(device=0) as third:
+            r = api.solve_batch_multi([mpc, same, third], st, cf, want_traj=True)
+            one = mpc.solve_batch(st, cf, want_traj=True)
+            np.testing.assert_array_equal(r["status"], one["status"])
+            np.testing.assert_array_equal(r["iters"], one["iters"])
+            np.testing.assert_allclose(r["traj"], one["traj"], rtol=0, atol=1e-9)
+            r2 = api.solve_batch_multi([mpc, same, third], st[:2], cf[:2])
+            np.testing.assert_allclose(r2["out8"], one["out8"][:2], rtol=0, atol=1e-9)
+
+
+def test_solves_on_one_handle_from_two_streams_are_serialised(mpc):
+    """One workspace per handle: a second device call on another stream waits (on the device) for the first."""
+    import torch
+    dev = torch.device("cuda", 0)
+    B = 4096
+    sts, cfs = synth.line_problems(2 * B)
+    outs = []
+    strs = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    for k in range(2):
+        st = torch.from_numpy(np.ascontiguousarray(sts[k * B:(k + 1) * B].T)).to(dev)
+        cf = torch.from_numpy(np.ascontiguousarray(cfs[k * B:(k + 1) * B].T)).to(dev)
+        out8 = torch.zeros((8, B), dtype=torch.float64, device=dev)
+        status = torch.full((B,), -7, dtype=torch.int32, device=dev)
+        outs.append((st, cf, out8, status))
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for k in range(2):
+            st, cf, out8, status = outs[k]
+            mpc.solve_batch_device(B, st.data_ptr(), cf.data_ptr(), 2, out8.data_ptr(), 0, 0, status.data_ptr(), 0, strs[k].cuda_stream)
+    torch.cuda.synchronize()
+    for k in range(2):
+        ref = mpc.solve_batch(sts[k * B:(k + 1) * B], cfs[k * B:(k + 1) * B])
+        assert (outs[k][3].cpu().numpy() == 0).all()
+        np.testing.assert_allclose(outs[k][2].T.cpu().numpy(), ref["out8"], rtol=0, atol=1e-9)
 
 
 def test_multi_device_sharding_in_one_process():

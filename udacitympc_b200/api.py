@@ -50,6 +50,7 @@ SYMBOLS = {
     "b200mpc_set_compaction": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_int]),
     "b200mpc_set_restoration": (ctypes.c_int, [_vp, ctypes.c_int]),
     "b200mpc_set_solver_mode": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "b200mpc_set_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
     "b200mpc_kernel_time_ms": (ctypes.c_int, [_vp, _dp, _ip, ctypes.c_int]),
     "b200mpc_measure_fp64_peak": (ctypes.c_int, [_vp, _dp]),
     "b200mpc_launch_count": (ctypes.c_longlong, [_vp]),
@@ -117,11 +118,14 @@ class MPC:
     (MPC.cpp:14-31) but keyword parameters with the same defaults, and batches are first class.
     Like the reference, Solve ignores the solver status (MPC.cpp:248-249); `last_status` exposes it."""
 
-    def __init__(self, device=0, print_cost=False, **params):
+    def __init__(self, device=0, print_cost=False, full_polynomial=False, **params):
         self._lib = load_library()
         self.params = default_params(**params)
         self.device = device
         self.print_cost = print_cost
+        # Solve(): the reference's FG_eval reads coeffs[0..1] only (MPC.cpp:117-118) whatever the vector's length, and
+        # so does Solve() unless this extension is switched on (solve_batch always uses every column it is given)
+        self.full_polynomial = full_polynomial
         h = _vp()
         _check(self._lib.b200mpc_create(ctypes.byref(self.params), device, ctypes.byref(h)))
         self._h = h
@@ -161,6 +165,10 @@ class MPC:
         coeffs = _f64(coeffs).ravel()
         if x0.size != 6:
             raise ValueError("state must have 6 entries (x, y, psi, v, cte, epsi)")
+        if coeffs.size < 2:
+            raise ValueError("coeffs must have at least 2 entries (MPC.cpp:117-118)")
+        if not self.full_polynomial:
+            coeffs = coeffs[:2]
         r = self.solve_batch(x0[None, :], coeffs[None, :], want_traj=False)
         self.last_status = int(r["status"][0])
         self.last_iters = int(r["iters"][0])
@@ -227,10 +235,10 @@ class MPC:
         when the caller overlaps several calls itself)."""
         _check(self._lib.b200mpc_set_batch_split(self._h, int(parts)))
 
-    def set_restoration(self, mode=True):
-        """What follows a failed line search: 0 / False = status -2 at the iteration where the reference's Ipopt enters
-        its restoration phase, 1 / True = the restoration step, 2 = Ipopt's soft restoration phase first, then the
-        restoration step.  See b200mpc_set_restoration."""
+    def set_restoration(self, mode=2):
+        """What follows a failed line search: 0 = status -2 at the iteration where the reference's Ipopt enters its
+        restoration phase, 1 = the restoration step, 2 (the library default) = Ipopt's soft restoration phase first,
+        then the restoration step.  See b200mpc_set_restoration."""
         _check(self._lib.b200mpc_set_restoration(self._h, int(mode)))
 
     def set_compaction(self, max_live_fraction=0.7, from_round=4):
@@ -243,6 +251,10 @@ class MPC:
         _check(self._lib.b200mpc_set_warm_start(self._h, int(enable), float(mu_init)))
 
     # -- measurement helpers
+    def set_timing(self, enable=True):
+        """Bracket every solve with CUDA events (read them with kernel_time_ms); off by default."""
+        _check(self._lib.b200mpc_set_timing(self._h, int(enable)))
+
     def kernel_time_ms(self, reset=True):
         t = ctypes.c_double()
         n = ctypes.c_int()

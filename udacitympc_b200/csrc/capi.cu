@@ -48,7 +48,12 @@ struct b200mpc_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
   DevBuf ws, in_aos, st_soa, cf_soa, out_soa, out_aos, traj_soa, traj_aos, obj, status, iters, misc0, misc1, misc2, misc3;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;   // around every solver-kernel launch
+  bool timing_on = false;                                    // b200mpc_set_timing: measurement only, off by default
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;   // around every solve while timing_on
+  cudaEvent_t done = nullptr;   // recorded after every solve: the next solve on this handle (any stream) waits for it
+  bool done_valid = false;
+  int resto_mode = 2;
+  b200mpc_params user_params;
   long long launches = 0;
   // CUDA graphs of whole solves (init + rounds x (factor, forward, step) + finisher), keyed by every launch argument
   struct GraphEntry {
@@ -76,6 +81,12 @@ Params to_core(const b200mpc_params& p) {
   return P;
 }
 
+bool same_params(const b200mpc_params& a, const b200mpc_params& b) {
+  return a.N == b.N && a.dt == b.dt && a.Lf == b.Lf && a.ref_v == b.ref_v && a.w_cte == b.w_cte && a.w_epsi == b.w_epsi &&
+         a.w_v == b.w_v && a.w_delta == b.w_delta && a.w_a == b.w_a && a.w_ddelta == b.w_ddelta && a.w_da == b.w_da &&
+         a.delta_max == b.delta_max && a.a_max == b.a_max && a.tol == b.tol && a.max_iter == b.max_iter;
+}
+
 int check_solve_args(const b200mpc_handle* h, int B, const void* st, const void* cf, int ncoef, const void* out8) {
   if (!h) return fail(B200MPC_ERR_ARG, "null handle");
   if (B < 0) return fail(B200MPC_ERR_ARG, "negative batch size");
@@ -84,20 +95,49 @@ int check_solve_args(const b200mpc_handle* h, int B, const void* st, const void*
   return 0;
 }
 
-// records a pair of events around the solver kernel so bench.py can read the kernel's own device time
+int run_solve(b200mpc_handle* h, int B, int steps, const double* st, const double* cf, int ncoef, double* out8,
+              double* traj, double* obj, int* status, int* iters, cudaStream_t s, bool caller_captures);
+
+// One solve on stream s.  The handle owns ONE workspace and one set of auxiliary streams, so solves on a handle are
+// serialised on the device whatever streams the caller uses (an event recorded after each solve, waited for by the
+// next).  With b200mpc_set_timing a pair of events brackets the solver kernels for bench.py.
 int timed_solve(b200mpc_handle* h, int B, int steps, const double* st, const double* cf, int ncoef, double* out8,
                 double* traj, double* obj, int* status, int* iters, cudaStream_t s) {
+  // the caller may be capturing its stream into a graph of its own: then no nested capture, no external events
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (s != nullptr && s != cudaStreamLegacy) { if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; } }
+  const bool caller_captures = cap != cudaStreamCaptureStatusNone;
+  if (caller_captures && h->ws.cap < solve_workspace_doubles(h->P.N, B) * sizeof(double))
+    return fail(B200MPC_ERR_ARG, "the stream is being captured and the workspace would have to grow: run one solve of this size first");
   CU(h->ws.ensure(solve_workspace_doubles(h->P.N, B) * sizeof(double)));
+  if (!caller_captures && h->done_valid) CU(cudaStreamWaitEvent(s, h->done, 0));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  const bool rec = h->timing.size() < 8192;
+  const bool rec = h->timing_on && !caller_captures && h->timing.size() < 8192;
   if (rec) {
-    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-    CU(cudaEventRecord(e0, s));
+    CU(cudaEventCreate(&e0));
+    if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); return cuda_fail(cudaGetLastError(), "cudaEventCreate"); }
+    cudaError_t e = cudaEventRecord(e0, s);
+    if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(e, "cudaEventRecord"); }
   }
+  int rc = run_solve(h, B, steps, st, cf, ncoef, out8, traj, obj, status, iters, s, caller_captures);
+  if (rec) {
+    cudaError_t e = rc == 0 ? cudaEventRecord(e1, s) : cudaErrorUnknown;
+    if (e == cudaSuccess) h->timing.emplace_back(e0, e1);
+    else { cudaEventDestroy(e0); cudaEventDestroy(e1); if (rc == 0) rc = cuda_fail(e, "cudaEventRecord"); }
+  }
+  if (rc == 0 && !caller_captures) {
+    CU(cudaEventRecord(h->done, s));
+    h->done_valid = true;
+  }
+  return rc;
+}
+
+int run_solve(b200mpc_handle* h, int B, int steps, const double* st, const double* cf, int ncoef, double* out8,
+              double* traj, double* obj, int* status, int* iters, cudaStream_t s, bool caller_captures) {
   // One solve is ~75 dependent launches; replaying a captured graph keeps the host out of the inner loop (several
   // ranks / streams per host otherwise become launch-bound).  The legacy default stream cannot be captured.
   bool done = false;
-  if (h->use_graphs && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) {
+  if (h->use_graphs && !caller_captures && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) {
     b200mpc_handle::GraphEntry key{B, steps, ncoef, h->cfg.mode, h->cfg.rounds, h->cfg.fused_below, h->cfg.warm_start ? 1 : 0, h->cfg.split, h->repack_gen, h->cfg.warm_mu, st, cf, h->ws.p, out8, traj, obj, status, iters, nullptr, 0};
     b200mpc_handle::GraphEntry* hit = nullptr;
     for (auto& g : h->graphs)
@@ -132,10 +172,6 @@ int timed_solve(b200mpc_handle* h, int B, int steps, const double* st, const dou
   }
   if (!done)
     CU(launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, &h->ss, &h->launches));
-  if (rec) {
-    CU(cudaEventRecord(e1, s));
-    h->timing.emplace_back(e0, e1);
-  }
   return 0;
 }
 
@@ -168,12 +204,16 @@ int b200mpc_create(const b200mpc_params* p, int device, b200mpc_handle** out) {
   b200mpc_handle* h = new (std::nothrow) b200mpc_handle();
   if (!h) return fail(B200MPC_ERR_NOMEM, "out of host memory");
   h->P = to_core(*p);
+  h->user_params = *p;
   h->device = device;
   if (const char* e = getenv("B200MPC_NO_GRAPHS")) h->use_graphs = !(e[0] == '1');
   if (const char* e = getenv("B200MPC_NO_COOP")) h->cfg.coop = !(e[0] == '1');
   if (const char* e = getenv("B200MPC_RESTORATION")) { int v = atoi(e); if (v >= 0 && v <= 2) h->P.resto = v; }
+  h->resto_mode = h->P.resto;
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
+  e = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
+  if (e != cudaSuccess) { cudaStreamDestroy(h->stream); delete h; return cuda_fail(e, "cudaEventCreate"); }
   for (int i = 0; i < 3; ++i) {   // auxiliary streams / events for the internal batch split
     if (cudaStreamCreateWithFlags(&h->ss.aux[i], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ss.join[i], cudaEventDisableTiming) != cudaSuccess) break;
@@ -205,6 +245,7 @@ void b200mpc_destroy(b200mpc_handle* h) {
     if (h->ss.join[i]) cudaEventDestroy(h->ss.join[i]);
   }
   if (h->ss.fork) cudaEventDestroy(h->ss.fork);
+  if (h->done) cudaEventDestroy(h->done);
   DevBuf* bufs[] = {&h->ws, &h->in_aos, &h->st_soa, &h->cf_soa, &h->out_soa, &h->out_aos, &h->traj_soa, &h->traj_aos,
                     &h->obj, &h->status, &h->iters, &h->misc0, &h->misc1, &h->misc2, &h->misc3};
   for (DevBuf* b : bufs) b->release();
@@ -251,6 +292,7 @@ int b200mpc_set_restoration(b200mpc_handle* h, int mode) {
   if (!h) return fail(B200MPC_ERR_ARG, "null handle");
   if (mode < 0 || mode > 2) return fail(B200MPC_ERR_ARG, "restoration: mode must be 0, 1 or 2");
   h->P.resto = mode;
+  h->resto_mode = mode;
   ++h->repack_gen;   // the parameters are baked into captured graphs
   return 0;
 }
@@ -319,6 +361,16 @@ int b200mpc_solve_batch_multi(b200mpc_handle* const* hs, int n_handles, int B, c
   for (int g = 0; g < n_handles; ++g)
     if (!hs[g]) return fail(B200MPC_ERR_ARG, "null handle in list");
   if (B < 0) return fail(B200MPC_ERR_ARG, "negative batch size");
+  // the shards write rows of one result array: same horizon / parameters everywhere, and no handle twice (two host
+  // threads would share one workspace and stream)
+  for (int g = 0; g < n_handles; ++g) {
+    for (int k = 0; k < g; ++k)
+      if (hs[k] == hs[g]) return fail(B200MPC_ERR_ARG, "handle " + std::to_string(g) + " repeats handle " + std::to_string(k));
+    if (!same_params(hs[g]->user_params, hs[0]->user_params) || hs[g]->resto_mode != hs[0]->resto_mode)
+      return fail(B200MPC_ERR_ARG, "handle " + std::to_string(g) + " was created with other parameters than handle 0");
+  }
+  if (int rc0 = check_solve_args(hs[0], B, state6, coeffs, ncoef, out8)) return rc0;
+  if (B == 0) return 0;
   std::vector<int> rc(n_handles, 0);
   std::vector<std::string> msg(n_handles);
   std::vector<std::thread> th;
@@ -542,6 +594,12 @@ int b200mpc_roadmap_reference_batch(b200mpc_handle* h, int B, const double* pose
 }
 
 // ------------------------------------------------------------------------------------------------
+int b200mpc_set_timing(b200mpc_handle* h, int enable) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  h->timing_on = enable != 0;
+  return 0;
+}
+
 int b200mpc_kernel_time_ms(b200mpc_handle* h, double* total_ms, int* launches, int reset) {
   if (!h) return fail(B200MPC_ERR_ARG, "null handle");
   CU(cudaSetDevice(h->device));
