@@ -211,6 +211,17 @@ MPC_HD double safe_slack(double v, double mu, double z, double bnd) {
   return v;
 }
 
+// The four slacks of one stage (delta and a against their lower / upper bounds) at once: one practically-never-taken
+// branch instead of four, so the reciprocals / divisions that follow form independent straight-line chains.
+MPC_HD void safe_slack4(double& sl0, double& su0, double& sl1, double& su1, double mu, double zl0, double zu0, double zl1,
+                        double zu1, const double* xl, const double* xu) {
+  const double thr = DBL_EPSILON * dmin(mu, 1.0);
+  if ((sl0 < thr) | (su0 < thr) | (sl1 < thr) | (su1 < thr)) {
+    sl0 = safe_slack(sl0, mu, zl0, xl[0]); su0 = safe_slack(su0, mu, zu0, xu[0]);
+    sl1 = safe_slack(sl1, mu, zl1, xl[1]); su1 = safe_slack(su1, mu, zu1, xu[1]);
+  }
+}
+
 // Linearised dynamics of one stage: non-trivial entries of A_t (6x6) and B_t (6x2), MPC.cpp:130-137.
 struct Lin {
   double a1, a2, a3, a4, a5, beta, pp, kap, sed, vce;
@@ -226,7 +237,7 @@ MPC_HD Lin make_lin(const Params& P, double v, double delta, double sp, double c
   L.a5 = delta * P.dtLf;      // d psi1 / d v0 = d epsi1 / d v0
   L.beta = v * P.dtLf;        // d psi1 / d delta0 = d epsi1 / d delta0
   L.pp = p1;                  // d cte1 / d x0
-  L.kap = p2 == 0.0 ? 0.0 : p2 / (1.0 + p1 * p1);  // -d epsi1 / d x0
+  L.kap = p2 / (1.0 + p1 * p1);   // -d epsi1 / d x0 (no branch around the division: 0 for a degree-1 reference)
   L.sed = se * P.dt;          // d cte1 / d v0
   L.vce = vdt * ce;           // d cte1 / d epsi0
   return L;
@@ -258,8 +269,7 @@ struct Hes {
 MPC_HD Hes make_hes(const Params& P, const double* lam, double v, double sp, double cp, double se, double ce, double p1,
                     double p2, double p3) {
   Hes H;
-  H.xx = 0.0;
-  if (p2 != 0.0 || p3 != 0.0) {
+  {   // 0 for a degree-1 reference (p2 = p3 = 0); evaluated without a branch
     const double q = 1.0 + p1 * p1;
     H.xx = -lam[4] * p2 + lam[5] * (p3 * q - 2.0 * p1 * p2 * p2) / (q * q);
   }
@@ -703,8 +713,9 @@ struct Solver {
         ru0 = gu0 - zl0 + zu0; ru1 = gu1 - zl1 + zu1;
       } else {
         const double bl0 = A.beta * (lamn[2] + lamn[5]), bl1 = P.dt * lamn[3];   // B_t^T lambda_{t+1}
-        const double isl0 = 1.0 / safe_slack(u0 - P.xl[0], mu, zl0, P.xl[0]), isu0 = 1.0 / safe_slack(P.xu[0] - u0, mu, zu0, P.xu[0]);
-        const double isl1 = 1.0 / safe_slack(u1 - P.xl[1], mu, zl1, P.xl[1]), isu1 = 1.0 / safe_slack(P.xu[1] - u1, mu, zu1, P.xu[1]);
+        double sl0 = u0 - P.xl[0], su0 = P.xu[0] - u0, sl1 = u1 - P.xl[1], su1 = P.xu[1] - u1;
+        safe_slack4(sl0, su0, sl1, su1, mu, zl0, zu0, zl1, zu1, P.xl, P.xu);
+        const double isl0 = 1.0 / sl0, isu0 = 1.0 / su0, isl1 = 1.0 / sl1, isu1 = 1.0 / su1;
         r0 = hess_u(0, t) + dw + zl0 * isl0 + zu0 * isu0;
         r1 = hess_u(1, t) + dw + zl1 * isl1 + zu1 * isu1;
         ru0 = gu0 - bl0 - mu * isl0 + mu * isu0;
@@ -860,22 +871,25 @@ struct Solver {
       if (!ls) {
         // objective / barrier directional derivative and step bounds for u_t
         const double zl0 = w(r + xZL), zl1 = w(r + xZL + 1), zu0 = w(r + xZU), zu1 = w(r + xZU + 1);
-        const double sl0 = safe_slack(u0 - P.xl[0], mu, zl0, P.xl[0]), su0 = safe_slack(P.xu[0] - u0, mu, zu0, P.xu[0]);
-        const double sl1 = safe_slack(u1 - P.xl[1], mu, zl1, P.xl[1]), su1 = safe_slack(P.xu[1] - u1, mu, zu1, P.xu[1]);
+        double sl0 = u0 - P.xl[0], su0 = P.xu[0] - u0, sl1 = u1 - P.xl[1], su1 = P.xu[1] - u1;
+        safe_slack4(sl0, su0, sl1, su1, mu, zl0, zu0, zl1, zu1, P.xl, P.xu);
         const double isl0 = 1.0 / sl0, isu0 = 1.0 / su0, isl1 = 1.0 / sl1, isu1 = 1.0 / su1;
         gbd += (grad_u(0, t, u0, um0, un0) - mu * isl0 + mu * isu0) * du0 + (grad_u(1, t, u1, um1, un1) - mu * isl1 + mu * isu1) * du1;
         gbd += gv2 * (s[3] - P.ref_v) * ds[3] + gc2 * s[4] * ds[4] + ge2 * s[5] * ds[5];
         // fraction to the boundary: alpha <= tau * slack / |du| (IpDenseVector.cpp:928-970)
-        if (du0 < 0.0) a_pr = dmin(a_pr, -tau / du0 * sl0);
-        if (du0 > 0.0) a_pr = dmin(a_pr, tau / du0 * su0);
-        if (du1 < 0.0) a_pr = dmin(a_pr, -tau / du1 * sl1);
-        if (du1 > 0.0) a_pr = dmin(a_pr, tau / du1 * su1);
+        // Written without branches so that the six divisions are independent chains the scheduler can interleave:
+        // -tau / d == -(tau / d) exactly, one quotient serves both signs of du; a direction component that does not
+        // move towards a bound contributes the neutral candidate 2 (alpha <= 1).
         const double dzl0 = (mu - sl0 * zl0 - zl0 * du0) * isl0, dzu0 = (mu - su0 * zu0 + zu0 * du0) * isu0;
         const double dzl1 = (mu - sl1 * zl1 - zl1 * du1) * isl1, dzu1 = (mu - su1 * zu1 + zu1 * du1) * isu1;
-        if (dzl0 < 0.0) a_du = dmin(a_du, -tau / dzl0 * zl0);
-        if (dzu0 < 0.0) a_du = dmin(a_du, -tau / dzu0 * zu0);
-        if (dzl1 < 0.0) a_du = dmin(a_du, -tau / dzl1 * zl1);
-        if (dzu1 < 0.0) a_du = dmin(a_du, -tau / dzu1 * zu1);
+        const double qu0 = tau / du0, qu1 = tau / du1;
+        const double qzl0 = tau / dzl0, qzu0 = tau / dzu0, qzl1 = tau / dzl1, qzu1 = tau / dzu1;
+        const double cu0 = du0 < 0.0 ? -qu0 * sl0 : (du0 > 0.0 ? qu0 * su0 : 2.0);
+        const double cu1 = du1 < 0.0 ? -qu1 * sl1 : (du1 > 0.0 ? qu1 * su1 : 2.0);
+        a_pr = dmin(a_pr, dmin(cu0, cu1));
+        const double czl0 = dzl0 < 0.0 ? -qzl0 * zl0 : 2.0, czu0 = dzu0 < 0.0 ? -qzu0 * zu0 : 2.0;
+        const double czl1 = dzl1 < 0.0 ? -qzl1 * zl1 : 2.0, czu1 = dzu1 < 0.0 ? -qzu1 * zu1 : 2.0;
+        a_du = dmin(a_du, dmin(dmin(czl0, czu0), dmin(czl1, czu1)));
         // tiny-step test |dx_i| / (|x_i| + 1) <= 10 eps for all i (IpBacktrackingLineSearch.cpp:1145-1200)
         nottiny = nottiny || fabs(du0) > tinytol * (fabs(u0) + 1.0) || fabs(du1) > tinytol * (fabs(u1) + 1.0);
 #pragma unroll
@@ -1083,25 +1097,33 @@ struct Solver {
       xm = dmax(xm, dmax(fabs(un[0]), fabs(un[1])));
       w(r + bN + xU) = un[0]; w(r + bN + xU + 1) = un[1];
       {
-        const double sl0 = safe_slack(u0 - P.xl[0], mu, zl0, P.xl[0]), su0 = safe_slack(P.xu[0] - u0, mu, zu0, P.xu[0]);
-        const double sl1 = safe_slack(u1 - P.xl[1], mu, zl1, P.xl[1]), su1 = safe_slack(P.xu[1] - u1, mu, zu1, P.xu[1]);
+        double sl0 = u0 - P.xl[0], su0 = P.xu[0] - u0, sl1 = u1 - P.xl[1], su1 = P.xu[1] - u1;
+        safe_slack4(sl0, su0, sl1, su1, mu, zl0, zu0, zl1, zu1, P.xl, P.xu);
         // the barrier of the trial point is evaluated with the current z (only matters in the slack safeguard)
-        const double b0 = safe_slack(un[0] - P.xl[0], mu, zl0, P.xl[0]) * safe_slack(P.xu[0] - un[0], mu, zu0, P.xu[0]);
-        const double b1 = safe_slack(un[1] - P.xl[1], mu, zl1, P.xl[1]) * safe_slack(P.xu[1] - un[1], mu, zu1, P.xu[1]);
+        double tl0 = un[0] - P.xl[0], tu0 = P.xu[0] - un[0], tl1 = un[1] - P.xl[1], tu1 = P.xu[1] - un[1];
+        safe_slack4(tl0, tu0, tl1, tu1, mu, zl0, zu0, zl1, zu1, P.xl, P.xu);
+        const double b0 = tl0 * tu0;
+        const double b1 = tl1 * tu1;
         slog += log(b0 * b1);
         zl0 += a_du * ((mu - sl0 * zl0 - zl0 * du0) / sl0);
         zu0 += a_du * ((mu - su0 * zu0 + zu0 * du0) / su0);
         zl1 += a_du * ((mu - sl1 * zl1 - zl1 * du1) / sl1);
         zu1 += a_du * ((mu - su1 * zu1 + zu1 * du1) / su1);
       }
-      const double nsl0 = safe_slack(un[0] - P.xl[0], mu, zl0, P.xl[0]), nsu0 = safe_slack(P.xu[0] - un[0], mu, zu0, P.xu[0]);
-      const double nsl1 = safe_slack(un[1] - P.xl[1], mu, zl1, P.xl[1]), nsu1 = safe_slack(P.xu[1] - un[1], mu, zu1, P.xu[1]);
-      {   // kappa_sigma = 1e10
-        const double m0 = mu / nsl0, m1 = mu / nsu0, m2 = mu / nsl1, m3 = mu / nsu1;
-        zl0 = dclamp(zl0, 1e-10 * m0, 1e10 * m0);
-        zu0 = dclamp(zu0, 1e-10 * m1, 1e10 * m1);
-        zl1 = dclamp(zl1, 1e-10 * m2, 1e10 * m2);
-        zu1 = dclamp(zu1, 1e-10 * m3, 1e10 * m3);
+      double nsl0 = un[0] - P.xl[0], nsu0 = P.xu[0] - un[0], nsl1 = un[1] - P.xl[1], nsu1 = P.xu[1] - un[1];
+      safe_slack4(nsl0, nsu0, nsl1, nsu1, mu, zl0, zu0, zl1, zu1, P.xl, P.xu);
+      {   // kappa_sigma = 1e10 (IpIpoptAlg.cpp:880-951): z stays within [1e-10, 1e10] * mu / slack.  The exact bounds need
+          // four divisions; they are evaluated only when the cheap product test says a multiplier is within a factor 4
+          // of one of them (any clamp the exact test would apply passes through here: the margin dwarfs the rounding)
+        const double lo = 4e-10 * mu, hi = 2.5e9 * mu;
+        const double q0 = nsl0 * zl0, q1 = nsu0 * zu0, q2 = nsl1 * zl1, q3 = nsu1 * zu1;
+        if (!((q0 > lo) & (q0 < hi) & (q1 > lo) & (q1 < hi) & (q2 > lo) & (q2 < hi) & (q3 > lo) & (q3 < hi))) {
+          const double m0 = mu / nsl0, m1 = mu / nsu0, m2 = mu / nsl1, m3 = mu / nsu1;
+          zl0 = dclamp(zl0, 1e-10 * m0, 1e10 * m0);
+          zu0 = dclamp(zu0, 1e-10 * m1, 1e10 * m1);
+          zl1 = dclamp(zl1, 1e-10 * m2, 1e10 * m2);
+          zu1 = dclamp(zu1, 1e-10 * m3, 1e10 * m3);
+        }
         w(r + bN + xZL) = zl0; w(r + bN + xZL + 1) = zl1; w(r + bN + xZU) = zu0; w(r + bN + xZU + 1) = zu1;
       }
       zz1 += zl0 + zl1 + zu0 + zu1;

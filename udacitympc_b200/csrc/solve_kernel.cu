@@ -30,7 +30,10 @@ constexpr int kBlock = MPC_BLOCK;
 #ifndef MPC_STEP_BLOCKS
 #define MPC_STEP_BLOCKS 6
 #endif
-constexpr int kFwdBlocks = MPC_FWD_BLOCKS, kStepBlocks = MPC_STEP_BLOCKS;
+#ifndef MPC_FACTOR_BLOCKS
+#define MPC_FACTOR_BLOCKS 4
+#endif
+constexpr int kFwdBlocks = MPC_FWD_BLOCKS, kStepBlocks = MPC_STEP_BLOCKS, kFactorBlocks = MPC_FACTOR_BLOCKS;
 
 // One workspace region holds every problem of a batch; the buffer the handle allocates has two of them (the batch
 // compaction moves the unfinished problems back and forth), two slot -> problem maps and the counters.
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(kBlock) mpc_init_kernel(const __grid_constant_
   if (S.phase == PH_DONE) write_result(P, A, b, S);   // invalid number at the starting point
 }
 
-__global__ void __launch_bounds__(kBlock) mpc_factor_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
+__global__ void __launch_bounds__(kBlock, kFactorBlocks) mpc_factor_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
   int slot, b;
   double* ws;
   if (!locate(A, blockIdx.x * blockDim.x + threadIdx.x, slot, b, ws)) return;
