@@ -179,6 +179,17 @@ int b200mpc_roadmap_reference_batch(b200mpc_handle* h, int B, const double* pose
 int b200mpc_roadmap_reference_batch_device(b200mpc_handle* h, int B, const double* d_pose4, const double* d_centerline,
                                            int n_wp, double* d_state6_out, double* d_coeffs_out, void* stream);
 
+/* Reads a roadmap file in the reference's format (mpc_to_line/roadmap.csv: 7 comma-separated numbers per line -- left
+ * edge x, y, right edge x, y, centre line x, y, slope) the way CustomMPC::readRoadmapFromCSV / parseRoadMapLine intend to
+ * (mpc_to_line/src/custom_MPC.h:25-44; the constructor at custom_MPC.cpp:201-212 keeps columns 4, 5 as the centre line
+ * and atan(column 6) as its direction): one waypoint per line, fields split at ','.  The reference converts every field
+ * with std::stof, i.e. through SINGLE precision; float_fields != 0 reproduces that, 0 parses doubles.  Host-only (no
+ * device, no handle).  The reference's reader opens the file NAME as a string stream (custom_MPC.h:28) and so never
+ * reads the file; that bug is not reproduced.
+ *   centerline_out  max_wp x 2, or NULL;  slope_out  max_wp, or NULL;  *n_wp = waypoints in the file (may exceed
+ *   max_wp: only the first max_wp are written) -- feed centerline_out to b200mpc_roadmap_reference_batch. */
+int b200mpc_read_roadmap_csv(const char* path, int float_fields, double* centerline_out, double* slope_out, int max_wp, int* n_wp);
+
 /* Execution mode of the solver (tuning; results do not depend on it).
  *   mode 0 (default)  throughput path + latency path.  Batches of at least `fused_below` problems (default 3072) run
  *                     rounds of the per-pass thread-per-problem kernels (factor, forward, step).  By default the

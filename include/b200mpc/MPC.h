@@ -17,6 +17,7 @@
 #include <cassert>
 #include <cstddef>
 #include <iostream>
+#include <cmath>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -138,6 +139,19 @@ class MPC {
   bool print_cost_ = true;
   bool full_polynomial_ = false;
 };
+
+// The centre line CustomMPC's constructor builds from the roadmap file (mpc_to_line/src/custom_MPC.cpp:201-212 with the
+// reader of custom_MPC.h:25-44): cl_x = column 4, cl_y = column 5, cl_phi = atan(column 6).  float_fields = true converts
+// the fields through single precision like the reference's std::stof.
+inline void readRoadmapCenterline(const std::string& roadmap_file_name, std::vector<double>& cl_x, std::vector<double>& cl_y,
+                                  std::vector<double>& cl_phi, bool float_fields = true) {
+  int n = 0;
+  b200mpc::detail::check(b200mpc_read_roadmap_csv(roadmap_file_name.c_str(), float_fields ? 1 : 0, nullptr, nullptr, 0, &n));
+  std::vector<double> cl((std::size_t)2 * n), slope((std::size_t)n);
+  b200mpc::detail::check(b200mpc_read_roadmap_csv(roadmap_file_name.c_str(), float_fields ? 1 : 0, cl.data(), slope.data(), n, &n));
+  cl_x.resize(n); cl_y.resize(n); cl_phi.resize(n);
+  for (int i = 0; i < n; ++i) { cl_x[i] = cl[2 * i]; cl_y[i] = cl[2 * i + 1]; cl_phi[i] = std::atan(slope[i]); }
+}
 
 // helpers.h:13-19
 template <class V>

@@ -19,6 +19,10 @@
 //   mpc_to_line/src/n_steps_kinematics_model/apply_ipopt_n_steps_kinematics_model.cpp:40-413.
 // Ipopt's `derivative_test second-order` is run over them by tests/test_ref_oracle.py.
 //
+// Cost weights: MPC.cpp:57-76 adds the seven squared terms with weight 1 (no factor in front of CppAD::pow).  The
+// weights w[7] = (cte, epsi, v, delta, a, ddelta, da) below multiply those terms (ref_mpc_solve_w); ref_mpc_solve passes
+// 1.0 for each, and 1.0 * t is t bit for bit, so the as-shipped problem is unchanged.
+//
 // Generalisation: MPC.cpp:117-118 hard-codes a degree-1 reference (f0 = c0 + c1*x0,
 // psides0 = atan(c1)).  For BASELINE configs 4/5 the natural degree-d form
 // f0 = p(x0), psides0 = atan(p'(x0)) is used; it is bit-identical to the shipped code when
@@ -59,6 +63,7 @@ struct TraceRow { double v[10]; };  // iter,obj,inf_pr,inf_du,mu,d_norm,regu,alp
 class MpcNlp : public TNLP {
  public:
   int N; double dt, Lf, ref_v, delta_max, a_max;
+  double w[7] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0};   // cte, epsi, v, delta, a, ddelta, da
   double s0[6];
   std::vector<double> coef;
   // outputs
@@ -102,35 +107,35 @@ class MpcNlp : public TNLP {
   bool eval_f(Index, const Number* x, bool, Number& f) override {
     f = 0.0;
     for (int t = 0; t < N; ++t) {
-      f += std::pow(x[cs() + t], 2);
-      f += std::pow(x[es() + t], 2);
-      f += std::pow(x[vs() + t] - ref_v, 2);
+      f += w[0] * std::pow(x[cs() + t], 2);
+      f += w[1] * std::pow(x[es() + t], 2);
+      f += w[2] * std::pow(x[vs() + t] - ref_v, 2);
     }
     for (int t = 0; t < N - 1; ++t) {
-      f += std::pow(x[ds() + t], 2);
-      f += std::pow(x[as() + t], 2);
+      f += w[3] * std::pow(x[ds() + t], 2);
+      f += w[4] * std::pow(x[as() + t], 2);
     }
     for (int t = 0; t < N - 2; ++t) {
-      f += std::pow(x[ds() + t + 1] - x[ds() + t], 2);
-      f += std::pow(x[as() + t + 1] - x[as() + t], 2);
+      f += w[5] * std::pow(x[ds() + t + 1] - x[ds() + t], 2);
+      f += w[6] * std::pow(x[as() + t + 1] - x[as() + t], 2);
     }
     return true;
   }
   bool eval_grad_f(Index n, const Number* x, bool, Number* g) override {
     for (int i = 0; i < n; ++i) g[i] = 0.0;
     for (int t = 0; t < N; ++t) {
-      g[cs() + t] = 2.0 * x[cs() + t];
-      g[es() + t] = 2.0 * x[es() + t];
-      g[vs() + t] = 2.0 * (x[vs() + t] - ref_v);
+      g[cs() + t] = w[0] * (2.0 * x[cs() + t]);
+      g[es() + t] = w[1] * (2.0 * x[es() + t]);
+      g[vs() + t] = w[2] * (2.0 * (x[vs() + t] - ref_v));
     }
     for (int t = 0; t < N - 1; ++t) {
-      g[ds() + t] += 2.0 * x[ds() + t];
-      g[as() + t] += 2.0 * x[as() + t];
+      g[ds() + t] += w[3] * (2.0 * x[ds() + t]);
+      g[as() + t] += w[4] * (2.0 * x[as() + t]);
     }
     for (int t = 0; t < N - 2; ++t) {
       double dd = x[ds() + t + 1] - x[ds() + t], da = x[as() + t + 1] - x[as() + t];
-      g[ds() + t + 1] += 2.0 * dd; g[ds() + t] -= 2.0 * dd;
-      g[as() + t + 1] += 2.0 * da; g[as() + t] -= 2.0 * da;
+      g[ds() + t + 1] += w[5] * (2.0 * dd); g[ds() + t] -= w[5] * (2.0 * dd);
+      g[as() + t + 1] += w[6] * (2.0 * da); g[as() + t] -= w[6] * (2.0 * da);
     }
     return true;
   }
@@ -193,13 +198,13 @@ class MpcNlp : public TNLP {
       ++k;
     };
     for (int t = 0; t < N; ++t) {
-      put(cs() + t, cs() + t, 2.0 * sig); put(es() + t, es() + t, 2.0 * sig); put(vs() + t, vs() + t, 2.0 * sig);
+      put(cs() + t, cs() + t, 2.0 * sig * w[0]); put(es() + t, es() + t, 2.0 * sig * w[1]); put(vs() + t, vs() + t, 2.0 * sig * w[2]);
     }
     for (int t = 0; t < N - 1; ++t) {
-      double w = 2.0 * sig * (1.0 + (t > 0 ? 1.0 : 0.0) + (t < N - 2 ? 1.0 : 0.0));
-      put(ds() + t, ds() + t, w); put(as() + t, as() + t, w);
+      const double nd = (t > 0 ? 1.0 : 0.0) + (t < N - 2 ? 1.0 : 0.0);
+      put(ds() + t, ds() + t, 2.0 * sig * (w[3] + nd * w[5])); put(as() + t, as() + t, 2.0 * sig * (w[4] + nd * w[6]));
     }
-    for (int t = 0; t < N - 2; ++t) { put(ds() + t + 1, ds() + t, -2.0 * sig); put(as() + t + 1, as() + t, -2.0 * sig); }
+    for (int t = 0; t < N - 2; ++t) { put(ds() + t + 1, ds() + t, -2.0 * sig * w[5]); put(as() + t + 1, as() + t, -2.0 * sig * w[6]); }
     for (int t = 1; t < N; ++t) {
       double x0 = 0, psi0 = 0, v0 = 0, epsi0 = 0, lx = 0, ly = 0, lp = 0, lc = 0, le = 0;
       double f0 = 0, d1 = 0, d2 = 0, d3 = 0;
@@ -243,11 +248,26 @@ extern "C" {
 
 // Options: `opts` is a newline separated list "name value" applied on top of Ipopt defaults + print_level 0.
 // Returns Ipopt's ApplicationReturnStatus (IpReturnCodes_inc.h:16-39).  Any output pointer may be NULL.
+int ref_mpc_solve_w(int N, double dt, double Lf, double ref_v, double delta_max, double a_max, const double* weights7,
+                    const double* state6, const double* coeffs, int ncoef, const char* opts, double* x_out, double* out8,
+                    double* obj_out, int* iters_out, double* lambda_out, double* zl_out, double* zu_out, double* trace_out,
+                    int trace_cap, int* trace_rows);
+
 int ref_mpc_solve(int N, double dt, double Lf, double ref_v, double delta_max, double a_max, const double* state6,
                   const double* coeffs, int ncoef, const char* opts, double* x_out /*8N-2*/, double* out8,
                   double* obj_out, int* iters_out, double* lambda_out /*6N*/, double* zl_out /*8N-2*/,
                   double* zu_out /*8N-2*/, double* trace_out /*trace_cap x 10*/, int trace_cap, int* trace_rows) {
+  return ref_mpc_solve_w(N, dt, Lf, ref_v, delta_max, a_max, nullptr, state6, coeffs, ncoef, opts, x_out, out8, obj_out, iters_out,
+                         lambda_out, zl_out, zu_out, trace_out, trace_cap, trace_rows);
+}
+
+// weights7 = (w_cte, w_epsi, w_v, w_delta, w_a, w_ddelta, w_da) multiplying the seven cost terms of MPC.cpp:57-76; NULL = 1.
+int ref_mpc_solve_w(int N, double dt, double Lf, double ref_v, double delta_max, double a_max, const double* weights7,
+                    const double* state6, const double* coeffs, int ncoef, const char* opts, double* x_out, double* out8,
+                    double* obj_out, int* iters_out, double* lambda_out, double* zl_out, double* zu_out, double* trace_out,
+                    int trace_cap, int* trace_rows) {
   SmartPtr<MpcNlp> nlp = new MpcNlp();
+  if (weights7) std::memcpy(nlp->w, weights7, sizeof(double) * 7);
   nlp->N = N; nlp->dt = dt; nlp->Lf = Lf; nlp->ref_v = ref_v; nlp->delta_max = delta_max; nlp->a_max = a_max;
   std::memcpy(nlp->s0, state6, sizeof(double) * 6);
   nlp->coef.assign(coeffs, coeffs + ncoef);

@@ -30,6 +30,11 @@ def write_centerline():
     with open(os.path.join(out, "roadmap_centerline.csv"), "w") as f:
         for x, y in rm[:, 4:6]:
             f.write(f"{float(x)!r},{float(y)!r}\n")
+    # the whole file in the reference's own 7-column format (left edge x,y, right edge x,y, centre x,y, slope): the input
+    # of the library's reader b200mpc_read_roadmap_csv
+    with open(os.path.join(out, "roadmap.csv"), "w") as f:
+        for row in rm:
+            f.write(",".join(repr(float(v)) for v in row) + "\n")
 
 
 def solve_set(states, coeffs, **kw):
@@ -39,7 +44,7 @@ def solve_set(states, coeffs, **kw):
     st = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32); resto = np.zeros(B, dtype=np.int32)
     regu = np.zeros(B); lsmax = np.zeros(B, dtype=np.int32)
     for b in range(B):
-        r = ob.ref_solve(states[b], coeffs[b], trace=True, **kw)
+        r = ob.ref_solve(states[b], coeffs[b], trace=True, **kw)   # kw: N, dt, Lf, ref_v, delta_max, a_max, weights
         out8[b] = r["out8"]; x[b] = r["x"]; obj[b] = r["obj"]; st[b] = r["status"]; it[b] = r["iters"]
         tr = r["trace"]
         resto[b] = int((tr[:, 9] >= 100).any())
@@ -114,8 +119,76 @@ def main():
     print("golden fixtures written to", HERE)
 
 
-if __name__ == "__main__" and not {"--config3", "--n100", "--resto", "--soft", "--long-filter", "--rare-paths"} & set(sys.argv):
+if __name__ == "__main__" and not {"--config3", "--n100", "--resto", "--soft", "--long-filter", "--rare-paths", "--weights", "--frontend"} & set(sys.argv):
     main()
+
+
+def weights():
+    """Non-unit cost weights through the reference binaries: the TNLP's seven weights (oracle/ref_build/mpc_tnlp.cpp,
+    ref_mpc_solve_w) multiply the seven terms MPC.cpp:57-76 adds with weight 1.  Two weight sets x (32 degree-1 problems
+    + 32 degree-3 roadmap problems)."""
+    from udacitympc_b200 import synth
+    st, cf = synth.line_problems(32)
+    g = np.load(os.path.join(HERE, "roadmap_256.npz"))
+    sets = {"a": [3.0, 0.5, 0.2, 10.0, 2.0, 50.0, 4.0], "b": [2000.0, 2000.0, 1.0, 5.0, 5.0, 200.0, 10.0]}
+    out = dict(line_states=st, line_coeffs=cf, road_states=g["states"][:32], road_coeffs=g["fit"][:32])
+    for name, w in sets.items():
+        out[f"w_{name}"] = np.array(w)
+        for kind, (s_, c_) in (("line", (st, cf)), ("road", (g["states"][:32], g["fit"][:32]))):
+            r = solve_set(s_, c_, weights=w)
+            for k, v in r.items():
+                out[f"{kind}_{name}_{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "weights_64.npz"), **out)
+    print({k: int(out[k].sum()) for k in out if k.endswith("used_restoration")}, {k: out[k].tolist() for k in out if k.endswith("_status")})
+
+
+if __name__ == "__main__" and "--weights" in sys.argv:
+    weights()
+
+
+def frontend():
+    """Roadmap front-end fixture (SURVEY 8f2): what produces (coeffs, cte, epsi) in front of MPC::Solve.  Built from the
+    reference's own pieces where they run: its roadmap.csv (columns 4, 5 = centre line, custom_MPC.cpp:206-211), the
+    nearest-centre-line-point rule of custom_MPC.cpp:177-185 (squared distance, first minimum = ind[0] of CppAD::index_sort),
+    the global -> vehicle frame transform, the reference's OWN polyfit (helpers.h:24-44, oracle/_ref/libhelpers_ref.so)
+    on the 6 waypoints from there, and cte = polyeval(coeffs, 0) - 0, epsi = 0 - atan(coeffs[1]) as solution/main.cpp:34-37
+    defines them.  custom_MPC.cpp itself cannot run (CppAD absent, hard-coded /home/honda path, file name parsed as file
+    content), so the selection rule and the frame change are restated here in numpy, the fit is the reference's."""
+    rm = np.loadtxt(os.path.join(REF, "mpc_to_line", "roadmap.csv"), delimiter=",")
+    cl = rm[:, 4:6]
+    rng = np.random.default_rng(20240607)
+    B = 256
+    idx = rng.integers(0, len(cl) - 1, size=B)
+    tng = cl[idx + 1] - cl[idx]
+    ang = np.arctan2(tng[:, 1], tng[:, 0])
+    nrm = np.stack([-np.sin(ang), np.cos(ang)], axis=1)
+    frac = rng.uniform(0, 1, size=B)[:, None]
+    pos = cl[idx] + frac * tng + rng.uniform(-3.0, 3.0, size=B)[:, None] * nrm
+    psi = ang + rng.uniform(-0.4, 0.4, size=B)
+    v = rng.uniform(3.0, 35.0, size=B)
+    poses = np.column_stack([pos, psi, v])
+    # a few poses far from the road and next to its end (window clamped to the last 6 points)
+    poses[0, :2] = cl[-1] + [1.0, 2.0]; poses[1, :2] = cl[-3] + [0.5, -0.5]; poses[2, :2] = cl[0] - [20.0, 5.0]
+    state6 = np.zeros((B, 6)); coeffs = np.zeros((B, 4)); nearest = np.zeros(B, dtype=np.int32)
+    for b in range(B):
+        x, y, p = poses[b, 0], poses[b, 1], poses[b, 2]
+        d = (x - cl[:, 0]) * (x - cl[:, 0]) + (y - cl[:, 1]) * (y - cl[:, 1])
+        i0 = int(np.argmin(d))   # first minimum
+        nearest[b] = i0
+        i0 = min(i0, len(cl) - 6)
+        dx, dy = cl[i0:i0 + 6, 0] - x, cl[i0:i0 + 6, 1] - y
+        lx = np.cos(p) * dx + np.sin(p) * dy
+        ly = np.cos(p) * dy - np.sin(p) * dx
+        c = ob.ref_polyfit(lx, ly, 3)
+        coeffs[b] = c
+        state6[b] = [0.0, 0.0, 0.0, poses[b, 3], ob.ref_polyeval(c, 0.0) - 0.0, 0.0 - np.arctan(c[1])]
+    np.savez_compressed(os.path.join(HERE, "frontend_256.npz"), poses=poses, centerline=cl, state6=state6, coeffs=coeffs, nearest=nearest)
+    print("frontend fixture:", B, "poses, nearest index range", nearest.min(), nearest.max())
+
+
+if __name__ == "__main__" and "--frontend" in sys.argv:
+    write_centerline()
+    frontend()
 
 
 def config3():

@@ -117,6 +117,9 @@ def ref():
         L.ref_mpc_solve.restype = ctypes.c_int
         L.ref_mpc_solve.argtypes = [ctypes.c_int] + [ctypes.c_double] * 5 + [dp, dp, ctypes.c_int, ctypes.c_char_p, dp,
                                                                              dp, dp, ip, dp, dp, dp, dp, ctypes.c_int, ip]
+        L.ref_mpc_solve_w.restype = ctypes.c_int
+        L.ref_mpc_solve_w.argtypes = [ctypes.c_int] + [ctypes.c_double] * 5 + [dp, dp, dp, ctypes.c_int, ctypes.c_char_p, dp,
+                                                                               dp, dp, ip, dp, dp, dp, dp, ctypes.c_int, ip]
         L.ref_mpc_eval.restype = ctypes.c_int
         L.ref_mpc_eval.argtypes = [ctypes.c_int] + [ctypes.c_double] * 3 + [dp, ctypes.c_int, dp, dp, ctypes.c_double,
                                                                              dp, dp, dp, dp, dp]
@@ -136,7 +139,9 @@ def ref_helpers():
     return _refh
 
 
-def ref_solve(state6, coeffs, N=25, dt=0.05, Lf=2.67, ref_v=40.0, delta_max=0.436332, a_max=1.0, opts="", trace=False):
+def ref_solve(state6, coeffs, N=25, dt=0.05, Lf=2.67, ref_v=40.0, delta_max=0.436332, a_max=1.0, opts="", trace=False,
+              weights=None):
+    """weights = (w_cte, w_epsi, w_v, w_delta, w_a, w_ddelta, w_da) on the seven cost terms of MPC.cpp:57-76 (None = 1)."""
     n = 8 * N - 2
     st = np.ascontiguousarray(state6, dtype=np.float64); c = np.ascontiguousarray(coeffs, dtype=np.float64)
     x = np.zeros(n); o8 = np.zeros(8); obj = ctypes.c_double(); it = ctypes.c_int()
@@ -144,9 +149,11 @@ def ref_solve(state6, coeffs, N=25, dt=0.05, Lf=2.67, ref_v=40.0, delta_max=0.43
     cwd = os.getcwd()
     os.chdir(os.path.join(ORACLE_DIR, "_ref"))  # a directory without ipopt.opt
     try:
-        rc = ref().ref_mpc_solve(N, dt, Lf, ref_v, delta_max, a_max, _p(st), _p(c), len(c), opts.encode(), _p(x), _p(o8),
-                                 ctypes.byref(obj), ctypes.byref(it), _p(lam), _p(zl), _p(zu), _p(tr), 3100,
-                                 ctypes.byref(nr))
+        wv = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        assert wv is None or wv.shape == (7,)
+        rc = ref().ref_mpc_solve_w(N, dt, Lf, ref_v, delta_max, a_max, _p(wv), _p(st), _p(c), len(c), opts.encode(), _p(x),
+                                   _p(o8), ctypes.byref(obj), ctypes.byref(it), _p(lam), _p(zl), _p(zu), _p(tr), 3100,
+                                   ctypes.byref(nr))
     finally:
         os.chdir(cwd)
     out = dict(status=rc, x=x, out8=o8, obj=obj.value, iters=it.value, lam=lam, zl=zl, zu=zu)

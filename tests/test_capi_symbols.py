@@ -81,3 +81,26 @@ def test_synth_rng_is_mt19937_64():
     assert int(r.raw(10000)[-1]) == 9981545732273789042   # the C++ standard's check value for std::mt19937_64
     u = MT19937_64(20261018).uniform(5)
     assert np.all((u >= 0) & (u < 1))
+
+
+def test_roadmap_csv_reader_needs_no_gpu(tmp_path):
+    """b200mpc_read_roadmap_csv: host-only parse of the reference's 7-column roadmap file (custom_MPC.h:25-44)."""
+    path = os.path.join(ROOT, "udacitympc_b200", "data", "roadmap.csv")
+    cl, slope = mp.read_roadmap_csv(path)
+    raw = np.loadtxt(path, delimiter=",")
+    assert cl.shape == (246, 2) and np.array_equal(cl, raw[:, 4:6]) and np.array_equal(slope, raw[:, 6])
+    from udacitympc_b200 import synth
+    assert np.array_equal(cl, synth.roadmap_centerline())
+    # the reference converts every field with std::stof: single precision
+    clf, slf = mp.read_roadmap_csv(path, float_fields=True)
+    assert np.array_equal(clf, raw[:, 4:6].astype(np.float32).astype(np.float64)) and not np.array_equal(clf, cl)
+    bad = tmp_path / "bad.csv"
+    bad.write_text("1,2,3,4,5,6,7\n1,2,3\n")
+    with pytest.raises(mp.B200MPCError) as e:
+        mp.read_roadmap_csv(str(bad))
+    assert "bad.csv:2" in str(e.value) and "7" in str(e.value)
+    bad.write_text("1,2,x,4,5,6,7\n")
+    with pytest.raises(mp.B200MPCError):
+        mp.read_roadmap_csv(str(bad))
+    with pytest.raises(mp.B200MPCError):
+        mp.read_roadmap_csv(str(tmp_path / "missing.csv"))

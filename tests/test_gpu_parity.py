@@ -402,6 +402,41 @@ def test_roadmap_front_end_and_pipeline(mpc):
         mp.roadmap_reference_batch(poses, cl[:4], mpc=mpc)
 
 
+def test_roadmap_front_end_vs_reference_fixture(mpc):
+    """tests/golden/frontend_256.npz (make_golden.py --frontend): the reference's roadmap.csv, the nearest-point rule of
+    custom_MPC.cpp:177-185, and the REFERENCE's polyfit (helpers.h:24-44, compiled from where it lies) on the 6 waypoints
+    from there in the vehicle frame.  The roadmap file goes through the library's own reader."""
+    import os
+    g = golden("frontend_256.npz")
+    cl, slope = mp.read_roadmap_csv(os.path.join(os.path.dirname(mp.__file__), "data", "roadmap.csv"))
+    np.testing.assert_array_equal(cl, g["centerline"])
+    st, cf = mp.roadmap_reference_batch(g["poses"], cl, mpc=mpc)
+    # polyfit tolerance of north_star (1e-10), relative to the size of the coefficients of a fit
+    scale = np.maximum(1.0, np.abs(g["coeffs"]).max(axis=1, keepdims=True))
+    assert (np.abs(cf - g["coeffs"]) <= TOL_FIT * scale).all(), np.abs(cf - g["coeffs"]).max()
+    np.testing.assert_allclose(st, g["state6"], rtol=0, atol=TOL_FIT * 10)
+    # and through the solver: same MPC answers from the fixture's inputs and from the library's front-end
+    a = mpc.solve_batch(st[:32], cf[:32])
+    b = mpc.solve_batch(g["state6"][:32], g["coeffs"][:32])
+    ok = (a["status"] == 0) & (b["status"] == 0)
+    assert ok.sum() >= 28
+    np.testing.assert_allclose(a["out8"][ok], b["out8"][ok], rtol=0, atol=TOL_TRAJ)
+
+
+def test_cost_weights_vs_reference_binaries(mpc):
+    """b200mpc_params.w_* against goldens made by the reference's Ipopt + MUMPS binaries on the weighted problem
+    (tests/golden/weights_64.npz, make_golden.py --weights; TNLP weights in oracle/ref_build/mpc_tnlp.cpp)."""
+    g = golden("weights_64.npz")
+    for name in ("a", "b"):
+        w = g[f"w_{name}"]
+        kw = dict(w_cte=w[0], w_epsi=w[1], w_v=w[2], w_delta=w[3], w_a=w[4], w_ddelta=w[5], w_da=w[6])
+        with mp.MPC(**kw) as m:
+            for kind in ("line", "road"):
+                r = m.solve_batch(g[f"{kind}_states"], g[f"{kind}_coeffs"], want_traj=True)
+                gg = {k: g[f"{kind}_{name}_{k}"] for k in ("status", "out8", "x", "obj", "iters")}
+                compare(r, gg)
+
+
 def test_reference_shaped_solve_reads_two_coefficients_like_fg_eval():
     """MPC.cpp:117-118 uses coeffs[0] and coeffs[1] whatever the vector's length; the full polynomial is an option."""
     state = np.array([0.0, 0.0, 0.0, 12.0, -0.7, 0.05])

@@ -119,3 +119,18 @@ def test_port_soft_restoration_phase_matches_reference():
         assert o["status"] == 0 and o["iters"] == g["iters"][b]
         np.testing.assert_allclose(o["x"], g["x"][b], rtol=0, atol=1e-10)
         assert abs(o["obj"] - g["obj"][b]) <= 1e-12 * abs(g["obj"][b])
+
+
+def test_frontend_fixture_fit_is_reproduced_by_the_port():
+    """frontend_256.npz: the fit stored there is the reference's polyfit; the port's QR restatement agrees to 1e-10."""
+    g = golden("frontend_256.npz")
+    cl = g["centerline"]
+    for b in range(0, 256, 5):
+        x, y, p = g["poses"][b, :3]
+        d = (x - cl[:, 0]) * (x - cl[:, 0]) + (y - cl[:, 1]) * (y - cl[:, 1])
+        i0 = int(np.argmin(d))
+        assert i0 == g["nearest"][b]
+        i0 = min(i0, len(cl) - 6)
+        dx, dy = cl[i0:i0 + 6, 0] - x, cl[i0:i0 + 6, 1] - y
+        c = ob.port_polyfit(np.cos(p) * dx + np.sin(p) * dy, np.cos(p) * dy - np.sin(p) * dx, 3)
+        np.testing.assert_allclose(c, g["coeffs"][b], rtol=0, atol=1e-10 * max(1.0, np.abs(c).max()))

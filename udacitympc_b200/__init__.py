@@ -27,9 +27,10 @@ from .api import (  # noqa: F401
     polyeval_batch,
     polyfit,
     polyfit_batch,
+    read_roadmap_csv,
     roadmap_reference_batch,
     rollout_batch,
 )
 
 __all__ = ["B200MPCError", "MPC", "MPCParams", "global_kinematic", "lib_path", "load_library", "polyeval",
-           "polyeval_batch", "polyfit", "polyfit_batch", "roadmap_reference_batch", "rollout_batch"]
+           "polyeval_batch", "polyfit", "polyfit_batch", "read_roadmap_csv", "roadmap_reference_batch", "rollout_batch"]

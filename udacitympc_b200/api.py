@@ -45,6 +45,7 @@ SYMBOLS = {
                                                     ctypes.c_double, _vp, _vp]),
     "b200mpc_roadmap_reference_batch": (ctypes.c_int, [_vp, ctypes.c_int, _dp, _dp, ctypes.c_int, _dp, _dp]),
     "b200mpc_roadmap_reference_batch_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp, _vp]),
+    "b200mpc_read_roadmap_csv": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, _dp, _dp, ctypes.c_int, _ip]),
     "b200mpc_set_warm_start": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double]),
     "b200mpc_set_batch_split": (ctypes.c_int, [_vp, ctypes.c_int]),
     "b200mpc_set_compaction": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_int]),
@@ -365,6 +366,18 @@ def roadmap_reference_batch(poses, centerline, mpc=None):
     st = np.empty((B, 6)); cf = np.empty((B, 4))
     _check(m_._lib.b200mpc_roadmap_reference_batch(m_.handle, B, _ptr(poses), _ptr(centerline), centerline.shape[0], _ptr(st), _ptr(cf)))
     return st, cf
+
+
+def read_roadmap_csv(path, float_fields=False):
+    """The reference's roadmap file (7 numbers per line) -> (centerline (n_wp, 2), slope (n_wp,)), parsed by the library's
+    host-side reader (b200mpc_read_roadmap_csv).  float_fields=True converts every field through single precision like
+    the reference's std::stof (mpc_to_line/src/custom_MPC.h:35-44)."""
+    lib = load_library()
+    n = ctypes.c_int()
+    _check(lib.b200mpc_read_roadmap_csv(os.fsencode(path), int(float_fields), None, None, 0, ctypes.byref(n)))
+    cl = np.empty((n.value, 2)); sl = np.empty(n.value)
+    _check(lib.b200mpc_read_roadmap_csv(os.fsencode(path), int(float_fields), _ptr(cl), _ptr(sl), n.value, ctypes.byref(n)))
+    return cl, sl
 
 
 def global_kinematic(state, actuators, dt, Lf=2.0, mpc=None):

@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <new>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <vector>
@@ -590,6 +592,45 @@ int b200mpc_roadmap_reference_batch(b200mpc_handle* h, int B, const double* pose
   CU(cudaMemcpyAsync(state6_out, ao, nb * 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(coeffs_out, ao + nb * 6, nb * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// Host-side reader of the reference's roadmap file (no device work): one waypoint per line, fields split at ',' and
+// converted one by one, as CustomMPC::parseRoadMapLine does (mpc_to_line/src/custom_MPC.h:35-44; std::stof there).
+int b200mpc_read_roadmap_csv(const char* path, int float_fields, double* centerline_out, double* slope_out, int max_wp, int* n_wp) {
+  if (!path || !n_wp) return fail(B200MPC_ERR_ARG, "null path / n_wp");
+  if (max_wp < 0) return fail(B200MPC_ERR_ARG, "negative max_wp");
+  std::ifstream f(path);
+  if (!f.good()) return fail(B200MPC_ERR_ARG, std::string("cannot open roadmap file ") + path);
+  std::string line;
+  int n = 0, lineno = 0;
+  while (std::getline(f, line)) {
+    ++lineno;
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.find_first_not_of(" \t") == std::string::npos) continue;   // blank line
+    std::istringstream ls(line);
+    std::string number;
+    double v[7];
+    int k = 0;
+    while (std::getline(ls, number, ',')) {
+      if (k >= 7) { ++k; break; }
+      try {
+        size_t used = 0;
+        v[k] = float_fields ? (double)std::stof(number, &used) : std::stod(number, &used);
+      } catch (...) {
+        return fail(B200MPC_ERR_ARG, std::string(path) + ":" + std::to_string(lineno) + ": field " + std::to_string(k + 1) + " is not a number");
+      }
+      ++k;
+    }
+    if (k != 7)
+      return fail(B200MPC_ERR_ARG, std::string(path) + ":" + std::to_string(lineno) + ": expected 7 comma-separated fields (left x,y, right x,y, centre x,y, slope)");
+    if (n < max_wp) {
+      if (centerline_out) { centerline_out[2 * n] = v[4]; centerline_out[2 * n + 1] = v[5]; }
+      if (slope_out) slope_out[n] = v[6];
+    }
+    ++n;
+  }
+  *n_wp = n;
   return 0;
 }
 
