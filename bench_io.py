@@ -1,108 +1,218 @@
 #!/usr/bin/env python
-"""bench_io.py -- HBM-roofline measurement of the batch I/O-style kernels (BASELINE.json configs[1]):
-  K4 polyfit   degree-3 fits of 6-point roadmap windows      128 B per fit  (16m + 8(d+1))
-  K5 rollout   bicycle-model steps, H = 1 and H = 25         80 B per step; 32+16H in, 32H out per rollout
-  K6 batch I/O [B][K] <-> [K][B] transposes through the host-buffer entry points (timed inside them by nothing here;
-               reported through the end-to-end polyfit call)
-Device-resident, field-major inputs; CUDA events on the launching stream; inputs larger than the 126 MB L2 so every
-iteration streams from HBM.  Prints one JSON object; `python bench_io.py > profiles/r1_io_kernels.json`."""
+"""bench_io.py -- BASELINE.json configs[1]: "global_kinematic_model + polyfit batched: 1M bicycle-model rollouts and
+degree-3 fits of roadmap.csv windows on 1 B200", as one JSON line shaped like bench.py's.
+
+    python bench_io.py [--units 1048576] [--steps 20] [--warmup 3] [--impl ours|reference] [--horizon 1]
+
+A "step" is one pass over the config: --units bicycle-model rollouts (K5: `globalKinematic`,
+global_kinematic_model/solution/main.cpp:36-62, H Euler steps each; H = 1 is the reference call) and --units degree-3
+fits of 6-point roadmap windows (K4: `polyfit`, helpers.h:24-44).  One unit = one rollout + one fit.
+
+value     units/s, kernels only: device-resident field-major inputs, CUDA events on the launching stream.  The inputs
+          cycle over 4 distinct sets (4 x 226 MB at H = 1), so every step streams from HBM, not from the 126 MB L2.
+e2e       the same through the host-buffer C-ABI calls the reference's functions bind (b200mpc_polyfit_batch,
+          b200mpc_rollout_batch): pinned host buffers in the reference's per-call order, H2D + D2H inside the timed
+          region.  The kernels read / write that order directly (K6 fused: no transpose launches).
+roofline  HBM: algorithmic bytes (128 B per fit = 16 m + 8 (d+1); 32 + 16 H in, 32 H out per rollout) over the
+          kernel's own duration (CUDA events around back-to-back launches of that kernel alone), against
+          MEASURED_PEAKS.json hbm_gbs.  The dominant kernel of the step is named in roofline.kernel; both are listed.
+cpu_baseline / --impl reference   the reference's own polyfit (Eigen HouseholderQR) and globalKinematic compiled from
+          /root/reference (oracle/_ref/libhelpers_ref.so; the C port when absent) on one host core, bounded sample.
+"""
 import argparse
 import ctypes
 import json
 import os
 import sys
+import time
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "rollout_and_polyfit_units_per_sec"
+UNIT = "units/s"
+M_PTS, ORDER = 6, 3
+
+
+def config_dict(args):
+    return dict(workload="BASELINE configs[1]: global_kinematic_model + polyfit batched, 1 048 576 bicycle-model rollouts and degree-3 fits "
+                         "of 6-point roadmap.csv windows per step",
+                units_per_step=args.units, rollout_horizon_H=args.horizon, fit_points=M_PTS, fit_order=ORDER, dt=0.3, Lf=2.0,
+                l2="inputs cycle over 4 distinct sets (> 126 MB L2 each pass)")
+
+
+def cpu_arm(args, xs, ys, st, act, n):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_bindings as ob
+    n = min(n, len(xs))
+    t0 = time.perf_counter()
+    cf, nx, kind = ob.cpu_fit_and_step_batch(xs[:n], ys[:n], ORDER, st[:n], act[:n, 0], 0.3, 2.0)
+    dt = time.perf_counter() - t0
+    return dict(value=n / dt, unit=UNIT, cores=1, kind=kind, seconds=dt,
+                sample=f"first {n} units of the workload (one polyfit + one globalKinematic call each, H = 1) in one native loop on one host core; "
+                       + ("the reference's helpers.h / globalKinematic compiled from /root/reference (Eigen 3.3.3 HouseholderQR)"
+                          if kind == "reference" else "C port of the reference functions")), cf, nx
+
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=4 * 1048576)
-    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--units", type=int, default=1048576)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--horizon", type=int, default=1, help="Euler steps per rollout (1 = the reference's globalKinematic call)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-units", type=int, default=1048576, help="cpu_baseline sample (units)")
+    ap.add_argument("--min-seconds", type=float, default=1.0)
     args = ap.parse_args()
+    from udacitympc_b200 import synth
+    B, H = args.units, args.horizon
+    nsets = 4
+    sets = []
+    for s in range(nsets):
+        xs, ys = synth.roadmap_windows(B, synth.MT19937_64(synth.SEED + 77 * s))
+        st, act = synth.kinematic_inputs(B, H=H, rng=synth.MT19937_64(synth.SEED + 2 + 77 * s))
+        sets.append((xs, ys, st, act))
+
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        times = []
+        for i in range(args.warmup + args.steps):
+            xs, ys, st, act = sets[i % nsets]
+            r, _, _ = cpu_arm(args, xs, ys, st, act, args.cpu_units)
+            if i >= args.warmup:
+                times.append(r["seconds"])
+        n = min(args.cpu_units, B)
+        v = n / float(np.mean(times))
+        print(json.dumps(dict(metric=METRIC, value=v, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                              ms_per_step=1e3 * float(np.mean(times)), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                              data="synthetic", config=config_dict(args), units_per_step_of_this_arm=n,
+                              cpu_baseline=dict(value=v, unit=UNIT, cores=1, kind=r["kind"], sample=r["sample"]),
+                              e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)))
+        return
+
     import torch
     import udacitympc_b200 as mp
-    from udacitympc_b200 import synth
     if not torch.cuda.is_available():
-        raise SystemExit("bench_io.py needs a CUDA device")
+        raise SystemExit("bench_io.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
     dev = torch.device("cuda", 0)
-    B = args.batch
     mpc = mp.MPC(device=0)
     lib = mp.load_library()
     stream = torch.cuda.Stream(device=dev)
+    vp, dp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm = peaks.get("hbm_gbs", 6650.0)
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-
-    def timeit(fn):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(args.reps):
-            fn()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / args.reps
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
     def chk(rc):
         if rc:
             raise RuntimeError(lib.b200mpc_last_error().decode())
 
-    out = dict(batch=B, reps=args.reps, hbm_peak_gbs=hbm, peak_source=peak_src, kernels={})
-    vp = ctypes.c_void_p
+    # device-resident, field-major copies of every input set
+    dsets = []
+    for xs, ys, st, act in sets:
+        dsets.append(dict(xs=torch.from_numpy(np.ascontiguousarray(xs.T)).to(dev), ys=torch.from_numpy(np.ascontiguousarray(ys.T)).to(dev),
+                          st=torch.from_numpy(np.ascontiguousarray(st.T)).to(dev),
+                          act=torch.from_numpy(np.ascontiguousarray(act.reshape(B, 2 * H).T)).to(dev)))
+    cf_d = torch.empty((ORDER + 1, B), dtype=torch.float64, device=dev)
+    ro_d = torch.empty((4 * H, B), dtype=torch.float64, device=dev)
 
-    # ---- K4: the 1M-window workload tiled up to B fits
-    nb = min(B, 1048576)
-    xs, ys = synth.roadmap_windows(nb)
-    reps_t = (B + nb - 1) // nb
-    xs_d = torch.from_numpy(np.ascontiguousarray(np.tile(xs, (reps_t, 1))[:B].T)).to(dev)
-    ys_d = torch.from_numpy(np.ascontiguousarray(np.tile(ys, (reps_t, 1))[:B].T)).to(dev)
-    cf_d = torch.empty((4, B), dtype=torch.float64, device=dev)
-    ms = timeit(lambda: chk(lib.b200mpc_polyfit_batch_device(mpc.handle, B, vp(xs_d.data_ptr()), vp(ys_d.data_ptr()), 6, 3,
-                                                             vp(cf_d.data_ptr()), vp(stream.cuda_stream))))
-    byt = 128.0 * B
-    out["kernels"]["polyfit_kernel<6,4>"] = dict(ms=ms, fits_per_s=B / (ms * 1e-3), bytes_per_unit=128, achieved_gbs=byt / (ms * 1e-3) / 1e9,
-                                                 frac=byt / (ms * 1e-3) / 1e9 / hbm)
-    # spot check against numpy
-    ref = np.linalg.lstsq(np.stack([xs[0] ** i for i in range(4)], axis=1), ys[0], rcond=None)[0]
-    assert np.allclose(cf_d[:, 0].cpu().numpy(), ref, atol=1e-9)
+    def fit(i):
+        d = dsets[i % nsets]
+        chk(lib.b200mpc_polyfit_batch_device(mpc.handle, B, vp(d["xs"].data_ptr()), vp(d["ys"].data_ptr()), M_PTS, ORDER, vp(cf_d.data_ptr()),
+                                             vp(stream.cuda_stream)))
 
-    # ---- K5: single step and 25-step rollouts
-    for H in (1, 25):
-        nbh = B if H == 1 else max(B // 8, 65536)
-        st, act = synth.kinematic_inputs(min(nbh, 262144), H=H)
-        t = (nbh + len(st) - 1) // len(st)
-        st_d = torch.from_numpy(np.ascontiguousarray(np.tile(st, (t, 1))[:nbh].T)).to(dev)
-        act_d = torch.from_numpy(np.ascontiguousarray(np.tile(act.reshape(len(st), -1), (t, 1))[:nbh].T)).to(dev)
-        o_d = torch.empty((4 * H, nbh), dtype=torch.float64, device=dev)
-        ms = timeit(lambda: chk(lib.b200mpc_rollout_batch_device(mpc.handle, nbh, H, vp(st_d.data_ptr()), vp(act_d.data_ptr()),
-                                                                 ctypes.c_double(0.3), ctypes.c_double(2.0), vp(o_d.data_ptr()),
-                                                                 vp(stream.cuda_stream))))
-        per = 32 + 16 * H + 32 * H
-        byt = float(per) * nbh
-        out["kernels"][f"rollout_kernel H={H}"] = dict(ms=ms, batch=nbh, rollouts_per_s=nbh / (ms * 1e-3), steps_per_s=nbh * H / (ms * 1e-3),
-                                                       bytes_per_unit=per, achieved_gbs=byt / (ms * 1e-3) / 1e9,
-                                                       frac=byt / (ms * 1e-3) / 1e9 / hbm)
+    def roll(i):
+        d = dsets[i % nsets]
+        chk(lib.b200mpc_rollout_batch_device(mpc.handle, B, H, vp(d["st"].data_ptr()), vp(d["act"].data_ptr()), ctypes.c_double(0.3),
+                                             ctypes.c_double(2.0), vp(ro_d.data_ptr()), vp(stream.cuda_stream)))
 
-    # ---- end to end (host buffers, K6 transposes + copies inside): 1M fits
-    import time
-    xs1, ys1 = xs[:nb], ys[:nb]
-    mp.polyfit_batch(xs1, ys1, 3, mpc=mpc)
+    def timed(fns, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            for f in fns:
+                f(i)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    W, K = max(3, args.warmup), args.steps
+    timed([fit, roll], W)
+    est = timed([fit, roll], K)
+    R = max(1, int(np.ceil(args.min_seconds * 1e3 / max(est, 1e-3))))
+    launches0 = mpc.launch_count()
+    ms_total = timed([fit, roll], K * R)
+    launches = mpc.launch_count() - launches0
+    value = B * K * R / (ms_total * 1e-3)
+    # each kernel alone (its own duration for the roofline)
+    fit_ms = timed([fit], K * R) / (K * R)
+    roll_ms = timed([roll], K * R) / (K * R)
+    fit_bytes, roll_bytes = 128.0 * B, float(32 + 16 * H + 32 * H) * B
+    kern = {"polyfit_kernel<6,4>": dict(avg_ms=fit_ms, bytes_per_unit=128, achieved=fit_bytes / (fit_ms * 1e-3) / 1e9),
+            "rollout_kernel": dict(avg_ms=roll_ms, bytes_per_unit=32 + 48 * H, achieved=roll_bytes / (roll_ms * 1e-3) / 1e9)}
+    for k in kern.values():
+        k["frac"] = k["achieved"] / hbm
+    dom = max(kern, key=lambda k: kern[k]["avg_ms"])
+
+    # parity spot check of the device results against the CPU arm on the last-used set
+    torch.cuda.synchronize()
+    fit(0); roll(0)
+    torch.cuda.synchronize()
+    xs, ys, st, act = sets[0]
+    cpu, cf_ref, nx_ref = cpu_arm(args, xs, ys, st, act, args.cpu_units)
+    n = len(cf_ref)
+    fit_err = float(np.abs(cf_d[:, :n].cpu().numpy().T - cf_ref).max())
+    roll_err = float(np.abs(ro_d[:4, :n].cpu().numpy().T - nx_ref).max())
+
+    # ---- e2e: pinned host buffers in the reference's per-call order through the host-buffer entry points
+    pin = []
+    for xs, ys, st, act in sets:
+        pin.append(tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (xs, ys, st, act.reshape(B, 2 * H))))
+    h_cf = torch.empty((B, ORDER + 1), dtype=torch.float64).pin_memory()
+    h_ro = torch.empty((B, 4 * H), dtype=torch.float64).pin_memory()
+
+    def host_step(i):
+        xs_, ys_, st_, act_ = pin[i % nsets]
+        chk(lib.b200mpc_polyfit_batch(mpc.handle, B, ctypes.cast(xs_.data_ptr(), dp), ctypes.cast(ys_.data_ptr(), dp), M_PTS, ORDER,
+                                      ctypes.cast(h_cf.data_ptr(), dp)))
+        chk(lib.b200mpc_rollout_batch(mpc.handle, B, H, ctypes.cast(st_.data_ptr(), dp), ctypes.cast(act_.data_ptr(), dp), ctypes.c_double(0.3),
+                                      ctypes.c_double(2.0), ctypes.cast(h_ro.data_ptr(), dp)))
+
+    for i in range(W):
+        host_step(i)
+    n_e2e = max(K, 10)
     t0 = time.perf_counter()
-    for _ in range(5):
-        mp.polyfit_batch(xs1, ys1, 3, mpc=mpc)
-    dt = (time.perf_counter() - t0) / 5
-    out["e2e_polyfit_host_buffers"] = dict(batch=nb, ms=dt * 1e3, fits_per_s=nb / dt, note="pageable numpy buffers, H2D + 3 transposes + fit + D2H")
-    print(json.dumps(out, indent=1))
+    for i in range(n_e2e):
+        host_step(i)
+    e2e_s = time.perf_counter() - t0
+    h2d = B * (2 * M_PTS + 4 + 2 * H) * 8
+    d2h = B * (ORDER + 1 + 4 * H) * 8
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=1, steps=K, warmup=W, ms_per_step=ms_total / (K * R), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config_dict(args),
+                timed=dict(passes=K * R, seconds=ms_total * 1e-3),
+                e2e=dict(value=B * n_e2e / e2e_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, passes=n_e2e, seconds=e2e_s,
+                         pcie_gbs=(h2d + d2h) * n_e2e / e2e_s / 1e9,
+                         note="pinned host buffers, two blocking host-buffer calls per step; bound by the host link: "
+                              "bytes moved per second in pcie_gbs"),
+                gpu_launches=int(launches),
+                roofline=dict(bound="hbm", kernel=dom, achieved=kern[dom]["achieved"], peak=hbm, unit="GB/s", frac=kern[dom]["frac"], traffic=None,
+                              peak_source=peak_src, kernels=kern,
+                              note="achieved = algorithmic bytes (SURVEY 8d) x units / the kernel's own average duration (that kernel launched "
+                                   "back to back, CUDA events); polyfit executes ~500 FP64 instructions per 128-byte fit (FP64-issue bound "
+                                   "near 80 % of the copy bandwidth), the rollout is a pure stream"),
+                parity=dict(units_checked=n, polyfit_max_abs_err=fit_err, rollout_max_abs_err=roll_err, against=cpu["kind"],
+                            tolerance="polyfit 1e-10, rollout 1e-12 (north_star)"),
+                cpu_baseline={k: v for k, v in cpu.items() if k != "seconds"})
+    assert fit_err < 1e-8 and roll_err < 1e-10, (fit_err, roll_err)
+    print(json.dumps(line))
     mpc.close()
 
 

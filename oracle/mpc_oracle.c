@@ -117,6 +117,14 @@ void oracle_global_kinematic(const double* s, const double* u, double dt, double
   nx[3] = v + a * dt;
 }
 
+/* loops over the two calls above (bench_io.py's cpu_baseline when oracle/_ref is absent) */
+void oracle_polyfit_batch(const double* xs, const double* ys, int B, int m, int order, double* coeffs_out) {
+  for (int b = 0; b < B; ++b) oracle_polyfit(xs + (size_t)b * m, ys + (size_t)b * m, m, order, coeffs_out + (size_t)b * (order + 1));
+}
+void oracle_global_kinematic_batch(const double* s, const double* u, int B, double dt, double Lf, double* nx) {
+  for (int b = 0; b < B; ++b) oracle_global_kinematic(s + (size_t)b * 4, u + (size_t)b * 2, dt, Lf, nx + (size_t)b * 4);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* The NLP of MPC.cpp                                                                          */
 /* ------------------------------------------------------------------------------------------ */

@@ -61,6 +61,9 @@ int oracle_polyfit(const double* xs, const double* ys, int m, int order, double*
 
 /* global_kinematic_model/solution/main.cpp:36-62 (one Euler step; Lf is a parameter: 2 there, 2.67 in MPC.cpp:27). */
 void oracle_global_kinematic(const double* state4, const double* act2, double dt, double Lf, double* next4);
+/* B calls of the two functions above: xs, ys [B][m] -> coeffs [B][order+1]; state4 [B][4], act2 [B][2] -> next4 [B][4] */
+void oracle_polyfit_batch(const double* xs, const double* ys, int B, int m, int order, double* coeffs_out);
+void oracle_global_kinematic_batch(const double* state4, const double* act2, int B, double dt, double Lf, double* next4);
 
 #ifdef __cplusplus
 }

@@ -35,4 +35,13 @@ void ref_global_kinematic(const double* state4, const double* act2, double dt, d
   for (int i = 0; i < 4; ++i) next4[i] = n[i];
 }
 
+// loops over the calls above (the CPU baseline of bench_io.py times these, so that the per-call cost is the
+// reference's own code and not the Python binding): xs, ys [B][m] -> coeffs [B][order+1]; state4 [B][4], act2 [B][2]
+void ref_polyfit_batch(const double* xs, const double* ys, int B, int m, int order, double* coeffs_out) {
+  for (int b = 0; b < B; ++b) ref_polyfit(xs + (size_t)b * m, ys + (size_t)b * m, m, order, coeffs_out + (size_t)b * (order + 1));
+}
+void ref_global_kinematic_batch(const double* state4, const double* act2, int B, double dt, double* next4) {
+  for (int b = 0; b < B; ++b) ref_global_kinematic(state4 + (size_t)b * 4, act2 + (size_t)b * 2, dt, next4 + (size_t)b * 4);
+}
+
 }  // extern "C"

@@ -93,6 +93,26 @@ def port_polyfit(xs, ys, order):
     return out
 
 
+def cpu_fit_and_step_batch(xs, ys, order, state4, act2, dt, Lf=2.0):
+    """B polyfit calls + B globalKinematic calls in one native loop each (bench_io.py's CPU arm): the reference's own
+    helpers.h / globalKinematic (oracle/_ref, Lf = 2 as in its source) when built, else the C port.  Returns
+    (coeffs (B, order+1), next4 (B, 4), kind)."""
+    xs = np.ascontiguousarray(xs, dtype=np.float64); ys = np.ascontiguousarray(ys, dtype=np.float64)
+    st = np.ascontiguousarray(state4, dtype=np.float64); ac = np.ascontiguousarray(act2, dtype=np.float64).reshape(len(st), 2)
+    B, m = xs.shape
+    cf = np.zeros((B, order + 1)); nx = np.zeros((len(st), 4))
+    if ref_available() and hasattr(ref_helpers(), "ref_polyfit_batch") and Lf == 2.0:
+        ref_helpers().ref_polyfit_batch(_p(xs), _p(ys), B, m, order, _p(cf))
+        ref_helpers().ref_global_kinematic_batch(_p(st), _p(ac), len(st), dt, _p(nx))
+        return cf, nx, "reference"
+    L = port()
+    L.oracle_polyfit_batch.argtypes = [dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp]
+    L.oracle_global_kinematic_batch.argtypes = [dp, dp, ctypes.c_int, ctypes.c_double, ctypes.c_double, dp]
+    L.oracle_polyfit_batch(_p(xs), _p(ys), B, m, order, _p(cf))
+    L.oracle_global_kinematic_batch(_p(st), _p(ac), len(st), dt, Lf, _p(nx))
+    return cf, nx, "port"
+
+
 def port_polyeval(coeffs, x):
     c = np.ascontiguousarray(coeffs, dtype=np.float64)
     return port().oracle_polyeval(_p(c), len(c), float(x))
@@ -135,6 +155,9 @@ def ref_helpers():
         H.ref_polyeval.restype = ctypes.c_double
         H.ref_polyeval.argtypes = [dp, ctypes.c_int, ctypes.c_double]
         H.ref_global_kinematic.argtypes = [dp, dp, ctypes.c_double, dp]
+        if hasattr(H, "ref_polyfit_batch"):
+            H.ref_polyfit_batch.argtypes = [dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp]
+            H.ref_global_kinematic_batch.argtypes = [dp, dp, ctypes.c_int, ctypes.c_double, dp]
         _refh = H
     return _refh
 

@@ -49,7 +49,7 @@ struct b200mpc_handle {
   SplitStreams ss;
   int device = 0;
   cudaStream_t stream = nullptr;
-  DevBuf ws, in_aos, st_soa, cf_soa, out_soa, out_aos, traj_soa, traj_aos, obj, status, iters, misc0, misc1, misc2, misc3;
+  DevBuf ws, in_aos, out_aos, traj_soa, traj_aos, obj, status, iters, misc0, misc3;
   bool timing_on = false;                                    // b200mpc_set_timing: measurement only, off by default
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;   // around every solve while timing_on
   cudaEvent_t done = nullptr;   // recorded after every solve: the next solve on this handle (any stream) waits for it
@@ -59,7 +59,7 @@ struct b200mpc_handle {
   long long launches = 0;
   // CUDA graphs of whole solves (init + rounds x (factor, forward, step) + finisher), keyed by every launch argument
   struct GraphEntry {
-    int B, steps, ncoef, mode, rounds, fused_below, warm, split, repack_gen;
+    int B, steps, ncoef, mode, rounds, fused_below, warm, split, repack_gen, io_aos;
     double warm_mu;
     const void *st, *cf, *ws, *out8, *traj, *obj, *status, *iters;
     cudaGraphExec_t exec;
@@ -98,13 +98,14 @@ int check_solve_args(const b200mpc_handle* h, int B, const void* st, const void*
 }
 
 int run_solve(b200mpc_handle* h, int B, int steps, const double* st, const double* cf, int ncoef, double* out8,
-              double* traj, double* obj, int* status, int* iters, cudaStream_t s, bool caller_captures);
+              double* traj, double* obj, int* status, int* iters, cudaStream_t s, bool caller_captures, int io_aos);
 
 // One solve on stream s.  The handle owns ONE workspace and one set of auxiliary streams, so solves on a handle are
 // serialised on the device whatever streams the caller uses (an event recorded after each solve, waited for by the
 // next).  With b200mpc_set_timing a pair of events brackets the solver kernels for bench.py.
+// io_aos = 1: st / cf / out8 are in the reference's per-problem order (host entry points); traj stays field-major.
 int timed_solve(b200mpc_handle* h, int B, int steps, const double* st, const double* cf, int ncoef, double* out8,
-                double* traj, double* obj, int* status, int* iters, cudaStream_t s) {
+                double* traj, double* obj, int* status, int* iters, cudaStream_t s, int io_aos = 0) {
   // the caller may be capturing its stream into a graph of its own: then no nested capture, no external events
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (s != nullptr && s != cudaStreamLegacy) { if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; } }
@@ -121,7 +122,7 @@ int timed_solve(b200mpc_handle* h, int B, int steps, const double* st, const dou
     cudaError_t e = cudaEventRecord(e0, s);
     if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(e, "cudaEventRecord"); }
   }
-  int rc = run_solve(h, B, steps, st, cf, ncoef, out8, traj, obj, status, iters, s, caller_captures);
+  int rc = run_solve(h, B, steps, st, cf, ncoef, out8, traj, obj, status, iters, s, caller_captures, io_aos);
   if (rec) {
     cudaError_t e = rc == 0 ? cudaEventRecord(e1, s) : cudaErrorUnknown;
     if (e == cudaSuccess) h->timing.emplace_back(e0, e1);
@@ -135,23 +136,23 @@ int timed_solve(b200mpc_handle* h, int B, int steps, const double* st, const dou
 }
 
 int run_solve(b200mpc_handle* h, int B, int steps, const double* st, const double* cf, int ncoef, double* out8,
-              double* traj, double* obj, int* status, int* iters, cudaStream_t s, bool caller_captures) {
+              double* traj, double* obj, int* status, int* iters, cudaStream_t s, bool caller_captures, int io_aos) {
   // One solve is ~75 dependent launches; replaying a captured graph keeps the host out of the inner loop (several
   // ranks / streams per host otherwise become launch-bound).  The legacy default stream cannot be captured.
   bool done = false;
   if (h->use_graphs && !caller_captures && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) {
-    b200mpc_handle::GraphEntry key{B, steps, ncoef, h->cfg.mode, h->cfg.rounds, h->cfg.fused_below, h->cfg.warm_start ? 1 : 0, h->cfg.split, h->repack_gen, h->cfg.warm_mu, st, cf, h->ws.p, out8, traj, obj, status, iters, nullptr, 0};
+    b200mpc_handle::GraphEntry key{B, steps, ncoef, h->cfg.mode, h->cfg.rounds, h->cfg.fused_below, h->cfg.warm_start ? 1 : 0, h->cfg.split, h->repack_gen, io_aos, h->cfg.warm_mu, st, cf, h->ws.p, out8, traj, obj, status, iters, nullptr, 0};
     b200mpc_handle::GraphEntry* hit = nullptr;
     for (auto& g : h->graphs)
       if (g.B == key.B && g.steps == key.steps && g.ncoef == key.ncoef && g.mode == key.mode && g.rounds == key.rounds &&
-          g.fused_below == key.fused_below && g.warm == key.warm && g.split == key.split && g.repack_gen == key.repack_gen && g.warm_mu == key.warm_mu && g.st == key.st && g.cf == key.cf && g.ws == key.ws && g.out8 == key.out8 &&
+          g.fused_below == key.fused_below && g.warm == key.warm && g.split == key.split && g.repack_gen == key.repack_gen && g.io_aos == key.io_aos && g.warm_mu == key.warm_mu && g.st == key.st && g.cf == key.cf && g.ws == key.ws && g.out8 == key.out8 &&
           g.traj == key.traj && g.obj == key.obj && g.status == key.status && g.iters == key.iters)
         hit = &g;
     if (!hit) {
       cudaGraph_t graph = nullptr;
       long long n = 0;
       if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
-        cudaError_t le = launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, &h->ss, &n);
+        cudaError_t le = launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, &h->ss, &n, io_aos);
         cudaError_t ce = cudaStreamEndCapture(s, &graph);
         if (le == cudaSuccess && ce == cudaSuccess && graph) {
           cudaGraphExec_t exec = nullptr;
@@ -173,7 +174,7 @@ int run_solve(b200mpc_handle* h, int B, int steps, const double* st, const doubl
     }
   }
   if (!done)
-    CU(launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, &h->ss, &h->launches));
+    CU(launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, &h->ss, &h->launches, io_aos));
   return 0;
 }
 
@@ -248,8 +249,7 @@ void b200mpc_destroy(b200mpc_handle* h) {
   }
   if (h->ss.fork) cudaEventDestroy(h->ss.fork);
   if (h->done) cudaEventDestroy(h->done);
-  DevBuf* bufs[] = {&h->ws, &h->in_aos, &h->st_soa, &h->cf_soa, &h->out_soa, &h->out_aos, &h->traj_soa, &h->traj_aos,
-                    &h->obj, &h->status, &h->iters, &h->misc0, &h->misc1, &h->misc2, &h->misc3};
+  DevBuf* bufs[] = {&h->ws, &h->in_aos, &h->out_aos, &h->traj_soa, &h->traj_aos, &h->obj, &h->status, &h->iters, &h->misc0, &h->misc3};
   for (DevBuf* b : bufs) b->release();
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -320,11 +320,10 @@ int b200mpc_solve_batch(b200mpc_handle* h, int B, const double* state6, const do
   cudaStream_t s = h->stream;
   const int nv = 8 * h->P.N - 2;
   const size_t nb = (size_t)B;
-  // stage: H2D (reference order) -> K6 transpose -> solve -> K6 transpose -> D2H
+  // stage: H2D -> solve -> D2H.  The solver kernels read state6 / coeffs and write out8 in the reference's per-problem
+  // order themselves (io_aos = 1: K6 fused into init / write_result); only the optional full trajectory goes through the
+  // tiled transpose.
   CU(h->in_aos.ensure(nb * (6 + ncoef) * sizeof(double)));
-  CU(h->st_soa.ensure(nb * 6 * sizeof(double)));
-  CU(h->cf_soa.ensure(nb * ncoef * sizeof(double)));
-  CU(h->out_soa.ensure(nb * 8 * sizeof(double)));
   CU(h->out_aos.ensure(nb * 8 * sizeof(double)));
   CU(h->obj.ensure(nb * sizeof(double)));
   CU(h->status.ensure(nb * sizeof(int)));
@@ -334,15 +333,9 @@ int b200mpc_solve_batch(b200mpc_handle* h, int B, const double* state6, const do
   double* d_cf = d_st + nb * 6;
   CU(cudaMemcpyAsync(d_st, state6, nb * 6 * sizeof(double), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(d_cf, coeffs, nb * ncoef * sizeof(double), cudaMemcpyHostToDevice, s));
-  CU(launch_aos_to_soa(d_st, h->st_soa.as<double>(), B, 6, s));
-  CU(launch_aos_to_soa(d_cf, h->cf_soa.as<double>(), B, ncoef, s));
-  h->launches += 2;
-  if (int rc = timed_solve(h, B, 1, h->st_soa.as<double>(), h->cf_soa.as<double>(), ncoef, h->out_soa.as<double>(),
-                           traj ? h->traj_soa.as<double>() : nullptr, h->obj.as<double>(), h->status.as<int>(),
-                           h->iters.as<int>(), s))
+  if (int rc = timed_solve(h, B, 1, d_st, d_cf, ncoef, h->out_aos.as<double>(), traj ? h->traj_soa.as<double>() : nullptr,
+                           h->obj.as<double>(), h->status.as<int>(), h->iters.as<int>(), s, 1))
     return rc;
-  CU(launch_soa_to_aos(h->out_soa.as<double>(), h->out_aos.as<double>(), B, 8, s));
-  h->launches += 1;
   CU(cudaMemcpyAsync(out8, h->out_aos.p, nb * 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (traj) {
     CU(launch_soa_to_aos(h->traj_soa.as<double>(), h->traj_aos.as<double>(), B, nv, s));
@@ -404,9 +397,6 @@ int b200mpc_closed_loop_batch(b200mpc_handle* h, int B, int steps, const double*
   cudaStream_t s = h->stream;
   const size_t nb = (size_t)B, ns = (size_t)steps;
   CU(h->in_aos.ensure(nb * (6 + ncoef) * sizeof(double)));
-  CU(h->st_soa.ensure(nb * 6 * sizeof(double)));
-  CU(h->cf_soa.ensure(nb * ncoef * sizeof(double)));
-  CU(h->out_soa.ensure(ns * nb * 8 * sizeof(double)));
   CU(h->out_aos.ensure(ns * nb * 8 * sizeof(double)));
   CU(h->obj.ensure(ns * nb * sizeof(double)));
   CU(h->iters.ensure(ns * nb * sizeof(int)));
@@ -414,16 +404,10 @@ int b200mpc_closed_loop_batch(b200mpc_handle* h, int B, int steps, const double*
   double* d_cf = d_st + nb * 6;
   CU(cudaMemcpyAsync(d_st, state6, nb * 6 * sizeof(double), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(d_cf, coeffs, nb * ncoef * sizeof(double), cudaMemcpyHostToDevice, s));
-  CU(launch_aos_to_soa(d_st, h->st_soa.as<double>(), B, 6, s));
-  CU(launch_aos_to_soa(d_cf, h->cf_soa.as<double>(), B, ncoef, s));
-  h->launches += 2;
-  if (int rc = timed_solve(h, B, steps, h->st_soa.as<double>(), h->cf_soa.as<double>(), ncoef, h->out_soa.as<double>(),
-                           nullptr, h->obj.as<double>(), nullptr, h->iters.as<int>(), s))
+  // every step's 8-vector is written as [B][8] rows by the solver kernels (and read back as the next initial state)
+  if (int rc = timed_solve(h, B, steps, d_st, d_cf, ncoef, h->out_aos.as<double>(), nullptr, h->obj.as<double>(), nullptr,
+                           h->iters.as<int>(), s, 1))
     return rc;
-  for (int k = 0; k < steps; ++k) {   // [8][B] -> [B][8] per step
-    CU(launch_soa_to_aos(h->out_soa.as<double>() + (size_t)k * 8 * nb, h->out_aos.as<double>() + (size_t)k * 8 * nb, B, 8, s));
-    h->launches += 1;
-  }
   CU(cudaMemcpyAsync(hist8, h->out_aos.p, ns * nb * 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (cost) CU(cudaMemcpyAsync(cost, h->obj.p, ns * nb * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (iters) CU(cudaMemcpyAsync(iters, h->iters.p, ns * nb * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -460,19 +444,13 @@ int b200mpc_polyfit_batch(b200mpc_handle* h, int B, const double* xs, const doub
   cudaStream_t s = h->stream;
   const size_t nb = (size_t)B;
   const int n = order + 1;
-  CU(h->misc0.ensure(nb * 2 * m * sizeof(double)));   // AoS xs | ys
-  CU(h->misc1.ensure(nb * 2 * m * sizeof(double)));   // SoA xs | ys
-  CU(h->misc2.ensure(nb * n * sizeof(double)));       // SoA coeffs
-  CU(h->misc3.ensure(nb * n * sizeof(double)));       // AoS coeffs
+  CU(h->misc0.ensure(nb * 2 * m * sizeof(double)));   // xs | ys, per-fit rows as the caller has them
+  CU(h->misc3.ensure(nb * n * sizeof(double)));       // coefficient rows
   double* a = h->misc0.as<double>();
-  double* so = h->misc1.as<double>();
   CU(cudaMemcpyAsync(a, xs, nb * m * sizeof(double), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(a + nb * m, ys, nb * m * sizeof(double), cudaMemcpyHostToDevice, s));
-  CU(launch_aos_to_soa(a, so, B, m, s));
-  CU(launch_aos_to_soa(a + nb * m, so + nb * m, B, m, s));
-  CU(launch_polyfit(so, so + nb * m, B, m, order, h->misc2.as<double>(), s));
-  CU(launch_soa_to_aos(h->misc2.as<double>(), h->misc3.as<double>(), B, n, s));
-  h->launches += 4;
+  CU(launch_polyfit(a, a + nb * m, B, m, order, h->misc3.as<double>(), s, 1));
+  h->launches += 1;
   CU(cudaMemcpyAsync(coeffs_out, h->misc3.p, nb * n * sizeof(double), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   return 0;
@@ -498,16 +476,14 @@ int b200mpc_polyeval_batch(b200mpc_handle* h, int B, const double* coeffs, int n
   CU(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   const size_t nb = (size_t)B;
-  CU(h->misc0.ensure(nb * (ncoef + 1) * sizeof(double)));
-  CU(h->misc1.ensure(nb * (ncoef + 1) * sizeof(double)));
+  CU(h->misc0.ensure(nb * (ncoef + 2) * sizeof(double)));   // coefficient rows | x | y
   double* a = h->misc0.as<double>();
-  double* so = h->misc1.as<double>();
+  double* dy = a + nb * (ncoef + 1);
   CU(cudaMemcpyAsync(a, coeffs, nb * ncoef * sizeof(double), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(a + nb * ncoef, x, nb * sizeof(double), cudaMemcpyHostToDevice, s));
-  CU(launch_aos_to_soa(a, so, B, ncoef, s));
-  CU(launch_polyeval(so, ncoef, a + nb * ncoef, so + nb * ncoef, B, s));
-  h->launches += 2;
-  CU(cudaMemcpyAsync(y, so + nb * ncoef, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(launch_polyeval(a, ncoef, a + nb * ncoef, dy, B, s, 1));
+  h->launches += 1;
+  CU(cudaMemcpyAsync(y, dy, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   return 0;
 }
@@ -535,19 +511,13 @@ int b200mpc_rollout_batch(b200mpc_handle* h, int B, int H, const double* state4,
   CU(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   const size_t nb = (size_t)B, hh = (size_t)H;
-  CU(h->misc0.ensure(nb * (4 + 2 * hh) * sizeof(double)));   // AoS state | act
-  CU(h->misc1.ensure(nb * (4 + 2 * hh) * sizeof(double)));   // SoA state | act
-  CU(h->misc2.ensure(nb * 4 * hh * sizeof(double)));         // SoA out
-  CU(h->misc3.ensure(nb * 4 * hh * sizeof(double)));         // AoS out
+  CU(h->misc0.ensure(nb * (4 + 2 * hh) * sizeof(double)));   // state rows | actuator rows
+  CU(h->misc3.ensure(nb * 4 * hh * sizeof(double)));         // trajectory rows
   double* a = h->misc0.as<double>();
-  double* so = h->misc1.as<double>();
   CU(cudaMemcpyAsync(a, state4, nb * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(a + nb * 4, act, nb * 2 * hh * sizeof(double), cudaMemcpyHostToDevice, s));
-  CU(launch_aos_to_soa(a, so, B, 4, s));
-  CU(launch_aos_to_soa(a + nb * 4, so + nb * 4, B, 2 * H, s));
-  CU(launch_rollout(so, so + nb * 4, B, H, dt, Lf, h->misc2.as<double>(), s));
-  CU(launch_soa_to_aos(h->misc2.as<double>(), h->misc3.as<double>(), B, 4 * H, s));
-  h->launches += 4;
+  CU(launch_rollout(a, a + nb * 4, B, H, dt, Lf, h->misc3.as<double>(), s, 1));
+  h->launches += 1;
   CU(cudaMemcpyAsync(out, h->misc3.p, nb * 4 * hh * sizeof(double), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   return 0;
@@ -574,21 +544,15 @@ int b200mpc_roadmap_reference_batch(b200mpc_handle* h, int B, const double* pose
   CU(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   const size_t nb = (size_t)B;
-  CU(h->misc0.ensure((nb * 4 + (size_t)2 * n_wp) * sizeof(double)));   // AoS pose | centre line
-  CU(h->misc1.ensure(nb * 4 * sizeof(double)));                         // SoA pose
-  CU(h->misc2.ensure(nb * 10 * sizeof(double)));                        // SoA state6 | coeffs
-  CU(h->misc3.ensure(nb * 10 * sizeof(double)));                        // AoS state6 | coeffs
+  CU(h->misc0.ensure((nb * 4 + (size_t)2 * n_wp) * sizeof(double)));   // pose rows | centre line
+  CU(h->misc3.ensure(nb * 10 * sizeof(double)));                        // state6 rows | coefficient rows
   double* a = h->misc0.as<double>();
   double* wp = a + nb * 4;
-  double* so = h->misc2.as<double>();
   double* ao = h->misc3.as<double>();
   CU(cudaMemcpyAsync(a, pose4, nb * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(wp, centerline, (size_t)2 * n_wp * sizeof(double), cudaMemcpyHostToDevice, s));
-  CU(launch_aos_to_soa(a, h->misc1.as<double>(), B, 4, s));
-  CU(launch_roadmap_reference(h->misc1.as<double>(), B, wp, n_wp, so, so + nb * 6, s));
-  CU(launch_soa_to_aos(so, ao, B, 6, s));
-  CU(launch_soa_to_aos(so + nb * 6, ao + nb * 6, B, 4, s));
-  h->launches += 4;
+  CU(launch_roadmap_reference(a, B, wp, n_wp, ao, ao + nb * 6, s, 1));
+  h->launches += 1;
   CU(cudaMemcpyAsync(state6_out, ao, nb * 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(coeffs_out, ao + nb * 6, nb * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));

@@ -4,7 +4,11 @@
 //                 Householder.h:64-131), polyeval helpers.h:13-19
 //   K5 rollout    /root/reference/global_kinematic_model/solution/main.cpp:36-62
 //   K6 batch I/O  the per-call unpack / pack of MPC.cpp:152-177 and :253-256, batched: [B][K] <-> [K][B]
-// Compute kernels read and write field-major (SoA) arrays: consecutive threads touch consecutive doubles.
+// Compute kernels read and write field-major (SoA) arrays -- consecutive threads touch consecutive doubles -- or, for
+// the host entry points, the reference's per-problem (AoS) rows directly: element k of problem b sits at
+// p[b * sb + k * sk] with (sb, sk) = (1, B) or (K, 1).  A warp's K strided loads of K-double rows cover the same 32-byte
+// sectors between them (L1 holds the 32 x 8K bytes in between), so the DRAM traffic is that of the coalesced layout and
+// the separate transpose launches (K6) are not needed on those paths.
 #include <float.h>
 
 #include "kernels.h"
@@ -155,28 +159,37 @@ __device__ __forceinline__ void polyfit_regs(const double* xs, const double* ys,
   }
 }
 
+// (sb, sk) of a K-field array in either layout
+struct Lay {
+  size_t sb, sk;
+  __host__ __device__ Lay(int aos, int B, int K) : sb(aos ? (size_t)K : 1), sk(aos ? 1 : (size_t)B) {}
+  __host__ __device__ size_t operator()(int b, int k) const { return (size_t)b * sb + (size_t)k * sk; }
+};
+
 template <int MM, int NN>
 __global__ void __launch_bounds__(128) polyfit_kernel(const double* __restrict__ xs, const double* __restrict__ ys, int B,
-                                                      double* __restrict__ coeffs) {
+                                                      double* __restrict__ coeffs, int aos) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  const Lay in(aos, B, MM), outl(aos, B, NN);
   double x[MM], y[MM], o[NN];
 #pragma unroll
-  for (int j = 0; j < MM; ++j) { x[j] = xs[(size_t)j * B + b]; y[j] = ys[(size_t)j * B + b]; }
+  for (int j = 0; j < MM; ++j) { x[j] = xs[in(b, j)]; y[j] = ys[in(b, j)]; }
   polyfit_regs<MM, NN>(x, y, o);
 #pragma unroll
-  for (int i = 0; i < NN; ++i) coeffs[(size_t)i * B + b] = o[i];
+  for (int i = 0; i < NN; ++i) coeffs[outl(b, i)] = o[i];
 }
 
 // generic shapes (m <= 16, order <= 7): same algorithm on thread-local arrays with run-time sizes
 __global__ void __launch_bounds__(128) polyfit_generic_kernel(const double* __restrict__ xs, const double* __restrict__ ys, int B,
-                                                              int m, int n, double* __restrict__ coeffs) {
+                                                              int m, int n, double* __restrict__ coeffs, int aos) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  const Lay in(aos, B, m), outl(aos, B, n);
   double A[8 * 16], c[16], h[8], out[8];
-  for (int j = 0; j < m; ++j) { A[j] = 1.0; c[j] = ys[(size_t)j * B + b]; }
+  for (int j = 0; j < m; ++j) { A[j] = 1.0; c[j] = ys[in(b, j)]; }
   for (int i = 0; i < n - 1; ++i)
-    for (int j = 0; j < m; ++j) A[(i + 1) * m + j] = A[i * m + j] * xs[(size_t)j * B + b];
+    for (int j = 0; j < m; ++j) A[(i + 1) * m + j] = A[i * m + j] * xs[in(b, j)];
   const int size = m < n ? m : n;
   for (int k = 0; k < size; ++k) {
     const int rr = m - k;
@@ -223,43 +236,44 @@ __global__ void __launch_bounds__(128) polyfit_generic_kernel(const double* __re
     for (int j = i + 1; j < size; ++j) s -= A[i + j * m] * out[j];
     out[i] = s / A[i + i * m];
   }
-  for (int i = 0; i < n; ++i) coeffs[(size_t)i * B + b] = out[i];
+  for (int i = 0; i < n; ++i) coeffs[outl(b, i)] = out[i];
 }
 
 template <int MM, int NN>
-static cudaError_t polyfit_launch_t(const double* xs, const double* ys, int B, double* coeffs, cudaStream_t stream) {
-  polyfit_kernel<MM, NN><<<(B + 127) / 128, 128, 0, stream>>>(xs, ys, B, coeffs);
+static cudaError_t polyfit_launch_t(const double* xs, const double* ys, int B, double* coeffs, cudaStream_t stream, int aos) {
+  polyfit_kernel<MM, NN><<<(B + 127) / 128, 128, 0, stream>>>(xs, ys, B, coeffs, aos);
   return cudaGetLastError();
 }
 
 cudaError_t launch_polyfit(const double* xs, const double* ys, int B, int m, int order, double* coeffs,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, int aos) {
   if (B <= 0) return cudaSuccess;
   const int n = order + 1;
-#define PF_CASE(MM, NN) if (m == MM && n == NN) return polyfit_launch_t<MM, NN>(xs, ys, B, coeffs, stream);
+#define PF_CASE(MM, NN) if (m == MM && n == NN) return polyfit_launch_t<MM, NN>(xs, ys, B, coeffs, stream, aos);
   PF_CASE(2, 2) PF_CASE(3, 2) PF_CASE(3, 3) PF_CASE(4, 2) PF_CASE(4, 3) PF_CASE(4, 4) PF_CASE(5, 3) PF_CASE(5, 4)
   PF_CASE(6, 2) PF_CASE(6, 3) PF_CASE(6, 4) PF_CASE(8, 4)
 #undef PF_CASE
-  polyfit_generic_kernel<<<(B + 127) / 128, 128, 0, stream>>>(xs, ys, B, m, n, coeffs);
+  polyfit_generic_kernel<<<(B + 127) / 128, 128, 0, stream>>>(xs, ys, B, m, n, coeffs, aos);
   return cudaGetLastError();
 }
 
 // helpers.h:13-19: result += coeffs[i] * pow(x, i), i ascending
 __global__ void __launch_bounds__(256) polyeval_kernel(const double* __restrict__ coeffs, int ncoef, const double* __restrict__ x,
-                                                       double* __restrict__ y, int B) {
+                                                       double* __restrict__ y, int B, int aos) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  const Lay cl(aos, B, ncoef);
   const double xv = x[b];
   double r = 0.0, xp = 1.0;
   for (int i = 0; i < ncoef; ++i) {
-    r += coeffs[(size_t)i * B + b] * xp;
+    r += coeffs[cl(b, i)] * xp;
     xp *= xv;
   }
   y[b] = r;
 }
-cudaError_t launch_polyeval(const double* coeffs, int ncoef, const double* x, double* y, int B, cudaStream_t stream) {
+cudaError_t launch_polyeval(const double* coeffs, int ncoef, const double* x, double* y, int B, cudaStream_t stream, int aos) {
   if (B <= 0) return cudaSuccess;
-  polyeval_kernel<<<(B + 255) / 256, 256, 0, stream>>>(coeffs, ncoef, x, y, B);
+  polyeval_kernel<<<(B + 255) / 256, 256, 0, stream>>>(coeffs, ncoef, x, y, B, aos);
   return cudaGetLastError();
 }
 
@@ -272,13 +286,14 @@ cudaError_t launch_polyeval(const double* coeffs, int ncoef, const double* x, do
 // The centre line is staged in shared memory once per block.
 constexpr int kWin = 6;
 __global__ void __launch_bounds__(128) roadmap_reference_kernel(const double* __restrict__ pose4, int B, const double* __restrict__ wp_xy,
-                                                                int n_wp, double* __restrict__ state6, double* __restrict__ coeffs) {
+                                                                int n_wp, double* __restrict__ state6, double* __restrict__ coeffs, int aos) {
   extern __shared__ double wp[];   // [2][n_wp]
   for (int i = threadIdx.x; i < n_wp; i += blockDim.x) { wp[i] = wp_xy[2 * i]; wp[n_wp + i] = wp_xy[2 * i + 1]; }
   __syncthreads();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const double x = pose4[b], y = pose4[(size_t)B + b], psi = pose4[(size_t)2 * B + b], v = pose4[(size_t)3 * B + b];
+  const Lay pl(aos, B, 4), sl(aos, B, 6), cfl(aos, B, 4);
+  const double x = pose4[pl(b, 0)], y = pose4[pl(b, 1)], psi = pose4[pl(b, 2)], v = pose4[pl(b, 3)];
   int best = 0;
   double bd = 1e300;
   for (int i = 0; i < n_wp; ++i) {
@@ -298,20 +313,20 @@ __global__ void __launch_bounds__(128) roadmap_reference_kernel(const double* __
   }
   polyfit_regs<kWin, 4>(lx, ly, c);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) coeffs[(size_t)i * B + b] = c[i];
-  state6[b] = 0.0; state6[(size_t)B + b] = 0.0; state6[(size_t)2 * B + b] = 0.0; state6[(size_t)3 * B + b] = v;
-  state6[(size_t)4 * B + b] = c[0];          // polyeval(coeffs, 0) - 0
-  state6[(size_t)5 * B + b] = -atan(c[1]);   // 0 - atan(p'(0))
+  for (int i = 0; i < 4; ++i) coeffs[cfl(b, i)] = c[i];
+  state6[sl(b, 0)] = 0.0; state6[sl(b, 1)] = 0.0; state6[sl(b, 2)] = 0.0; state6[sl(b, 3)] = v;
+  state6[sl(b, 4)] = c[0];          // polyeval(coeffs, 0) - 0
+  state6[sl(b, 5)] = -atan(c[1]);   // 0 - atan(p'(0))
 }
 cudaError_t launch_roadmap_reference(const double* pose4, int B, const double* wp_xy, int n_wp, double* state6, double* coeffs,
-                                     cudaStream_t stream) {
+                                     cudaStream_t stream, int aos) {
   if (B <= 0) return cudaSuccess;
   const size_t smem = (size_t)2 * n_wp * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(roadmap_reference_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  roadmap_reference_kernel<<<(B + 127) / 128, 128, smem, stream>>>(pose4, B, wp_xy, n_wp, state6, coeffs);
+  roadmap_reference_kernel<<<(B + 127) / 128, 128, smem, stream>>>(pose4, B, wp_xy, n_wp, state6, coeffs, aos);
   return cudaGetLastError();
 }
 
@@ -319,12 +334,13 @@ cudaError_t launch_roadmap_reference(const double* pose4, int B, const double* w
 // K5: H Euler steps of the bicycle model per vehicle, global_kinematic_model/solution/main.cpp:56-59
 // (note the evaluation order v / Lf * delta * dt there).
 __global__ void __launch_bounds__(256) rollout_kernel(const double* __restrict__ state4, const double* __restrict__ act, int B, int H,
-                                                      double dt, double Lf, double* __restrict__ out) {
+                                                      double dt, double Lf, double* __restrict__ out, int aos) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  double x = state4[b], y = state4[(size_t)B + b], psi = state4[(size_t)2 * B + b], v = state4[(size_t)3 * B + b];
+  const Lay sl(aos, B, 4), al(aos, B, 2 * H), ol(aos, B, 4 * H);
+  double x = state4[sl(b, 0)], y = state4[sl(b, 1)], psi = state4[sl(b, 2)], v = state4[sl(b, 3)];
   for (int s = 0; s < H; ++s) {
-    const double delta = act[(size_t)(2 * s) * B + b], a = act[(size_t)(2 * s + 1) * B + b];
+    const double delta = act[al(b, 2 * s)], a = act[al(b, 2 * s + 1)];
     double sp, cp;
     sincos(psi, &sp, &cp);
     const double nx = x + v * cp * dt;
@@ -332,16 +348,16 @@ __global__ void __launch_bounds__(256) rollout_kernel(const double* __restrict__
     const double np = psi + v / Lf * delta * dt;
     const double nv = v + a * dt;
     x = nx; y = ny; psi = np; v = nv;
-    out[(size_t)(4 * s + 0) * B + b] = x;
-    out[(size_t)(4 * s + 1) * B + b] = y;
-    out[(size_t)(4 * s + 2) * B + b] = psi;
-    out[(size_t)(4 * s + 3) * B + b] = v;
+    out[ol(b, 4 * s + 0)] = x;
+    out[ol(b, 4 * s + 1)] = y;
+    out[ol(b, 4 * s + 2)] = psi;
+    out[ol(b, 4 * s + 3)] = v;
   }
 }
 cudaError_t launch_rollout(const double* state4, const double* act, int B, int H, double dt, double Lf, double* out,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, int aos) {
   if (B <= 0 || H <= 0) return cudaSuccess;
-  rollout_kernel<<<(B + 255) / 256, 256, 0, stream>>>(state4, act, B, H, dt, Lf, out);
+  rollout_kernel<<<(B + 255) / 256, 256, 0, stream>>>(state4, act, B, H, dt, Lf, out, aos);
   return cudaGetLastError();
 }
 

@@ -44,22 +44,25 @@ struct SplitStreams {   // auxiliary streams / events owned by the handle (n_aux
 };
 cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6, const double* coeffs, int ncoef,
                          double* ws, double* out8, double* traj, double* obj, int* status, int* iters,
-                         const SolveConfig& cfg, cudaStream_t stream, const SplitStreams* ss, long long* n_launches);
+                         const SolveConfig& cfg, cudaStream_t stream, const SplitStreams* ss, long long* n_launches,
+                         int io_aos = 0);   // io_aos = 1: state6 [B][6], coeffs [B][ncoef], out8 [steps][B][8] (reference order)
 
 // K6 batch I/O: [B][K] <-> [K][B]
 cudaError_t launch_aos_to_soa(const double* in, double* out, int B, int K, cudaStream_t stream);
 cudaError_t launch_soa_to_aos(const double* in, double* out, int B, int K, cudaStream_t stream);
 
-// K4 polyfit / polyeval, K5 rollout (SoA)
+// K4 polyfit / polyeval, K5 rollout.  aos = 0: field-major arrays ([k][B], what device-resident callers pass);
+// aos = 1: the reference's per-problem order ([B][k], what the host entry points receive) -- the kernels index either
+// layout themselves, so the host paths need no transpose launches (K6 fused into K4 / K5)
 cudaError_t launch_polyfit(const double* xs, const double* ys, int B, int m, int order, double* coeffs,
-                           cudaStream_t stream);
-cudaError_t launch_polyeval(const double* coeffs, int ncoef, const double* x, double* y, int B, cudaStream_t stream);
+                           cudaStream_t stream, int aos = 0);
+cudaError_t launch_polyeval(const double* coeffs, int ncoef, const double* x, double* y, int B, cudaStream_t stream, int aos = 0);
 cudaError_t launch_rollout(const double* state4, const double* act, int B, int H, double dt, double Lf, double* out,
-                           cudaStream_t stream);
+                           cudaStream_t stream, int aos = 0);
 
 // roadmap front-end: pose4 [4][B] (x,y,psi,v global), wp_xy [n_wp][2] -> state6 [6][B], coeffs [4][B] (vehicle frame)
 cudaError_t launch_roadmap_reference(const double* pose4, int B, const double* wp_xy, int n_wp, double* state6, double* coeffs,
-                                     cudaStream_t stream);
+                                     cudaStream_t stream, int aos = 0);
 
 // DFMA throughput microbenchmark: returns FLOP executed per launch; time it outside.
 cudaError_t launch_fp64_peak(double* sink, int blocks, int threads, int iters, cudaStream_t stream, double* flop);

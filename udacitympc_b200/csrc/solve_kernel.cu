@@ -49,6 +49,8 @@ size_t solve_workspace_doubles(int N, int B) { return 2 * region_doubles(N, B) +
 
 struct SolveArgs {
   int B, steps, step, ncoef;
+  int io_aos;             // layout of state6 / coeffs / out8: 0 = field-major [k][B] (device callers), 1 = the reference's
+                          // per-problem order [B][k] (host entry points: no separate transpose kernels, K6 is fused here)
   int b0, b1;             // this launch covers problems [b0, b1) of the B-problem batch (B stays the array stride)
   int warm;               // closed loop: steps > 0 start from the shifted previous solution
   double mu_warm;
@@ -88,21 +90,26 @@ __device__ __forceinline__ bool locate(const SolveArgs& A, int i, int& slot, int
   return true;
 }
 __device__ __forceinline__ void load_coeffs(const SolveArgs& A, int b, double* cf) {
+  const size_t sb = A.io_aos ? (size_t)A.ncoef : 1, sk = A.io_aos ? 1 : (size_t)A.B;
 #pragma unroll
-  for (int i = 0; i < kMaxCoef; ++i) cf[i] = i < A.ncoef ? A.coeffs[(size_t)i * A.B + b] : 0.0;
+  for (int i = 0; i < kMaxCoef; ++i) cf[i] = i < A.ncoef ? A.coeffs[(size_t)b * sb + (size_t)i * sk] : 0.0;
+}
+// element k of the returned 8-vector of problem b at closed-loop step `step`
+__device__ __forceinline__ size_t out8_index(const SolveArgs& A, int step, int k, int b) {
+  return (size_t)step * 8 * A.B + (A.io_aos ? (size_t)b * 8 + k : (size_t)k * A.B + b);
 }
 // initial state of closed-loop step `step`: the caller's state for step 0, else the previous step's out8[0..5]
 // (solution/main.cpp:66)
 __device__ __forceinline__ void load_state6(const SolveArgs& A, int b, double* s0) {
 #pragma unroll
   for (int k = 0; k < 6; ++k)
-    s0[k] = A.step == 0 ? A.state6[(size_t)k * A.B + b] : A.out8[((size_t)(A.step - 1) * 8 + k) * A.B + b];
+    s0[k] = A.step == 0 ? A.state6[A.io_aos ? (size_t)b * 6 + k : (size_t)k * A.B + b] : A.out8[out8_index(A, A.step - 1, k, b)];
 }
 __device__ __forceinline__ void write_result(const Params& P, const SolveArgs& A, int b, Solver<32>& S) {
   Result R;
   S.finish(R, (A.traj && A.step == A.steps - 1) ? A.traj + b : nullptr, (size_t)A.B);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) A.out8[((size_t)A.step * 8 + k) * A.B + b] = R.out8[k];
+  for (int k = 0; k < 8; ++k) A.out8[out8_index(A, A.step, k, b)] = R.out8[k];
   if (A.obj) A.obj[(size_t)A.step * A.B + b] = R.obj;
   if (A.iters) A.iters[(size_t)A.step * A.B + b] = R.iters;
   if (A.status && A.step == A.steps - 1) A.status[b] = R.status;
@@ -353,7 +360,7 @@ static cudaError_t launch_part(const Params& P, SolveArgs A, const SolveConfig& 
 // one part behind the bulk of another even when the caller uses a single stream.
 cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6, const double* coeffs, int ncoef,
                          double* ws, double* out8, double* traj, double* obj, int* status, int* iters,
-                         const SolveConfig& cfg, cudaStream_t stream, const SplitStreams* ss, long long* n_launches) {
+                         const SolveConfig& cfg, cudaStream_t stream, const SplitStreams* ss, long long* n_launches, int io_aos) {
   if (B <= 0) return cudaSuccess;
   // buffer layout: region 0 | region 1 | map 0 | map 1 | compaction state of every part
   const size_t reg = region_doubles(P.N, B);
@@ -362,7 +369,7 @@ cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6
   int* desc = ints + 2 * map_ints;
   // a warm-started step reads the previous solution at the problem's own slot: no compaction then
   if (!(cfg.compact_max_live > 0.0) || cfg.warm_start) desc = nullptr;
-  SolveArgs A{B, steps, 0, ncoef, 0, B, cfg.warm_start ? 1 : 0, cfg.warm_mu, state6, coeffs, ws, ws + reg, ints, ints + map_ints, desc, 0,
+  SolveArgs A{B, steps, 0, ncoef, io_aos ? 1 : 0, 0, B, cfg.warm_start ? 1 : 0, cfg.warm_mu, state6, coeffs, ws, ws + reg, ints, ints + map_ints, desc, 0,
               out8, traj, obj, status, iters};
   long long n = 0;
   int parts = 1;
