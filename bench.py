@@ -15,7 +15,7 @@ value        whole-job solves/s with inputs already resident in HBM (device-poin
 e2e          the same through the host-buffer C-ABI call the reference's MPC::Solve would bind: pinned host buffers,
              H2D + D2H inside the timed region
 lone_caller  one handle, one stream, one call at a time (the figures above overlap consecutive steps on several handles)
-one_process_multi_gpu (N > 1)  b200mpc_solve_batch_multi on the whole batch from rank 0: one host thread per GPU, host
+one_process_multi_gpu (N > 1)  b200mpc_solve_batch_multi on the whole batch from rank 0: every GPU's shard queued from one host thread, host
              gather, per-call latency percentiles
 weak_scaling (N > 1)  the weak-scaling figure next to the strong one
 """
@@ -277,6 +277,12 @@ def run_ours(args):
     for m in mpcs:
         m.set_solver_mode({"perpass": 0, "fused": 1}[args.mode], args.rounds, -1)
         m.set_batch_split(split)
+    # --pipeline D: the device-timed region issues its S overlapped streams to ONE handle in pipelined mode (bulk in one
+    # full-size workspace, tails in D small contexts) instead of S handles with a full-size workspace each
+    dev_handles = mpcs
+    if args.pipeline > 0:
+        mpcs[0].set_pipeline(args.pipeline, args.pipeline_slots if args.pipeline_slots > 0 else max(1024, Bl // 16))
+        dev_handles = [mpcs[0]] * S
     mpc = mpcs[0]
     # Four distinct B-problem input sets, cycled step by step (every rank generates the same sets and keeps its index
     # range); about half of such sets contain a 30-50 iteration straggler, so cycling several makes the
@@ -340,10 +346,10 @@ def run_ours(args):
     # warm-up: at least W steps, and every (solver handle, input set) pair once -- each pair is its own CUDA graph,
     # captured and instantiated at its first use
     wsteps = max(W, S * nsets // math.gcd(S, nsets))
-    e0, e1 = timed_device_region(mpcs, streams, Bl, d_in, d_out, wsteps)
+    e0, e1 = timed_device_region(dev_handles, streams, Bl, d_in, d_out, wsteps)
     barrier()
     # the timed region is R repetitions of the K-step sequence, R chosen so that it lasts >= --min-seconds
-    e0, e1 = timed_device_region(mpcs, streams, Bl, d_in, d_out, K)
+    e0, e1 = timed_device_region(dev_handles, streams, Bl, d_in, d_out, K)
     barrier()
     est_ms, _ = agreed(e0.elapsed_time(e1))
     R = max(1, int(math.ceil(args.min_seconds * 1e3 / max(est_ms, 1e-3))))
@@ -351,7 +357,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
-    e0, e1 = timed_device_region(mpcs, streams, Bl, d_in, d_out, K * R)
+    e0, e1 = timed_device_region(dev_handles, streams, Bl, d_in, d_out, K * R)
     barrier()
     ms_total, per_rank_total = agreed(e0.elapsed_time(e1))
     launches = sum(m.launch_count() for m in mpcs) - launches0
@@ -399,6 +405,10 @@ def run_ours(args):
 
     hout = [host_outputs(Bl) for _ in range(S)]
 
+    if args.pipeline > 0:
+        torch.cuda.synchronize()
+        mpcs[0].set_pipeline(0, 0)   # the host-buffer calls below block: one handle per host thread, as without --pipeline
+
     def host_step(i, k, handle=None, out=None):
         st, cf = pin[i % nsets]
         o = out or hout[k]
@@ -441,7 +451,7 @@ def run_ours(args):
     clocks = sampler.stop()
     cmhz, per_rank_mhz = agreed(clocks.get("sm_mhz") or 0.0)
 
-    # ---- one process, one host thread per GPU, host gather: b200mpc_solve_batch_multi on the WHOLE batch (rank 0
+    # ---- one process, every GPU's shard queued from one host thread, host gather: b200mpc_solve_batch_multi on the WHOLE batch (rank 0
     # only, the other ranks wait; SURVEY 8e "results gathered by the host")
     multi = None
     barrier()
@@ -509,7 +519,8 @@ def run_ours(args):
             higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f64", data="synthetic",
             config=config_dict(args),
             timed=dict(passes=K * R, repeats_of_the_k_step_sequence=R, seconds=ms_total * 1e-3, min_seconds=args.min_seconds,
-                       problems_per_gpu_per_step=Bl, streams=S, batch_split=split,
+                       problems_per_gpu_per_step=Bl, streams=S, batch_split=split, solver_handles=len(set(id(m) for m in dev_handles)),
+                       pipeline_depth=args.pipeline,
                        note="value = problems_per_step x passes / seconds (max over ranks of the CUDA-event time)"),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=total_per_step * (6 + ncoef) * 8,
                      d2h_bytes_per_step=total_per_step * (8 + 1) * 8 + 2 * total_per_step * 4, passes=n_e2e, seconds=e2e_max_s,
@@ -601,6 +612,9 @@ def main():
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads (one solver handle each) of the end-to-end leg (0 = auto)")
     ap.add_argument("--split", type=int, default=0, help="internal batch split of one solve call (0 = 1 with several streams, 4 with one)")
     ap.add_argument("--streams", type=int, default=0, help="solver handles / CUDA streams consecutive steps alternate between (0 = auto: 6 at 65 536 problems per GPU, up to 16 for smaller shards)")
+    ap.add_argument("--pipeline", type=int, default=0, help="> 0: the overlapped streams of the device-timed region share ONE solver handle in pipelined mode "
+                    "with this many tail contexts (b200mpc_set_pipeline) instead of one handle per stream")
+    ap.add_argument("--pipeline-slots", type=int, default=0, help="problems a tail context holds (0 = max(1024, batch / 16))")
     ap.add_argument("--mode", default="perpass", choices=["perpass", "fused"], help="solver execution mode (include/b200mpc.h)")
     ap.add_argument("--rounds", type=int, default=0, help="per-pass mode: rounds before the fused finisher (0 = library default)")
     args = ap.parse_args()

@@ -22,6 +22,9 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--streams", type=int, default=1, help="solver handles / streams whose batches overlap (as bench.py does); "
                     "1 = one batch at a time, where the slowest problem of a batch sets its time")
+    ap.add_argument("--pipeline", type=int, default=0, help="> 0: the overlapped batches go to ONE solver handle in pipelined mode with this many tail "
+                    "contexts (b200mpc_set_pipeline): memory of one full-size workspace + the tail contexts instead of one workspace per stream")
+    ap.add_argument("--pipeline-slots", type=int, default=0, help="problems a tail context holds (0 = max(1024, batch / 16))")
     ap.add_argument("--rounds", type=int, default=0, help="per-pass rounds before the cooperative finisher (0 = library default)")
     args = ap.parse_args()
     import torch
@@ -43,17 +46,20 @@ def main():
             t = (B + nb - 1) // nb
             st_d = torch.from_numpy(np.ascontiguousarray(np.tile(st, (t, 1))[:B].T)).to(dev)
             cf_d = torch.from_numpy(np.ascontiguousarray(np.tile(fit, (t, 1))[:B].T)).to(dev)
-            S = max(1, min(args.streams, int(150e9 // (2 * B * 83 * (N + 2) * 8))))
+            S = max(1, min(args.streams, int(150e9 // (2 * B * 83 * (N + 2) * 8)))) if args.pipeline <= 0 else max(1, args.streams)
             streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(S - 1)]
             out8 = [torch.empty((8, B), dtype=torch.float64, device=dev) for _ in range(S)]
             status = torch.empty((S, B), dtype=torch.int32, device=dev)
             iters = torch.empty((S, B), dtype=torch.int32, device=dev)
-            handles = [mp.MPC(device=0, N=N) for _ in range(S)]
+            own = [mp.MPC(device=0, N=N) for _ in range(S if args.pipeline <= 0 else 1)]
+            handles = own if args.pipeline <= 0 else own * S
             try:
-                for m in handles:
+                for m in own:
                     m.set_solver_mode(0, args.rounds, -1)
                     if S > 1:
                         m.set_batch_split(1)   # the caller overlaps the batches itself
+                    if args.pipeline > 0 and S > 1:
+                        m.set_pipeline(args.pipeline, args.pipeline_slots if args.pipeline_slots > 0 else max(1024, B // 16))
 
                 def step(k):
                     handles[k].solve_batch_device(B, st_d.data_ptr(), cf_d.data_ptr(), 4, out8[k].data_ptr(), 0, 0,
@@ -76,13 +82,13 @@ def main():
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / (args.reps * S)
             finally:
-                for m in handles:
+                for m in own:
                     m.close()
             status, iters = status[0], iters[0]
             sc = status.cpu().numpy()
             it = iters.cpu().numpy()
             hist = {int(k): int(v) for k, v in zip(*np.unique(sc, return_counts=True))}
-            rows.append(dict(N=N, batch=B, rounds=args.rounds, streams=S, ms_per_batch=ms, solves_per_s=B / (ms * 1e-3), mean_iters=float(it.mean()),
+            rows.append(dict(N=N, batch=B, rounds=args.rounds, streams=S, pipeline_depth=args.pipeline if S > 1 else 0, solver_handles=len(own), ms_per_batch=ms, solves_per_s=B / (ms * 1e-3), mean_iters=float(it.mean()),
                              max_iters=int(it.max()), status_hist=hist, solved_fraction=float((sc == 0).mean())))
             print(json.dumps(rows[-1]), file=sys.stderr)
             del st_d, cf_d, out8

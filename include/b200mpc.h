@@ -95,10 +95,13 @@ int b200mpc_solve_batch_device(b200mpc_handle* h, int B, const double* d_state6,
                                void* stream);
 
 /* The same batch sharded by contiguous index ranges over several handles (normally one per device; several handles on
- * one device are allowed), one host thread per handle, no inter-device communication: handle g solves
- * problems [g * (B / n), (g + 1) * (B / n)), the last one also the remainder.  Host buffers as b200mpc_solve_batch.
+ * one device are allowed), no inter-device communication: handle g solves
+ * problems [g * (B / n), (g + 1) * (B / n)), the last one also the remainder.  The calling thread queues every shard
+ * (copy in, solve, copy out: asynchronous on the handle's own stream) and then waits for the devices in turn, so the
+ * shards run concurrently when the host buffers are pinned (cudaHostAlloc / cudaHostRegister); pageable buffers make
+ * the copies synchronous and serialise the devices.  Host buffers as b200mpc_solve_batch.
  * Every handle must have been created with the same b200mpc_params and the same restoration mode, and no handle may
- * appear twice (B200MPC_ERR_ARG otherwise: the result rows of the shards would not line up, or two threads would share
+ * appear twice (B200MPC_ERR_ARG otherwise: the result rows of the shards would not line up, or two shards would share
  * one workspace). */
 int b200mpc_solve_batch_multi(b200mpc_handle* const* hs, int n_handles, int B, const double* state6,
                               const double* coeffs, int ncoef, double* out8, double* traj, double* obj, int* status,
@@ -125,6 +128,19 @@ int b200mpc_set_warm_start(b200mpc_handle* h, int enable, double mu_init);
  * bit of the few problems that finish on the other side of it).  Default 4: best for a caller that issues one call at a
  * time; a caller that already overlaps several calls on several handles / streams should set 1. */
 int b200mpc_set_batch_split(b200mpc_handle* h, int parts);
+
+/* Pipelined solves on one handle (the generalisation of the one-call-at-a-time loop of solution/main.cpp:51-54 to a
+ * stream of batches).  Iteration counts have a thin, long tail (N = 25: mean 12, a few problems in 10^5 need 30-50;
+ * N = 100: mean 19, 2 % need more than 100, the slowest about 1000), and a batch is done when its slowest problem is.
+ * With depth > 0 every b200mpc_solve_batch_device call of more than tail_slots problems is queued in two parts: the
+ * bulk runs in the handle's full-size workspace until at most tail_slots problems are still iterating; those move to one
+ * of `depth` small tail contexts (used round robin) and finish there, while the next call's bulk already runs.  Calls
+ * stay stream-ordered for their caller -- the outputs of a call are complete when the work queued on ITS stream is --
+ * so the overlap exists between calls issued on DIFFERENT streams (the bulks are ordered among themselves by the
+ * library).  Memory: depth x the workspace of tail_slots problems instead of one full workspace per overlapped call.
+ * Results do not depend on it beyond the last bits a hand-over between the thread-per-problem sweeps and the
+ * cooperative kernel may change.  depth = 0 (default) switches it off; it synchronises the device. */
+int b200mpc_set_pipeline(b200mpc_handle* h, int depth, int tail_slots);
 
 /* Batch compaction of the throughput path: after every round from `from_round` on, when the problems that are still
  * iterating fill at most `max_live_fraction` of the occupied workspace slots, they are moved to consecutive slots, so

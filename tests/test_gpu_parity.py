@@ -633,6 +633,47 @@ def test_overlapped_solves_are_deterministic():
             h.close()
 
 
+def test_pipelined_solves_on_one_handle_match_plain_solves():
+    """b200mpc_set_pipeline: batches issued on different streams to ONE handle (bulk in the main workspace, the last
+    unfinished problems in small tail contexts, overlapped with the next bulk) give the results of plain solves: same
+    status and iteration counts, solution to 1e-9 (a hand-over between the thread sweeps and the cooperative kernel may
+    change last bits).  Three different batches, N = 25 and N = 50, depth 3 < number of calls (contexts are reused)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    for N, B, slots in ((25, 16384, 1024), (50, 8192, 512), (25, 65536, 4096)):
+        sets = []
+        with mp.MPC(device=0, N=N) as plain:
+            for k in range(3):
+                xs, ys = synth.roadmap_windows(B, synth.MT19937_64(synth.SEED + 500 + k))
+                fit = mp.polyfit_batch(xs, ys, 3, mpc=plain)
+                st = synth.roadmap_problems(B, fit, synth.MT19937_64(synth.SEED + 600 + k))
+                sets.append((st, fit, plain.solve_batch(st, fit)))
+        with mp.MPC(device=0, N=N) as piped:
+            piped.set_batch_split(1)
+            piped.set_pipeline(3, slots)
+            streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
+            d_in = [(torch.from_numpy(np.ascontiguousarray(st.T)).to(dev), torch.from_numpy(np.ascontiguousarray(cf.T)).to(dev)) for st, cf, _ in sets]
+            calls = 8
+            outs = [dict(out8=torch.zeros((8, B), dtype=torch.float64, device=dev), obj=torch.zeros(B, dtype=torch.float64, device=dev),
+                         status=torch.full((B,), -7, dtype=torch.int32, device=dev), iters=torch.zeros(B, dtype=torch.int32, device=dev))
+                    for _ in range(calls)]
+            torch.cuda.synchronize()
+            for i, o in enumerate(outs):
+                st_d, cf_d = d_in[i % 3]
+                piped.solve_batch_device(B, st_d.data_ptr(), cf_d.data_ptr(), 4, o["out8"].data_ptr(), 0, o["obj"].data_ptr(),
+                                         o["status"].data_ptr(), o["iters"].data_ptr(), streams[i % 4].cuda_stream)
+            torch.cuda.synchronize()
+            for i, o in enumerate(outs):
+                ref = sets[i % 3][2]
+                assert (o["status"].cpu().numpy() == ref["status"]).all(), (N, i)
+                assert (o["iters"].cpu().numpy() == ref["iters"]).mean() > 0.999, (N, i)
+                np.testing.assert_allclose(o["out8"].T.cpu().numpy(), ref["out8"], rtol=0, atol=1e-9)
+                np.testing.assert_allclose(o["obj"].cpu().numpy(), ref["cost"], rtol=1e-12, atol=0)
+            # a plain host-buffer call on the same handle afterwards (smaller than the tail: not pipelined) still works
+            small = piped.solve_batch(sets[0][0][:256], sets[0][1][:256])
+            np.testing.assert_allclose(small["out8"], sets[0][2]["out8"][:256], rtol=0, atol=1e-9)
+
+
 def test_invalid_numbers_are_reported_per_problem():
     """NaN / Inf inputs: status -13 (Ipopt's Invalid_Number_Detected) for those problems only, on both paths."""
     g = golden("line_256.npz")

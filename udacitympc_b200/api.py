@@ -49,6 +49,7 @@ SYMBOLS = {
     "b200mpc_set_warm_start": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double]),
     "b200mpc_set_batch_split": (ctypes.c_int, [_vp, ctypes.c_int]),
     "b200mpc_set_compaction": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_int]),
+    "b200mpc_set_pipeline": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
     "b200mpc_set_restoration": (ctypes.c_int, [_vp, ctypes.c_int]),
     "b200mpc_set_solver_mode": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "b200mpc_set_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
@@ -246,6 +247,12 @@ class MPC:
         """Throughput path: after every round from `from_round` on, move the unfinished problems to consecutive
         workspace slots when they fill at most this fraction of the occupied slots (0 = off)."""
         _check(self._lib.b200mpc_set_compaction(self._h, float(max_live_fraction), int(from_round)))
+
+    def set_pipeline(self, depth=8, tail_slots=4096):
+        """Pipelined solves: solve_batch_device calls issued on different streams overlap on this one handle -- the
+        bulk of a batch runs in the full-size workspace, its last `tail_slots` unfinished problems finish in one of
+        `depth` small tail contexts while the next batch's bulk runs (0 = off).  See b200mpc_set_pipeline."""
+        _check(self._lib.b200mpc_set_pipeline(self._h, int(depth), int(tail_slots)))
 
     def set_warm_start(self, enable=True, mu_init=1e-4):
         """closed_loop() only: steps after the first start from the shifted previous solution (not reference behaviour)."""

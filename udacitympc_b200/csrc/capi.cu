@@ -9,7 +9,6 @@
 #include <new>
 #include <sstream>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "../../include/b200mpc.h"
@@ -59,7 +58,8 @@ struct b200mpc_handle {
   long long launches = 0;
   // CUDA graphs of whole solves (init + rounds x (factor, forward, step) + finisher), keyed by every launch argument
   struct GraphEntry {
-    int B, steps, ncoef, mode, rounds, fused_below, warm, split, repack_gen, io_aos;
+    int B, steps, ncoef, mode, rounds, fused_below, warm, split, repack_gen, io_aos, phase;   // phase: 0 whole solve, 1 bulk, 2 tail
+    const void* tail;
     double warm_mu;
     const void *st, *cf, *ws, *out8, *traj, *obj, *status, *iters;
     cudaGraphExec_t exec;
@@ -68,6 +68,15 @@ struct b200mpc_handle {
   std::vector<GraphEntry> graphs;
   bool use_graphs = true;
   int repack_gen = 0;   // bumped when the compaction schedule changes (part of the graph key)
+  // pipelined solves (b200mpc_set_pipeline): tail contexts, used round robin, and the events that order the calls
+  static constexpr int kMaxPipe = 32;
+  int pipe_depth = 0, pipe_slots = 0;
+  DevBuf tail_ws;
+  size_t tail_ctx_doubles = 0;          // of the allocation in tail_ws (pipe_depth contexts)
+  int tail_ctx_N = 0, tail_ctx_slots = 0;
+  cudaEvent_t main_free = nullptr, tail_free[kMaxPipe] = {};
+  bool main_free_valid = false, tail_free_valid[kMaxPipe] = {};
+  unsigned long long pipe_calls = 0;
 };
 
 namespace {
@@ -98,7 +107,8 @@ int check_solve_args(const b200mpc_handle* h, int B, const void* st, const void*
 }
 
 int run_solve(b200mpc_handle* h, int B, int steps, const double* st, const double* cf, int ncoef, double* out8,
-              double* traj, double* obj, int* status, int* iters, cudaStream_t s, bool caller_captures, int io_aos);
+              double* traj, double* obj, int* status, int* iters, cudaStream_t s, bool caller_captures, int io_aos,
+              int phase = 0, TailCtx tail = TailCtx());
 
 // One solve on stream s.  The handle owns ONE workspace and one set of auxiliary streams, so solves on a handle are
 // serialised on the device whatever streams the caller uses (an event recorded after each solve, waited for by the
@@ -112,7 +122,40 @@ int timed_solve(b200mpc_handle* h, int B, int steps, const double* st, const dou
   const bool caller_captures = cap != cudaStreamCaptureStatusNone;
   if (caller_captures && h->ws.cap < solve_workspace_doubles(h->P.N, B) * sizeof(double))
     return fail(B200MPC_ERR_ARG, "the stream is being captured and the workspace would have to grow: run one solve of this size first");
+  // Pipelined mode (b200mpc_set_pipeline): the solve is queued as bulk + tail, ordered against the neighbouring calls by
+  // events instead of the one-solve-at-a-time rule below.
+  const bool pipelined = h->pipe_depth > 0 && !caller_captures && steps == 1 && !h->cfg.warm_start && h->cfg.mode == kModePerPass &&
+                         B >= h->cfg.fused_below && B > h->pipe_slots && h->cfg.compact_max_live > 0.0;
+  if (h->ws.cap < solve_workspace_doubles(h->P.N, B) * sizeof(double) || !pipelined) {
+    // a growing workspace, or a plain solve after pipelined ones: everything queued on this handle has to finish first
+    for (int k = 0; k < h->pipe_depth; ++k)
+      if (h->tail_free_valid[k]) CU(cudaStreamWaitEvent(s, h->tail_free[k], 0));
+    if (h->main_free_valid) CU(cudaStreamWaitEvent(s, h->main_free, 0));
+    if (h->ws.cap < solve_workspace_doubles(h->P.N, B) * sizeof(double) && h->pipe_calls) CU(cudaDeviceSynchronize());
+  }
   CU(h->ws.ensure(solve_workspace_doubles(h->P.N, B) * sizeof(double)));
+  if (pipelined) {
+    const size_t ctx = solve_workspace_doubles(h->P.N, h->pipe_slots);
+    if (h->tail_ctx_N != h->P.N || h->tail_ctx_slots != h->pipe_slots || h->tail_ws.cap < ctx * h->pipe_depth * sizeof(double)) {
+      if (h->pipe_calls) CU(cudaDeviceSynchronize());
+      CU(h->tail_ws.ensure(ctx * h->pipe_depth * sizeof(double)));
+      h->tail_ctx_N = h->P.N; h->tail_ctx_slots = h->pipe_slots; h->tail_ctx_doubles = ctx;
+    }
+    const int k = (int)(h->pipe_calls++ % (unsigned long long)h->pipe_depth);
+    TailCtx tail;
+    tail.ws = h->tail_ws.as<double>() + (size_t)k * h->tail_ctx_doubles;
+    tail.slots = h->pipe_slots;
+    if (h->done_valid) { CU(cudaStreamWaitEvent(s, h->done, 0)); h->done_valid = false; }   // a plain solve queued before
+    if (h->main_free_valid) CU(cudaStreamWaitEvent(s, h->main_free, 0));
+    if (h->tail_free_valid[k]) CU(cudaStreamWaitEvent(s, h->tail_free[k], 0));
+    if (int rc = run_solve(h, B, 1, st, cf, ncoef, out8, traj, obj, status, iters, s, false, io_aos, 1, tail)) return rc;
+    CU(cudaEventRecord(h->main_free, s));
+    h->main_free_valid = true;
+    if (int rc = run_solve(h, B, 1, st, cf, ncoef, out8, traj, obj, status, iters, s, false, io_aos, 2, tail)) return rc;
+    CU(cudaEventRecord(h->tail_free[k], s));
+    h->tail_free_valid[k] = true;
+    return 0;
+  }
   if (!caller_captures && h->done_valid) CU(cudaStreamWaitEvent(s, h->done, 0));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   const bool rec = h->timing_on && !caller_captures && h->timing.size() < 8192;
@@ -136,28 +179,35 @@ int timed_solve(b200mpc_handle* h, int B, int steps, const double* st, const dou
 }
 
 int run_solve(b200mpc_handle* h, int B, int steps, const double* st, const double* cf, int ncoef, double* out8,
-              double* traj, double* obj, int* status, int* iters, cudaStream_t s, bool caller_captures, int io_aos) {
+              double* traj, double* obj, int* status, int* iters, cudaStream_t s, bool caller_captures, int io_aos,
+              int phase, TailCtx tail) {
+  // the launch sequence: the whole solve, or one half of a pipelined one
+  auto launch = [&](long long* n) -> cudaError_t {
+    if (phase == 1) return launch_solve_bulk(h->P, B, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, n, io_aos, tail);
+    if (phase == 2) return launch_solve_tail(h->P, B, st, cf, ncoef, out8, traj, obj, status, iters, h->cfg, s, n, io_aos, tail);
+    return launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, &h->ss, n, io_aos);
+  };
   // One solve is ~75 dependent launches; replaying a captured graph keeps the host out of the inner loop (several
   // ranks / streams per host otherwise become launch-bound).  The legacy default stream cannot be captured.
   bool done = false;
   if (h->use_graphs && !caller_captures && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) {
-    b200mpc_handle::GraphEntry key{B, steps, ncoef, h->cfg.mode, h->cfg.rounds, h->cfg.fused_below, h->cfg.warm_start ? 1 : 0, h->cfg.split, h->repack_gen, io_aos, h->cfg.warm_mu, st, cf, h->ws.p, out8, traj, obj, status, iters, nullptr, 0};
+    b200mpc_handle::GraphEntry key{B, steps, ncoef, h->cfg.mode, h->cfg.rounds, h->cfg.fused_below, h->cfg.warm_start ? 1 : 0, h->cfg.split, h->repack_gen, io_aos, phase, tail.ws, h->cfg.warm_mu, st, cf, h->ws.p, out8, traj, obj, status, iters, nullptr, 0};
     b200mpc_handle::GraphEntry* hit = nullptr;
     for (auto& g : h->graphs)
       if (g.B == key.B && g.steps == key.steps && g.ncoef == key.ncoef && g.mode == key.mode && g.rounds == key.rounds &&
-          g.fused_below == key.fused_below && g.warm == key.warm && g.split == key.split && g.repack_gen == key.repack_gen && g.io_aos == key.io_aos && g.warm_mu == key.warm_mu && g.st == key.st && g.cf == key.cf && g.ws == key.ws && g.out8 == key.out8 &&
+          g.fused_below == key.fused_below && g.warm == key.warm && g.split == key.split && g.repack_gen == key.repack_gen && g.io_aos == key.io_aos && g.phase == key.phase && g.tail == key.tail && g.warm_mu == key.warm_mu && g.st == key.st && g.cf == key.cf && g.ws == key.ws && g.out8 == key.out8 &&
           g.traj == key.traj && g.obj == key.obj && g.status == key.status && g.iters == key.iters)
         hit = &g;
     if (!hit) {
       cudaGraph_t graph = nullptr;
       long long n = 0;
       if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
-        cudaError_t le = launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, &h->ss, &n, io_aos);
+        cudaError_t le = launch(&n);
         cudaError_t ce = cudaStreamEndCapture(s, &graph);
         if (le == cudaSuccess && ce == cudaSuccess && graph) {
           cudaGraphExec_t exec = nullptr;
           if (cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
-            if (h->graphs.size() >= 16) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+            if (h->graphs.size() >= 96) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
             key.exec = exec; key.n_kernels = n;
             h->graphs.push_back(key);
             hit = &h->graphs.back();
@@ -174,7 +224,7 @@ int run_solve(b200mpc_handle* h, int B, int steps, const double* st, const doubl
     }
   }
   if (!done)
-    CU(launch_solve(h->P, B, steps, st, cf, ncoef, h->ws.as<double>(), out8, traj, obj, status, iters, h->cfg, s, &h->ss, &h->launches, io_aos));
+    CU(launch(&h->launches));
   return 0;
 }
 
@@ -249,6 +299,11 @@ void b200mpc_destroy(b200mpc_handle* h) {
   }
   if (h->ss.fork) cudaEventDestroy(h->ss.fork);
   if (h->done) cudaEventDestroy(h->done);
+  if (h->main_free) cudaEventDestroy(h->main_free);
+  for (int k = 0; k < b200mpc_handle::kMaxPipe; ++k)
+    if (h->tail_free[k]) cudaEventDestroy(h->tail_free[k]);
+  cudaDeviceSynchronize();   // pipelined tails run on the callers' streams
+  h->tail_ws.release();
   DevBuf* bufs[] = {&h->ws, &h->in_aos, &h->out_aos, &h->traj_soa, &h->traj_aos, &h->obj, &h->status, &h->iters, &h->misc0, &h->misc3};
   for (DevBuf* b : bufs) b->release();
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -290,6 +345,24 @@ int b200mpc_set_compaction(b200mpc_handle* h, double max_live_fraction, int from
   return 0;
 }
 
+int b200mpc_set_pipeline(b200mpc_handle* h, int depth, int tail_slots) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  if (depth < 0 || depth > b200mpc_handle::kMaxPipe) return fail(B200MPC_ERR_ARG, "pipeline: depth must be in [0, 32]");
+  if (depth > 0 && (tail_slots < 64 || tail_slots > (1 << 20))) return fail(B200MPC_ERR_ARG, "pipeline: tail_slots must be in [64, 1048576]");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());   // nothing of this handle is in flight while the contexts change
+  for (int k = 0; k < depth; ++k)
+    if (!h->tail_free[k]) CU(cudaEventCreateWithFlags(&h->tail_free[k], cudaEventDisableTiming));
+  if (depth > 0 && !h->main_free) CU(cudaEventCreateWithFlags(&h->main_free, cudaEventDisableTiming));
+  for (int k = 0; k < b200mpc_handle::kMaxPipe; ++k) h->tail_free_valid[k] = false;
+  h->main_free_valid = false;
+  h->pipe_depth = depth;
+  h->pipe_slots = depth > 0 ? (tail_slots + 63) / 64 * 64 : 0;
+  h->pipe_calls = 0;
+  ++h->repack_gen;
+  return 0;
+}
+
 int b200mpc_set_restoration(b200mpc_handle* h, int mode) {
   if (!h) return fail(B200MPC_ERR_ARG, "null handle");
   if (mode < 0 || mode > 2) return fail(B200MPC_ERR_ARG, "restoration: mode must be 0, 1 or 2");
@@ -312,8 +385,10 @@ int b200mpc_solve_batch_device(b200mpc_handle* h, int B, const double* d_state6,
   return timed_solve(h, B, 1, d_state6, d_coeffs, ncoef, d_out8, d_traj, d_obj, d_status, d_iters, s);
 }
 
-int b200mpc_solve_batch(b200mpc_handle* h, int B, const double* state6, const double* coeffs, int ncoef, double* out8,
-                        double* traj, double* obj, int* status, int* iters) {
+// Everything b200mpc_solve_batch does except the final wait: copies, solve and copies back are queued on the handle's
+// stream (asynchronous when the host buffers are pinned).
+static int enqueue_solve_batch(b200mpc_handle* h, int B, const double* state6, const double* coeffs, int ncoef, double* out8,
+                               double* traj, double* obj, int* status, int* iters) {
   if (int rc = check_solve_args(h, B, state6, coeffs, ncoef, out8)) return rc;
   if (B == 0) return 0;
   CU(cudaSetDevice(h->device));
@@ -345,7 +420,15 @@ int b200mpc_solve_batch(b200mpc_handle* h, int B, const double* state6, const do
   if (obj) CU(cudaMemcpyAsync(obj, h->obj.p, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (status) CU(cudaMemcpyAsync(status, h->status.p, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
   if (iters) CU(cudaMemcpyAsync(iters, h->iters.p, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int b200mpc_solve_batch(b200mpc_handle* h, int B, const double* state6, const double* coeffs, int ncoef, double* out8,
+                        double* traj, double* obj, int* status, int* iters) {
+  if (int rc = enqueue_solve_batch(h, B, state6, coeffs, ncoef, out8, traj, obj, status, iters)) return rc;
+  if (B == 0) return 0;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
@@ -366,25 +449,30 @@ int b200mpc_solve_batch_multi(b200mpc_handle* const* hs, int n_handles, int B, c
   }
   if (int rc0 = check_solve_args(hs[0], B, state6, coeffs, ncoef, out8)) return rc0;
   if (B == 0) return 0;
-  std::vector<int> rc(n_handles, 0);
-  std::vector<std::string> msg(n_handles);
-  std::vector<std::thread> th;
+  // One host thread queues every device's shard (copies in, solve graph, copies out: all asynchronous) and then waits
+  // for the devices one after the other; the shards run concurrently on the GPUs.  (Pageable host buffers make the
+  // copies synchronous, which serialises the devices: pass pinned buffers.)
   const int nv = 8 * hs[0]->P.N - 2;
-  for (int g = 0; g < n_handles; ++g) {
+  int first_rc = 0;
+  std::string first_msg;
+  int queued = 0;
+  for (int g = 0; g < n_handles && !first_rc; ++g) {
     // contiguous index ranges, remainder to the last device
     const long long lo = (long long)B / n_handles * g;
     const long long hi = g == n_handles - 1 ? B : (long long)B / n_handles * (g + 1);
-    th.emplace_back([=, &rc, &msg]() {
-      const int n = (int)(hi - lo);
-      rc[g] = b200mpc_solve_batch(hs[g], n, state6 + lo * 6, coeffs + lo * ncoef, ncoef, out8 + lo * 8,
-                                  traj ? traj + lo * nv : nullptr, obj ? obj + lo : nullptr,
-                                  status ? status + lo : nullptr, iters ? iters + lo : nullptr);
-      if (rc[g]) msg[g] = b200mpc_last_error();
-    });
+    const int n = (int)(hi - lo);
+    int rc = enqueue_solve_batch(hs[g], n, state6 + lo * 6, coeffs + lo * ncoef, ncoef, out8 + lo * 8,
+                                 traj ? traj + lo * nv : nullptr, obj ? obj + lo : nullptr, status ? status + lo : nullptr,
+                                 iters ? iters + lo : nullptr);
+    if (rc) { first_rc = rc; first_msg = "device shard " + std::to_string(g) + ": " + b200mpc_last_error(); }
+    else queued = g + 1;
   }
-  for (auto& t : th) t.join();
-  for (int g = 0; g < n_handles; ++g)
-    if (rc[g]) return fail(rc[g], "device shard " + std::to_string(g) + ": " + msg[g]);
+  for (int g = 0; g < queued; ++g) {   // always drain what was queued, also after an error
+    cudaError_t e = cudaSetDevice(hs[g]->device);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(hs[g]->stream);
+    if (e != cudaSuccess && !first_rc) { first_rc = B200MPC_ERR_CUDA; first_msg = "device shard " + std::to_string(g) + ": " + cudaGetErrorString(e); }
+  }
+  if (first_rc) return fail(first_rc, first_msg);
   return 0;
 }
 

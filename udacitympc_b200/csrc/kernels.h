@@ -35,6 +35,9 @@ struct SolveConfig {
   int handover_max_rounds = 0;    // 0 = by horizon: 20 up to N = 50, 2 N - 80 above (120 at N = 100); see launch_solve
   double compact_max_live = 0.7;
   int compact_from = 4;
+  // pipelined solves (launch_solve_bulk / launch_solve_tail): rounds the tail context runs before its finisher (0 = by
+  // horizon: 10 up to N = 50, 2 N - 80 above)
+  int tail_rounds = 0;
   bool coop = true;       // latency path = cooperative warp-per-problem kernel (false: thread-per-problem fused kernel)
 };
 struct SplitStreams {   // auxiliary streams / events owned by the handle (n_aux <= 3)
@@ -46,6 +49,19 @@ cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6
                          double* ws, double* out8, double* traj, double* obj, int* status, int* iters,
                          const SolveConfig& cfg, cudaStream_t stream, const SplitStreams* ss, long long* n_launches,
                          int io_aos = 0);   // io_aos = 1: state6 [B][6], coeffs [B][ncoef], out8 [steps][B][8] (reference order)
+
+// Pipelined solves: one solve as two launch sequences (see solve_kernel.cu).  A tail context is a workspace of
+// solve_workspace_doubles(N, slots) doubles.
+struct TailCtx {
+  double* ws = nullptr;
+  int slots = 0;
+};
+cudaError_t launch_solve_bulk(const Params& P, int B, const double* state6, const double* coeffs, int ncoef, double* ws, double* out8,
+                              double* traj, double* obj, int* status, int* iters, const SolveConfig& cfg, cudaStream_t stream,
+                              long long* n_launches, int io_aos, const TailCtx& tail);
+cudaError_t launch_solve_tail(const Params& P, int B, const double* state6, const double* coeffs, int ncoef, double* out8, double* traj,
+                              double* obj, int* status, int* iters, const SolveConfig& cfg, cudaStream_t stream, long long* n_launches,
+                              int io_aos, const TailCtx& tail);
 
 // K6 batch I/O: [B][K] <-> [K][B]
 cudaError_t launch_aos_to_soa(const double* in, double* out, int B, int K, cudaStream_t stream);

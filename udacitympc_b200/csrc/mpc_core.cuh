@@ -101,6 +101,7 @@ enum Status {
 constexpr int kMaxCoef = 4;   // reference polynomial degree <= 3
 constexpr int kMaxFilter = 41;   // filter entries (phi, theta); they fill one workspace record of their own (record N+1)
 constexpr int kCarry = 24;    // stage-to-stage values of the STEP sweep
+constexpr int kStageVals = 24;   // values of one stage the factor sweep stages asynchronously: S U LAM ZL ZU TR (22) + u_{t-1} (2)
 #ifndef MPC_RESTO_BETA
 #define MPC_RESTO_BETA 0.05
 #endif
@@ -181,6 +182,22 @@ struct Ws {
 #endif
   }
 };
+
+// MPC_ASYNC_STAGE (device, per-pass factor sweep): the rows of the NEXT stage are copied into shared memory by
+// per-thread asynchronous copies (cp.async / LDGSTS: each thread moves the 8-byte elements of its own problem, so no
+// barrier and no cross-thread hand-over is involved -- a thread waits only for its own copy group) while the current
+// stage is computed, instead of the L1 prefetch + ordinary loads.
+#ifndef MPC_ASYNC_STAGE
+#define MPC_ASYNC_STAGE 0
+#endif
+#if defined(__CUDA_ARCH__) && MPC_ASYNC_STAGE
+__device__ __forceinline__ void async_copy8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#endif
 
 MPC_HD double dmax(double a, double b) { return a > b ? a : b; }
 MPC_HD double dmin(double a, double b) { return a < b ? a : b; }
@@ -363,8 +380,12 @@ struct Solver {
   // a thread-local array elsewhere.  Must be set before step_sweep() runs.
   double* cr;
   int cs;
+  // stage buffers of the asynchronous staging (MPC_ASYNC_STAGE; element i of buffer b at sb[(b * kStageVals + i) * sbs]),
+  // null = ordinary loads
+  double* sb;
+  int sbs;
 
-  MPC_HD Solver(const Params& p, double* base, int lane = 0) : P(p), w{base, lane}, N(p.N), M(p.N - 1), cr(nullptr), cs(1) {}
+  MPC_HD Solver(const Params& p, double* base, int lane = 0) : P(p), w{base, lane}, N(p.N), M(p.N - 1), cr(nullptr), cs(1), sb(nullptr), sbs(1) {}
 
   MPC_HD bool fl(int f) const { return (flags & f) != 0; }
   MPC_HD void setfl(int f, bool v) { flags = v ? (flags | f) : (flags & ~f); }
@@ -641,6 +662,21 @@ struct Solver {
     phase = PH_STEP;
   }
 
+#if defined(__CUDA_ARCH__) && MPC_ASYNC_STAGE
+  // asynchronous copy of the 22 iterate rows of stage t (copy bX) and of u_{t-1} into stage buffer t & 1
+  __device__ __forceinline__ void stage_request(int t, int bX) {
+    double* q = sb + (size_t)((t & 1) * kStageVals) * sbs;
+    const double* g = &w(rec(t) + bX);
+#pragma unroll
+    for (int k = 0; k < 22; ++k) async_copy8(q + k * sbs, g + (size_t)k * LANES);
+    if (t > 0) {
+      const double* gm = &w(rec(t - 1) + bX + xU);
+      async_copy8(q + 22 * sbs, gm);
+      async_copy8(q + 23 * sbs, gm + LANES);
+    }
+    async_commit();
+  }
+#endif
   // ------------------------------------------------------------------------------------------
   // Backward Riccati sweep: factor + feed-forward for the right-hand side (grad L_mu, c).  use_csoc selects the
   // constraint right-hand side (second-order correction).  Returns false on wrong inertia.
@@ -671,21 +707,42 @@ struct Solver {
     }
     double un0 = 0.0, un1 = 0.0;         // u_{t+1}
     bool ok = true;
+#if defined(__CUDA_ARCH__) && MPC_ASYNC_STAGE && MPC_STORE_TRIG
+    const bool staged = sb != nullptr;
+    if (staged) stage_request(M - 1, bX);
+#else
+    const bool staged = false;
+#endif
     for (int t = M - 1; t >= 0; --t) {
       const int r = rec(t) + bX, rn = rec(t + 1);
-      if (t > 0) {   // rows of stage t-1: S,U,LAM,ZL,ZU(,TR) are contiguous, then the residual of rows t
+      if (t > 0 && !staged) {   // rows of stage t-1: S,U,LAM,ZL,ZU(,TR) are contiguous, then the residual of rows t
         w.prefetch(r - kRec + xS, MPC_STORE_TRIG ? 22 : 18);
         if (!ls && (MPC_STORE_C || use_csoc)) w.prefetch(rec(t) + bC, 6);
       }
       double s[6], lam[6];
+      double u0, u1, um0 = 0.0, um1 = 0.0, sp, cp, se, ce, zl0, zl1, zu0, zu1;
+#if defined(__CUDA_ARCH__) && MPC_ASYNC_STAGE && MPC_STORE_TRIG
+      if (sb) {
+        // this stage's rows were requested one stage ago (the prologue for t = M-1); request the next stage's, then use
+        async_wait_all();
+        const double* q = sb + (size_t)((t & 1) * kStageVals) * sbs;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { s[k] = w(r + xS + k); lam[k] = ls ? 0.0 : w(r + xLAM + k); }
-      const double u0 = w(r + xU), u1 = w(r + xU + 1);
-      double um0 = 0.0, um1 = 0.0;
-      if (t > 0) { um0 = w(r - kRec + xU); um1 = w(r - kRec + xU + 1); }
-      double sp, cp, se, ce;
-      trig_of(r, s, sp, cp, se, ce);
-      const double zl0 = w(r + xZL), zl1 = w(r + xZL + 1), zu0 = w(r + xZU), zu1 = w(r + xZU + 1);
+        for (int k = 0; k < 6; ++k) { s[k] = q[(xS + k) * sbs]; lam[k] = ls ? 0.0 : q[(xLAM + k) * sbs]; }
+        u0 = q[xU * sbs]; u1 = q[(xU + 1) * sbs];
+        zl0 = q[xZL * sbs]; zl1 = q[(xZL + 1) * sbs]; zu0 = q[xZU * sbs]; zu1 = q[(xZU + 1) * sbs];
+        sp = q[xTR * sbs]; cp = q[(xTR + 1) * sbs]; se = q[(xTR + 2) * sbs]; ce = q[(xTR + 3) * sbs];
+        if (t > 0) { um0 = q[22 * sbs]; um1 = q[23 * sbs]; }
+        if (t > 0) stage_request(t - 1, bX);
+      } else
+#endif
+      {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { s[k] = w(r + xS + k); lam[k] = ls ? 0.0 : w(r + xLAM + k); }
+        u0 = w(r + xU); u1 = w(r + xU + 1);
+        if (t > 0) { um0 = w(r - kRec + xU); um1 = w(r - kRec + xU + 1); }
+        trig_of(r, s, sp, cp, se, ce);
+        zl0 = w(r + xZL); zl1 = w(r + xZL + 1); zu0 = w(r + xZU); zu1 = w(r + xZU + 1);
+      }
       double p0, p1, p2, p3;
       poly_eval(cf, s[0], p0, p1, p2, p3);
       // constraint right-hand side of rows t+1

@@ -143,6 +143,10 @@ __global__ void __launch_bounds__(kBlock, kFactorBlocks) mpc_factor_kernel(const
   if (!locate(A, blockIdx.x * blockDim.x + threadIdx.x, slot, b, ws)) return;
   Solver<32> S(P, slot_base(P, ws, slot), slot & 31);
   if (S.load_phase() != PH_FACTOR) return;
+#if MPC_ASYNC_STAGE
+  __shared__ double stage[2 * kStageVals * kBlock];   // [buffer][value][thread]
+  S.sb = stage + threadIdx.x; S.sbs = kBlock;
+#endif
   load_coeffs(A, b, S.cf);
   S.kernel_factor();
   if (S.phase == PH_DONE) {   // inertia correction exhausted (IpPDPerturbationHandler.cpp:380-388)
@@ -185,12 +189,18 @@ __global__ void __launch_bounds__(kBlock, kStepBlocks) mpc_step_kernel(const __g
 // level in desc.  The running lanes of a warp take consecutive destination slots, so the rows they write are
 // contiguous; the slot order among warps is first come, first served (results do not depend on the slot a problem
 // sits in).  The last block to finish commits the new level and clears the counters.
+// Tail hand-off (pipelined solves, launch_solve_bulk / launch_solve_tail): with export_below > 0 the kernel moves the live
+// problems OUT of this workspace as soon as at most export_below are left -- into region 1 of a small tail context
+// (T.ws1, slot -> problem map T.map0, level 1 in T.desc) -- and leaves this workspace empty (level >= 1, no occupied
+// slots: every later launch on it finds nothing to do).  The tail context is finished by its own launches while the
+// next batch already runs in this workspace.
 __global__ void __launch_bounds__(256) mpc_repack_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A,
-                                                         double max_live) {
+                                                         double max_live, int export_below, double* t_ws1, int* t_map0, int* t_desc) {
   int* desc = A.desc;
   const int level = desc[kLevel], live_n = desc[kLive];
   const int occupied = level == 0 ? A.b1 - A.b0 : desc[kCount];
-  const bool go = live_n > 0 && (double)live_n <= max_live * (double)occupied;
+  const bool exp = export_below > 0 && live_n > 0 && live_n <= export_below;
+  const bool go = exp || (live_n > 0 && (double)live_n <= max_live * (double)occupied);
   if (go) {
     int slot = 0, b = 0;
     double* ws = A.ws;
@@ -203,19 +213,32 @@ __global__ void __launch_bounds__(256) mpc_repack_kernel(const __grid_constant__
     if (m != 0 && lane == 0) base = atomicAdd(desc + kAlloc, __popc(m));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (live) {
-      const int ds = A.b0 + base + __popc(m & ((1u << lane) - 1u));
-      (((level + 1) & 1) ? A.map0 : A.map1)[ds] = b;
-      repack_problem(P, src, Ws<32>{slot_base(P, ((level + 1) & 1) ? A.ws1 : A.ws, ds), ds & 31});
+      const int rank = base + __popc(m & ((1u << lane) - 1u));
+      if (exp) {
+        t_map0[rank] = b;
+        repack_problem(P, src, Ws<32>{slot_base(P, t_ws1, rank), rank & 31});
+      } else {
+        const int ds = A.b0 + rank;
+        (((level + 1) & 1) ? A.map0 : A.map1)[ds] = b;
+        repack_problem(P, src, Ws<32>{slot_base(P, ((level + 1) & 1) ? A.ws1 : A.ws, ds), ds & 31});
+      }
     }
   }
   __syncthreads();   // every thread of the block has read desc
   if (threadIdx.x == 0) {
     __threadfence();
     if (atomicAdd(desc + kTicket, 1) == (int)gridDim.x - 1) {
-      if (go) { desc[kCount] = desc[kAlloc]; desc[kLevel] = level + 1; }
+      if (exp) {
+        t_desc[kLevel] = 1; t_desc[kCount] = desc[kAlloc];
+        desc[kCount] = 0; desc[kLevel] = level > 0 ? level : 1;
+      } else if (go) { desc[kCount] = desc[kAlloc]; desc[kLevel] = level + 1; }
       desc[kLive] = 0; desc[kAlloc] = 0; desc[kTicket] = 0;
     }
   }
+}
+// an empty tail context: level 1 with no occupied slots (level 0 would mean "slot == problem" for every slot)
+__global__ void mpc_tail_reset_kernel(int* t_desc) {
+  if (threadIdx.x < kDescInts) t_desc[threadIdx.x] = threadIdx.x == kLevel ? 1 : 0;
 }
 
 // ---- fused kernel: finishes whatever is still active (fresh == 1: starts from the inputs) ---------------------
@@ -297,6 +320,20 @@ cudaError_t solver_prepare_device() {
 }
 
 static size_t coop_doubles_per_warp(int N) { return (size_t)N * kCoopStageDoubles + (sizeof(CoopPub) + 7) / 8; }
+// warps of the cooperative kernel that are resident on the device at once (0: the horizon does not fit): 128-thread blocks
+// of up to 4 problems, 2 blocks per SM by registers, per-problem scratch in shared memory
+static int coop_resident_warps(int N) {
+  const size_t per_warp = coop_doubles_per_warp(N) * sizeof(double), limit = 200 * 1024;
+  if (per_warp > limit) return 0;
+  int wpb = (int)(limit / per_warp);
+  if (wpb > 4) wpb = 4;
+  int blocks = (int)((size_t)227 * 1024 / (per_warp * wpb));
+  if (blocks > 2) blocks = 2;
+  int sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms * blocks * wpb;
+}
 
 // launches the cooperative kernel if the horizon fits in shared memory; returns false otherwise
 static bool launch_coop(const Params& P, const SolveArgs& A, int fresh, cudaStream_t stream, cudaError_t* err, int take_below = 0) {
@@ -336,7 +373,7 @@ static cudaError_t launch_part(const Params& P, SolveArgs A, const SolveConfig& 
         mpc_forward_kernel<<<grid, kBlock, 0, stream>>>(P, A);
         mpc_step_kernel<<<grid, kBlock, 0, stream>>>(P, Ar);
         if (attempt) {
-          mpc_repack_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(P, A, cfg.compact_max_live);
+          mpc_repack_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(P, A, cfg.compact_max_live, 0, nullptr, nullptr, nullptr);
           *n += 1;
           if (take_below > 0 && r + 1 >= cfg.handover_from && cfg.coop && launch_coop(P, A, 0, stream, &ce, take_below)) {
             if (ce != cudaSuccess) return ce;
@@ -409,6 +446,103 @@ cudaError_t launch_solve(const Params& P, int B, int steps, const double* state6
   }
   if (n_launches) *n_launches += n;
   return e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pipelined solves on one handle (b200mpc_set_pipeline).  A solve is cut in two launch sequences:
+//   bulk  init + rounds in the handle's main workspace; as soon as at most tail.slots problems are still iterating they
+//         are moved to the tail context and the main workspace is free for the next batch;
+//   tail  rounds (with compaction and the conditional hand-over to the cooperative kernel) + finisher on the tail context.
+// The caller orders them with events: bulk(i+1) after bulk(i), tail(i) after bulk(i), bulk(i+depth) after tail(i), so
+// the thin tail of one batch -- latency bound: a straggler needs up to hundreds of iterations at long horizons -- runs
+// under the bulk of the following batches instead of holding a full-size workspace.  Results do not depend on where a
+// problem is finished.
+static SolveArgs tail_args(const Params& P, int B, const double* state6, const double* coeffs, int ncoef, double* out8, double* traj,
+                           double* obj, int* status, int* iters, int io_aos, const TailCtx& tail) {
+  const size_t reg = region_doubles(P.N, tail.slots);
+  int* ints = reinterpret_cast<int*>(tail.ws + 2 * reg);
+  const size_t map_ints = ((size_t)tail.slots + 1) / 2 * 2;
+  return SolveArgs{B, 1, 0, ncoef, io_aos ? 1 : 0, 0, tail.slots, 0, 0.0, state6, coeffs, tail.ws, tail.ws + reg, ints, ints + map_ints,
+                   ints + 2 * map_ints, 0, out8, traj, obj, status, iters};
+}
+static int auto_rounds(const Params& P, const SolveConfig& cfg) {
+  return cfg.rounds > 0 ? cfg.rounds : (cfg.handover_max_rounds > 0 ? cfg.handover_max_rounds : (P.N <= 50 ? 20 : 2 * P.N - 80));
+}
+
+cudaError_t launch_solve_bulk(const Params& P, int B, const double* state6, const double* coeffs, int ncoef, double* ws, double* out8,
+                              double* traj, double* obj, int* status, int* iters, const SolveConfig& cfg, cudaStream_t stream,
+                              long long* n_launches, int io_aos, const TailCtx& tail) {
+  if (B <= 0) return cudaSuccess;
+  const size_t reg = region_doubles(P.N, B);
+  int* ints = reinterpret_cast<int*>(ws + 2 * reg);
+  const size_t map_ints = ((size_t)B + 1) / 2 * 2;
+  SolveArgs A{B, 1, 0, ncoef, io_aos ? 1 : 0, 0, B, 0, 0.0, state6, coeffs, ws, ws + reg, ints, ints + map_ints, ints + 2 * map_ints, 0,
+              out8, traj, obj, status, iters};
+  const SolveArgs T = tail_args(P, B, state6, coeffs, ncoef, out8, traj, obj, status, iters, io_aos, tail);
+  const int grid = (B + kBlock - 1) / kBlock;
+  const int rounds = auto_rounds(P, cfg);
+  long long n = 0;
+  mpc_tail_reset_kernel<<<1, 32, 0, stream>>>(T.desc);
+  mpc_init_kernel<<<grid, kBlock, 0, stream>>>(P, A);
+  n += 2;
+  for (int r = 0; r < rounds; ++r) {
+    const bool attempt = r + 1 >= cfg.compact_from;
+    SolveArgs Ar = A;
+    Ar.count_live = attempt ? 1 : 0;
+    mpc_factor_kernel<<<grid, kBlock, 0, stream>>>(P, A);
+    mpc_forward_kernel<<<grid, kBlock, 0, stream>>>(P, A);
+    mpc_step_kernel<<<grid, kBlock, 0, stream>>>(P, Ar);
+    n += 3;
+    if (attempt) {
+      mpc_repack_kernel<<<(B + 255) / 256, 256, 0, stream>>>(P, A, cfg.compact_max_live, tail.slots, T.ws1, T.map0, T.desc);
+      n += 1;
+    }
+  }
+  // whatever never fitted the tail context is finished in place
+  cudaError_t ce = cudaSuccess;
+  if (!(cfg.coop && launch_coop(P, A, 0, stream, &ce))) mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 0);
+  n += 1;
+  if (ce == cudaSuccess) ce = cudaGetLastError();
+  if (n_launches) *n_launches += n;
+  return ce;
+}
+
+cudaError_t launch_solve_tail(const Params& P, int B, const double* state6, const double* coeffs, int ncoef, double* out8, double* traj,
+                              double* obj, int* status, int* iters, const SolveConfig& cfg, cudaStream_t stream, long long* n_launches,
+                              int io_aos, const TailCtx& tail) {
+  if (B <= 0) return cudaSuccess;
+  const SolveArgs A = tail_args(P, B, state6, coeffs, ncoef, out8, traj, obj, status, iters, io_aos, tail);
+  const int nb = tail.slots, grid = (nb + kBlock - 1) / kBlock;
+  // the hand-over to the cooperative kernel pays once the rest fits its resident warps; at long horizons its per-problem
+  // scratch leaves few of them (2 per SM at N = 100), and the sweeps keep a longer tail (see launch_solve)
+  const int rounds = cfg.tail_rounds > 0 ? cfg.tail_rounds : (P.N <= 50 ? 10 : 2 * P.N - 80);
+  int take_below = 0;
+  if (cfg.coop && cfg.handover_below > 0) {
+    const int resident = coop_resident_warps(P.N);
+    take_below = cfg.handover_below < resident ? cfg.handover_below : resident;
+    if (take_below > nb) take_below = nb;
+  }
+  long long n = 0;
+  cudaError_t ce = cudaSuccess;
+  for (int r = 0; r < rounds; ++r) {
+    SolveArgs Ar = A;
+    Ar.count_live = 1;
+    mpc_factor_kernel<<<grid, kBlock, 0, stream>>>(P, A);
+    mpc_forward_kernel<<<grid, kBlock, 0, stream>>>(P, A);
+    mpc_step_kernel<<<grid, kBlock, 0, stream>>>(P, Ar);
+    mpc_repack_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(P, A, cfg.compact_max_live, 0, nullptr, nullptr, nullptr);
+    n += 4;
+    if (take_below > 0 && launch_coop(P, A, 0, stream, &ce, take_below)) {
+      if (ce != cudaSuccess) return ce;
+      n += 1;
+    }
+  }
+  // what is left after the last round: the thread loop (the cooperative kernel took over above if the rest fits it)
+  mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 0);
+  n += 1;
+  if (ce == cudaSuccess) ce = cudaGetLastError();
+  if (n_launches) *n_launches += n;
+  return ce;
 }
 
 // ---------------------------------------------------------------------------------------------
