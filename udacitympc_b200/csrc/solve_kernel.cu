@@ -513,15 +513,24 @@ cudaError_t launch_solve_tail(const Params& P, int B, const double* state6, cons
   if (B <= 0) return cudaSuccess;
   const SolveArgs A = tail_args(P, B, state6, coeffs, ncoef, out8, traj, obj, status, iters, io_aos, tail);
   const int nb = tail.slots, grid = (nb + kBlock - 1) / kBlock;
-  // the hand-over to the cooperative kernel pays once the rest fits its resident warps; at long horizons its per-problem
-  // scratch leaves few of them (2 per SM at N = 100), and the sweeps keep a longer tail (see launch_solve)
-  const int rounds = cfg.tail_rounds > 0 ? cfg.tail_rounds : (P.N <= 50 ? 10 : 2 * P.N - 80);
+  // Up to N = 50 the tail is short (the slowest problems need a few dozen iterations): a few rounds, after each of which
+  // the cooperative kernel takes the rest over once it fits its resident warps, as in launch_solve.  Above that the tail
+  // is long (N = 100: 2 % of the problems need more than 100 iterations, the slowest about 1000) and the tails of many
+  // batches are in flight at once: they stay with the compacted thread-per-problem sweeps -- full warps whose blocks come
+  // and go, so the tails of all batches share the machine like one large batch -- because the cooperative kernel holds
+  // 100 KB of shared memory per problem there (2 resident warps per SM) and a thread loop that runs to completion holds its
+  // registers until the slowest problem of the block is done (measured: with either as the finisher of 32 tails in flight
+  // the bulk of the following batches runs at a third of its speed).  Only the last few problems go to the cooperative kernel.
+  const bool long_tail = P.N > 50;
+  const int rounds = cfg.tail_rounds > 0 ? cfg.tail_rounds : (long_tail ? 6 * P.N : 10);
   int take_below = 0;
   if (cfg.coop && cfg.handover_below > 0) {
     const int resident = coop_resident_warps(P.N);
-    take_below = cfg.handover_below < resident ? cfg.handover_below : resident;
+    take_below = long_tail ? 32 : (cfg.handover_below < resident ? cfg.handover_below : resident);
+    if (take_below > resident) take_below = resident;
     if (take_below > nb) take_below = nb;
   }
+  const int coop_every = long_tail ? 8 : 1;
   long long n = 0;
   cudaError_t ce = cudaSuccess;
   for (int r = 0; r < rounds; ++r) {
@@ -532,10 +541,14 @@ cudaError_t launch_solve_tail(const Params& P, int B, const double* state6, cons
     mpc_step_kernel<<<grid, kBlock, 0, stream>>>(P, Ar);
     mpc_repack_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(P, A, cfg.compact_max_live, 0, nullptr, nullptr, nullptr);
     n += 4;
-    if (take_below > 0 && launch_coop(P, A, 0, stream, &ce, take_below)) {
+    if (take_below > 0 && (r + 1) % coop_every == 0 && launch_coop(P, A, 0, stream, &ce, take_below)) {
       if (ce != cudaSuccess) return ce;
       n += 1;
     }
+  }
+  if (take_below > 0 && launch_coop(P, A, 0, stream, &ce, take_below)) {
+    if (ce != cudaSuccess) return ce;
+    n += 1;
   }
   // what is left after the last round: the thread loop (the cooperative kernel took over above if the rest fits it)
   mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 0);
