@@ -75,6 +75,7 @@ struct b200mpc_handle {
   size_t tail_ctx_doubles = 0;          // of the allocation in tail_ws (pipe_depth contexts)
   int tail_ctx_N = 0, tail_ctx_slots = 0;
   cudaEvent_t main_free = nullptr, tail_free[kMaxPipe] = {};
+  cudaStream_t tail_stream[kMaxPipe] = {};   // highest priority: the small kernels of a tail must not queue behind bulk blocks
   bool main_free_valid = false, tail_free_valid[kMaxPipe] = {};
   unsigned long long pipe_calls = 0;
 };
@@ -151,9 +152,14 @@ int timed_solve(b200mpc_handle* h, int B, int steps, const double* st, const dou
     if (int rc = run_solve(h, B, 1, st, cf, ncoef, out8, traj, obj, status, iters, s, false, io_aos, 1, tail)) return rc;
     CU(cudaEventRecord(h->main_free, s));
     h->main_free_valid = true;
-    if (int rc = run_solve(h, B, 1, st, cf, ncoef, out8, traj, obj, status, iters, s, false, io_aos, 2, tail)) return rc;
-    CU(cudaEventRecord(h->tail_free[k], s));
+    // the tail runs on the context's own high-priority stream, behind the bulk; the caller's stream then waits for it,
+    // so the call stays stream-ordered for its caller
+    cudaStream_t ts = h->tail_stream[k] ? h->tail_stream[k] : s;
+    if (ts != s) CU(cudaStreamWaitEvent(ts, h->main_free, 0));
+    if (int rc = run_solve(h, B, 1, st, cf, ncoef, out8, traj, obj, status, iters, ts, false, io_aos, 2, tail)) return rc;
+    CU(cudaEventRecord(h->tail_free[k], ts));
     h->tail_free_valid[k] = true;
+    if (ts != s) CU(cudaStreamWaitEvent(s, h->tail_free[k], 0));
     return 0;
   }
   if (!caller_captures && h->done_valid) CU(cudaStreamWaitEvent(s, h->done, 0));
@@ -281,6 +287,10 @@ int b200mpc_create(const b200mpc_params* p, int device, b200mpc_handle** out) {
     h->cfg.handover_below = atoi(hb);
     if (const char* c = strchr(hb, ',')) { int v = atoi(c + 1); if (v > 0) h->cfg.handover_max_rounds = v; }
   }
+  if (const char* tr = getenv("B200MPC_TAIL")) {   // tuning override: "<tail rounds>[,<occupied slots for the cooperative kernel>]"
+    h->cfg.tail_rounds = atoi(tr) > 0 ? atoi(tr) : 0;
+    if (const char* c = strchr(tr, ',')) h->cfg.tail_take_below = atoi(c + 1) > 0 ? atoi(c + 1) : 0;
+  }
   if (const char* rr = getenv("B200MPC_ROUNDS")) { int v = atoi(rr); if (v > 0) h->cfg.rounds = v; }
   if (const char* sp = getenv("B200MPC_SPLIT")) { int v = atoi(sp); if (v >= 1 && v <= 4) h->cfg.split = v; }
   *out = h;
@@ -300,9 +310,11 @@ void b200mpc_destroy(b200mpc_handle* h) {
   if (h->ss.fork) cudaEventDestroy(h->ss.fork);
   if (h->done) cudaEventDestroy(h->done);
   if (h->main_free) cudaEventDestroy(h->main_free);
-  for (int k = 0; k < b200mpc_handle::kMaxPipe; ++k)
+  cudaDeviceSynchronize();   // pipelined bulks run on the callers' streams
+  for (int k = 0; k < b200mpc_handle::kMaxPipe; ++k) {
     if (h->tail_free[k]) cudaEventDestroy(h->tail_free[k]);
-  cudaDeviceSynchronize();   // pipelined tails run on the callers' streams
+    if (h->tail_stream[k]) cudaStreamDestroy(h->tail_stream[k]);
+  }
   h->tail_ws.release();
   DevBuf* bufs[] = {&h->ws, &h->in_aos, &h->out_aos, &h->traj_soa, &h->traj_aos, &h->obj, &h->status, &h->iters, &h->misc0, &h->misc3};
   for (DevBuf* b : bufs) b->release();
@@ -351,8 +363,12 @@ int b200mpc_set_pipeline(b200mpc_handle* h, int depth, int tail_slots) {
   if (depth > 0 && (tail_slots < 64 || tail_slots > (1 << 20))) return fail(B200MPC_ERR_ARG, "pipeline: tail_slots must be in [64, 1048576]");
   CU(cudaSetDevice(h->device));
   CU(cudaDeviceSynchronize());   // nothing of this handle is in flight while the contexts change
-  for (int k = 0; k < depth; ++k)
+  int prio_lo = 0, prio_hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  for (int k = 0; k < depth; ++k) {
     if (!h->tail_free[k]) CU(cudaEventCreateWithFlags(&h->tail_free[k], cudaEventDisableTiming));
+    if (!h->tail_stream[k]) CU(cudaStreamCreateWithPriority(&h->tail_stream[k], cudaStreamNonBlocking, prio_hi));
+  }
   if (depth > 0 && !h->main_free) CU(cudaEventCreateWithFlags(&h->main_free, cudaEventDisableTiming));
   for (int k = 0; k < b200mpc_handle::kMaxPipe; ++k) h->tail_free_valid[k] = false;
   h->main_free_valid = false;

@@ -38,6 +38,7 @@ struct SolveConfig {
   // pipelined solves (launch_solve_bulk / launch_solve_tail): rounds the tail context runs before its finisher (0 = by
   // horizon: 10 up to N = 50, 2 N - 80 above)
   int tail_rounds = 0;
+  int tail_take_below = 0;   // long horizons: occupied slots at which the cooperative kernel takes a tail over (0 = 32)
   bool coop = true;       // latency path = cooperative warp-per-problem kernel (false: thread-per-problem fused kernel)
 };
 struct SplitStreams {   // auxiliary streams / events owned by the handle (n_aux <= 3)

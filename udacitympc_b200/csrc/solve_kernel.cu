@@ -286,31 +286,37 @@ __global__ void __launch_bounds__(128) mpc_coop_kernel(const __grid_constant__ P
     if (!A.desc || A.desc[kLevel] == 0 || A.desc[kCount] > take_below) return;
     if (threadIdx.x == 0) A.desc[kHanded] = 1;   // only the sweeps read it
   }
-  int slot, b;   // one problem per warp
-  double* ws;
-  if (wib >= warps_per_block || !locate(A, blockIdx.x * warps_per_block + wib, slot, b, ws, false)) return;
+  if (wib >= warps_per_block) return;
   double* mine = coop_smem + (size_t)wib * doubles_per_warp;
   CoopStage* st = reinterpret_cast<CoopStage*>(mine);
   CoopPub* pub = reinterpret_cast<CoopPub*>(mine + (size_t)P.N * kCoopStageDoubles);
-  Solver<32> S(P, slot_base(P, ws, slot), slot & 31);
-  load_coeffs(A, b, S.cf);
-  CoopSolver<32, DevExec> C(S, st, pub, DevExec{lane});
-  if (fresh) {
-    double s0[6];
-    load_state6(A, b, s0);
-    if (A.warm && A.step > 0) {
-      if (lane == 0) S.init_warm(s0, A.mu_warm);
+  // one problem per warp at a time; the grid is capped at a few waves and every warp walks on through the slots (a
+  // launch that finds little or nothing to do must not cost thousands of 100 KB-shared-memory blocks)
+  for (int idx = blockIdx.x * warps_per_block + wib;; idx += gridDim.x * warps_per_block) {
+    int slot, b;
+    double* ws;
+    if (!locate(A, idx, slot, b, ws, false)) return;
+    Solver<32> S(P, slot_base(P, ws, slot), slot & 31);
+    load_coeffs(A, b, S.cf);
+    CoopSolver<32, DevExec> C(S, st, pub, DevExec{lane});
+    if (fresh) {
+      double s0[6];
+      load_state6(A, b, s0);
+      if (A.warm && A.step > 0) {
+        if (lane == 0) S.init_warm(s0, A.mu_warm);
+        __syncwarp();
+      } else C.init(s0);
+    } else {
+      if (S.load_phase() == PH_DONE) continue;   // whole warp
+      if (lane == 0) S.load_state();
       __syncwarp();
-    } else C.init(s0);
-  } else {
-    if (S.load_phase() == PH_DONE) return;   // whole warp
-    if (lane == 0) S.load_state();
+    }
+    C.run();
+    if (lane == 0) {
+      S.store_state();
+      write_result(P, A, b, S);
+    }
     __syncwarp();
-  }
-  C.run();
-  if (lane == 0) {
-    S.store_state();
-    write_result(P, A, b, S);
   }
 }
 
@@ -344,7 +350,9 @@ static bool launch_coop(const Params& P, const SolveArgs& A, int fresh, cudaStre
   if (wpb > 4) wpb = 4;
   const size_t smem = per_warp * wpb;
   const int n = take_below > 0 && take_below < A.b1 - A.b0 ? take_below : A.b1 - A.b0;
-  const int grid = (n + wpb - 1) / wpb;
+  int grid = (n + wpb - 1) / wpb;
+  const int cap = 4 * coop_resident_warps(P.N) / wpb;   // four waves; the warps stride over the rest
+  if (cap > 0 && grid > cap) grid = cap;
   mpc_coop_kernel<<<grid, 128, smem, stream>>>(P, A, fresh, wpb, (int)coop_doubles_per_warp(P.N), take_below);
   *err = cudaGetLastError();
   return true;
@@ -498,11 +506,13 @@ cudaError_t launch_solve_bulk(const Params& P, int B, const double* state6, cons
       n += 1;
     }
   }
-  // whatever never fitted the tail context is finished in place
-  cudaError_t ce = cudaSuccess;
-  if (!(cfg.coop && launch_coop(P, A, 0, stream, &ce))) mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 0);
+  // Whatever never fitted the tail context is finished in place, by the thread loop: in the normal case the workspace
+  // is empty by now and the launch must be cheap -- a cooperative-kernel launch, even one that finds nothing to do,
+  // asks for 100-200 KB of shared memory per block and has to wait for SMs to drain while the tails of the previous
+  // batches keep them busy (measured at N = 100 with 32 tails in flight: ~150 ms per bulk).
+  mpc_fused_kernel<<<grid, kBlock, 0, stream>>>(P, A, 0);
   n += 1;
-  if (ce == cudaSuccess) ce = cudaGetLastError();
+  cudaError_t ce = cudaGetLastError();
   if (n_launches) *n_launches += n;
   return ce;
 }
@@ -526,7 +536,7 @@ cudaError_t launch_solve_tail(const Params& P, int B, const double* state6, cons
   int take_below = 0;
   if (cfg.coop && cfg.handover_below > 0) {
     const int resident = coop_resident_warps(P.N);
-    take_below = long_tail ? 32 : (cfg.handover_below < resident ? cfg.handover_below : resident);
+    take_below = long_tail ? (cfg.tail_take_below > 0 ? cfg.tail_take_below : 32) : (cfg.handover_below < resident ? cfg.handover_below : resident);
     if (take_below > resident) take_below = resident;
     if (take_below > nb) take_below = nb;
   }
