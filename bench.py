@@ -259,6 +259,8 @@ def run_ours(args):
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # the ranks that sit out the one-process leg wait on the host (gloo), not inside an NCCL kernel on their GPU
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B, K, W = args.batch, args.steps, args.warmup
@@ -409,12 +411,13 @@ def run_ours(args):
         torch.cuda.synchronize()
         mpcs[0].set_pipeline(0, 0)   # the host-buffer calls below block: one handle per host thread, as without --pipeline
 
-    def host_step(i, k, handle=None, out=None):
+    def host_step(i, k, handle=None, out=None, wait=True):
         st, cf = pin[i % nsets]
         o = out or hout[k]
-        rc = lib.b200mpc_solve_batch((handle or mpcs[k]).handle, Bl, ctypes.cast(st.data_ptr(), dp), ctypes.cast(cf.data_ptr(), dp), ncoef,
-                                     ctypes.cast(o["out8"].data_ptr(), dp), None, ctypes.cast(o["obj"].data_ptr(), dp),
-                                     ctypes.cast(o["status"].data_ptr(), ip), ctypes.cast(o["iters"].data_ptr(), ip))
+        fn = lib.b200mpc_solve_batch if wait else lib.b200mpc_solve_batch_async
+        rc = fn((handle or mpcs[k]).handle, Bl, ctypes.cast(st.data_ptr(), dp), ctypes.cast(cf.data_ptr(), dp), ncoef,
+                ctypes.cast(o["out8"].data_ptr(), dp), None, ctypes.cast(o["obj"].data_ptr(), dp),
+                ctypes.cast(o["status"].data_ptr(), ip), ctypes.cast(o["iters"].data_ptr(), ip))
         if rc:
             raise RuntimeError(lib.b200mpc_last_error().decode())
 
@@ -423,12 +426,27 @@ def run_ours(args):
     T = args.e2e_threads if args.e2e_threads > 0 else min(S, max(3, (os.cpu_count() or 6) // world))
     T = max(1, min(S, T))
 
+    # host thread k drives the handles k, k + T, k + 2T, ... (one pinned output set each): it queues a step on each of
+    # them with the asynchronous host-buffer call and waits for a handle's previous step (b200mpc_wait: its results are
+    # then in the caller's buffers) just before giving it the next one, so S calls are in flight per GPU whatever the
+    # number of host cores.  With T = S this is one blocking call per thread, as the reference's MPC::Solve would be used.
     def worker(k, n):
+        mine = list(range(k, S, T))
+        busy = {h: False for h in mine}
+        j = 0
         for i in range(k, n, T):
-            host_step(i, k)
+            h = mine[j % len(mine)]
+            j += 1
+            if busy[h]:
+                mpcs[h].wait()
+            host_step(i, h, wait=False)
+            busy[h] = True
+        for h in mine:
+            if busy[h]:
+                mpcs[h].wait()
 
-    for i in range(max(3, T)):   # every handle of the leg allocates its staging buffers and captures its graph here
-        host_step(i, i % T)
+    for i in range(max(3, S)):   # every handle of the leg allocates its staging buffers and captures its graph here
+        host_step(i, i % S)
     barrier()
     n_e2e = K * R
     with ThreadPoolExecutor(T) as ex:
@@ -483,6 +501,8 @@ def run_ours(args):
         finally:
             for h in hs:
                 h.close()
+    if world > 1:
+        dist.barrier(group=cpu_group)
     barrier()
 
     # ---- weak-scaling figure next to the strong one (N > 1): every rank solves a whole B-problem batch per step
@@ -524,7 +544,9 @@ def run_ours(args):
                        note="value = problems_per_step x passes / seconds (max over ranks of the CUDA-event time)"),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=total_per_step * (6 + ncoef) * 8,
                      d2h_bytes_per_step=total_per_step * (8 + 1) * 8 + 2 * total_per_step * 4, passes=n_e2e, seconds=e2e_max_s,
-                     host_threads_per_gpu=T, p50_batch_latency_ms=1e3 * p50, p99_batch_latency_ms=1e3 * p99, latency_reps=len(lat),
+                     host_threads_per_gpu=T, calls_in_flight_per_gpu=S,
+                     entry="b200mpc_solve_batch_async + b200mpc_wait, one pinned buffer set per solver handle" if T < S else "b200mpc_solve_batch",
+                     p50_batch_latency_ms=1e3 * p50, p99_batch_latency_ms=1e3 * p99, latency_reps=len(lat),
                      latency_note="one host-buffer call at a time on one handle with library defaults, this rank's share of the batch"),
             lone_caller=dict(value=lone_value, unit=UNIT, handles=1, streams=1, batch_split=4, passes=n_lone,
                              avg_kernel_ms=lone_kernel_ms, launches_timed=lone_kern_n,

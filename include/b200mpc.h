@@ -89,6 +89,14 @@ int b200mpc_num_vars(const b200mpc_handle* h);
 int b200mpc_solve_batch(b200mpc_handle* h, int B, const double* state6, const double* coeffs, int ncoef, double* out8,
                         double* traj, double* obj, int* status, int* iters);
 
+/* b200mpc_solve_batch without the final wait: the copies in, the solve and the copies out are queued on the handle's own
+ * stream and the call returns (truly asynchronous only with pinned host buffers).  The input buffers must stay valid
+ * and the output buffers untouched until b200mpc_wait(h) -- which waits for everything queued on the handle -- or a
+ * later blocking call on the handle returns.  Lets one host thread keep several handles busy. */
+int b200mpc_solve_batch_async(b200mpc_handle* h, int B, const double* state6, const double* coeffs, int ncoef,
+                              double* out8, double* traj, double* obj, int* status, int* iters);
+int b200mpc_wait(b200mpc_handle* h);
+
 /* Same on device buffers, field-major: d_state6[k*B+b], d_coeffs[i*B+b], d_out8[k*B+b], d_traj[i*B+b]. */
 int b200mpc_solve_batch_device(b200mpc_handle* h, int B, const double* d_state6, const double* d_coeffs, int ncoef,
                                double* d_out8, double* d_traj, double* d_obj, int* d_status, int* d_iters,
@@ -96,10 +104,10 @@ int b200mpc_solve_batch_device(b200mpc_handle* h, int B, const double* d_state6,
 
 /* The same batch sharded by contiguous index ranges over several handles (normally one per device; several handles on
  * one device are allowed), no inter-device communication: handle g solves
- * problems [g * (B / n), (g + 1) * (B / n)), the last one also the remainder.  The calling thread queues every shard
- * (copy in, solve, copy out: asynchronous on the handle's own stream) and then waits for the devices in turn, so the
- * shards run concurrently when the host buffers are pinned (cudaHostAlloc / cudaHostRegister); pageable buffers make
- * the copies synchronous and serialise the devices.  Host buffers as b200mpc_solve_batch.
+ * problems [g * (B / n), (g + 1) * (B / n)), the last one also the remainder.  Shard 0 is queued and waited for by the
+ * calling thread, every other shard by a persistent host thread of the library (created on first use), so the devices
+ * start together; one multi call at a time uses those threads (concurrent multi calls are serialised).  Host buffers as
+ * b200mpc_solve_batch; pinned ones (cudaHostAlloc / cudaHostRegister) keep the copies asynchronous.
  * Every handle must have been created with the same b200mpc_params and the same restoration mode, and no handle may
  * appear twice (B200MPC_ERR_ARG otherwise: the result rows of the shards would not line up, or two shards would share
  * one workspace). */

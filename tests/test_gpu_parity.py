@@ -633,6 +633,42 @@ def test_overlapped_solves_are_deterministic():
             h.close()
 
 
+def test_asynchronous_host_buffer_calls_from_one_thread(mpc):
+    """b200mpc_solve_batch_async + b200mpc_wait: one host thread keeps three handles busy from pinned buffers; results are
+    those of the blocking call."""
+    import torch
+    B = 8192
+    sts, cfs = synth.line_problems(3 * B)
+    ref = [mpc.solve_batch(sts[k * B:(k + 1) * B], cfs[k * B:(k + 1) * B]) for k in range(3)]
+    lib = mp.load_library()
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+    hs = [mp.MPC(device=0) for _ in range(3)]
+    try:
+        bufs = []
+        for k in range(3):
+            bufs.append(dict(st=torch.from_numpy(np.ascontiguousarray(sts[k * B:(k + 1) * B])).pin_memory(),
+                             cf=torch.from_numpy(np.ascontiguousarray(cfs[k * B:(k + 1) * B])).pin_memory(),
+                             out8=torch.zeros((B, 8), dtype=torch.float64).pin_memory(), obj=torch.zeros(B, dtype=torch.float64).pin_memory(),
+                             status=torch.full((B,), -7, dtype=torch.int32).pin_memory(), iters=torch.zeros(B, dtype=torch.int32).pin_memory()))
+        for rep in range(2):
+            for k, (h, b) in enumerate(zip(hs, bufs)):
+                rc = lib.b200mpc_solve_batch_async(h.handle, B, ctypes.cast(b["st"].data_ptr(), dp), ctypes.cast(b["cf"].data_ptr(), dp), 2,
+                                                   ctypes.cast(b["out8"].data_ptr(), dp), None, ctypes.cast(b["obj"].data_ptr(), dp),
+                                                   ctypes.cast(b["status"].data_ptr(), ip), ctypes.cast(b["iters"].data_ptr(), ip))
+                assert rc == 0, lib.b200mpc_last_error()
+            for h in hs:
+                h.wait()
+        for k, b in enumerate(bufs):
+            assert (b["status"].numpy() == 0).all()
+            assert (b["iters"].numpy() == ref[k]["iters"]).all()
+            np.testing.assert_allclose(b["out8"].numpy(), ref[k]["out8"], rtol=0, atol=1e-12)
+            np.testing.assert_allclose(b["obj"].numpy(), ref[k]["cost"], rtol=1e-13, atol=0)
+        assert lib.b200mpc_wait(None) == -1
+    finally:
+        for h in hs:
+            h.close()
+
+
 def test_pipelined_solves_on_one_handle_match_plain_solves():
     """b200mpc_set_pipeline: batches issued on different streams to ONE handle (bulk in the main workspace, the last
     unfinished problems in small tail contexts, overlapped with the next bulk) give the results of plain solves: same

@@ -32,6 +32,8 @@ SYMBOLS = {
     "b200mpc_last_error": (ctypes.c_char_p, []),
     "b200mpc_num_vars": (ctypes.c_int, [_vp]),
     "b200mpc_solve_batch": (ctypes.c_int, [_vp, ctypes.c_int, _dp, _dp, ctypes.c_int, _dp, _dp, _dp, _ip, _ip]),
+    "b200mpc_solve_batch_async": (ctypes.c_int, [_vp, ctypes.c_int, _dp, _dp, ctypes.c_int, _dp, _dp, _dp, _ip, _ip]),
+    "b200mpc_wait": (ctypes.c_int, [_vp]),
     "b200mpc_solve_batch_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200mpc_solve_batch_multi": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, _dp, _dp, ctypes.c_int,
                                                  _dp, _dp, _dp, _ip, _ip]),
@@ -211,6 +213,10 @@ class MPC:
         """Raw device-pointer call (integers), field-major buffers; asynchronous on `stream`."""
         _check(self._lib.b200mpc_solve_batch_device(self._h, B, d_state6, d_coeffs, ncoef, d_out8, d_traj or None,
                                                     d_obj or None, d_status or None, d_iters or None, stream or None))
+
+    def wait(self):
+        """Waits for everything queued on this handle's own stream (b200mpc_solve_batch_async calls)."""
+        _check(self._lib.b200mpc_wait(self._h))
 
     def closed_loop(self, states, coeffs, steps):
         """solution/main.cpp:51-76 for B vehicles: returns dict(hist8 (steps,B,8), cost (steps,B), iters (steps,B))."""

@@ -5,6 +5,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <fstream>
 #include <new>
 #include <sstream>
@@ -236,6 +241,62 @@ int run_solve(b200mpc_handle* h, int B, int steps, const double* st, const doubl
 
 }  // namespace
 
+namespace {
+
+// Persistent host threads for b200mpc_solve_batch_multi: one per extra device shard, created on first use and kept
+// (a thread's first CUDA call costs about a millisecond of per-thread runtime set-up; a thread per call paid it every
+// time).  Worker g queues and waits for shard g + 1 while the calling thread does shard 0.
+struct Worker {
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::function<void()> task;
+  bool has = false, quit = false;
+  Worker() {
+    th = std::thread([this]() {
+      for (;;) {
+        std::function<void()> t;
+        {
+          std::unique_lock<std::mutex> lk(m);
+          cv.wait(lk, [this]() { return has || quit; });
+          if (quit) return;
+          t = std::move(task);
+        }
+        t();
+        {
+          std::lock_guard<std::mutex> lk(m);
+          has = false;
+        }
+        cv.notify_all();
+      }
+    });
+  }
+  void start(std::function<void()> t) {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      task = std::move(t);
+      has = true;
+    }
+    cv.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [this]() { return !has; });
+  }
+  ~Worker() {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      quit = true;
+    }
+    cv.notify_all();
+    if (th.joinable()) th.join();
+  }
+};
+std::mutex g_multi_mutex;                       // one multi call at a time uses the pool
+std::vector<std::unique_ptr<Worker>> g_workers;
+
+}  // namespace
+
 extern "C" {
 
 void b200mpc_default_params(b200mpc_params* p) {
@@ -448,6 +509,18 @@ int b200mpc_solve_batch(b200mpc_handle* h, int B, const double* state6, const do
   return 0;
 }
 
+int b200mpc_solve_batch_async(b200mpc_handle* h, int B, const double* state6, const double* coeffs, int ncoef, double* out8,
+                              double* traj, double* obj, int* status, int* iters) {
+  return enqueue_solve_batch(h, B, state6, coeffs, ncoef, out8, traj, obj, status, iters);
+}
+
+int b200mpc_wait(b200mpc_handle* h) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int b200mpc_solve_batch_multi(b200mpc_handle* const* hs, int n_handles, int B, const double* state6,
                               const double* coeffs, int ncoef, double* out8, double* traj, double* obj, int* status,
                               int* iters) {
@@ -465,30 +538,28 @@ int b200mpc_solve_batch_multi(b200mpc_handle* const* hs, int n_handles, int B, c
   }
   if (int rc0 = check_solve_args(hs[0], B, state6, coeffs, ncoef, out8)) return rc0;
   if (B == 0) return 0;
-  // One host thread queues every device's shard (copies in, solve graph, copies out: all asynchronous) and then waits
-  // for the devices one after the other; the shards run concurrently on the GPUs.  (Pageable host buffers make the
-  // copies synchronous, which serialises the devices: pass pinned buffers.)
+  // Shard g is queued (copies in, solve graph, copies out: all asynchronous on the handle's stream) and waited for by
+  // its own persistent host thread, shard 0 by the calling thread, so the devices start within microseconds of each
+  // other.  (Pageable host buffers make the copies synchronous; the shards still overlap, one thread each.)
   const int nv = 8 * hs[0]->P.N - 2;
-  int first_rc = 0;
-  std::string first_msg;
-  int queued = 0;
-  for (int g = 0; g < n_handles && !first_rc; ++g) {
+  std::lock_guard<std::mutex> pool_lock(g_multi_mutex);
+  while ((int)g_workers.size() < n_handles - 1) g_workers.emplace_back(new Worker());
+  std::vector<int> rc(n_handles, 0);
+  std::vector<std::string> msg(n_handles);
+  auto shard = [&](int g) {
     // contiguous index ranges, remainder to the last device
     const long long lo = (long long)B / n_handles * g;
     const long long hi = g == n_handles - 1 ? B : (long long)B / n_handles * (g + 1);
-    const int n = (int)(hi - lo);
-    int rc = enqueue_solve_batch(hs[g], n, state6 + lo * 6, coeffs + lo * ncoef, ncoef, out8 + lo * 8,
-                                 traj ? traj + lo * nv : nullptr, obj ? obj + lo : nullptr, status ? status + lo : nullptr,
-                                 iters ? iters + lo : nullptr);
-    if (rc) { first_rc = rc; first_msg = "device shard " + std::to_string(g) + ": " + b200mpc_last_error(); }
-    else queued = g + 1;
-  }
-  for (int g = 0; g < queued; ++g) {   // always drain what was queued, also after an error
-    cudaError_t e = cudaSetDevice(hs[g]->device);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(hs[g]->stream);
-    if (e != cudaSuccess && !first_rc) { first_rc = B200MPC_ERR_CUDA; first_msg = "device shard " + std::to_string(g) + ": " + cudaGetErrorString(e); }
-  }
-  if (first_rc) return fail(first_rc, first_msg);
+    rc[g] = b200mpc_solve_batch(hs[g], (int)(hi - lo), state6 + lo * 6, coeffs + lo * ncoef, ncoef, out8 + lo * 8,
+                                traj ? traj + lo * nv : nullptr, obj ? obj + lo : nullptr, status ? status + lo : nullptr,
+                                iters ? iters + lo : nullptr);
+    if (rc[g]) msg[g] = b200mpc_last_error();   // thread-local: read on the thread that failed
+  };
+  for (int g = 1; g < n_handles; ++g) g_workers[g - 1]->start([&shard, g]() { shard(g); });
+  shard(0);
+  for (int g = 1; g < n_handles; ++g) g_workers[g - 1]->wait();
+  for (int g = 0; g < n_handles; ++g)
+    if (rc[g]) return fail(rc[g], "device shard " + std::to_string(g) + ": " + msg[g]);
   return 0;
 }
 
