@@ -240,6 +240,9 @@ def auto_streams(per_gpu_batch):
 
 
 def run_ours(args):
+    # one hardware work queue per overlapped stream (the default of 8 makes 12-16 streams share queues: kernels of one
+    # stream then wait behind another stream's); read by the CUDA runtime when the context is created
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     import ctypes
     import math
     from concurrent.futures import ThreadPoolExecutor
@@ -580,6 +583,16 @@ def run_ours(args):
             line["one_process_multi_gpu"] = multi
         if weak:
             line["weak_scaling"] = weak
+        if world == 1 and not args.no_sweep:
+            # BASELINE configs[4] in brief (bench_sweep.py has the full grid): other horizons at this batch size, 4
+            # overlapped batches; N = 100 on one handle in pipelined mode (its tails are hundreds of iterations long)
+            import bench_sweep
+            sst, sfit = sets[0][0][:min(B, 65536)], sets[0][1][:min(B, 65536)]
+            line["horizon_sweep"] = dict(
+                note="solves/s at other horizons, same workload and batch size, device-resident inputs; 4 overlapped batches on 4 handles, "
+                     "N = 100: 16 overlapped batches on ONE handle in pipelined mode (b200mpc_set_pipeline)",
+                rows=[bench_sweep.run_point(mpcmod, torch, n_, B, sst, sfit, streams=s_, pipeline=p_, reps=r_, device=local)
+                      for n_, s_, p_, r_ in ((10, 4, 0, 3), (50, 4, 0, 3), (100, 16, 16, 1))])
         if world == 1 and not args.no_cpu_baseline:
             st, cf = sets[0]
             line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate(st[:8192], cf[:8192], args.cpu_per_core).items()}
@@ -630,6 +643,7 @@ def main():
     ap.add_argument("--latency-reps", type=int, default=100)
     ap.add_argument("--cpu-per-core", type=int, default=400, help="cpu_baseline: solves per host core in the sample (>= 2 s per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="N = 1: skip the short horizon sweep (BASELINE configs[4]) appended to the line")
     ap.add_argument("--input-sets", type=int, default=4, help="distinct synthetic input batches cycled over the steps")
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads (one solver handle each) of the end-to-end leg (0 = auto)")
     ap.add_argument("--split", type=int, default=0, help="internal batch split of one solve call (0 = 1 with several streams, 4 with one)")
