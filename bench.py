@@ -282,6 +282,8 @@ def run_ours(args):
     for m in mpcs:
         m.set_solver_mode({"perpass": 0, "fused": 1}[args.mode], args.rounds, -1)
         m.set_batch_split(split)
+        if S > 1 and args.handover >= 0:
+            m.set_handover(args.handover, 14)   # overlapped calls: a later hand-over to the cooperative kernel (b200mpc_set_handover)
     # --pipeline D: the device-timed region issues its S overlapped streams to ONE handle in pipelined mode (bulk in one
     # full-size workspace, tails in D small contexts) instead of S handles with a full-size workspace each
     dev_handles = mpcs
@@ -542,7 +544,7 @@ def run_ours(args):
             higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f64", data="synthetic",
             config=config_dict(args),
             timed=dict(passes=K * R, repeats_of_the_k_step_sequence=R, seconds=ms_total * 1e-3, min_seconds=args.min_seconds,
-                       problems_per_gpu_per_step=Bl, streams=S, batch_split=split, solver_handles=len(set(id(m) for m in dev_handles)),
+                       problems_per_gpu_per_step=Bl, streams=S, batch_split=split, handover_below=(args.handover if S > 1 and args.handover >= 0 else 1184), solver_handles=len(set(id(m) for m in dev_handles)),
                        pipeline_depth=args.pipeline,
                        note="value = problems_per_step x passes / seconds (max over ranks of the CUDA-event time)"),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=total_per_step * (6 + ncoef) * 8,
@@ -648,6 +650,8 @@ def main():
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads (one solver handle each) of the end-to-end leg (0 = auto)")
     ap.add_argument("--split", type=int, default=0, help="internal batch split of one solve call (0 = 1 with several streams, 4 with one)")
     ap.add_argument("--streams", type=int, default=0, help="solver handles / CUDA streams consecutive steps alternate between (0 = auto: 6 at 65 536 problems per GPU, up to 16 for smaller shards)")
+    ap.add_argument("--handover", type=int, default=64, help="overlapped solver handles: occupied slots at which the cooperative kernel takes a batch's "
+                    "tail over (b200mpc_set_handover; -1 = library default 1184, which suits one call at a time)")
     ap.add_argument("--pipeline", type=int, default=0, help="> 0: the overlapped streams of the device-timed region share ONE solver handle in pipelined mode "
                     "with this many tail contexts (b200mpc_set_pipeline) instead of one handle per stream")
     ap.add_argument("--pipeline-slots", type=int, default=0, help="problems a tail context holds (0 = max(1024, batch / 16))")

@@ -137,6 +137,16 @@ int b200mpc_set_warm_start(b200mpc_handle* h, int enable, double mu_init);
  * time; a caller that already overlaps several calls on several handles / streams should set 1. */
 int b200mpc_set_batch_split(b200mpc_handle* h, int parts);
 
+/* Hand-over of the thin tail of a batch to the cooperative (warp-per-problem) kernel: after every round from
+ * `from_round` on, once the batch has been compacted to at most `occupied_slots` problems, that kernel finishes them
+ * (0 = only after the last round).  The cooperative kernel advances a problem 6x faster than the sweeps do but costs
+ * 12x the machine time per iteration, so the threshold trades the latency of a lone call against the throughput of
+ * overlapped calls: default 1184 from round 14 (its resident warps on a B200; best for one call at a time); a caller
+ * that overlaps several calls on several handles / streams should set about 64-256 (measured with 64, 65 536 / 8 192
+ * problems per call: +2 % / +11 % solves/s; a lone 8 192-problem call gets 13 % slower with 0).  Results do not depend on it beyond the last bits a
+ * hand-over may change. */
+int b200mpc_set_handover(b200mpc_handle* h, int occupied_slots, int from_round);
+
 /* Pipelined solves on one handle (the generalisation of the one-call-at-a-time loop of solution/main.cpp:51-54 to a
  * stream of batches).  Iteration counts have a thin, long tail (N = 25: mean 12, a few problems in 10^5 need 30-50;
  * N = 100: mean 19, 2 % need more than 100, the slowest about 1000), and a batch is done when its slowest problem is.

@@ -47,7 +47,7 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.b200mpc_polyfit_batch(None, 1, None, None, 6, 3, None) == -1
     assert lib.b200mpc_num_vars(None) == 0
     for setter, args in (("b200mpc_set_restoration", (1,)), ("b200mpc_set_batch_split", (2,)), ("b200mpc_set_compaction", (0.7, 4)),
-                         ("b200mpc_set_warm_start", (1, 1e-4)), ("b200mpc_set_pipeline", (4, 4096))):
+                         ("b200mpc_set_warm_start", (1, 1e-4)), ("b200mpc_set_pipeline", (4, 4096)), ("b200mpc_set_handover", (256, 14))):
         assert getattr(lib, setter)(None, *args) == -1 and b"null handle" in lib.b200mpc_last_error()
 
 

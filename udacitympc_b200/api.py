@@ -52,6 +52,7 @@ SYMBOLS = {
     "b200mpc_set_batch_split": (ctypes.c_int, [_vp, ctypes.c_int]),
     "b200mpc_set_compaction": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_int]),
     "b200mpc_set_pipeline": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
+    "b200mpc_set_handover": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
     "b200mpc_set_restoration": (ctypes.c_int, [_vp, ctypes.c_int]),
     "b200mpc_set_solver_mode": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "b200mpc_set_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
@@ -253,6 +254,11 @@ class MPC:
         """Throughput path: after every round from `from_round` on, move the unfinished problems to consecutive
         workspace slots when they fill at most this fraction of the occupied slots (0 = off)."""
         _check(self._lib.b200mpc_set_compaction(self._h, float(max_live_fraction), int(from_round)))
+
+    def set_handover(self, occupied_slots=1184, from_round=14):
+        """Occupied workspace slots at which the cooperative kernel takes the rest of a batch over (default 1184: best for
+        one call at a time; 64-256 for a caller that overlaps several calls).  See b200mpc_set_handover."""
+        _check(self._lib.b200mpc_set_handover(self._h, int(occupied_slots), int(from_round)))
 
     def set_pipeline(self, depth=8, tail_slots=4096):
         """Pipelined solves: solve_batch_device calls issued on different streams overlap on this one handle -- the

@@ -418,6 +418,16 @@ int b200mpc_set_compaction(b200mpc_handle* h, double max_live_fraction, int from
   return 0;
 }
 
+int b200mpc_set_handover(b200mpc_handle* h, int occupied_slots, int from_round) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  if (occupied_slots < 0 || occupied_slots > (1 << 20)) return fail(B200MPC_ERR_ARG, "hand-over: occupied_slots must be in [0, 1048576]");
+  if (from_round < 1) return fail(B200MPC_ERR_ARG, "hand-over: from_round must be >= 1");
+  h->cfg.handover_below = occupied_slots;
+  h->cfg.handover_from = from_round;
+  ++h->repack_gen;   // part of the captured launch sequence
+  return 0;
+}
+
 int b200mpc_set_pipeline(b200mpc_handle* h, int depth, int tail_slots) {
   if (!h) return fail(B200MPC_ERR_ARG, "null handle");
   if (depth < 0 || depth > b200mpc_handle::kMaxPipe) return fail(B200MPC_ERR_ARG, "pipeline: depth must be in [0, 32]");
