@@ -371,7 +371,7 @@ void b200mpc_destroy(b200mpc_handle* h) {
   if (h->ss.fork) cudaEventDestroy(h->ss.fork);
   if (h->done) cudaEventDestroy(h->done);
   if (h->main_free) cudaEventDestroy(h->main_free);
-  cudaDeviceSynchronize();   // pipelined bulks run on the callers' streams
+  if (h->pipe_calls) cudaDeviceSynchronize();   // pipelined bulks ran on the callers' streams, tails on the handle's
   for (int k = 0; k < b200mpc_handle::kMaxPipe; ++k) {
     if (h->tail_free[k]) cudaEventDestroy(h->tail_free[k]);
     if (h->tail_stream[k]) cudaStreamDestroy(h->tail_stream[k]);
