@@ -39,10 +39,10 @@ def golden(name):
 
 # ---- host build of the solver core (tests/hostsim): algorithm tests without a GPU
 class _HostSim:
-    def __init__(self):
+    def __init__(self, libname="libhostsim.so"):
         import oracle_bindings as ob
         self.ob = ob
-        self.lib = ctypes.CDLL(os.path.join(ROOT, "tests", "hostsim", "libhostsim.so"))
+        self.lib = ctypes.CDLL(os.path.join(ROOT, "tests", "hostsim", libname))
         self.dp = ctypes.POINTER(ctypes.c_double)
 
     def solve(self, state6, coeffs, mode=0, **params):
@@ -77,3 +77,9 @@ class _HostSim:
 @pytest.fixture(scope="session")
 def hostsim(_build_everything):
     return _HostSim()
+
+
+@pytest.fixture(scope="session")
+def hostsim_fuse(_build_everything):
+    """The solver core compiled with MPC_FUSE_FACTOR=1 (the fused step + factor sweep, an experiment the product leaves out)."""
+    return _HostSim("libhostsim_fuse.so")

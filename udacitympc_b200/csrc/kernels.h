@@ -39,6 +39,7 @@ struct SolveConfig {
   // horizon: 10 up to N = 50, 2 N - 80 above)
   int tail_rounds = 0;
   int tail_take_below = 0;   // long horizons: occupied slots at which the cooperative kernel takes a tail over (0 = 32)
+  bool fuse_factor = false;  // MPC_FUSE_FACTOR builds only (experiment, 13 % slower): the next iteration's Riccati factorisation rides on the step sweep
   bool coop = true;       // latency path = cooperative warp-per-problem kernel (false: thread-per-problem fused kernel)
 };
 struct SplitStreams {   // auxiliary streams / events owned by the handle (n_aux <= 3)

@@ -130,7 +130,7 @@ struct CoopSolver {
     } else {
       c.sl[0] = safe_slack(c.u[0] - P.xl[0], mu, zl0, P.xl[0]); c.sl[1] = safe_slack(P.xu[0] - c.u[0], mu, zu0, P.xu[0]);
       c.sl[2] = safe_slack(c.u[1] - P.xl[1], mu, zl1, P.xl[1]); c.sl[3] = safe_slack(P.xu[1] - c.u[1], mu, zu1, P.xu[1]);
-      const double isl0 = 1.0 / c.sl[0], isu0 = 1.0 / c.sl[1], isl1 = 1.0 / c.sl[2], isu1 = 1.0 / c.sl[3];
+      const double isl0 = drcp(c.sl[0]), isu0 = drcp(c.sl[1]), isl1 = drcp(c.sl[2]), isu1 = drcp(c.sl[3]);
       const double bl0 = A.beta * (cn.lam[2] + cn.lam[5]), bl1 = P.dt * cn.lam[3];
       c.r0 = hess_u(df, 0, t) + dw + zl0 * isl0 + zu0 * isu0;
       c.r1 = hess_u(df, 1, t) + dw + zl1 * isl1 + zu1 * isu1;
@@ -191,7 +191,7 @@ struct CoopSolver {
       const double L11 = c.r1 + P.dt * T1[3] + Tu11;
       const double det = L00 * L11 - L10 * L10;
       if (!(L00 > 0.0) || !(det > 0.0)) ok = false;
-      const double idet = 1.0 / det;
+      const double idet = drcp(det);
       const double i00 = L11 * idet, i10 = -L10 * idet, i11 = L00 * idet;
       double G0[4], G1[4];
       applyA(A, T0[0], T0[1], T0[2], T0[3], T0[4], G0[0], G0[1], G0[2], G0[3]);
@@ -290,18 +290,18 @@ struct CoopSolver {
       const double up0 = t < M - 1 ? st[t + 1].u[0] : 0.0, up1 = t < M - 1 ? st[t + 1].u[1] : 0.0;
       const double sl0 = c.sl[0], su0 = c.sl[1], sl1 = c.sl[2], su1 = c.sl[3];
       const double zl0 = c.z[0], zu0 = c.z[1], zl1 = c.z[2], zu1 = c.z[3];
-      const double isl0 = 1.0 / sl0, isu0 = 1.0 / su0, isl1 = 1.0 / sl1, isu1 = 1.0 / su1;
+      const double isl0 = drcp(sl0), isu0 = drcp(su0), isl1 = drcp(sl1), isu1 = drcp(su1);
       gbd += (grad_u(df, 0, t, u0, um0, up0) - mu * isl0 + mu * isu0) * du0 + (grad_u(df, 1, t, u1, um1, up1) - mu * isl1 + mu * isu1) * du1;
-      if (du0 < 0.0) a_pr = dmin(a_pr, -tau / du0 * sl0);
-      if (du0 > 0.0) a_pr = dmin(a_pr, tau / du0 * su0);
-      if (du1 < 0.0) a_pr = dmin(a_pr, -tau / du1 * sl1);
-      if (du1 > 0.0) a_pr = dmin(a_pr, tau / du1 * su1);
+      if (du0 < 0.0) a_pr = dmin(a_pr, -ddiv(tau, du0) * sl0);
+      if (du0 > 0.0) a_pr = dmin(a_pr, ddiv(tau, du0) * su0);
+      if (du1 < 0.0) a_pr = dmin(a_pr, -ddiv(tau, du1) * sl1);
+      if (du1 > 0.0) a_pr = dmin(a_pr, ddiv(tau, du1) * su1);
       const double dzl0 = (mu - sl0 * zl0 - zl0 * du0) * isl0, dzu0 = (mu - su0 * zu0 + zu0 * du0) * isu0;
       const double dzl1 = (mu - sl1 * zl1 - zl1 * du1) * isl1, dzu1 = (mu - su1 * zu1 + zu1 * du1) * isu1;
-      if (dzl0 < 0.0) a_du = dmin(a_du, -tau / dzl0 * zl0);
-      if (dzu0 < 0.0) a_du = dmin(a_du, -tau / dzu0 * zu0);
-      if (dzl1 < 0.0) a_du = dmin(a_du, -tau / dzl1 * zl1);
-      if (dzu1 < 0.0) a_du = dmin(a_du, -tau / dzu1 * zu1);
+      if (dzl0 < 0.0) a_du = dmin(a_du, -ddiv(tau, dzl0) * zl0);
+      if (dzu0 < 0.0) a_du = dmin(a_du, -ddiv(tau, dzu0) * zu0);
+      if (dzl1 < 0.0) a_du = dmin(a_du, -ddiv(tau, dzl1) * zl1);
+      if (dzu1 < 0.0) a_du = dmin(a_du, -ddiv(tau, dzu1) * zu1);
       nottiny = nottiny || fabs(du0) > tinytol * (fabs(u0) + 1.0) || fabs(du1) > tinytol * (fabs(u1) + 1.0);
     }
     c.red[0] = a_pr; c.red[1] = a_du; c.red[2] = gbd; c.red[3] = nottiny ? 1.0 : 0.0;
@@ -346,10 +346,10 @@ struct CoopSolver {
       const double b1 = safe_slack(c.un[1] - P.xl[1], mu, zl1, P.xl[1]) * safe_slack(P.xu[1] - c.un[1], mu, zu1, P.xu[1]);
       slog = log(b0 * b1);
       if (!ls) {
-        zl0 += a_du * ((mu - sl0 * zl0 - zl0 * du0) / sl0);
-        zu0 += a_du * ((mu - su0 * zu0 + zu0 * du0) / su0);
-        zl1 += a_du * ((mu - sl1 * zl1 - zl1 * du1) / sl1);
-        zu1 += a_du * ((mu - su1 * zu1 + zu1 * du1) / su1);
+        zl0 += a_du * ddiv(mu - sl0 * zl0 - zl0 * du0, sl0);
+        zu0 += a_du * ddiv(mu - su0 * zu0 + zu0 * du0, su0);
+        zl1 += a_du * ddiv(mu - sl1 * zl1 - zl1 * du1, sl1);
+        zu1 += a_du * ddiv(mu - su1 * zu1 + zu1 * du1, su1);
       }
       const double nsl0 = safe_slack(c.un[0] - P.xl[0], mu, zl0, P.xl[0]), nsu0 = safe_slack(P.xu[0] - c.un[0], mu, zu0, P.xu[0]);
       const double nsl1 = safe_slack(c.un[1] - P.xl[1], mu, zl1, P.xl[1]), nsu1 = safe_slack(P.xu[1] - c.un[1], mu, zu1, P.xu[1]);
@@ -416,7 +416,9 @@ struct CoopSolver {
     if (t < M && !ls) {
       double p0, p1, p2, p3, cres[6];
       poly_eval(S.cf, c.sn[0], p0, p1, p2, p3);
-      S.residual(c.sn, c.un, st[t + 1].sn, c.trn[0], c.trn[1], c.trn[2], p0, atan(p1), cres);
+      const double psides = atan(p1);
+      S.residual(c.sn, c.un, st[t + 1].sn, c.trn[0], c.trn[1], c.trn[2], p0, psides, cres);
+      S.store_psides(rN, psides);   // the thread-per-problem sweeps read it (MPC_STORE_PSIDES)
       for (int k = 0; k < 6; ++k) {
 #if MPC_STORE_C
         S.w(S.rec(t + 1) + kX * (pub->cur ^ 1) + xC + k) = cres[k];

@@ -98,9 +98,25 @@ enum Status {
   kInvalidNumberDetected = -13  // NaN / Inf at the starting point
 };
 
+// MPC_FUSE_FACTOR 1: the Riccati factorisation of the NEXT iteration can ride on the STEP sweep (step_sweep<true>,
+//                     kernel_stepfactor): the trial iterate the sweep has just computed in registers is factorised stage by
+//                     stage instead of being read back by a factor sweep, with the feed-forward split as k = ka + mu kb
+//                     because the barrier parameter of the next iteration is only known after the sweep.
+//                     Built, verified (tests/test_hostsim_golden.py, 18 GPU parity tests) and measured on the B200
+//                     (gpurun_out/r2_fuse*): the fused kernel moves 24 % fewer bytes and executes 9 % fewer instructions
+//                     than the step and factor kernels together and takes exactly as long (268-280 us against 156 + 114 us
+//                     per round of 65 536 problems) -- at 8 warps per SM the sweeps are bound by the length of the dependent
+//                     instruction chain of a stage, and the fused chain is the sum of the two -- while the compaction has to
+//                     move the factors too.  13 % slower overall, so it is compiled out of the product (0); the host
+//                     build of the tests keeps it alive (tests/hostsim/libhostsim_fuse.so).
+#ifndef MPC_FUSE_FACTOR
+#define MPC_FUSE_FACTOR 0
+#endif
 constexpr int kMaxCoef = 4;   // reference polynomial degree <= 3
 constexpr int kMaxFilter = 41;   // filter entries (phi, theta); they fill one workspace record of their own (record N+1)
 constexpr int kCarry = 24;    // stage-to-stage values of the STEP sweep
+constexpr int kRicCarry = 39; // stage-to-stage values of the Riccati recursion when it rides on the STEP sweep (step_sweep<true>)
+constexpr int kKF = 13 + 2 * MPC_FUSE_FACTOR;   // rows of the Riccati factors of one stage
 constexpr int kStageVals = 24;   // values of one stage the factor sweep stages asynchronously: S U LAM ZL ZU TR (22) + u_{t-1} (2)
 #ifndef MPC_RESTO_BETA
 #define MPC_RESTO_BETA 0.05
@@ -120,11 +136,12 @@ enum StageOff {
   xZL = 14, xZU = 16,   // bound multipliers of u_t (2+2)
   xTR = 18,    // sin/cos(psi_t), sin/cos(epsi_t) (4)
   xC = 22,     // constraint residual of the rows of time t (6)
+  xPD = 22,    // MPC_STORE_PSIDES: atan(p'(x_t)), the reference heading at s_t (shares the first residual row, unused with MPC_STORE_C 0)
   kX = 28,
   oDS = 56, oDU = 62,   // search direction (6+2)
   oCSOC = 64,  // second-order-correction right-hand side (6)
-  oKF = 70,    // Riccati factors of stage t: K (2x4), Lambda^-1 (3), k (2)
-  kRec = 83
+  oKF = 70,    // Riccati factors of stage t: K (2x4), Lambda^-1 (3), feed-forward k (2); MPC_FUSE_FACTOR: k = ka + mu kb, kb (2)
+  kRec = 83 + 2 * MPC_FUSE_FACTOR
 };
 enum ScalarD {
   dDF, dMU, dTAU, dMUMIN, dDWC, dDWL, dTHMAX, dTHMIN, dF, dTH, dPINF, dDINF, dLAM1, dZ1, dSZMAX, dSZMIN, dSLOG, dXMAX,
@@ -146,6 +163,18 @@ MPC_HD int workspace_doubles_per_problem(int N) { return kRec * (N + 2); }
 #ifndef MPC_STORE_C
 #define MPC_STORE_C 0
 #endif
+//   MPC_STORE_PSIDES 1: the reference heading atan(p'(x_t)) of the iterate (MPC.cpp:118) is stored by whoever writes the
+//                       iterate (it is evaluated there anyway) instead of being re-evaluated by the factor and forward
+//                       sweeps for their residuals: 3 doubles/stage/iter more traffic for two atan() (~130 instructions)
+//                       less.  Bit-identical results (the same value, computed once).  Measured: 1.3 % SLOWER
+//                       (13.84 -> 13.66 M solves/s, gpurun_out/r2_psd_*.json) -- bytes weigh more than instructions -- so off.
+#ifndef MPC_STORE_PSIDES
+#define MPC_STORE_PSIDES 0
+#endif
+#if MPC_STORE_PSIDES && (!MPC_STORE_TRIG || MPC_STORE_C)
+#error "MPC_STORE_PSIDES needs MPC_STORE_TRIG 1 and MPC_STORE_C 0 (it uses the first residual row, next to the trig rows)"
+#endif
+constexpr int kIterRows = MPC_STORE_C ? 28 : (MPC_STORE_PSIDES ? 23 : 22);   // rows of an iterate copy that hold data
 // MPC_PREFETCH: 0 = off, 1 = prefetch.global.L1, 2 = prefetch.global.L2 (device only)
 #ifndef MPC_PREFETCH
 #define MPC_PREFETCH 1
@@ -199,6 +228,49 @@ __device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_g
 __device__ __forceinline__ void async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 #endif
 
+// MPC_FAST_DIV (device): reciprocals and quotients of the sweeps without the IEEE slow path.  The compiler's double
+// division is MUFU.RCP64H + Newton steps + a range check that CALLS a slow path (denormals, huge exponents): ~20
+// instructions and, worse, a branch per division -- 25 of them per stage and iteration cut the stage bodies into
+// basic blocks the scheduler cannot interleave.  Here: rcp.approx.ftz.f64 (20+ bits) + two Newton steps (+ one residual
+// correction for a quotient), straight-line, within 1 ulp of the rounded result for operands in the normal range; for a
+// zero / denormal / infinite divisor the unrefined value is returned (+-inf or 0, what the exact quotient is or rounds
+// to for every use here: step-size candidates that are then not the minimum).  Host build: plain division.
+// MPC_SPECIALIZE_SWEEPS: the factor / forward sweeps are instantiated per loop-invariant case (multiplier
+// initialisation, second-order correction, the usual Newton system) instead of branching inside the stage body
+#ifndef MPC_SPECIALIZE_SWEEPS
+#define MPC_SPECIALIZE_SWEEPS 1
+#endif
+#ifndef MPC_FAST_DIV
+#define MPC_FAST_DIV 1
+#endif
+MPC_HD double drcp(double b) {
+#if defined(__CUDA_ARCH__) && MPC_FAST_DIV
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(b));
+  double e = fma(-b, r0, 1.0);
+  double r = fma(r0, e, r0);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  return (fabs(r0) <= DBL_MAX && r0 != 0.0) ? r : r0;
+#else
+  return 1.0 / b;
+#endif
+}
+MPC_HD double ddiv(double a, double b) {
+#if defined(__CUDA_ARCH__) && MPC_FAST_DIV
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(b));
+  double e = fma(-b, r0, 1.0);
+  double r = fma(r0, e, r0);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  double q = a * r;
+  q = fma(fma(-b, q, a), r, q);
+  return (fabs(r0) <= DBL_MAX && r0 != 0.0) ? q : a * r0;
+#else
+  return a / b;
+#endif
+}
 MPC_HD double dmax(double a, double b) { return a > b ? a : b; }
 MPC_HD double dmin(double a, double b) { return a < b ? a : b; }
 MPC_HD double dclamp(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -254,7 +326,7 @@ MPC_HD Lin make_lin(const Params& P, double v, double delta, double sp, double c
   L.a5 = delta * P.dtLf;      // d psi1 / d v0 = d epsi1 / d v0
   L.beta = v * P.dtLf;        // d psi1 / d delta0 = d epsi1 / d delta0
   L.pp = p1;                  // d cte1 / d x0
-  L.kap = p2 / (1.0 + p1 * p1);   // -d epsi1 / d x0 (no branch around the division: 0 for a degree-1 reference)
+  L.kap = ddiv(p2, 1.0 + p1 * p1);   // -d epsi1 / d x0 (no branch around the division: 0 for a degree-1 reference)
   L.sed = se * P.dt;          // d cte1 / d v0
   L.vce = vdt * ce;           // d cte1 / d epsi0
   return L;
@@ -288,7 +360,7 @@ MPC_HD Hes make_hes(const Params& P, const double* lam, double v, double sp, dou
   Hes H;
   {   // 0 for a degree-1 reference (p2 = p3 = 0); evaluated without a branch
     const double q = 1.0 + p1 * p1;
-    H.xx = -lam[4] * p2 + lam[5] * (p3 * q - 2.0 * p1 * p2 * p2) / (q * q);
+    H.xx = -lam[4] * p2 + ddiv(lam[5] * (p3 * q - 2.0 * p1 * p2 * p2), q * q);
   }
   const double vdt = v * P.dt;
   H.pp = (lam[0] * cp + lam[1] * sp) * vdt;
@@ -339,7 +411,7 @@ MPC_HD void repack_problem(const Params& P, const Ws<LS_>& s, const Ws<LD_>& d) 
   repack_rows(s, d, (P.N + 1) * kRec, 2 * (int)s(iNF));   // the filter entries in use
   const int phase = (int)s(iPHASE), flags = (int)s(iFLAGS), cur = (int)s(iCUR);
   if (phase == PH_FACTOR && !(flags & F_INSOC)) {
-    constexpr int n = MPC_STORE_C ? (int)kX : (int)xC;
+    constexpr int n = kIterRows;
     const int lo = kX * cur;
     int t = 0;
     for (; t + 2 <= P.N; t += 2) {   // two stages (44 rows) in flight per lane
@@ -351,6 +423,21 @@ MPC_HD void repack_problem(const Params& P, const Ws<LS_>& s, const Ws<LD_>& d) 
       for (int k = 0; k < n; ++k) { d(r0 + k) = v[k]; d(r1 + k) = v[n + k]; }
     }
     if (t < P.N) repack_rows(s, d, (t + 1) * kRec + lo, n);
+  } else if (phase == PH_FORWARD && !(flags & F_INSOC)) {
+    // waits for its forward sweep (the usual state after kernel_stepfactor): the current iterate and the Riccati factors
+    const int lo = kX * cur;
+    for (int t = 0; t < P.N; ++t) {   // one stage (iterate + factors) in flight per lane
+      const int r0 = (t + 1) * kRec + lo, r1 = (t + 1) * kRec + oKF;
+      double v[kIterRows + kKF];
+#pragma unroll
+      for (int k = 0; k < kIterRows; ++k) v[k] = s(r0 + k);
+#pragma unroll
+      for (int k = 0; k < kKF; ++k) v[kIterRows + k] = s(r1 + k);
+#pragma unroll
+      for (int k = 0; k < kIterRows; ++k) d(r0 + k) = v[k];
+#pragma unroll
+      for (int k = 0; k < kKF; ++k) d(r1 + k) = v[kIterRows + k];
+    }
   } else {
     for (int t = 0; t < P.N; ++t) repack_rows(s, d, (t + 1) * kRec, (int)kRec);
   }
@@ -380,12 +467,16 @@ struct Solver {
   // a thread-local array elsewhere.  Must be set before step_sweep() runs.
   double* cr;
   int cs;
+  // carry buffer of the Riccati recursion that rides on the STEP sweep (kRicCarry doubles, element i at rq[i*rqs]); set
+  // before step_sweep<true>() runs
+  double* rq;
+  int rqs;
   // stage buffers of the asynchronous staging (MPC_ASYNC_STAGE; element i of buffer b at sb[(b * kStageVals + i) * sbs]),
   // null = ordinary loads
   double* sb;
   int sbs;
 
-  MPC_HD Solver(const Params& p, double* base, int lane = 0) : P(p), w{base, lane}, N(p.N), M(p.N - 1), cr(nullptr), cs(1), sb(nullptr), sbs(1) {}
+  MPC_HD Solver(const Params& p, double* base, int lane = 0) : P(p), w{base, lane}, N(p.N), M(p.N - 1), cr(nullptr), cs(1), rq(nullptr), rqs(1), sb(nullptr), sbs(1) {}
 
   MPC_HD bool fl(int f) const { return (flags & f) != 0; }
   MPC_HD void setfl(int f, bool v) { flags = v ? (flags | f) : (flags & ~f); }
@@ -460,6 +551,23 @@ struct Solver {
     (void)r;
     sincos(s[2], &sp, &cp);
     sincos(s[5], &se, &ce);
+#endif
+  }
+  // reference heading at s_t of the iterate copy starting at row r (stored or recomputed from p'(x_t))
+  MPC_HD double psides_of(int r, double p1) const {
+#if MPC_STORE_PSIDES
+    (void)p1;
+    return w(r + xPD);
+#else
+    (void)r;
+    return atan(p1);
+#endif
+  }
+  MPC_HD void store_psides(int r, double psides) const {
+#if MPC_STORE_PSIDES
+    w(r + xPD) = psides;
+#else
+    (void)r; (void)psides;
 #endif
   }
   // constraint residual of the rows of time t+1 at the iterate copy `buf` (rare paths only)
@@ -538,10 +646,12 @@ struct Solver {
         sincos(s[2], &sp, &cp);
         sincos(s[5], &se, &ce);
         poly_eval(cf, s[0], p0, p1, p2, p3);
-        residual(s, u, sn, sp, cp, se, p0, atan(p1), c);
+        const double psides = atan(p1);
+        residual(s, u, sn, sp, cp, se, p0, psides, c);
 #if MPC_STORE_TRIG
         w(r + xTR) = sp; w(r + xTR + 1) = cp; w(r + xTR + 2) = se; w(r + xTR + 3) = ce;
 #endif
+        store_psides(r, psides);
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
 #if MPC_STORE_C
@@ -612,6 +722,7 @@ struct Solver {
 #if MPC_STORE_TRIG
       w(r + xTR) = sp; w(r + xTR + 1) = cp; w(r + xTR + 2) = se; w(r + xTR + 3) = ce;
 #endif
+      store_psides(r, psides);
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
 #if MPC_STORE_C
@@ -680,8 +791,22 @@ struct Solver {
   // ------------------------------------------------------------------------------------------
   // Backward Riccati sweep: factor + feed-forward for the right-hand side (grad L_mu, c).  use_csoc selects the
   // constraint right-hand side (second-order correction).  Returns false on wrong inertia.
-  MPC_HD bool factor(double dw, bool use_csoc) {
-    const bool ls = fl(F_LS);
+  MPC_HD bool factor(double dw, bool use_csoc) { return factor_body(dw, fl(F_LS), use_csoc); }
+  // The multiplier-initialisation system (F_LS) and the second-order-correction right-hand side are loop invariants of
+  // the sweep: the per-pass kernels run one instantiation per case, which keeps those branches out of the stage body
+  // (larger basic blocks to schedule); the looping kernels keep the one generic body (instruction footprint).
+  MPC_HD bool factor_spec(double dw, bool use_csoc) {
+#if MPC_SPECIALIZE_SWEEPS
+    if (fl(F_LS)) return factor_t<true, false>(dw);
+    if (use_csoc) return factor_t<false, true>(dw);
+    return factor_t<false, false>(dw);
+#else
+    return factor_body(dw, fl(F_LS), use_csoc);
+#endif
+  }
+  template <bool LS, bool CSOC>
+  MPC_HD bool factor_t(double dw) { return factor_body(dw, LS, CSOC); }
+  MPC_HD bool factor_body(double dw, const bool ls, const bool use_csoc) {
     const double qv = ls ? 1.0 : 2.0 * P.w_v * df + dw, qe = ls ? 1.0 : 2.0 * P.w_epsi * df + dw,
                  qc = ls ? 1.0 : 2.0 * P.w_cte * df + dw, q0 = ls ? 1.0 : dw;
     const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df, gc2 = 2.0 * P.w_cte * df;
@@ -716,7 +841,7 @@ struct Solver {
     for (int t = M - 1; t >= 0; --t) {
       const int r = rec(t) + bX, rn = rec(t + 1);
       if (t > 0 && !staged) {   // rows of stage t-1: S,U,LAM,ZL,ZU(,TR) are contiguous, then the residual of rows t
-        w.prefetch(r - kRec + xS, MPC_STORE_TRIG ? 22 : 18);
+        w.prefetch(r - kRec + xS, MPC_STORE_TRIG ? (MPC_STORE_PSIDES ? 23 : 22) : 18);
         if (!ls && (MPC_STORE_C || use_csoc)) w.prefetch(rec(t) + bC, 6);
       }
       double s[6], lam[6];
@@ -754,7 +879,7 @@ struct Solver {
       } else {
         double c[6];
         const double uu[2] = {u0, u1};
-        residual(s, uu, sT, sp, cp, se, p0, atan(p1), c);
+        residual(s, uu, sT, sp, cp, se, p0, staged ? atan(p1) : psides_of(r, p1), c);
         rb[0] = -c[0]; rb[1] = -c[1]; rb[2] = -c[2]; rb[3] = -c[3]; cc = c[4]; rb[4] = -c[5];
       }
       const Lin A = make_lin(P, s[3], u0, sp, cp, se, ce, p1, p2);
@@ -772,7 +897,7 @@ struct Solver {
         const double bl0 = A.beta * (lamn[2] + lamn[5]), bl1 = P.dt * lamn[3];   // B_t^T lambda_{t+1}
         double sl0 = u0 - P.xl[0], su0 = P.xu[0] - u0, sl1 = u1 - P.xl[1], su1 = P.xu[1] - u1;
         safe_slack4(sl0, su0, sl1, su1, mu, zl0, zu0, zl1, zu1, P.xl, P.xu);
-        const double isl0 = 1.0 / sl0, isu0 = 1.0 / su0, isl1 = 1.0 / sl1, isu1 = 1.0 / su1;
+        const double isl0 = drcp(sl0), isu0 = drcp(su0), isl1 = drcp(sl1), isu1 = drcp(su1);
         r0 = hess_u(0, t) + dw + zl0 * isl0 + zu0 * isu0;
         r1 = hess_u(1, t) + dw + zl1 * isl1 + zu1 * isu1;
         ru0 = gu0 - bl0 - mu * isl0 + mu * isu0;
@@ -802,7 +927,7 @@ struct Solver {
       const double L11 = r1 + P.dt * T1[3] + Tu11;
       const double det = L00 * L11 - L10 * L10;
       if (!(L00 > 0.0) || !(det > 0.0)) ok = false;
-      const double idet = 1.0 / det;
+      const double idet = drcp(det);
       const double i00 = L11 * idet, i10 = -L10 * idet, i11 = L00 * idet;
       double G0[4], G1[4];
       applyA(A, T0[0], T0[1], T0[2], T0[3], T0[4], G0[0], G0[1], G0[2], G0[3]);
@@ -818,6 +943,9 @@ struct Solver {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { w(ko + j) = K0[j]; w(ko + 4 + j) = K1[j]; }
         w(ko + 8) = i00; w(ko + 9) = i10; w(ko + 10) = i11; w(ko + 11) = k0; w(ko + 12) = k1;
+#if MPC_FUSE_FACTOR
+        w(ko + 13) = 0.0; w(ko + 14) = 0.0;   // the barrier parameter is already in k (see ric_stage for the split form)
+#endif
       }
       // Y = Pss * Abar (5x4), S = Abar^T Y (4x4, lower)
       double Y[5][4];
@@ -872,10 +1000,158 @@ struct Solver {
     return ok;
   }
 
+
+#if MPC_FUSE_FACTOR
+  // ------------------------------------------------------------------------------------------
+  // The Riccati recursion riding on the STEP sweep (MPC_FUSE_FACTOR).  ric_stage() is the stage body of factor() for a
+  // new system (dw = 0, no second-order correction) at the iterate the STEP sweep has just formed -- its inputs are the
+  // trial values the sweep holds in registers -- with the feed-forward split as k = ka + mu kb: of the right-hand side
+  // only the barrier term of the controls, -mu / sl + mu / su, depends on mu, and the mu of the next iteration is decided
+  // after the sweep (IpMonotoneMuUpdate.cpp:132-232, top_of_loop()).  Carried from stage to stage (RQ(i) = rq[i * rqs]):
+  //   0..14 Pss   15..22 Psu   23..25 Puu   26..30 pv   31..32 pu   33..36 the mu-part of pv (its epsi entry is 0)
+  //   37..38 the mu-part of pu
+  // Returns false on a non-positive-definite control block (wrong inertia: the separate factor sweep takes over with
+  // the delta_w ladder).
+#define RQ(i) rq[(i) * rqs]
+  MPC_HD void ric_terminal(const double* sT, const double* lamT) {
+    const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df;
+#pragma unroll
+    for (int i = 0; i < kRicCarry; ++i) RQ(i) = 0.0;
+    RQ(9) = gv2; RQ(14) = ge2;   // PS(3,3) = qv, PS(4,4) = qe; q0 = dw = 0
+    RQ(26) = lamT[0]; RQ(27) = lamT[1]; RQ(28) = lamT[2];
+    RQ(29) = gv2 * (sT[3] - P.ref_v) + lamT[3];
+    RQ(30) = ge2 * sT[5] + lamT[5];
+  }
+  // s, lam: s_t, lambda_t; lamn, cteN: lambda_{t+1}, cte_{t+1}; u, z (zl0, zl1, zu0, zu1), sl (sl0, su0, sl1, su1): controls
+  // of time t with their multipliers and slacks; gub0/gub1: grad_u f - B^T lambda_{t+1}; c: residual of the rows of time
+  // t+1; A, ATl: linearisation at (s_t, u_t) and A^T lambda_{t+1}
+  MPC_HD bool ric_stage(int t, const double* s, const double* lam, const double* lamn, double cteN, double zl0, double zl1,
+                        double zu0, double zu1, double sl0, double su0, double sl1, double su1, double gub0, double gub1,
+                        double sp, double cp, double se, double ce, double p1, double p2, double p3, const double* c,
+                        const Lin& A, const double* ATl) {
+    const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df, gc2 = 2.0 * P.w_cte * df;
+    const double qv = gv2, qe = ge2, qc = gc2;
+    double pss[15], psu[4][2], pv[5], pvb[4];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) pss[i] = RQ(i);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { psu[i][0] = RQ(15 + 2 * i); psu[i][1] = RQ(16 + 2 * i); }
+    const double puu00 = RQ(23), puu10 = RQ(24), puu11 = RQ(25);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) pv[i] = RQ(26 + i);
+    const double pu0 = RQ(31), pu1 = RQ(32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pvb[i] = RQ(33 + i);
+    const double pub0 = RQ(37), pub1 = RQ(38);
+    const double rb[5] = {-c[0], -c[1], -c[2], -c[3], -c[5]}, cc = c[4];
+    const Hes H = make_hes(P, lamn, s[3], sp, cp, se, ce, p1, p2, p3);
+    const double isl0 = drcp(sl0), isu0 = drcp(su0), isl1 = drcp(sl1), isu1 = drcp(su1);
+    const double r0 = hess_u(0, t) + zl0 * isl0 + zu0 * isu0;
+    const double r1 = hess_u(1, t) + zl1 * isl1 + zu1 * isu1;
+    const double rub0 = isu0 - isl0, rub1 = isu1 - isl1;   // d(ru) / d(mu)
+    const double gc = (gc2 * cteN + lamn[4]) - qc * cc;   // linear coefficient on a_c^T dsigma (cte fold)
+    // ---- recursion
+    double wv[5], wu0 = pu0, wu1 = pu1;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      double a = pv[i];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) a += PS(i, j) * rb[j];
+      wv[i] = a;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { wu0 += psu[i][0] * rb[i]; wu1 += psu[i][1] * rb[i]; }
+    double T0[5], T1[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      T0[j] = A.beta * (PS(2, j) + PS(4, j)) + (j < 4 ? psu[j < 4 ? j : 0][0] : 0.0);
+      T1[j] = P.dt * PS(3, j) + (j < 4 ? psu[j < 4 ? j : 0][1] : 0.0);
+    }
+    const double Tu00 = A.beta * psu[2][0] + puu00, Tu10 = P.dt * psu[3][0] + puu10, Tu11 = P.dt * psu[3][1] + puu11;
+    const double L00 = r0 + A.beta * (T0[2] + T0[4]) + Tu00;
+    const double L10 = A.beta * (T1[2] + T1[4]) + Tu10;
+    const double L11 = r1 + P.dt * T1[3] + Tu11;
+    const double det = L00 * L11 - L10 * L10;
+    const bool ok = (L00 > 0.0) && (det > 0.0);
+    const double idet = drcp(det);
+    const double i00 = L11 * idet, i10 = -L10 * idet, i11 = L00 * idet;
+    double G0[4], G1[4];
+    applyA(A, T0[0], T0[1], T0[2], T0[3], T0[4], G0[0], G0[1], G0[2], G0[3]);
+    applyA(A, T1[0], T1[1], T1[2], T1[3], T1[4], G1[0], G1[1], G1[2], G1[3]);
+    G0[3] += H.m;
+    const double h0 = gub0 + A.beta * (wv[2] + wv[4]) + wu0, h1 = gub1 + P.dt * wv[3] + wu1;
+    const double hb0 = rub0 + A.beta * pvb[2] + pub0, hb1 = rub1 + P.dt * pvb[3] + pub1;
+    double K0[4], K1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { K0[j] = i00 * G0[j] + i10 * G1[j]; K1[j] = i10 * G0[j] + i11 * G1[j]; }
+    const double k0 = i00 * h0 + i10 * h1, k1 = i10 * h0 + i11 * h1;
+    const double kb0 = i00 * hb0 + i10 * hb1, kb1 = i10 * hb0 + i11 * hb1;
+    {
+      const int ko = rec(t) + oKF;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { w(ko + j) = K0[j]; w(ko + 4 + j) = K1[j]; }
+      w(ko + 8) = i00; w(ko + 9) = i10; w(ko + 10) = i11; w(ko + 11) = k0; w(ko + 12) = k1; w(ko + 13) = kb0; w(ko + 14) = kb1;
+    }
+    // Y = Pss * Abar (5x4), S = Abar^T Y (4x4, lower)
+    double Y[5][4];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) applyA(A, PS(i, 0), PS(i, 1), PS(i, 2), PS(i, 3), PS(i, 4), Y[i][0], Y[i][1], Y[i][2], Y[i][3]);
+    double Sm[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) applyA(A, Y[0][j], Y[1][j], Y[2][j], Y[3][j], Y[4][j], Sm[0][j], Sm[1][j], Sm[2][j], Sm[3][j]);
+    double aw[4], awb[4];
+    applyA(A, wv[0], wv[1], wv[2], wv[3], wv[4], aw[0], aw[1], aw[2], aw[3]);
+    applyA(A, pvb[0], pvb[1], pvb[2], pvb[3], 0.0, awb[0], awb[1], awb[2], awb[3]);
+    const double ac[4] = {A.pp, -1.0, 0.0, A.sed};
+    double rs[5];
+    rs[0] = lam[0] - ATl[0];
+    rs[1] = lam[1] - ATl[1];
+    rs[2] = lam[2] - ATl[2];
+    rs[3] = gv2 * (s[3] - P.ref_v) + lam[3] - ATl[3];
+    rs[4] = ge2 * s[5] + lam[5] - ATl[5];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j)
+        RQ(i * (i + 1) / 2 + j) = Sm[i][j] + qc * ac[i] * ac[j] - (G0[i] * K0[j] + G1[i] * K1[j]) +
+                                  (i == j ? (i == 0 ? H.xx : (i == 2 ? H.pp : (i == 3 ? qv : 0.0))) : (i == 3 && j == 2 ? H.vp : 0.0));
+    const double qvce = qc * A.vce;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) RQ(10 + j) = qvce * ac[j] + (j == 3 ? H.ev : 0.0);
+    RQ(14) = qe + H.ee + qvce * A.vce;
+    double d0 = 0.0, d1 = 0.0;   // coupling with u_{t-1}
+    if (t > 0) { d0 = 2.0 * df * P.w_ddelta; d1 = 2.0 * df * P.w_da; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { RQ(15 + 2 * i) = K0[i] * d0; RQ(16 + 2 * i) = K1[i] * d1; }
+    RQ(23) = -d0 * d0 * i00; RQ(24) = -d0 * d1 * i10; RQ(25) = -d1 * d1 * i11;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      RQ(26 + i) = rs[i] + aw[i] + gc * ac[i] - (G0[i] * k0 + G1[i] * k1);
+      RQ(33 + i) = awb[i] - (G0[i] * kb0 + G1[i] * kb1);
+    }
+    RQ(30) = rs[4] + gc * A.vce;
+    RQ(31) = d0 * k0; RQ(32) = d1 * k1;
+    RQ(37) = d0 * kb0; RQ(38) = d1 * kb1;
+    return ok;
+  }
+#undef RQ
+#endif
+
   // ------------------------------------------------------------------------------------------
   // Forward sweep: dx (-> DS, DU), fraction-to-the-boundary steps, directional derivative of the barrier.
-  MPC_HD void forward(bool use_csoc) {
-    const bool ls = fl(F_LS);
+  MPC_HD void forward(bool use_csoc) { forward_body(fl(F_LS), use_csoc); }
+  MPC_HD void forward_spec(bool use_csoc) {
+#if MPC_SPECIALIZE_SWEEPS
+    if (fl(F_LS)) forward_t<true, false>();
+    else if (use_csoc) forward_t<false, true>();
+    else forward_t<false, false>();
+#else
+    forward_body(fl(F_LS), use_csoc);
+#endif
+  }
+  template <bool LS, bool CSOC>
+  MPC_HD void forward_t() { forward_body(LS, CSOC); }
+  MPC_HD void forward_body(const bool ls, const bool use_csoc) {
     const int bX = kX * cur, bC = use_csoc ? (int)oCSOC : bX + xC;
     const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df, gc2 = 2.0 * P.w_cte * df;
     const double tinytol = 10.0 * DBL_EPSILON;
@@ -892,8 +1168,8 @@ struct Solver {
     for (int t = 0; t < M; ++t) {
       const int r = rec(t) + bX, rn = rec(t + 1);
       if (t + 1 < M) {
-        w.prefetch(rn + oKF, 13); w.prefetch(rn + kRec + bX + xS, 8);
-        w.prefetch(rn + bX + xZL, MPC_STORE_TRIG ? 8 : 4);   // ZL, ZU and the trig values are contiguous
+        w.prefetch(rn + oKF, kKF); w.prefetch(rn + kRec + bX + xS, 8);
+        w.prefetch(rn + bX + xZL, MPC_STORE_TRIG ? (MPC_STORE_PSIDES ? 9 : 8) : 4);   // ZL, ZU, the trig values and the reference heading are contiguous
         if (!ls && (MPC_STORE_C || use_csoc)) w.prefetch(rn + kRec + bC, 6);
       }
 #pragma unroll
@@ -902,7 +1178,12 @@ struct Solver {
       double K0[4], K1[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) { K0[j] = w(ko + j); K1[j] = w(ko + 4 + j); }
-      const double i00 = w(ko + 8), i10 = w(ko + 9), i11 = w(ko + 10), k0 = w(ko + 11), k1 = w(ko + 12);
+      const double i00 = w(ko + 8), i10 = w(ko + 9), i11 = w(ko + 10);
+#if MPC_FUSE_FACTOR
+      const double k0 = w(ko + 11) + mu * w(ko + 13), k1 = w(ko + 12) + mu * w(ko + 14);   // kb = 0 from factor()
+#else
+      const double k0 = w(ko + 11), k1 = w(ko + 12);
+#endif
       double sp, cp, se, ce;
       trig_of(r, s, sp, cp, se, ce);
       double p0, p1, p2, p3;
@@ -914,7 +1195,7 @@ struct Solver {
         for (int k = 0; k < 6; ++k) c[k] = w(rn + bC + k);
       } else {
         const double uu[2] = {u0, u1};
-        residual(s, uu, snx, sp, cp, se, p0, atan(p1), c);
+        residual(s, uu, snx, sp, cp, se, p0, psides_of(r, p1), c);
       }
       double un0 = 0.0, un1 = 0.0;
       if (t < M - 1) { un0 = w(rn + bX + xU); un1 = w(rn + bX + xU + 1); }
@@ -930,7 +1211,7 @@ struct Solver {
         const double zl0 = w(r + xZL), zl1 = w(r + xZL + 1), zu0 = w(r + xZU), zu1 = w(r + xZU + 1);
         double sl0 = u0 - P.xl[0], su0 = P.xu[0] - u0, sl1 = u1 - P.xl[1], su1 = P.xu[1] - u1;
         safe_slack4(sl0, su0, sl1, su1, mu, zl0, zu0, zl1, zu1, P.xl, P.xu);
-        const double isl0 = 1.0 / sl0, isu0 = 1.0 / su0, isl1 = 1.0 / sl1, isu1 = 1.0 / su1;
+        const double isl0 = drcp(sl0), isu0 = drcp(su0), isl1 = drcp(sl1), isu1 = drcp(su1);
         gbd += (grad_u(0, t, u0, um0, un0) - mu * isl0 + mu * isu0) * du0 + (grad_u(1, t, u1, um1, un1) - mu * isl1 + mu * isu1) * du1;
         gbd += gv2 * (s[3] - P.ref_v) * ds[3] + gc2 * s[4] * ds[4] + ge2 * s[5] * ds[5];
         // fraction to the boundary: alpha <= tau * slack / |du| (IpDenseVector.cpp:928-970)
@@ -939,8 +1220,8 @@ struct Solver {
         // move towards a bound contributes the neutral candidate 2 (alpha <= 1).
         const double dzl0 = (mu - sl0 * zl0 - zl0 * du0) * isl0, dzu0 = (mu - su0 * zu0 + zu0 * du0) * isu0;
         const double dzl1 = (mu - sl1 * zl1 - zl1 * du1) * isl1, dzu1 = (mu - su1 * zu1 + zu1 * du1) * isu1;
-        const double qu0 = tau / du0, qu1 = tau / du1;
-        const double qzl0 = tau / dzl0, qzu0 = tau / dzu0, qzl1 = tau / dzl1, qzu1 = tau / dzu1;
+        const double qu0 = ddiv(tau, du0), qu1 = ddiv(tau, du1);
+        const double qzl0 = ddiv(tau, dzl0), qzu0 = ddiv(tau, dzu0), qzl1 = ddiv(tau, dzl1), qzu1 = ddiv(tau, dzu1);
         const double cu0 = du0 < 0.0 ? -qu0 * sl0 : (du0 > 0.0 ? qu0 * su0 : 2.0);
         const double cu1 = du1 < 0.0 ? -qu1 * sl1 : (du1 > 0.0 ? qu1 * su1 : 2.0);
         a_pr = dmin(a_pr, dmin(cu0, cu1));
@@ -1064,7 +1345,11 @@ struct Solver {
   // (IpIpoptAlg.cpp:880-951), and every norm the convergence test / mu update need at the trial iterate
   // (IpIpoptCalculatedQuantities.cpp:2672-2832, 3279-3306).  Everything is written to the OTHER copy of the iterate
   // block; the caller flips `cur` if the trial point is accepted.
-  MPC_HD void step_sweep(double a, double a_lam, double a_du, double dw) {
+  // FUSE (MPC_FUSE_FACTOR): the Riccati factorisation of the next iteration's system at the trial iterate rides on the
+  // sweep (ric_stage); the return value says whether it is usable (right inertia, slack safeguard not involved).
+  template <bool FUSE = false>
+  MPC_HD bool step_sweep(double a, double a_lam, double a_du, double dw) {
+    bool ric_ok = true;
     const double qv = 2.0 * P.w_v * df + dw, qe = 2.0 * P.w_epsi * df + dw, qc = 2.0 * P.w_cte * df + dw, q0 = dw;
     const double gv2 = 2.0 * P.w_v * df, ge2 = 2.0 * P.w_epsi * df, gc2 = 2.0 * P.w_cte * df;
     const int bO = kX * cur, bN = kX * (cur ^ 1);
@@ -1100,6 +1385,9 @@ struct Solver {
       dinf = dmax(dinf, fabs(gv2 * (snn[3] - P.ref_v) + ln[3]));
       dinf = dmax(dinf, fabs(gc2 * snn[4] + ln[4]));
       dinf = dmax(dinf, fabs(ge2 * snn[5] + ln[5]));
+#if MPC_FUSE_FACTOR
+      if (FUSE) ric_terminal(snn, ln);
+#endif
     }
     double unn0 = 0.0, unn1 = 0.0;   // u_new at t+1
     double uc0 = 0.0, uc1 = 0.0, duc0 = 0.0, duc1 = 0.0;
@@ -1162,12 +1450,16 @@ struct Solver {
         const double b0 = tl0 * tu0;
         const double b1 = tl1 * tu1;
         slog += log(b0 * b1);
-        zl0 += a_du * ((mu - sl0 * zl0 - zl0 * du0) / sl0);
-        zu0 += a_du * ((mu - su0 * zu0 + zu0 * du0) / su0);
-        zl1 += a_du * ((mu - sl1 * zl1 - zl1 * du1) / sl1);
-        zu1 += a_du * ((mu - su1 * zu1 + zu1 * du1) / su1);
+        zl0 += a_du * ddiv(mu - sl0 * zl0 - zl0 * du0, sl0);
+        zu0 += a_du * ddiv(mu - su0 * zu0 + zu0 * du0, su0);
+        zl1 += a_du * ddiv(mu - sl1 * zl1 - zl1 * du1, sl1);
+        zu1 += a_du * ddiv(mu - su1 * zu1 + zu1 * du1, su1);
       }
       double nsl0 = un[0] - P.xl[0], nsu0 = P.xu[0] - un[0], nsl1 = un[1] - P.xl[1], nsu1 = P.xu[1] - un[1];
+      if (FUSE) {   // the slack safeguard depends on mu (practically never active): leave such a system to factor()
+        const double thr = DBL_EPSILON * dmin(mu, 1.0);
+        if ((nsl0 < thr) | (nsu0 < thr) | (nsl1 < thr) | (nsu1 < thr)) ric_ok = false;
+      }
       safe_slack4(nsl0, nsu0, nsl1, nsu1, mu, zl0, zu0, zl1, zu1, P.xl, P.xu);
       {   // kappa_sigma = 1e10 (IpIpoptAlg.cpp:880-951): z stays within [1e-10, 1e10] * mu / slack.  The exact bounds need
           // four divisions; they are evaluated only when the cheap product test says a multiplier is within a factor 4
@@ -1198,10 +1490,12 @@ struct Solver {
         double snn[6], ln[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) { snn[k] = CR(18 + k); ln[k] = CR(12 + k); }
-        residual(sn, un, snn, spn, cpn, sen, p0, atan(p1), c);
+        const double psides = atan(p1);
+        residual(sn, un, snn, spn, cpn, sen, p0, psides, c);
 #if MPC_STORE_TRIG
         w(r + bN + xTR) = spn; w(r + bN + xTR + 1) = cpn; w(r + bN + xTR + 2) = sen; w(r + bN + xTR + 3) = cen;
 #endif
+        store_psides(r + bN, psides);
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
 #if MPC_STORE_C
@@ -1218,9 +1512,18 @@ struct Solver {
         dinf = dmax(dinf, fabs(gv2 * (sn[3] - P.ref_v) + lnew[3] - at[3]));
         dinf = dmax(dinf, fabs(gc2 * sn[4] + lnew[4]));
         dinf = dmax(dinf, fabs(ge2 * sn[5] + lnew[5] - at[5]));
-        const double g0 = grad_u(0, t, un[0], umn0, unn0) - A.beta * (ln[2] + ln[5]) - zl0 + zu0;
-        const double g1 = grad_u(1, t, un[1], umn1, unn1) - P.dt * ln[3] - zl1 + zu1;
+        const double gub0 = grad_u(0, t, un[0], umn0, unn0) - A.beta * (ln[2] + ln[5]);   // grad_u f - B^T lambda_{t+1}
+        const double gub1 = grad_u(1, t, un[1], umn1, unn1) - P.dt * ln[3];
+        const double g0 = gub0 - zl0 + zu0;
+        const double g1 = gub1 - zl1 + zu1;
         dinf = dmax(dinf, dmax(fabs(g0), fabs(g1)));
+#if MPC_FUSE_FACTOR
+        if (FUSE) {
+          const bool ok = ric_stage(t, sn, lnew, ln, snn[4], zl0, zl1, zu0, zu1, nsl0, nsu0, nsl1, nsu1, gub0, gub1, spn, cpn, sen, cen,
+                                    p1, p2, p3, c, A, at);
+          ric_ok = ric_ok && ok;
+        }
+#endif
       }
 #pragma unroll
       for (int k = 0; k < 6; ++k) { CR(12 + k) = lnew[k]; CR(18 + k) = sn[k]; }
@@ -1230,6 +1533,7 @@ struct Solver {
     dualinf = dinf; lam1 = l1; z1 = zz1; sz_max = szmx; sz_min = szmn; xmaxabs = xm; dlam_max = dlm;
     tr_f = df * f; tr_theta = th; tr_priminf = cm; tr_sumlog = slog;
 #undef CR
+    return ric_ok;
   }
 
   // ------------------------------------------------------------------------------------------
@@ -1573,10 +1877,12 @@ struct Solver {
       sincos(sn[2], &sp, &cp);
       sincos(sn[5], &se, &ce);
       poly_eval(cf, sn[0], p0, p1, p2, p3);
-      residual(sn, u, zero, sp, cp, se, p0, atan(p1), cn);
+      const double psides = atan(p1);
+      residual(sn, u, zero, sp, cp, se, p0, psides, cn);
 #if MPC_STORE_TRIG
       w(r + xTR) = sp; w(r + xTR + 1) = cp; w(r + xTR + 2) = se; w(r + xTR + 3) = ce;
 #endif
+      store_psides(r, psides);
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         so[k] = son[k];
@@ -1633,7 +1939,7 @@ struct Solver {
   MPC_HD void kernel_factor() {
     LDI(iFLAGS, flags); LDI(iCUR, cur); LDD(dDF, df); LDD(dMU, mu); LDD(dDWC, dw_curr);
     phase = PH_FACTOR;
-    const bool ok = factor(dw_curr, fl(F_INSOC));
+    const bool ok = factor_spec(dw_curr, fl(F_INSOC));
     if (ok) { w(iPHASE) = (double)PH_FORWARD; return; }
     LDD(dDWL, dw_last); LDI(iSTATUS, status);
     factor_failed();
@@ -1642,7 +1948,7 @@ struct Solver {
   MPC_HD void kernel_forward() {
     LDI(iFLAGS, flags); LDI(iCUR, cur); LDD(dDF, df); LDD(dMU, mu); LDD(dTAU, tau);
     phase = PH_FORWARD;
-    forward(fl(F_INSOC));
+    forward_spec(fl(F_INSOC));
     LDD(dTH, theta_cur); LDD(dF, f_cur); LDD(dSLOG, sumlog); LDD(dTHMIN, theta_min);
     LDD(dALPHA, alpha); LDD(dAMAX, alpha_max); LDD(dAMIN, alpha_min); LDD(dRTH, ref_theta); LDD(dRBARR, ref_barr);
     LDD(dRGBD, ref_gbd); LDD(dADU, alpha_du); LDI(iNSTEPS, n_steps);
@@ -1667,6 +1973,38 @@ struct Solver {
     STI(iSOCCNT, soc_count); STI(iNSTEPS, n_steps); STI(iNF, nf); STI(iFRCNT, filt_rej_count); STI(iACCCNT, acceptable_counter); STI(iITER, iter);
     STI(iCUR, cur); STI(iFLAGS, flags); STI(iSTATUS, status); STI(iPHASE, phase);
   }
+#if MPC_FUSE_FACTOR
+  // STEP pass with the next iteration's Riccati factorisation riding on it.  If the trial point is accepted and the solve
+  // goes on, the factors of the new system are already in the workspace: the problem goes straight to its forward sweep
+  // (or, on wrong inertia, to the separate factor sweep with the first delta_w of the ladder -- what kernel_factor would
+  // have found).  Anything else (rejected trial point, second-order correction, multiplier initialisation) is
+  // kernel_step's business as before.
+  MPC_HD void kernel_stepfactor() {
+    LDI(iFLAGS, flags); LDI(iCUR, cur); LDD(dDF, df); LDD(dMU, mu); LDD(dALPHA, alpha); LDD(dADU, alpha_du); LDD(dDWC, dw_curr);
+    phase = PH_STEP;
+    const bool spec = !fl(F_LS);
+    bool ric_ok = false;
+    if (spec) ric_ok = step_sweep<true>(alpha, alpha, alpha_du, dw_curr);
+    else accept_ls(!fl(F_LSKEEP));
+    LDD(dRTH, ref_theta); LDD(dRBARR, ref_barr); LDD(dRGBD, ref_gbd); LDD(dTHMAX, theta_max); LDD(dTHMIN, theta_min);
+    LDD(dATEST, alpha_test); LDD(dAMAX, alpha_max); LDD(dAMIN, alpha_min); LDD(dTHSOC, theta_soc_old); LDD(dASOC, alpha_soc);
+    LDD(dTAU, tau); LDD(dMUMIN, mu_min); LDD(dCOBJ, curr_obj); LDD(dLOBJ, last_obj); LDD(dDWL, dw_last);
+    LDD(dF, f_cur); LDD(dTH, theta_cur); LDD(dPINF, priminf); LDD(dSLOG, sumlog);
+    LDI(iSOCCNT, soc_count); LDI(iNSTEPS, n_steps); LDI(iNF, nf); LDI(iFRCNT, filt_rej_count); LDI(iSTATUS, status); LDI(iACCCNT, acceptable_counter);
+    LDI(iITER, iter);
+    const int cur_before = cur;
+    step_logic<false>();
+    if (spec && phase == PH_FACTOR && cur != cur_before) {   // accepted, not finished: dw_curr = 0, no correction pending
+      if (ric_ok) phase = PH_FORWARD;
+      else factor_failed();   // may end the solve (delta_w ladder exhausted); the caller looks at phase
+    }
+    STD_(dTHMAX, theta_max); STD_(dTHMIN, theta_min); STD_(dATEST, alpha_test); STD_(dALPHA, alpha); STD_(dTHSOC, theta_soc_old);
+    STD_(dASOC, alpha_soc); STD_(dF, f_cur); STD_(dTH, theta_cur); STD_(dPINF, priminf); STD_(dSLOG, sumlog); STD_(dMU, mu);
+    STD_(dTAU, tau); STD_(dCOBJ, curr_obj); STD_(dLOBJ, last_obj); STD_(dDWC, dw_curr); STD_(dDWL, dw_last);
+    STI(iSOCCNT, soc_count); STI(iNSTEPS, n_steps); STI(iNF, nf); STI(iFRCNT, filt_rej_count); STI(iACCCNT, acceptable_counter); STI(iITER, iter);
+    STI(iCUR, cur); STI(iFLAGS, flags); STI(iSTATUS, status); STI(iPHASE, phase);
+  }
+#endif
 #undef LDD
 #undef LDI
 #undef STD_

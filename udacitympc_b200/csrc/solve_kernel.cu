@@ -6,7 +6,7 @@
 // workspace (each workspace access of a warp is one coalesced 256-byte row) and the 7x7 Riccati blocks live in
 // registers.  One interior-point iteration = three sweeps over the horizon, each its own kernel
 //   init | factor | forward | step        launched round after round on one stream (replayed as one CUDA graph),
-// with its own register budget (the Riccati factorisation needs ~250 registers, the step sweep 168 with its
+// with its own register budget (the Riccati factorisation needs ~250 registers, the step sweep 228 with its
 // stage-to-stage values in shared memory, the forward sweep 168) and a small instruction footprint.
 // Between rounds mpc_repack_kernel compacts the problems that are still iterating into consecutive workspace slots
 // (second workspace region, slot -> problem map, level state in device memory), so late rounds run full warps.
@@ -27,11 +27,23 @@ constexpr int kBlock = MPC_BLOCK;
 #ifndef MPC_FWD_BLOCKS
 #define MPC_FWD_BLOCKS 6
 #endif
+// The step sweep runs at 4 blocks per SM: 228 registers, nothing spilled.  At 6 blocks (168 registers, 240 B of spill
+// stores and 352 B of spill loads per thread and stage) it is 3 % slower with one caller and with overlapped callers
+// (gpurun_out/r2_sb*.json: 13.59 -> 14.05 M solves/s; 5 blocks: 13.57 M) -- the sweep is bound by its dependent
+// instruction chains, not by the number of resident warps.
 #ifndef MPC_STEP_BLOCKS
-#define MPC_STEP_BLOCKS 6
+#define MPC_STEP_BLOCKS 4
 #endif
 #ifndef MPC_FACTOR_BLOCKS
 #define MPC_FACTOR_BLOCKS 4
+#endif
+// stage-to-stage values of the step sweep: in registers (250 registers, nothing spilled, no shared memory; 0.6-0.8 % faster
+// than the shared-memory carry at 4 blocks per SM, gpurun_out/r2_creg_*.json, r2_psd_*.json) or in shared memory
+#ifndef MPC_STEP_CARRY_SMEM
+#define MPC_STEP_CARRY_SMEM 0
+#endif
+#ifndef MPC_STEPFACTOR_BLOCKS
+#define MPC_STEPFACTOR_BLOCKS 4
 #endif
 constexpr int kFwdBlocks = MPC_FWD_BLOCKS, kStepBlocks = MPC_STEP_BLOCKS, kFactorBlocks = MPC_FACTOR_BLOCKS;
 
@@ -175,12 +187,49 @@ __global__ void __launch_bounds__(kBlock, kStepBlocks) mpc_step_kernel(const __g
     if (A.count_live && ph != PH_DONE) count_live(A.desc + kLive);
     return;
   }
+#if MPC_STEP_CARRY_SMEM
   __shared__ double carry[kCarry * kBlock];   // stage-to-stage values of the sweep, [value][thread]
   S.cr = carry + threadIdx.x; S.cs = kBlock;
+#else
+  double carry[kCarry];
+  S.cr = carry; S.cs = 1;
+#endif
   load_coeffs(A, b, S.cf);
   S.kernel_step();
   if (S.phase == PH_DONE) write_result(P, A, b, S);
   else if (A.count_live) count_live(A.desc + kLive);
+}
+
+#if MPC_FUSE_FACTOR
+// STEP sweep with the Riccati factorisation of the next iteration riding on it (Solver::kernel_stepfactor): the trial
+// iterate is factorised from the registers that have just produced it, so an accepted step is followed by the forward
+// sweep directly and the factor kernel only sees the rare cases (first iteration, rejected trial points, second-order
+// corrections, inertia corrections).  Both carry sets (24 + 39 doubles per thread) live in shared memory.
+__global__ void __launch_bounds__(kBlock, MPC_STEPFACTOR_BLOCKS) mpc_stepfactor_kernel(const __grid_constant__ Params P, const __grid_constant__ SolveArgs A) {
+  int slot, b;
+  double* ws;
+  if (!locate(A, blockIdx.x * blockDim.x + threadIdx.x, slot, b, ws)) return;
+  Solver<32> S(P, slot_base(P, ws, slot), slot & 31);
+  const int ph = S.load_phase();
+  if (ph != PH_STEP) {
+    if (A.count_live && ph != PH_DONE) count_live(A.desc + kLive);
+    return;
+  }
+  __shared__ double carry[(kCarry + kRicCarry) * kBlock];   // [value][thread]
+  S.cr = carry + threadIdx.x; S.cs = kBlock;
+  S.rq = carry + kCarry * kBlock + threadIdx.x; S.rqs = kBlock;
+  load_coeffs(A, b, S.cf);
+  S.kernel_stepfactor();
+  if (S.phase == PH_DONE) write_result(P, A, b, S);
+  else if (A.count_live) count_live(A.desc + kLive);
+}
+#endif
+static void launch_step(const Params& P, const SolveArgs& A, const SolveConfig& cfg, int grid, cudaStream_t stream) {
+#if MPC_FUSE_FACTOR
+  if (cfg.fuse_factor) { mpc_stepfactor_kernel<<<grid, kBlock, 0, stream>>>(P, A); return; }
+#endif
+  (void)cfg;
+  mpc_step_kernel<<<grid, kBlock, 0, stream>>>(P, A);
 }
 
 // ---- batch compaction ------------------------------------------------------------------------------------------
@@ -353,7 +402,7 @@ static bool launch_coop(const Params& P, const SolveArgs& A, int fresh, cudaStre
   int grid = (n + wpb - 1) / wpb;
   const int cap = 4 * coop_resident_warps(P.N) / wpb;   // four waves; the warps stride over the rest
   if (cap > 0 && grid > cap) grid = cap;
-  mpc_coop_kernel<<<grid, 128, smem, stream>>>(P, A, fresh, wpb, (int)coop_doubles_per_warp(P.N), take_below);
+  mpc_coop_kernel<<<grid, 32 * wpb, smem, stream>>>(P, A, fresh, wpb, (int)coop_doubles_per_warp(P.N), take_below);   // no idle warps: their registers would stay allocated
   *err = cudaGetLastError();
   return true;
 }
@@ -379,7 +428,7 @@ static cudaError_t launch_part(const Params& P, SolveArgs A, const SolveConfig& 
         Ar.count_live = attempt ? 1 : 0;
         mpc_factor_kernel<<<grid, kBlock, 0, stream>>>(P, A);
         mpc_forward_kernel<<<grid, kBlock, 0, stream>>>(P, A);
-        mpc_step_kernel<<<grid, kBlock, 0, stream>>>(P, Ar);
+        launch_step(P, Ar, cfg, grid, stream);
         if (attempt) {
           mpc_repack_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(P, A, cfg.compact_max_live, 0, nullptr, nullptr, nullptr);
           *n += 1;
@@ -499,7 +548,7 @@ cudaError_t launch_solve_bulk(const Params& P, int B, const double* state6, cons
     Ar.count_live = attempt ? 1 : 0;
     mpc_factor_kernel<<<grid, kBlock, 0, stream>>>(P, A);
     mpc_forward_kernel<<<grid, kBlock, 0, stream>>>(P, A);
-    mpc_step_kernel<<<grid, kBlock, 0, stream>>>(P, Ar);
+    launch_step(P, Ar, cfg, grid, stream);
     n += 3;
     if (attempt) {
       mpc_repack_kernel<<<(B + 255) / 256, 256, 0, stream>>>(P, A, cfg.compact_max_live, tail.slots, T.ws1, T.map0, T.desc);
@@ -548,7 +597,7 @@ cudaError_t launch_solve_tail(const Params& P, int B, const double* state6, cons
     Ar.count_live = 1;
     mpc_factor_kernel<<<grid, kBlock, 0, stream>>>(P, A);
     mpc_forward_kernel<<<grid, kBlock, 0, stream>>>(P, A);
-    mpc_step_kernel<<<grid, kBlock, 0, stream>>>(P, Ar);
+    launch_step(P, Ar, cfg, grid, stream);
     mpc_repack_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(P, A, cfg.compact_max_live, 0, nullptr, nullptr, nullptr);
     n += 4;
     if (take_below > 0 && (r + 1) % coop_every == 0 && launch_coop(P, A, 0, stream, &ce, take_below)) {
