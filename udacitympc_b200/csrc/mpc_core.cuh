@@ -108,7 +108,7 @@ enum Status {
 //                     per round of 65 536 problems) -- at 8 warps per SM the sweeps are bound by the length of the dependent
 //                     instruction chain of a stage, and the fused chain is the sum of the two -- while the compaction has to
 //                     move the factors too.  13 % slower overall, so it is compiled out of the product (0); the host
-//                     build of the tests keeps it alive (tests/hostsim/libhostsim_fuse.so).
+//                     build of the CPU tests compiles a copy with the switch on and keeps it alive.
 #ifndef MPC_FUSE_FACTOR
 #define MPC_FUSE_FACTOR 0
 #endif
