@@ -215,9 +215,11 @@ struct Ws {
 // MPC_ASYNC_STAGE (device, per-pass factor sweep): the rows of the NEXT stage are copied into shared memory by
 // per-thread asynchronous copies (cp.async / LDGSTS: each thread moves the 8-byte elements of its own problem, so no
 // barrier and no cross-thread hand-over is involved -- a thread waits only for its own copy group) while the current
-// stage is computed, instead of the L1 prefetch + ordinary loads.
+// stage is computed, instead of the L1 prefetch + ordinary loads.  24 KB of shared memory per 64-thread block.  Measured
+// with the final kernels of round 2: +0.7 % with overlapped callers, +1.4 % for a lone caller (gpurun_out/r2_misc_*.json;
+// +1.2 % / -1.5 % before the chain-length work on the sweeps), so it is on.
 #ifndef MPC_ASYNC_STAGE
-#define MPC_ASYNC_STAGE 0
+#define MPC_ASYNC_STAGE 1
 #endif
 #if defined(__CUDA_ARCH__) && MPC_ASYNC_STAGE
 __device__ __forceinline__ void async_copy8(double* smem_dst, const double* gsrc) {
