@@ -1,4 +1,5 @@
 #!/bin/bash
+# needs a library built with -DMPC_FUSE_FACTOR=1 (udacitympc_b200.build.build_variant + B200MPC_LIB, or the default build of that commit)
 # round 2, GPU call 25: STEP sweep with the next iteration's Riccati factorisation riding on it (mpc_stepfactor_kernel):
 # parity tests with it on, then A/B of the default bench against the separate kernels (B200MPC_FUSE=0)
 mkdir -p gpurun_out

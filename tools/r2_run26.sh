@@ -1,4 +1,5 @@
 #!/bin/bash
+# needs a library built with -DMPC_FUSE_FACTOR=1 (udacitympc_b200.build.build_variant + B200MPC_LIB, or the default build of that commit)
 # round 2, GPU call 26: ncu launch list (durations, DRAM bytes, instructions) of one solve with the fused step + factor
 # sweep (B200MPC_FUSE=1) and with the separate kernels (B200MPC_FUSE=0)
 mkdir -p gpurun_out
