@@ -246,6 +246,11 @@ int b200mpc_set_timing(b200mpc_handle* h, int enable);
 int b200mpc_kernel_time_ms(b200mpc_handle* h, double* total_ms, int* launches, int reset);
 /* Sustained FP64 FMA throughput of the device in TFLOP/s (dependent-chain DFMA microbenchmark, 2 FLOP per FMA). */
 int b200mpc_measure_fp64_peak(b200mpc_handle* h, double* tflops);
+/* Arithmetic self-test (host arrays of n doubles): quot[i] = a[i] / b[i] and rcp[i] = 1 / b[i] as the sweeps compute
+ * them -- rcp.approx.ftz.f64 refined by Newton steps, within 1 ulp of the IEEE result for operands in the normal range,
+ * +-inf / 0 / NaN like the exact operation for a zero or infinite divisor -- so a caller (tests/test_gpu_parity.py) can
+ * hold the library's arithmetic against its own.  No reference counterpart: Ipopt divides with the host FPU. */
+int b200mpc_selftest_division(b200mpc_handle* h, int n, const double* a, const double* b, double* quot, double* rcp);
 /* Number of kernels this handle has launched since creation. */
 long long b200mpc_launch_count(const b200mpc_handle* h);
 

@@ -326,6 +326,34 @@ def test_fp64_peak_is_plausible(mpc):
     assert 5.0 < tf < 80.0, tf
 
 
+def test_sweep_arithmetic_reciprocals_and_quotients_within_one_ulp(mpc):
+    """The sweeps divide without the IEEE slow path (drcp / ddiv in mpc_core.cuh: rcp.approx.ftz.f64 + Newton steps).
+    Against numpy's correctly rounded results: within 1 ulp for operands in the normal range (magnitudes 1e-150 ..
+    1e150, the solver's slacks / determinants / step components live in 1e-25 .. 1e12), and the IEEE special values for a
+    zero / infinite divisor (what the fraction-to-the-boundary rule relies on: such a candidate is never the minimum)."""
+    rng = np.random.default_rng(7)
+    n = 1 << 18
+    sign = lambda k: np.where(rng.random(k) < 0.5, -1.0, 1.0)
+    a = sign(n) * 10.0 ** rng.uniform(-150, 150, n)
+    b = sign(n) * 10.0 ** rng.uniform(-150, 150, n)
+    a[: n // 4] = sign(n // 4) * rng.uniform(0.0, 2.0, n // 4)          # the tau of the step-size rule, slack-sized operands
+    b[: n // 4] = sign(n // 4) * 10.0 ** rng.uniform(-25, 12, n // 4)
+    q, r = mpc.selftest_division(a, b)
+    with np.errstate(over="ignore", under="ignore"):
+        q_ref, r_ref = a / b, 1.0 / b
+    ok = np.isfinite(q_ref) & (np.abs(q_ref) > 1e-290) & (np.abs(q_ref) < 1e290)
+    assert ok.mean() > 0.8
+    assert (np.abs(q[ok] - q_ref[ok]) <= np.spacing(np.abs(q_ref[ok]))).all()
+    assert (np.abs(r - r_ref) <= np.spacing(np.abs(r_ref))).all()
+    # special divisors
+    a2 = np.array([1.0, -2.0, 0.99, 0.0, 3.0, -3.0, 1.0])
+    b2 = np.array([0.0, 0.0, -0.0, 0.0, np.inf, np.inf, -np.inf])
+    q2, r2 = mpc.selftest_division(a2, b2)
+    assert q2[0] == np.inf and q2[1] == -np.inf and q2[2] == -np.inf and np.isnan(q2[3])
+    assert q2[4] == 0.0 and q2[5] == 0.0 and q2[6] == 0.0
+    assert r2[0] == np.inf and r2[2] == -np.inf and r2[4] == 0.0 and r2[6] == 0.0
+
+
 def test_cpp_drop_in_closed_loop(tmp_path):
     """examples/mpc_to_line_main.cpp = the reference's solution/main.cpp loop on the C++ drop-in class
     (include/b200mpc/MPC.h): compiled with g++ against libb200mpc.so, its printed trace must match the golden one."""

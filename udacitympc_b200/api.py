@@ -58,6 +58,7 @@ SYMBOLS = {
     "b200mpc_set_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
     "b200mpc_kernel_time_ms": (ctypes.c_int, [_vp, _dp, _ip, ctypes.c_int]),
     "b200mpc_measure_fp64_peak": (ctypes.c_int, [_vp, _dp]),
+    "b200mpc_selftest_division": (ctypes.c_int, [_vp, ctypes.c_int, _dp, _dp, _dp, _dp]),
     "b200mpc_launch_count": (ctypes.c_longlong, [_vp]),
 }
 
@@ -285,6 +286,16 @@ class MPC:
         t = ctypes.c_double()
         _check(self._lib.b200mpc_measure_fp64_peak(self._h, ctypes.byref(t)))
         return t.value
+
+    def selftest_division(self, a, b):
+        """(a / b, 1 / b) as the solver's sweeps compute them on the device (b200mpc_selftest_division)."""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        assert a.shape == b.shape and a.ndim == 1
+        q, r = np.empty_like(a), np.empty_like(a)
+        _check(self._lib.b200mpc_selftest_division(self._h, len(a), a.ctypes.data_as(_dp), b.ctypes.data_as(_dp),
+                                                   q.ctypes.data_as(_dp), r.ctypes.data_as(_dp)))
+        return q, r
 
     def launch_count(self):
         return int(self._lib.b200mpc_launch_count(self._h))

@@ -810,6 +810,26 @@ int b200mpc_kernel_time_ms(b200mpc_handle* h, double* total_ms, int* launches, i
   return 0;
 }
 
+int b200mpc_selftest_division(b200mpc_handle* h, int n, const double* a, const double* b, double* quot, double* rcp) {
+  if (!h) return fail(B200MPC_ERR_ARG, "null handle");
+  if (n < 0) return fail(B200MPC_ERR_ARG, "negative count");
+  if (n == 0) return 0;
+  if (!a || !b || !quot || !rcp) return fail(B200MPC_ERR_ARG, "null operand / result array");
+  CU(cudaSetDevice(h->device));
+  const size_t bytes = (size_t)n * sizeof(double);
+  CU(h->misc3.ensure(4 * bytes));
+  double* d = h->misc3.as<double>();
+  cudaStream_t s = h->stream;
+  CU(cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d + n, b, bytes, cudaMemcpyHostToDevice, s));
+  CU(launch_division_selftest(n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, s));
+  CU(cudaMemcpyAsync(quot, d + 2 * (size_t)n, bytes, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(rcp, d + 3 * (size_t)n, bytes, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  h->launches += 1;
+  return 0;
+}
+
 int b200mpc_measure_fp64_peak(b200mpc_handle* h, double* tflops) {
   if (!h || !tflops) return fail(B200MPC_ERR_ARG, "null handle / output");
   CU(cudaSetDevice(h->device));

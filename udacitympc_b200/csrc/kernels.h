@@ -84,5 +84,7 @@ cudaError_t launch_roadmap_reference(const double* pose4, int B, const double* w
 
 // DFMA throughput microbenchmark: returns FLOP executed per launch; time it outside.
 cudaError_t launch_fp64_peak(double* sink, int blocks, int threads, int iters, cudaStream_t stream, double* flop);
+// drcp / ddiv of the sweeps on n operand pairs (device pointers): quot[i] = ddiv(a[i], b[i]), rcp[i] = drcp(b[i])
+cudaError_t launch_division_selftest(int n, const double* a, const double* b, double* quot, double* rcp, cudaStream_t stream);
 
 }  // namespace b200mpc

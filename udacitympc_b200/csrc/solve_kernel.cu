@@ -633,6 +633,21 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters)
   if (s == 123.456) sink[0] = s;   // keeps the chains live, never true in practice
 }
 
+// ---------------------------------------------------------------------------------------------
+// Arithmetic self-test: the sweeps' reciprocal / quotient (drcp / ddiv, mpc_core.cuh) on caller-supplied operands, so a
+// test can hold them against the IEEE results.
+__global__ void division_selftest_kernel(int n, const double* a, const double* b, double* quot, double* rcp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  quot[i] = ddiv(a[i], b[i]);
+  rcp[i] = drcp(b[i]);
+}
+cudaError_t launch_division_selftest(int n, const double* a, const double* b, double* quot, double* rcp, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  division_selftest_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, a, b, quot, rcp);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fp64_peak(double* sink, int blocks, int threads, int iters, cudaStream_t stream, double* flop) {
   fp64_peak_kernel<<<blocks, threads, 0, stream>>>(sink, iters);
   *flop = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
