@@ -118,6 +118,7 @@ constexpr int kCarry = 24;    // stage-to-stage values of the STEP sweep
 constexpr int kRicCarry = 39; // stage-to-stage values of the Riccati recursion when it rides on the STEP sweep (step_sweep<true>)
 constexpr int kKF = 13 + 2 * MPC_FUSE_FACTOR;   // rows of the Riccati factors of one stage
 constexpr int kStageVals = 24;   // values of one stage the factor sweep stages asynchronously: S U LAM ZL ZU TR (22) + u_{t-1} (2)
+constexpr int kStepStageVals = 32;   // step sweep: S U LAM ZL ZU TR of stage t (22), DS of stage t (6), u_{t-1} (2), du_{t-1} (2)
 #ifndef MPC_RESTO_BETA
 #define MPC_RESTO_BETA 0.05
 #endif
@@ -217,7 +218,9 @@ struct Ws {
 // barrier and no cross-thread hand-over is involved -- a thread waits only for its own copy group) while the current
 // stage is computed, instead of the L1 prefetch + ordinary loads.  24 KB of shared memory per 64-thread block.  Measured
 // with the final kernels of round 2: +0.7 % with overlapped callers, +1.4 % for a lone caller (gpurun_out/r2_misc_*.json;
-// +1.2 % / -1.5 % before the chain-length work on the sweeps), so it is on.
+// +1.2 % / -1.5 % before the chain-length work on the sweeps), so it is on.  MPC_STEP_ASYNC_STAGE: the same in the step
+// sweep (32 values per stage, 32 KB per block: +1.1 %, gpurun_out/r2_sa_*.json), on; in the forward sweep it was 1.5 %
+// slower with overlapped callers (29 values, 178 KB per SM at 6 blocks -- the L1 it takes away matters more there).
 #ifndef MPC_ASYNC_STAGE
 #define MPC_ASYNC_STAGE 1
 #endif
@@ -241,6 +244,9 @@ __device__ __forceinline__ void async_wait_all() { asm volatile("cp.async.wait_g
 // initialisation, second-order correction, the usual Newton system) instead of branching inside the stage body
 #ifndef MPC_SPECIALIZE_SWEEPS
 #define MPC_SPECIALIZE_SWEEPS 1
+#endif
+#ifndef MPC_STEP_ASYNC_STAGE
+#define MPC_STEP_ASYNC_STAGE 1
 #endif
 #ifndef MPC_FAST_DIV
 #define MPC_FAST_DIV 1
@@ -786,6 +792,25 @@ struct Solver {
       const double* gm = &w(rec(t - 1) + bX + xU);
       async_copy8(q + 22 * sbs, gm);
       async_copy8(q + 23 * sbs, gm + LANES);
+    }
+    async_commit();
+  }
+  // step sweep: what stage t reads, into stage buffer t & 1 (element i of buffer b at sb[(b * kStepStageVals + i) * sbs])
+  __device__ __forceinline__ void step_stage_request(int t, int bO) {
+    double* q = sb + (size_t)((t & 1) * kStepStageVals) * sbs;
+    const double* g = &w(rec(t) + bO);
+#pragma unroll
+    for (int k = 0; k < 22; ++k) async_copy8(q + k * sbs, g + (size_t)k * LANES);
+    const double* gd = &w(rec(t) + oDS);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) async_copy8(q + (22 + k) * sbs, gd + (size_t)k * LANES);
+    if (t > 0) {
+      const double* gu = &w(rec(t - 1) + bO + xU);
+      async_copy8(q + 28 * sbs, gu);
+      async_copy8(q + 29 * sbs, gu + LANES);
+      const double* gdu = &w(rec(t - 1) + oDU);
+      async_copy8(q + 30 * sbs, gdu);
+      async_copy8(q + 31 * sbs, gdu + LANES);
     }
     async_commit();
   }
@@ -1361,6 +1386,12 @@ struct Solver {
 #define CR(i) cr[(i) * cs]
     double dinf = 0.0, l1 = 0.0, zz1 = 0.0, szmx = 0.0, szmn = 1e300, xm = 0.0, dlm = 0.0;
     double f = 0.0, th = 0.0, cm = 0.0, slog = 0.0;
+#if defined(__CUDA_ARCH__) && MPC_ASYNC_STAGE && MPC_STEP_ASYNC_STAGE && MPC_STORE_TRIG
+    const bool staged = !FUSE && sb != nullptr;
+    if (staged) step_stage_request(M - 1, bO);
+#else
+    const bool staged = false;
+#endif
     {
       const int r = rec(M);
       double s[6], ds[6], lam[6];
@@ -1396,14 +1427,31 @@ struct Solver {
     { const int r = rec(M - 1); uc0 = w(r + bO + xU); uc1 = w(r + bO + xU + 1); duc0 = w(r + oDU); duc1 = w(r + oDU + 1); }
     for (int t = M - 1; t >= 0; --t) {
       const int r = rec(t);
-      if (t > 0) { w.prefetch(r - kRec + bO + xS, MPC_STORE_TRIG ? 22 : 18); w.prefetch(r - kRec + oDS, 8); }
+      if (t > 0 && !staged) { w.prefetch(r - kRec + bO + xS, MPC_STORE_TRIG ? 22 : 18); w.prefetch(r - kRec + oDS, 8); }
       double s[6], ds[6], lam[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) { s[k] = w(r + bO + xS + k); ds[k] = w(r + oDS + k); lam[k] = w(r + bO + xLAM + k); }
       const double u0 = uc0, u1 = uc1, du0 = duc0, du1 = duc1;
       double um0 = 0.0, um1 = 0.0, dum0 = 0.0, dum1 = 0.0;
-      if (t > 0) { um0 = w(r - kRec + bO + xU); um1 = w(r - kRec + bO + xU + 1); dum0 = w(r - kRec + oDU); dum1 = w(r - kRec + oDU + 1); }
-      double zl0 = w(r + bO + xZL), zl1 = w(r + bO + xZL + 1), zu0 = w(r + bO + xZU), zu1 = w(r + bO + xZU + 1);
+      double zl0, zl1, zu0, zu1;
+      double trs0 = 0.0, trs1 = 0.0, trs2 = 0.0, trs3 = 0.0;   // staged sin / cos values of the current point
+#if defined(__CUDA_ARCH__) && MPC_ASYNC_STAGE && MPC_STEP_ASYNC_STAGE && MPC_STORE_TRIG
+      if (staged) {
+        // this stage's rows were requested one stage ago (before the terminal block for t = M-1); request the next, then use
+        async_wait_all();
+        if (t > 0) step_stage_request(t - 1, bO);
+        const double* q = sb + (size_t)((t & 1) * kStepStageVals) * sbs;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { s[k] = q[(xS + k) * sbs]; lam[k] = q[(xLAM + k) * sbs]; ds[k] = q[(22 + k) * sbs]; }
+        zl0 = q[xZL * sbs]; zl1 = q[(xZL + 1) * sbs]; zu0 = q[xZU * sbs]; zu1 = q[(xZU + 1) * sbs];
+        trs0 = q[xTR * sbs]; trs1 = q[(xTR + 1) * sbs]; trs2 = q[(xTR + 2) * sbs]; trs3 = q[(xTR + 3) * sbs];
+        if (t > 0) { um0 = q[28 * sbs]; um1 = q[29 * sbs]; dum0 = q[30 * sbs]; dum1 = q[31 * sbs]; }
+      } else
+#endif
+      {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { s[k] = w(r + bO + xS + k); ds[k] = w(r + oDS + k); lam[k] = w(r + bO + xLAM + k); }
+        if (t > 0) { um0 = w(r - kRec + bO + xU); um1 = w(r - kRec + bO + xU + 1); dum0 = w(r - kRec + oDU); dum1 = w(r - kRec + oDU + 1); }
+        zl0 = w(r + bO + xZL); zl1 = w(r + bO + xZL + 1); zu0 = w(r + bO + xZU); zu1 = w(r + bO + xZU + 1);
+      }
       // ---- current point: lambda^+_t from the stationarity rows
       double lpn[6];   // lambda^+_t
       {
@@ -1411,7 +1459,8 @@ struct Solver {
 #pragma unroll
         for (int k = 0; k < 6; ++k) { lp[k] = CR(k); lo[k] = CR(6 + k); }
         double spo, cpo, seo, ceo;
-        trig_of(r + bO, s, spo, cpo, seo, ceo);
+        if (staged) { spo = trs0; cpo = trs1; seo = trs2; ceo = trs3; }
+        else trig_of(r + bO, s, spo, cpo, seo, ceo);
         double p0, p1, p2, p3;
         poly_eval(cf, s[0], p0, p1, p2, p3);
         const Lin A = make_lin(P, s[3], u0, spo, cpo, seo, ceo, p1, p2);

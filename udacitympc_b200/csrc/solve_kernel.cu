@@ -194,6 +194,10 @@ __global__ void __launch_bounds__(kBlock, kStepBlocks) mpc_step_kernel(const __g
   double carry[kCarry];
   S.cr = carry; S.cs = 1;
 #endif
+#if MPC_ASYNC_STAGE && MPC_STEP_ASYNC_STAGE
+  __shared__ double stage[2 * kStepStageVals * kBlock];   // [buffer][value][thread]
+  S.sb = stage + threadIdx.x; S.sbs = kBlock;
+#endif
   load_coeffs(A, b, S.cf);
   S.kernel_step();
   if (S.phase == PH_DONE) write_result(P, A, b, S);
